@@ -1,0 +1,433 @@
+"""Structured RT0/P0 multilevel hierarchy provider (the stand-in for ParELAG in this repo).
+
+In the reference the agglomerated hierarchy (prolongators P, the Raviart-Thomas / L2 spaces,
+the B and W operators, per-agglomerate mass blocks) is built once on the host by ParELAG
+(`/root/reference/src/DarcySolver.cpp:60-244`, `/root/reference/src/PDESampler.cpp:177-334`) and is
+NOT part of the per-sample hot path.  ParELAG/MFEM are not available here, so this module produces the
+same *kind* of data for Cartesian quad/hex meshes with geometric (tensor-product) agglomeration:
+
+  * lowest-order Raviart-Thomas dofs = total flux through a face in the +axis direction,
+  * piecewise-constant (VALUE-type) L2 dofs, so W = diag(|e|), D = signed incidence / |e|, B = W D,
+  * prolongators: P_u = coarse RT0 functions expressed in fine flux dofs, P_s = 0/1 aggregation,
+  * per-element dense local mass blocks for the unit coefficient (`VectorFEMassIntegrator(1)`,
+    `/root/reference/examples/MLMC.cpp:225`).
+
+On nested Cartesian meshes the ParELAG order-0 coarse spaces coincide with the coarse RT0/P0 spaces
+(the coarse RT0 function is the minimum-energy extension of a uniform face flux), so this is the same
+discretisation, not an approximation of it.  Everything downstream (oracle, C-ABI upload) consumes plain
+CSR arrays and does not care where they came from.
+
+Mesh conventions follow MFEM's Cartesian mesh generator as used by the reference's inline meshes
+(`/root/reference/meshes/cube_hex.mesh`, `/root/reference/meshes/inline_quad.mesh`):
+boundary attributes 3D: bottom(z=0)=1, front(y=0)=2, right(x=L)=3, back(y=L)=4, left(x=0)=5, top(z=L)=6;
+2D: bottom(y=0)=1, right(x=L)=2, top(y=L)=3, left(x=0)=4.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+from typing import List, Optional, Sequence
+
+import numpy as np
+import scipy.sparse as sp
+
+
+# --------------------------------------------------------------------------------------
+# closed-form constants of the path
+# --------------------------------------------------------------------------------------
+def matern_scaling_coefficient(corlen: float, ndim: int) -> float:
+    """g of `ComputeScalingCoefficientForSPDE` (`/root/reference/src/Utilities.hpp:188-200`).
+
+    Uses tgamma(nu + d) exactly as the code does (not the doc comment's nu + d/2).
+    """
+    d = float(ndim)
+    nu = 2.0 - d / 2.0
+    gnu = math.gamma(nu)
+    gnudim = math.gamma(nu + d)
+    c = math.pow(16.0 * math.atan(1.0), 0.5 * d)
+    k = math.pow(1.0 / corlen, 2.0 * nu)
+    return math.sqrt(c * gnudim * k / gnu)
+
+
+def spde_alpha(corlen: float) -> float:
+    """alpha = kappa^2 = 1/corlen^2 (`/root/reference/src/PDESampler.cpp:42`)."""
+    return 1.0 / (corlen * corlen)
+
+
+# --------------------------------------------------------------------------------------
+# one level of a tensor-product box mesh
+# --------------------------------------------------------------------------------------
+@dataclass
+class BoxLevel:
+    """One level: a tensor-product grid given by its node coordinates per axis."""
+
+    nodes: List[np.ndarray]            # per axis, increasing coordinates, len n_a + 1
+    dim: int = field(init=False)
+    n: np.ndarray = field(init=False)  # elements per axis
+    Ne: int = field(init=False)
+    Nf: int = field(init=False)
+    face_off: np.ndarray = field(init=False)  # offset of each axis' face block
+
+    def __post_init__(self):
+        self.dim = len(self.nodes)
+        self.n = np.array([len(x) - 1 for x in self.nodes], dtype=np.int64)
+        self.Ne = int(np.prod(self.n))
+        cnt = []
+        for a in range(self.dim):
+            m = self.n.copy()
+            m[a] += 1
+            cnt.append(int(np.prod(m)))
+        self.face_off = np.concatenate([[0], np.cumsum(cnt)]).astype(np.int64)
+        self.Nf = int(self.face_off[-1])
+
+    # -- index helpers (x fastest) --------------------------------------------------------
+    def elem_index(self, idx: Sequence[np.ndarray]) -> np.ndarray:
+        e = np.zeros_like(idx[0], dtype=np.int64)
+        stride = 1
+        for a in range(self.dim):
+            e = e + stride * idx[a]
+            stride *= int(self.n[a])
+        return e
+
+    def face_index(self, axis: int, idx: Sequence[np.ndarray]) -> np.ndarray:
+        """Face normal to `axis`; idx[axis] in [0, n_axis], the others in [0, n_b)."""
+        f = np.zeros_like(idx[0], dtype=np.int64)
+        stride = 1
+        for a in range(self.dim):
+            f = f + stride * idx[a]
+            stride *= int(self.n[a]) + (1 if a == axis else 0)
+        return f + int(self.face_off[axis])
+
+    def elem_grid(self) -> List[np.ndarray]:
+        """Per-axis integer index arrays of all elements, in element numbering order."""
+        grids = np.meshgrid(*[np.arange(int(m)) for m in self.n], indexing="ij")
+        # element numbering is x fastest -> order 'F'
+        return [g.ravel(order="F") for g in grids]
+
+    def h(self, axis: int) -> np.ndarray:
+        return np.diff(self.nodes[axis])
+
+    def elem_sizes(self) -> List[np.ndarray]:
+        idx = self.elem_grid()
+        return [self.h(a)[idx[a]] for a in range(self.dim)]
+
+    def volumes(self) -> np.ndarray:
+        v = np.ones(self.Ne)
+        for s in self.elem_sizes():
+            v = v * s
+        return v
+
+
+def _csr(mat) -> sp.csr_matrix:
+    m = sp.csr_matrix(mat)
+    m.sum_duplicates()
+    m.sort_indices()
+    m.indices = m.indices.astype(np.int32)
+    m.indptr = m.indptr.astype(np.int32)
+    return m
+
+
+@dataclass
+class LevelData:
+    """Everything ParELAG would hand over for one level (host arrays, uploaded once)."""
+
+    dim: int
+    Ne: int
+    Nf: int
+    # element -> RT dofs and dense unit-coefficient local mass blocks
+    elem_ptr: np.ndarray      # int32 [Ne+1]
+    elem_dofs: np.ndarray     # int32 [sum n_e]
+    elem_mat_ptr: np.ndarray  # int64 [Ne+1] offsets into elem_mat (n_e^2 each)
+    elem_mat: np.ndarray      # float64
+    Wdiag: np.ndarray         # float64 [Ne]  (L2 mass, diagonal)
+    D: sp.csr_matrix          # Ne x Nf  discrete divergence
+    B: sp.csr_matrix          # Ne x Nf  = W D
+    bdr_face: np.ndarray      # int32 [nb] boundary RT dofs
+    bdr_attr: np.ndarray      # int32 [nb] attribute (1-based)
+    bdr_sign: np.ndarray      # float64 [nb] +1 if dof orientation is outward, else -1
+    P_u: Optional[sp.csr_matrix] = None   # Nf x Nf_coarse   (to the next coarser level)
+    P_s: Optional[sp.csr_matrix] = None   # Ne x Ne_coarse
+    grid: Optional[BoxLevel] = None
+
+    @property
+    def N(self) -> int:
+        return self.Nf + self.Ne
+
+    def assemble_M(self, k: Optional[np.ndarray] = None) -> sp.csr_matrix:
+        """M(k) = sum_e k_e R_e^T M_e R_e  (`DeRhamSequence::ComputeMassOperator(uform[,k])`,
+        call sites `/root/reference/src/DarcySolver.cpp:479`, `/root/reference/src/PDESampler.cpp:232`)."""
+        ne = np.diff(self.elem_ptr)
+        rows = np.repeat(self.elem_dofs, np.repeat(ne, ne))
+        # column index: for each element, tile dofs n_e times
+        cols = np.concatenate([np.tile(self.elem_dofs[self.elem_ptr[e]:self.elem_ptr[e + 1]], ne[e])
+                               for e in range(self.Ne)]) if not _uniform(ne) else _tile_uniform(
+            self.elem_dofs, int(ne[0]))
+        vals = self.elem_mat
+        if k is not None:
+            vals = vals * np.repeat(np.asarray(k, dtype=np.float64), ne * ne)
+        M = sp.coo_matrix((vals, (rows, cols)), shape=(self.Nf, self.Nf))
+        return _csr(M)
+
+
+def _uniform(ne: np.ndarray) -> bool:
+    return bool(np.all(ne == ne[0]))
+
+
+def _tile_uniform(elem_dofs: np.ndarray, n: int) -> np.ndarray:
+    d = elem_dofs.reshape(-1, n)
+    return np.repeat(d[:, None, :], n, axis=1).reshape(-1)
+
+
+def _build_level(grid: BoxLevel) -> LevelData:
+    dim = grid.dim
+    idx = grid.elem_grid()
+    hs = grid.elem_sizes()
+    vol = grid.volumes()
+    nloc = 2 * dim
+    Ne = grid.Ne
+    # element dofs: [x-, x+, y-, y+, (z-, z+)]
+    dofs = np.empty((Ne, nloc), dtype=np.int64)
+    for a in range(dim):
+        lo = [i.copy() for i in idx]
+        hi = [i.copy() for i in idx]
+        hi[a] = hi[a] + 1
+        dofs[:, 2 * a] = grid.face_index(a, lo)
+        dofs[:, 2 * a + 1] = grid.face_index(a, hi)
+    # local mass: direction a block = h_a^2 / |e| * [[1/3, 1/6], [1/6, 1/3]]
+    # (flux dofs: u_a = (F0 (1-t) + F1 t) / (|e| / h_a)  =>  int u_a^2 = h_a^2/|e| * (F0^2/3 + F0 F1/3 + F1^2/3))
+    mats = np.zeros((Ne, nloc, nloc))
+    for a in range(dim):
+        c = hs[a] * hs[a] / vol
+        mats[:, 2 * a, 2 * a] = c / 3.0
+        mats[:, 2 * a + 1, 2 * a + 1] = c / 3.0
+        mats[:, 2 * a, 2 * a + 1] = c / 6.0
+        mats[:, 2 * a + 1, 2 * a] = c / 6.0
+    # divergence in VALUE-type P0 dofs: (sum of outward fluxes) / |e|
+    rows = np.repeat(np.arange(Ne, dtype=np.int64), nloc)
+    sgn = np.tile(np.array([-1.0, 1.0] * dim), Ne)
+    Binc = _csr(sp.coo_matrix((sgn, (rows, dofs.ravel())), shape=(Ne, grid.Nf)))
+    D = _csr(sp.diags(1.0 / vol) @ Binc)
+    B = _csr(sp.diags(vol) @ D)
+    # boundary faces and attributes
+    if dim == 3:
+        attr = {(2, 0): 1, (1, 0): 2, (0, 1): 3, (1, 1): 4, (0, 0): 5, (2, 1): 6}
+    elif dim == 2:
+        attr = {(1, 0): 1, (0, 1): 2, (1, 1): 3, (0, 0): 4}
+    else:
+        raise ValueError("dim must be 2 or 3")
+    bf, ba, bs = [], [], []
+    for a in range(dim):
+        others = [b for b in range(dim) if b != a]
+        grids = np.meshgrid(*[np.arange(int(grid.n[b])) for b in others], indexing="ij")
+        for side in (0, 1):
+            ii = [None] * dim
+            for b, g in zip(others, grids):
+                ii[b] = g.ravel(order="F")
+            ii[a] = np.full_like(ii[others[0]], 0 if side == 0 else int(grid.n[a]))
+            f = grid.face_index(a, ii)
+            bf.append(f)
+            ba.append(np.full(f.shape, attr[(a, side)], dtype=np.int32))
+            bs.append(np.full(f.shape, -1.0 if side == 0 else 1.0))
+    return LevelData(
+        dim=dim, Ne=Ne, Nf=grid.Nf,
+        elem_ptr=(np.arange(Ne + 1, dtype=np.int64) * nloc).astype(np.int32),
+        elem_dofs=dofs.ravel().astype(np.int32),
+        elem_mat_ptr=np.arange(Ne + 1, dtype=np.int64) * nloc * nloc,
+        elem_mat=mats.ravel(),
+        Wdiag=vol.copy(),
+        D=D, B=B,
+        bdr_face=np.concatenate(bf).astype(np.int32),
+        bdr_attr=np.concatenate(ba).astype(np.int32),
+        bdr_sign=np.concatenate(bs),
+        grid=grid,
+    )
+
+
+def _coarsen_axis(nodes: np.ndarray, factor: int = 2):
+    """Group consecutive fine cells by `factor`; a short remainder group closes the axis."""
+    n = len(nodes) - 1
+    starts = np.arange(0, n, factor)
+    cnodes = np.concatenate([nodes[starts], nodes[-1:]])
+    parent = np.minimum(np.arange(n) // factor, len(starts) - 1)
+    return cnodes, parent.astype(np.int64), np.concatenate([starts, [n]]).astype(np.int64)
+
+
+def _prolongators(fine: BoxLevel, coarse: BoxLevel, parents, starts):
+    dim = fine.dim
+    # --- P_s : 0/1 aggregation ---
+    fidx = fine.elem_grid()
+    cidx = [parents[a][fidx[a]] for a in range(dim)]
+    ce = coarse.elem_index(cidx)
+    P_s = _csr(sp.coo_matrix((np.ones(fine.Ne), (np.arange(fine.Ne), ce)), shape=(fine.Ne, coarse.Ne)))
+    # --- P_u : coarse RT0 flux functions sampled on fine faces ---
+    rows, cols, vals = [], [], []
+    for a in range(dim):
+        m = fine.n.copy()
+        m[a] += 1
+        grids = np.meshgrid(*[np.arange(int(x)) for x in m], indexing="ij")
+        ii = [g.ravel(order="F") for g in grids]
+        f = fine.face_index(a, ii)
+        # transverse share = fine face area / coarse face area
+        share = np.ones(f.shape)
+        cpar = [None] * dim
+        for b in range(dim):
+            if b == a:
+                continue
+            cpar[b] = parents[b][ii[b]]
+            share = share * fine.h(b)[ii[b]] / coarse.h(b)[cpar[b]]
+        # position along the axis: fine node ii[a] lies in coarse cell I (or on a coarse node)
+        xa = fine.nodes[a][ii[a]]
+        # coarse cell containing the node (right-closed at the end)
+        I = np.minimum(np.searchsorted(coarse.nodes[a], xa, side="right") - 1, int(coarse.n[a]) - 1)
+        t = (xa - coarse.nodes[a][I]) / coarse.h(a)[I]
+        on_left = ii[a] == starts[a][I]
+        on_right = ii[a] == starts[a][I + 1]
+        t = np.where(on_left, 0.0, np.where(on_right, 1.0, t))
+        for side, w in ((0, (1.0 - t) * share), (1, t * share)):
+            jj = [c for c in cpar]
+            jj[a] = I + side
+            F = coarse.face_index(a, jj)
+            keep = w != 0.0
+            rows.append(f[keep])
+            cols.append(F[keep])
+            vals.append(w[keep])
+    P_u = _csr(sp.coo_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))),
+                             shape=(fine.Nf, coarse.Nf)))
+    return P_u, P_s
+
+
+def build_box_hierarchy(n_fine: Sequence[int], lengths: Sequence[float], nlevels: int,
+                        factor: int = 2) -> List[LevelData]:
+    """Levels 0 (finest) .. nlevels-1 (coarsest) of an n_fine box mesh on [0,lengths]."""
+    dim = len(n_fine)
+    nodes = [np.linspace(0.0, float(lengths[a]), int(n_fine[a]) + 1) for a in range(dim)]
+    grids = [BoxLevel(nodes)]
+    maps = []
+    for _ in range(nlevels - 1):
+        cn, par, st = [], [], []
+        for a in range(dim):
+            c, p, s = _coarsen_axis(grids[-1].nodes[a], factor)
+            cn.append(c)
+            par.append(p)
+            st.append(s)
+        grids.append(BoxLevel(cn))
+        maps.append((par, st))
+    levels = [_build_level(g) for g in grids]
+    for l in range(nlevels - 1):
+        P_u, P_s = _prolongators(grids[l], grids[l + 1], *maps[l])
+        levels[l].P_u = P_u
+        levels[l].P_s = P_s
+    return levels
+
+
+# --------------------------------------------------------------------------------------
+# host-once setup that the reference performs in BuildHierarchy / Build*Functional
+# --------------------------------------------------------------------------------------
+@dataclass
+class SamplerLevel:
+    """Operators of `[M B^T; B -alpha W]` for one level, as `PDESampler::BuildHierarchy` leaves them
+    (`/root/reference/src/PDESampler.cpp:218-284`)."""
+
+    Ne: int
+    Nf: int
+    M: sp.csr_matrix        # eliminated: essential rows/cols zeroed, unit diagonal
+    B: sp.csr_matrix        # W * D with essential columns zeroed
+    Wdiag: np.ndarray       # diag(W) (positive, before the -alpha scaling)
+    w_sqrt: np.ndarray      # sqrt(diag W)
+    ess_u: np.ndarray       # int32 0/1 mask over RT dofs
+    P: Optional[sp.csr_matrix]  # Ne x Ne_coarse  (Ps[i], `PDESampler.cpp:189-193`)
+    nnz: int
+
+
+def _eliminate_rowcol(M: sp.csr_matrix, ess: np.ndarray) -> sp.csr_matrix:
+    """mfem::SparseMatrix::EliminateRowCol(rc) with the default DIAG_ONE policy."""
+    keep = sp.diags((ess == 0).astype(np.float64))
+    return _csr(keep @ M @ keep + sp.diags((ess != 0).astype(np.float64)))
+
+
+def build_sampler_levels(levels: List[LevelData]) -> List[SamplerLevel]:
+    out = []
+    for lv in levels:
+        ess = np.zeros(lv.Nf, dtype=np.int32)
+        ess[lv.bdr_face] = 1                          # u.n = 0 on the whole boundary (`:210-214`)
+        M = _eliminate_rowcol(lv.assemble_M(), ess)   # `:232,236-241`
+        Dt = _csr(lv.D @ sp.diags((ess == 0).astype(np.float64)))   # EliminateCols `:243`
+        Dt.eliminate_zeros()
+        B = _csr(sp.diags(lv.Wdiag) @ Dt)             # `:245`
+        B.eliminate_zeros()
+        nnz = M.nnz + 2 * B.nnz + lv.Ne               # `:265`
+        out.append(SamplerLevel(Ne=lv.Ne, Nf=lv.Nf, M=M, B=B, Wdiag=lv.Wdiag.copy(),
+                                w_sqrt=np.sqrt(lv.Wdiag), ess_u=ess, P=lv.P_s, nnz=int(nnz)))
+    return out
+
+
+@dataclass
+class DarcyLevel:
+    """Per-level data of `DarcySolver` after BuildHierachySpaces / Build*ObservationFunctional /
+    SetEssBdrConditions / BuildForcingTerms (`/root/reference/src/DarcySolver.cpp:60-414`)."""
+
+    Ne: int
+    Nf: int
+    elem_ptr: np.ndarray
+    elem_dofs: np.ndarray
+    elem_mat_ptr: np.ndarray
+    elem_mat: np.ndarray
+    B: sp.csr_matrix        # un-eliminated W*D (`:203-207`)
+    ess_u: np.ndarray       # int32 0/1 mask of essential RT dofs
+    ess_data: np.ndarray    # float64 [N]
+    rhs: np.ndarray         # float64 [N]
+    obs: np.ndarray         # float64 [N]
+    P_u: Optional[sp.csr_matrix]
+    P_p: Optional[sp.csr_matrix]
+
+    @property
+    def N(self):
+        return self.Nf + self.Ne
+
+
+def build_darcy_levels(levels: List[LevelData], ess_attr: Sequence[int], obs_attr: Sequence[int],
+                       inflow_attr: Sequence[int], p_inflow: float = -1.0,
+                       qoi: str = "eff_perm") -> List[DarcyLevel]:
+    """The MLMC drivers' deterministic problem (`/root/reference/examples/MLMC.cpp:214-239`):
+    f = 0, q = 0, p_bdr = p_inflow on inflow attributes, u.n = 0 on essential attributes,
+    QoI = int_{Gamma_obs} u.n  (eff_perm) or int p (p_int)."""
+    ess_attr = np.asarray(ess_attr)
+    obs_attr = np.asarray(obs_attr)
+    inflow_attr = np.asarray(inflow_attr)
+    out = []
+    rhs = obs = None
+    for l, lv in enumerate(levels):
+        N = lv.N
+        if l == 0:
+            rhs = np.zeros(N)
+            obs = np.zeros(N)
+            a = lv.bdr_attr - 1
+            # VectorFEBoundaryFluxLFIntegrator(coef): int coef * (phi . n_outward); phi.n integrates to +-1
+            inflow = inflow_attr[a] != 0
+            np.add.at(rhs, lv.bdr_face[inflow], p_inflow * lv.bdr_sign[inflow])
+            if qoi == "eff_perm":
+                ob = obs_attr[a] != 0
+                np.add.at(obs, lv.bdr_face[ob], lv.bdr_sign[ob])
+            elif qoi == "p_int":
+                obs[lv.Nf:] = lv.Wdiag
+            else:
+                raise ValueError(qoi)
+        else:
+            prev = levels[l - 1]
+            Pblk = sp.block_diag([prev.P_u, prev.P_s], format="csr")
+            rhs = Pblk.T @ rhs          # `DarcySolver.cpp:410-411`
+            obs = Pblk.T @ obs          # `:314-315`
+        ess = np.zeros(lv.Nf, dtype=np.int32)
+        on_ess = ess_attr[lv.bdr_attr - 1] != 0
+        ess[lv.bdr_face[on_ess]] = 1
+        out.append(DarcyLevel(Ne=lv.Ne, Nf=lv.Nf, elem_ptr=lv.elem_ptr, elem_dofs=lv.elem_dofs,
+                              elem_mat_ptr=lv.elem_mat_ptr, elem_mat=lv.elem_mat, B=lv.B,
+                              ess_u=ess, ess_data=np.zeros(N), rhs=np.asarray(rhs).copy(),
+                              obs=np.asarray(obs).copy(), P_u=lv.P_u, P_p=lv.P_s))
+    return out
+
+
+# The reference's default MLMC problem (`examples/example_helpers/CreateMLMCParameterList.hpp:27-41`)
+MLMC_DEFAULT_BC = dict(ess_attr=[0, 1, 1, 1, 1, 0], obs_attr=[1, 0, 0, 0, 0, 0], inflow_attr=[0, 0, 0, 0, 0, 1])
+# SPE10 XML (`examples/SPE10/spe10_3D_parameters.xml:45-49`)
+SPE10_BC = dict(ess_attr=[1, 0, 1, 0, 1, 1], obs_attr=[0, 1, 0, 0, 0, 0], inflow_attr=[0, 0, 0, 1, 0, 0])
