@@ -1,0 +1,295 @@
+"""ctypes binding of the product library `parelagmc_b200/lib/libpmc_b200.so` (C ABI: `include/pmc_b200.h`).
+
+There is no CPU fallback: importing this module is harmless, but `load()` raises if the CUDA library has
+not been built, and every compute call raises `PmcError` if no sm_100 GPU is usable.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from typing import Optional, Sequence
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libpmc_b200.so")
+CSRC = os.path.join(_HERE, "csrc")
+
+K_CLASSES = ["saddle_apply", "lanczos_update", "solution_update", "mass_smooth", "schur_smooth", "transfer",
+             "setup", "scalar", "rng", "misc"]
+
+# every symbol include/pmc_b200.h declares (checked by tests/test_abi.py against the header text)
+SYMBOLS = [
+    "pmc_create", "pmc_destroy", "pmc_last_error", "pmc_set_stream", "pmc_synchronize", "pmc_set_tolerances",
+    "pmc_set_preconditioner", "pmc_set_batch", "pmc_upload_sampler_level", "pmc_upload_darcy_level", "pmc_prepare",
+    "pmc_rng_init", "pmc_rng_fill_int", "pmc_rng_fill", "pmc_sampler_sample_batch", "pmc_sampler_eval_batch",
+    "pmc_darcy_solve_batch", "pmc_darcy_apply_batch", "pmc_mlmc_level_batch", "pmc_mc_level_batch", "pmc_profile",
+    "pmc_reset_stats", "pmc_kernel_stats",
+]
+
+
+class PmcError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"pmc_b200 error {code}: {msg}")
+        self.code = code
+
+
+class KernelStats(C.Structure):
+    _fields_ = [("launches", C.c_int64 * 10), ("algo_bytes", C.c_double * 10), ("ms", C.c_double * 10),
+                ("timed_launches", C.c_int64 * 10)]
+
+
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int)
+
+
+def build(force: bool = False) -> str:
+    """Compile the CUDA library in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
+    srcs = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(_HERE, "..", "include", "pmc_b200.h")]
+    stale = (not os.path.exists(LIB_PATH)) or any(os.path.getmtime(s) > os.path.getmtime(LIB_PATH) for s in srcs)
+    if force or stale:
+        subprocess.check_call(["make", "-C", CSRC], stdout=subprocess.DEVNULL)
+    return LIB_PATH
+
+
+_lib = None
+
+
+def load():
+    """Load the CUDA library; raises (loudly) when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                          f"or `make -C parelagmc_b200/csrc`.  There is no CPU fallback.")
+    L = C.CDLL(LIB_PATH)
+    vp = C.c_void_p
+    L.pmc_create.argtypes = [C.c_int, C.c_int, C.POINTER(vp)]
+    L.pmc_destroy.argtypes = [vp]
+    L.pmc_destroy.restype = None
+    L.pmc_last_error.argtypes = [vp]
+    L.pmc_last_error.restype = C.c_char_p
+    L.pmc_set_stream.argtypes = [vp, vp]
+    L.pmc_synchronize.argtypes = [vp]
+    L.pmc_set_tolerances.argtypes = [vp, C.c_double, C.c_double, C.c_int]
+    L.pmc_set_preconditioner.argtypes = [vp, C.c_int, C.c_int, C.c_double, C.c_int, C.c_double]
+    L.pmc_set_batch.argtypes = [vp, C.c_int, C.c_int]
+    L.pmc_upload_sampler_level.argtypes = [vp, C.c_int, C.c_int, C.c_int, _ip, _ip, _dp, _ip, _ip, _dp, _dp,
+                                           C.c_int, _ip, _ip, _dp, C.c_double, C.c_double, C.c_int]
+    L.pmc_upload_darcy_level.argtypes = [vp, C.c_int, C.c_int, C.c_int, _ip, _ip, _dp, _ip, _ip, _dp, _ip, _dp,
+                                         _dp, _dp, C.c_int, _ip, _ip, _dp]
+    L.pmc_prepare.argtypes = [vp]
+    L.pmc_rng_init.argtypes = [vp, C.c_double, C.c_double, C.c_int, C.c_int]
+    L.pmc_rng_fill_int.argtypes = [vp, C.c_uint64, C.c_int64, C.POINTER(C.c_int32)]
+    L.pmc_rng_fill.argtypes = [vp, C.c_uint64, C.c_int64, _dp]
+    L.pmc_sampler_sample_batch.argtypes = [vp, C.c_int, C.c_int, C.c_uint64, _dp]
+    L.pmc_sampler_eval_batch.argtypes = [vp, C.c_int, C.c_int, C.c_int, _dp, _dp, C.c_int, C.c_int, _dp, _dp, _ip]
+    L.pmc_darcy_solve_batch.argtypes = [vp, C.c_int, C.c_int, _dp, _dp, _dp, _dp, _ip]
+    L.pmc_darcy_apply_batch.argtypes = [vp, C.c_int, C.c_int, _dp, _dp, _dp]
+    L.pmc_mlmc_level_batch.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_uint64, _dp, _dp, C.POINTER(C.c_int64)]
+    L.pmc_mc_level_batch.argtypes = [vp, C.c_int, C.c_int, C.c_uint64, _dp, _dp, C.POINTER(C.c_int64)]
+    L.pmc_profile.argtypes = [vp, C.c_uint]
+    L.pmc_reset_stats.argtypes = [vp]
+    L.pmc_kernel_stats.argtypes = [vp, C.POINTER(KernelStats)]
+    for name in SYMBOLS:
+        f = getattr(L, name)
+        if name not in ("pmc_destroy", "pmc_last_error"):
+            f.restype = C.c_int
+    _lib = L
+    return L
+
+
+def _d(a):
+    return None if a is None else a.ctypes.data_as(_dp)
+
+
+def _i(a):
+    return None if a is None else a.ctypes.data_as(_ip)
+
+
+def _csr(m):
+    if m is None:
+        return None, None, None, ()
+    rp = np.ascontiguousarray(m.indptr, dtype=np.int32)
+    ci = np.ascontiguousarray(m.indices, dtype=np.int32)
+    v = np.ascontiguousarray(m.data, dtype=np.float64)
+    return _i(rp), _i(ci), _d(v), (rp, ci, v)
+
+
+class Context:
+    """One `pmc_handle`: a GPU-resident hierarchy plus the batched per-sample path on it."""
+
+    def __init__(self, nlevels: int, device: int = 0):
+        self._L = load()
+        self._h = C.c_void_p()
+        rc = self._L.pmc_create(device, nlevels, C.byref(self._h))
+        if rc != 0:
+            raise PmcError(rc, (self._L.pmc_last_error(None) or b"").decode())
+        self.nlevels = nlevels
+        self.device = device
+        self.Ne = [0] * nlevels
+        self.Nf = [0] * nlevels
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.pmc_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc: int):
+        if rc != 0:
+            raise PmcError(rc, (self._L.pmc_last_error(self._h) or b"").decode())
+
+    # -- configuration -----------------------------------------------------------------------------
+    def set_stream(self, cuda_stream: int):
+        self._ck(self._L.pmc_set_stream(self._h, C.c_void_p(cuda_stream)))
+
+    def synchronize(self):
+        self._ck(self._L.pmc_synchronize(self._h))
+
+    def set_tolerances(self, rel: float, abs_: float, maxit: int):
+        self._ck(self._L.pmc_set_tolerances(self._h, rel, abs_, maxit))
+
+    def set_preconditioner(self, mass_degree=0, schur_degree=0, schur_ratio=0.0, coarse_degree=0, coarse_ratio=0.0):
+        self._ck(self._L.pmc_set_preconditioner(self._h, mass_degree, schur_degree, schur_ratio, coarse_degree,
+                                                coarse_ratio))
+
+    def set_batch(self, max_batch: int = 0, check_every: int = 0):
+        self._ck(self._L.pmc_set_batch(self._h, max_batch, check_every))
+
+    # -- uploads -----------------------------------------------------------------------------------
+    def upload_sampler_level(self, level: int, s, alpha: float, g: float, lognormal: bool):
+        """`s`: a `hierarchy.SamplerLevel`-shaped object (M, B, Wdiag, P in scipy CSR / numpy)."""
+        mr, mc, mv, k1 = _csr(s.M)
+        br, bc, bv, k2 = _csr(s.B)
+        pr, pc, pv, k3 = _csr(s.P)
+        wd = np.ascontiguousarray(s.Wdiag, dtype=np.float64)
+        self._ck(self._L.pmc_upload_sampler_level(self._h, level, s.Ne, s.Nf, mr, mc, mv, br, bc, bv, _d(wd),
+                                                  0 if s.P is None else s.P.shape[1], pr, pc, pv, alpha, g,
+                                                  1 if lognormal else 0))
+        self.Ne[level], self.Nf[level] = s.Ne, s.Nf
+
+    def upload_darcy_level(self, level: int, d):
+        """`d`: a `hierarchy.DarcyLevel`-shaped object."""
+        br, bc, bv, k2 = _csr(d.B)
+        pr, pc, pv, k3 = _csr(d.P_p)
+        ep = np.ascontiguousarray(d.elem_ptr, dtype=np.int32)
+        ed = np.ascontiguousarray(d.elem_dofs, dtype=np.int32)
+        em = np.ascontiguousarray(d.elem_mat, dtype=np.float64)
+        eu = np.ascontiguousarray(d.ess_u, dtype=np.int32)
+        ev = np.ascontiguousarray(d.ess_data, dtype=np.float64)
+        rh = np.ascontiguousarray(d.rhs, dtype=np.float64)
+        ob = np.ascontiguousarray(d.obs, dtype=np.float64)
+        self._ck(self._L.pmc_upload_darcy_level(self._h, level, d.Ne, d.Nf, _i(ep), _i(ed), _d(em), br, bc, bv,
+                                                _i(eu), _d(ev), _d(rh), _d(ob),
+                                                0 if d.P_p is None else d.P_p.shape[1], pr, pc, pv))
+        self.Ne[level], self.Nf[level] = d.Ne, d.Nf
+
+    def prepare(self):
+        self._ck(self._L.pmc_prepare(self._h))
+
+    # -- RNG ---------------------------------------------------------------------------------------
+    def rng_init(self, mu: float = 0.0, sigma: float = 1.0, nparts: int = 1, mypart: int = 0):
+        self._ck(self._L.pmc_rng_init(self._h, mu, sigma, nparts, mypart))
+
+    def rng_fill_int(self, pos: int, n: int) -> np.ndarray:
+        out = np.empty(n, dtype=np.int32)
+        self._ck(self._L.pmc_rng_fill_int(self._h, C.c_uint64(pos), n, out.ctypes.data_as(C.POINTER(C.c_int32))))
+        return out
+
+    def rng_fill(self, pos: int, n: int) -> np.ndarray:
+        out = np.empty(n, dtype=np.float64)
+        self._ck(self._L.pmc_rng_fill(self._h, C.c_uint64(pos), n, _d(out)))
+        return out
+
+    # -- sampler -----------------------------------------------------------------------------------
+    def sampler_sample_batch(self, level: int, nsamples: int, pos0: int) -> np.ndarray:
+        out = np.empty((nsamples, self.Ne[level]), dtype=np.float64)
+        self._ck(self._L.pmc_sampler_sample_batch(self._h, level, nsamples, C.c_uint64(pos0), _d(out)))
+        return out
+
+    def sampler_eval_batch(self, level: int, xi: np.ndarray, xi_level: Optional[int] = None,
+                           init_s: Optional[np.ndarray] = None, init_level: int = 0, use_init: int = -1,
+                           want_embed: bool = True):
+        """Returns (s [n, Ne], embed_s [n, Ne] | None, iters [n])."""
+        xi = np.ascontiguousarray(xi, dtype=np.float64)
+        if xi.ndim == 1:
+            xi = xi[None, :]
+        n = xi.shape[0]
+        if xi_level is None:
+            xi_level = self.Ne.index(xi.shape[1])
+        assert xi.shape[1] == self.Ne[xi_level]
+        if init_s is not None:
+            init_s = np.ascontiguousarray(init_s, dtype=np.float64).reshape(n, -1)
+            assert init_s.shape[1] == self.Ne[init_level]
+        s = np.empty((n, self.Ne[level]))
+        emb = np.empty((n, self.Ne[level])) if want_embed else None
+        it = np.zeros(n, dtype=np.int32)
+        self._ck(self._L.pmc_sampler_eval_batch(self._h, level, xi_level, n, _d(xi), _d(init_s), init_level,
+                                                use_init, _d(s), _d(emb), _i(it)))
+        return s, emb, it
+
+    # -- Darcy -------------------------------------------------------------------------------------
+    def darcy_solve_batch(self, level: int, k: np.ndarray, want_sol: bool = False):
+        """Returns (Q [n], C [n], sol [n, N] | None, iters [n])."""
+        k = np.ascontiguousarray(k, dtype=np.float64)
+        if k.ndim == 1:
+            k = k[None, :]
+        n = k.shape[0]
+        assert k.shape[1] == self.Ne[level]
+        Q = np.empty(n)
+        Cc = np.empty(n)
+        sol = np.empty((n, self.Ne[level] + self.Nf[level])) if want_sol else None
+        it = np.zeros(n, dtype=np.int32)
+        self._ck(self._L.pmc_darcy_solve_batch(self._h, level, n, _d(k), _d(Q), _d(Cc), _d(sol), _i(it)))
+        return Q, Cc, sol, it
+
+    def darcy_apply_batch(self, level: int, k: np.ndarray, x: np.ndarray) -> np.ndarray:
+        k = np.ascontiguousarray(k, dtype=np.float64).reshape(-1, self.Ne[level])
+        x = np.ascontiguousarray(x, dtype=np.float64).reshape(k.shape[0], -1)
+        y = np.empty_like(x)
+        self._ck(self._L.pmc_darcy_apply_batch(self._h, level, k.shape[0], _d(k), _d(x), _d(y)))
+        return y
+
+    # -- manager loops -----------------------------------------------------------------------------
+    def mlmc_level_batch(self, level: int, nsamples: int, pos0: int, nlevels: Optional[int] = None,
+                         want_rows: bool = False, sums: Optional[np.ndarray] = None):
+        """Returns (sums[9] (accumulated), rows [n,4] | None, total_iters)."""
+        sums = np.zeros(9) if sums is None else sums
+        rows = np.zeros((nsamples, 4)) if want_rows else None
+        its = C.c_int64(0)
+        self._ck(self._L.pmc_mlmc_level_batch(self._h, level, nlevels or self.nlevels, nsamples, C.c_uint64(pos0),
+                                              _d(sums), _d(rows), C.byref(its)))
+        return sums, rows, its.value
+
+    def mc_level_batch(self, level: int, nsamples: int, pos0: int, want_rows: bool = False,
+                       sums: Optional[np.ndarray] = None):
+        sums = np.zeros(4) if sums is None else sums
+        rows = np.zeros((nsamples, 2)) if want_rows else None
+        its = C.c_int64(0)
+        self._ck(self._L.pmc_mc_level_batch(self._h, level, nsamples, C.c_uint64(pos0), _d(sums), _d(rows),
+                                            C.byref(its)))
+        return sums, rows, its.value
+
+    # -- instrumentation ---------------------------------------------------------------------------
+    def profile(self, classes: Sequence[str] = ()):
+        mask = 0
+        for n in classes:
+            mask |= 1 << K_CLASSES.index(n)
+        self._ck(self._L.pmc_profile(self._h, mask))
+
+    def reset_stats(self):
+        self._ck(self._L.pmc_reset_stats(self._h))
+
+    def kernel_stats(self) -> dict:
+        st = KernelStats()
+        self._ck(self._L.pmc_kernel_stats(self._h, C.byref(st)))
+        return {n: dict(launches=st.launches[i], algo_bytes=st.algo_bytes[i], ms=st.ms[i],
+                        timed_launches=st.timed_launches[i]) for i, n in enumerate(K_CLASSES)}

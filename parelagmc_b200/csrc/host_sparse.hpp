@@ -1,0 +1,197 @@
+// host_sparse.hpp -- small host-side CSR toolkit used once per upload to derive the device operators
+// (block saddle matrices, Schur-complement hierarchies, value maps) from the arrays ParELAG hands over.
+// Nothing here runs per sample.
+#pragma once
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <numeric>
+#include <vector>
+
+namespace pmc {
+
+struct HCsr {
+    int rows = 0, cols = 0;
+    std::vector<int> rowptr{0};
+    std::vector<int> col;
+    std::vector<double> val;
+    int nnz() const { return (int)col.size(); }
+};
+
+struct Coo {
+    int r, c;
+    double v;
+};
+
+// COO -> CSR, columns sorted within rows, duplicates summed.
+inline HCsr csr_from_coo(int rows, int cols, std::vector<Coo> &e, bool drop_zeros = false)
+{
+    std::sort(e.begin(), e.end(), [](const Coo &a, const Coo &b) { return a.r != b.r ? a.r < b.r : a.c < b.c; });
+    HCsr A;
+    A.rows = rows;
+    A.cols = cols;
+    A.rowptr.assign(rows + 1, 0);
+    size_t i = 0;
+    while (i < e.size()) {
+        size_t j = i;
+        double s = 0;
+        while (j < e.size() && e[j].r == e[i].r && e[j].c == e[i].c) s += e[j++].v;
+        if (!(drop_zeros && s == 0.0)) {
+            A.col.push_back(e[i].c);
+            A.val.push_back(s);
+            A.rowptr[e[i].r + 1]++;
+        }
+        i = j;
+    }
+    for (int r = 0; r < rows; ++r) A.rowptr[r + 1] += A.rowptr[r];
+    return A;
+}
+
+inline HCsr csr_copy(int rows, int cols, const int *rp, const int *ci, const double *v)
+{
+    HCsr A;
+    A.rows = rows;
+    A.cols = cols;
+    A.rowptr.assign(rp, rp + rows + 1);
+    A.col.assign(ci, ci + rp[rows]);
+    A.val.assign(v, v + rp[rows]);
+    return A;
+}
+
+inline HCsr csr_transpose(const HCsr &A)
+{
+    HCsr T;
+    T.rows = A.cols;
+    T.cols = A.rows;
+    T.rowptr.assign(T.rows + 1, 0);
+    for (int c : A.col) T.rowptr[c + 1]++;
+    for (int i = 0; i < T.rows; ++i) T.rowptr[i + 1] += T.rowptr[i];
+    T.col.resize(A.nnz());
+    T.val.resize(A.nnz());
+    std::vector<int> pos(T.rowptr.begin(), T.rowptr.end() - 1);
+    for (int i = 0; i < A.rows; ++i)
+        for (int p = A.rowptr[i]; p < A.rowptr[i + 1]; ++p) {
+            int q = pos[A.col[p]]++;
+            T.col[q] = i;
+            T.val[q] = A.val[p];
+        }
+    return T;
+}
+
+// C = A * B, sorted columns.
+inline HCsr csr_matmul(const HCsr &A, const HCsr &B)
+{
+    HCsr C;
+    C.rows = A.rows;
+    C.cols = B.cols;
+    C.rowptr.assign(C.rows + 1, 0);
+    std::vector<int> mark(C.cols, -1);
+    std::vector<double> acc(C.cols, 0.0);
+    std::vector<int> cols_here;
+    for (int i = 0; i < A.rows; ++i) {
+        cols_here.clear();
+        for (int p = A.rowptr[i]; p < A.rowptr[i + 1]; ++p) {
+            int k = A.col[p];
+            double a = A.val[p];
+            for (int q = B.rowptr[k]; q < B.rowptr[k + 1]; ++q) {
+                int j = B.col[q];
+                if (mark[j] != i) {
+                    mark[j] = i;
+                    acc[j] = a * B.val[q];
+                    cols_here.push_back(j);
+                } else
+                    acc[j] += a * B.val[q];
+            }
+        }
+        std::sort(cols_here.begin(), cols_here.end());
+        for (int j : cols_here) {
+            C.col.push_back(j);
+            C.val.push_back(acc[j]);
+        }
+        C.rowptr[i + 1] = (int)C.col.size();
+    }
+    return C;
+}
+
+inline std::vector<double> csr_diag(const HCsr &A)
+{
+    std::vector<double> d(A.rows, 0.0);
+    for (int i = 0; i < A.rows; ++i)
+        for (int p = A.rowptr[i]; p < A.rowptr[i + 1]; ++p)
+            if (A.col[p] == i) d[i] += A.val[p];
+    return d;
+}
+
+inline void csr_mult(const HCsr &A, const double *x, double *y)
+{
+    for (int i = 0; i < A.rows; ++i) {
+        double s = 0;
+        for (int p = A.rowptr[i]; p < A.rowptr[i + 1]; ++p) s += A.val[p] * x[A.col[p]];
+        y[i] = s;
+    }
+}
+
+// Largest eigenvalue of D^-1 A (A symmetric positive semi-definite, D = diag d > 0) by power iteration.
+inline double lambda_max_scaled(const HCsr &A, const std::vector<double> &d, int iters = 60)
+{
+    int n = A.rows;
+    if (n == 0) return 1.0;
+    std::vector<double> x(n), y(n);
+    uint64_t s = 0x9E3779B97F4A7C15ULL;
+    for (int i = 0; i < n; ++i) {
+        s = s * 6364136223846793005ULL + 1442695040888963407ULL;
+        x[i] = 0.5 + (double)(s >> 40) / (double)(1 << 24);
+    }
+    double lam = 1.0;
+    for (int it = 0; it < iters; ++it) {
+        csr_mult(A, x.data(), y.data());
+        double nrm = 0;
+        for (int i = 0; i < n; ++i) {
+            y[i] /= d[i];
+            nrm = std::max(nrm, std::fabs(y[i]));
+        }
+        if (nrm == 0) return 1.0;
+        lam = nrm;
+        for (int i = 0; i < n; ++i) x[i] = y[i] / nrm;
+    }
+    // Rayleigh-type refinement in the D inner product
+    csr_mult(A, x.data(), y.data());
+    double num = 0, den = 0;
+    for (int i = 0; i < n; ++i) {
+        num += x[i] * y[i];
+        den += x[i] * d[i] * x[i];
+    }
+    if (den > 0) lam = std::max(lam, num / den);
+    return lam;
+}
+
+// Largest eigenvalue of diag(A)^-1 A for a small dense symmetric positive (semi-)definite n x n block.
+inline double dense_lambda_max_scaled(const double *A, int n, int iters = 200)
+{
+    std::vector<double> x(n, 1.0), y(n);
+    for (int i = 0; i < n; ++i) x[i] = 1.0 + 0.37 * ((i * 7) % 5);
+    double lam = 1.0;
+    for (int it = 0; it < iters; ++it) {
+        double nrm = 0;
+        for (int i = 0; i < n; ++i) {
+            double s = 0;
+            for (int j = 0; j < n; ++j) s += A[i * n + j] * x[j];
+            double d = A[i * n + i];
+            y[i] = d > 0 ? s / d : 0.0;
+            nrm = std::max(nrm, std::fabs(y[i]));
+        }
+        if (nrm == 0) return 1.0;
+        lam = nrm;
+        for (int i = 0; i < n; ++i) x[i] = y[i] / nrm;
+    }
+    // Gershgorin-type cap keeps this an upper bound even if the power iteration has not converged
+    double cap = 0;
+    for (int i = 0; i < n; ++i) {
+        double s = 0, d = A[i * n + i];
+        for (int j = 0; j < n; ++j) s += std::fabs(A[i * n + j]);
+        if (d > 0) cap = std::max(cap, s / d);
+    }
+    return std::max(1.0, std::min(1.05 * lam, cap));
+}
+
+}  // namespace pmc

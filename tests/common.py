@@ -1,0 +1,56 @@
+"""Shared problem builders for the tests: the hierarchy (host once), the oracle problem (checker) and the
+GPU context (product), all fed with the same arrays."""
+from __future__ import annotations
+
+import functools
+
+import numpy as np
+
+from parelagmc_b200 import hierarchy as H
+
+
+@functools.lru_cache(maxsize=None)
+def hex_problem(n=16, nlevels=3, corlen=0.1, length=2.0, bc="mlmc"):
+    """The reference's default MLMC problem (examples/MLMC.cpp with CreateMLMCParameterList.hpp):
+    hex n^3 on [0,2]^3 coarsened by 2 per direction."""
+    L = H.build_box_hierarchy([n] * 3, [length] * 3, nlevels)
+    SL = H.build_sampler_levels(L)
+    DL = H.build_darcy_levels(L, **(H.MLMC_DEFAULT_BC if bc == "mlmc" else H.SPE10_BC))
+    return dict(levels=L, sampler=SL, darcy=DL, alpha=H.spde_alpha(corlen),
+                g=H.matern_scaling_coefficient(corlen, 3), nlevels=nlevels)
+
+
+@functools.lru_cache(maxsize=None)
+def quad_problem(n=4, nlevels=2, corlen=0.1):
+    """PDESamplerTest on inline_quad.mesh: unit square, 2x2 quads refined to n x n."""
+    L = H.build_box_hierarchy([n] * 2, [1.0] * 2, nlevels)
+    SL = H.build_sampler_levels(L)
+    return dict(levels=L, sampler=SL, darcy=None, alpha=H.spde_alpha(corlen),
+                g=H.matern_scaling_coefficient(corlen, 2), nlevels=nlevels)
+
+
+def make_oracle(p, lognormal=True, rel=1e-12, abs_=1e-30, maxit=2000):
+    from oracle.binding import OracleProblem
+    op = OracleProblem(p["sampler"], p["darcy"], p["alpha"], p["g"], lognormal)
+    op.set_tolerances(rel, abs_, maxit)
+    return op
+
+
+def make_context(p, lognormal=True, rel=1e-12, abs_=1e-30, maxit=2000, device=0):
+    from parelagmc_b200.capi import Context
+    ctx = Context(p["nlevels"], device)
+    for l, s in enumerate(p["sampler"]):
+        ctx.upload_sampler_level(l, s, p["alpha"], p["g"], lognormal)
+    if p["darcy"] is not None:
+        for l, d in enumerate(p["darcy"]):
+            ctx.upload_darcy_level(l, d)
+    ctx.set_tolerances(rel, abs_, maxit)
+    ctx.rng_init(0.0, 1.0, 1, 0)
+    ctx.prepare()
+    return ctx
+
+
+def rel_l2(a, b):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300))

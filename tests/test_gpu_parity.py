@@ -1,0 +1,232 @@
+"""GPU parity tests: the CUDA path (through the C ABI, include/pmc_b200.h) against the CPU oracle on the same
+seeded inputs.  Bars (BASELINE.json north_star): integer stream bit-exact; per-sample fields and Darcy solutions
+within 1e-8 relative L2 at solver tolerance 1e-12; per-level MLMC mean/variance within 1e-6 relative."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from common import hex_problem, quad_problem, make_oracle, make_context, rel_l2
+
+pytestmark = pytest.mark.gpu
+
+FIELD_TOL = 1e-8      # north_star: per-sample field / solution, relative L2
+MOMENT_TOL = 1e-6     # north_star: per-level mean and variance, relative
+
+
+@pytest.fixture(scope="module")
+def prob():
+    return hex_problem(8, 3)
+
+
+@pytest.fixture(scope="module")
+def ctx(prob):
+    c = make_context(prob)
+    yield c
+    c.close()
+
+
+@pytest.fixture(scope="module")
+def orc(prob):
+    return make_oracle(prob)
+
+
+def test_yarn5_integer_stream_bit_exact(ctx):
+    from oracle.binding import Yarn5
+    for pos, n in [(0, 1), (0, 1000), (5, 77), (123456789, 4097), (2**40 + 12345, 513)]:
+        ref = Yarn5().jump(pos).ints(n)
+        got = ctx.rng_fill_int(pos, n)
+        assert np.array_equal(ref, got), (pos, n)
+
+
+def test_yarn5_split_streams_bit_exact(prob):
+    from oracle.binding import Yarn5
+    from parelagmc_b200.capi import Context
+    c = Context(1)
+    try:
+        for nparts, mypart in [(2, 0), (2, 1), (8, 5)]:
+            c.rng_init(0.0, 1.0, nparts, mypart)
+            ref = Yarn5().split(nparts, mypart).ints(300)
+            assert np.array_equal(ref, c.rng_fill_int(0, 300))
+            # leapfrog property against the parent stream
+            parent = Yarn5().ints(300 * nparts)
+            assert np.array_equal(ref, parent[mypart::nparts][:300])
+    finally:
+        c.close()
+
+
+def test_normal_deviates_match_oracle(ctx):
+    """Doubles: the integer draw is bit-exact; inv_Phi goes through CUDA's erf/erfc/exp/log instead of glibc's,
+    so equality is asserted to a few ulp and the bit-exact fraction is reported."""
+    from oracle.binding import Yarn5
+    n = 200000
+    ref = Yarn5().jump(1000).normals(n, 0.0, 1.0)
+    got = ctx.rng_fill(1000, n)
+    # Both sides run the same Acklam + Halley sequence on the same integer draw; only erf/erfc/exp/log differ
+    # (CUDA's vs glibc's, each within a few ulp).  The Halley step divides the CDF residual by the density phi(y),
+    # so a 1-ulp difference in Phi(y) (ulp(1) = 2.2e-16 in the upper tail, where Phi -> 1) moves y by ulp(1)/phi(y):
+    # the bound is a few ulp(1) scaled by max(1, 1/phi(y)).
+    phi = np.exp(-0.5 * ref * ref) / np.sqrt(2.0 * np.pi)
+    tol = 4.0 * np.spacing(1.0) * np.maximum(1.0, 1.0 / phi)
+    err = np.abs(got - ref)
+    exact = float(np.mean(got == ref))
+    print(f"normal deviates: bit-exact fraction {exact:.4f}, max abs error {err.max():.3e}, "
+          f"max error/bound {np.max(err / tol):.3f}")
+    assert np.all(err <= tol)
+    assert exact > 0.8
+    assert abs(got.mean()) < 0.01 and abs(got.std() - 1.0) < 0.01
+
+
+def test_sample_batch_is_stream_in_order(ctx, prob):
+    from oracle.binding import Yarn5
+    Ne = prob["sampler"][1].Ne
+    xi = ctx.sampler_sample_batch(1, 5, 777)
+    ref = Yarn5().jump(777).normals(5 * Ne).reshape(5, Ne)
+    assert np.allclose(xi, ref, rtol=0, atol=1e-14)
+
+
+def test_darcy_operator_apply_matches_assembled(ctx, prob):
+    """Batched element kernel: A_bc(k) x against scipy assembly + EliminateRowCol."""
+    rng = np.random.default_rng(1)
+    for lev in range(prob["nlevels"]):
+        d, lv = prob["darcy"][lev], prob["levels"][lev]
+        n = 5
+        k = np.exp(rng.standard_normal((n, d.Ne)))
+        x = rng.standard_normal((n, d.N))
+        y = ctx.darcy_apply_batch(lev, k, x)
+        keep = sp.diags((d.ess_u == 0).astype(float))
+        for j in range(n):
+            M = lv.assemble_M(k[j])
+            Me = keep @ M @ keep + sp.diags((d.ess_u != 0).astype(float))
+            Be = d.B @ keep
+            A = sp.bmat([[Me, Be.T], [Be, None]], format="csr")
+            assert rel_l2(y[j], A @ x[j]) < 1e-13
+
+
+def test_darcy_known_answer_Q2(ctx, prob):
+    """DarcyDeterministicTest (/root/reference/examples/CMakeLists.txt:62-66): k == 1 gives Q = 2 on every level."""
+    for lev in range(prob["nlevels"]):
+        d = prob["darcy"][lev]
+        Q, C, sol, it = ctx.darcy_solve_batch(lev, np.ones((3, d.Ne)), want_sol=True)
+        assert np.allclose(Q, 2.0, rtol=0, atol=1e-9), Q
+        assert np.all(C == d.N)
+
+
+def test_darcy_solve_matches_oracle(ctx, orc, prob):
+    rng = np.random.default_rng(2)
+    for lev in range(prob["nlevels"]):
+        d = prob["darcy"][lev]
+        n = 7
+        k = np.exp(rng.standard_normal((n, d.Ne)))
+        Q, C, sol, it = ctx.darcy_solve_batch(lev, k, want_sol=True)
+        print(f"darcy level {lev}: iterations {it.min()}..{it.max()}")
+        for j in range(n):
+            q, c, s, _ = orc.darcy_solve(lev, k[j], want_sol=True)
+            assert rel_l2(sol[j], s) < FIELD_TOL, (lev, j, rel_l2(sol[j], s))
+            assert abs(Q[j] - q) <= 1e-8 * abs(q)
+        assert it.max() < 2000
+
+
+def test_sampler_eval_matches_oracle(ctx, orc, prob):
+    from oracle.binding import Yarn5
+    for lev in range(prob["nlevels"]):
+        Ne = prob["sampler"][lev].Ne
+        n = 6
+        xi = Yarn5().jump(31 * lev).normals(n * Ne).reshape(n, Ne)
+        s, emb, it = ctx.sampler_eval_batch(lev, xi)
+        print(f"sampler level {lev}: iterations {it.min()}..{it.max()}")
+        for j in range(n):
+            so, eo, _ = orc.sampler_eval(lev, xi[j])
+            assert rel_l2(emb[j], eo) < FIELD_TOL
+            assert rel_l2(s[j], so) < FIELD_TOL
+
+
+def test_sampler_eval_coarse_noise_and_warm_start(ctx, orc, prob):
+    """Eval(l+1, xi_l, ., init, false) then Eval(l, xi_l, ., init, true) as in MLMC_Manager.cpp:150-155."""
+    from oracle.binding import Yarn5
+    lev = 0
+    Ne = prob["sampler"][lev].Ne
+    n = 4
+    xi = Yarn5().normals(n * Ne).reshape(n, Ne)
+    sc, embc, _ = ctx.sampler_eval_batch(lev + 1, xi, xi_level=lev, use_init=0)
+    sf, embf, itw = ctx.sampler_eval_batch(lev, xi, xi_level=lev, init_s=embc, init_level=lev + 1, use_init=1)
+    _, _, itc = ctx.sampler_eval_batch(lev, xi, xi_level=lev)
+    print(f"warm start iterations {itw.mean():.1f} vs cold {itc.mean():.1f}")
+    for j in range(n):
+        so, eo, _ = orc.sampler_eval(lev + 1, xi[j], xi_level=lev, embed_s=None, use_init=0)
+        assert rel_l2(embc[j], eo) < FIELD_TOL
+        so2, eo2, _ = orc.sampler_eval(lev, xi[j], xi_level=lev, embed_s=eo, init_level=lev + 1, use_init=1)
+        assert rel_l2(embf[j], eo2) < FIELD_TOL
+
+
+def test_mlmc_level_batch_matches_oracle(ctx, orc, prob):
+    pos0 = 4242
+    for lev, ns in [(2, 24), (1, 12), (0, 6)]:
+        sums, rows, its = ctx.mlmc_level_batch(lev, ns, pos0, want_rows=True)
+        osums, orows, _ = orc.mlmc_level(lev, ns, pos0, nthreads=8)
+        assert np.allclose(rows[:, :3], orows[:, :3], rtol=1e-7, atol=1e-9), (lev, np.abs(rows - orows).max())
+        assert np.array_equal(rows[:, 3], orows[:, 3])
+        n = float(ns)
+        for a, b in [(sums[1] / n, osums[1] / n), (sums[4] / n, osums[4] / n)]:
+            assert abs(a - b) <= MOMENT_TOL * abs(b)
+
+        def var(s2, s1):
+            return (s2 / n - (s1 / n) ** 2) * n / (n - 1)
+
+        assert abs(var(sums[0], sums[1]) - var(osums[0], osums[1])) <= MOMENT_TOL * abs(var(osums[0], osums[1])) + 1e-15
+        assert abs(var(sums[3], sums[4]) - var(osums[3], osums[4])) <= MOMENT_TOL * abs(var(osums[3], osums[4]))
+        assert its > 0
+
+
+def test_batch_split_independence(ctx, prob):
+    """Per-sample results must not depend on how realisations are grouped into launches."""
+    ns, pos0, lev = 70, 99, 1
+    ctx.set_batch(64, 0)
+    s1, r1, _ = ctx.mlmc_level_batch(lev, ns, pos0, want_rows=True)
+    ctx.set_batch(16, 0)
+    s2, r2, _ = ctx.mlmc_level_batch(lev, ns, pos0, want_rows=True)
+    ctx.set_batch(0, 0)
+    assert np.array_equal(r1, r2)
+
+
+def test_mc_level_batch(ctx, orc, prob):
+    ns, pos0, lev = 10, 5, 1
+    sums, rows, _ = ctx.mc_level_batch(lev, ns, pos0, want_rows=True)
+    # single-level loop == coarsest-style loop of the oracle on that level
+    osums, orows, _ = orc.mlmc_level(lev, ns, pos0, nthreads=8, nlevels=lev + 1)
+    assert np.allclose(rows[:, 0], orows[:, 1], rtol=1e-7)
+    assert abs(sums[1] - osums[4]) <= 1e-7 * abs(osums[4])
+
+
+def test_quad_sampler_gaussian():
+    """Config 1 (PDESamplerTest on inline_quad.mesh, Gaussian field, 2 levels 16/4 elements)."""
+    from oracle.binding import Yarn5
+    p = quad_problem(4, 2)
+    c = make_context(p, lognormal=False)
+    o = make_oracle(p, lognormal=False)
+    try:
+        for lev in range(2):
+            Ne = p["sampler"][lev].Ne
+            xi = Yarn5().normals(100 * Ne).reshape(100, Ne)
+            s, emb, it = c.sampler_eval_batch(lev, xi)
+            for j in range(0, 100, 9):
+                so, _, _ = o.sampler_eval(lev, xi[j])
+                assert rel_l2(s[j], so) < FIELD_TOL
+            assert np.array_equal(s, emb)
+    finally:
+        c.close()
+
+
+def test_empty_and_error_paths(ctx, prob):
+    from parelagmc_b200.capi import PmcError
+    Ne = prob["sampler"][0].Ne
+    s, emb, it = ctx.sampler_eval_batch(0, np.zeros((0, Ne)), xi_level=0)
+    assert s.shape == (0, Ne)
+    sums, rows, its = ctx.mlmc_level_batch(0, 0, 0)
+    assert np.all(sums == 0)
+    with pytest.raises(PmcError):
+        ctx.mlmc_level_batch(7, 1, 0)
+    with pytest.raises(PmcError):
+        ctx.sampler_eval_batch(0, np.zeros((1, prob["sampler"][1].Ne)), xi_level=1)  # noise coarser than level
+    # zero noise -> zero field, converges in 0 iterations
+    s, emb, it = ctx.sampler_eval_batch(1, np.zeros((2, prob["sampler"][1].Ne)))
+    assert np.all(emb == 0) and np.all(it == 0) and np.all(s == 1.0)
