@@ -1,0 +1,385 @@
+#!/usr/bin/env python
+"""bench.py -- MLMC samples/sec (SPDE sample + Darcy solve) on the 3D hex Darcy MLMC workload.
+
+Workload (BASELINE.json configs[1]): MLMC.cpp's default problem -- cube_hex 16^3 -> 8^3 -> 4^3 on [0,2]^3
+(N = 17152 / 2240 / 304 dofs), lognormal field, variance 1, correlation length 0.1, eff_perm QoI, the reference's
+default Krylov stopping rule (rel 1e-6, abs 1e-12, 300 iterations; CreateMLMCParameterList.hpp:58-70) -- with a
+fixed sample array {1000, 3000, 6000} (levels 0, 1, 2) = 1e4 samples per GPU per step.  One "step" is one
+MLMC_Manager::InitRun over that array (src/MLMC_Manager.cpp:103-179): for every sample the noise draw, the SPDE
+saddle solve(s), exp, the Darcy saddle solve(s), the QoI and the moment sums.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]         product arm (CUDA, one rank per GPU under torchrun)
+  python bench.py --impl reference ...                         reference arm: the CPU path on the host cores
+
+One JSON line on stdout (rank 0).  See the task contract for the keys.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+METRIC = "MLMC samples/sec per level (SPDE sample + Darcy solve)"
+LEVEL_SAMPLES = [1000, 3000, 6000]   # levels 0 (fine) .. 2 (coarse); "Array number of samples"
+REL, ABS, MAXIT = 1e-6, 1e-12, 300   # CreateMLMCParameterList.hpp:67-69
+
+
+def build_problem():
+    from common import hex_problem
+    return hex_problem(16, 3)
+
+
+def stream_positions(p, samples, rank, world):
+    """Absolute yarn5 positions: InitRun draws the coarsest level first (MLMC_Manager.cpp:110,140); within a level,
+    rank r owns global samples [r*n, (r+1)*n) of the world*n realisations."""
+    pos, base = {}, 0
+    for lev in range(p["nlevels"] - 1, -1, -1):
+        Ne = p["sampler"][lev].Ne
+        pos[lev] = base + rank * samples[lev] * Ne
+        base += world * samples[lev] * Ne
+    return pos
+
+
+# ------------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for l in self.lines:
+            f = [x.strip() for x in l.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def cpu_reference_run(p, samples, threads, pos):
+    """The CPU path (oracle port of the reference algorithm) on `threads` host threads; returns seconds."""
+    from common import make_oracle
+    o = cpu_reference_run.oracle
+    if o is None:
+        o = cpu_reference_run.oracle = make_oracle(p, True, REL, ABS, MAXIT)
+    t0 = time.perf_counter()
+    for lev in range(p["nlevels"] - 1, -1, -1):
+        if samples[lev] > 0:
+            o.mlmc_level(lev, samples[lev], pos[lev], nthreads=threads)
+    return time.perf_counter() - t0
+
+
+cpu_reference_run.oracle = None
+
+
+def bounded_sample(p, threads, target_s):
+    """A sample of the workload in the same 1:3:6 level proportions, sized for ~target_s of wall time."""
+    probe = [max(1, threads // 4), max(1, 3 * threads // 4), max(1, 6 * threads // 4)]
+    pos = stream_positions(p, probe, 0, 1)
+    t = cpu_reference_run(p, probe, threads, pos)
+    scale = max(1.0, target_s / max(t, 1e-3))
+    return [max(1, int(round(x * scale))) for x in probe]
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    p = build_problem()
+    threads = os.cpu_count() or 1
+    per_step_target = max(2.0, min(20.0, 150.0 / max(1, args.steps + args.warmup)))
+    samples = bounded_sample(p, threads, per_step_target)
+    pos = stream_positions(p, samples, 0, 1)
+    for _ in range(args.warmup):
+        cpu_reference_run(p, samples, threads, pos)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_reference_run(p, samples, threads, pos)
+    dt = time.perf_counter() - t0
+    total = sum(samples) * args.steps
+    v = total / dt
+    sample_desc = (f"{samples[0]}/{samples[1]}/{samples[2]} samples on levels 0/1/2 per step (same 1:3:6 proportions as "
+                   f"the 1000/3000/6000 workload), {threads} OpenMP threads over samples")
+    out = {"impl": "reference", "metric": METRIC, "value": v, "unit": "samples/s", "n_gpus": args.gpus,
+           "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / max(1, args.steps),
+           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "config": workload_config(1),
+           "cpu_baseline": {"value": v, "unit": "samples/s", "cores": threads, "kind": "port", "sample": sample_desc},
+           "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "note": "reference cannot be built here (needs MPI, MFEM, hypre, ParELAG, TRNG); this arm times the "
+                   "oracle's C restatement of its per-sample path"}
+    print(json.dumps(out), flush=True)
+
+
+def workload_config(world):
+    return {"workload": "MLMC.cpp SPDE sampler + Darcy, cube_hex 16^3/8^3/4^3 (N=17152/2240/304), lognormal, "
+                        "corlen 0.1, variance 1, eff_perm QoI",
+            "level_samples_per_gpu": LEVEL_SAMPLES, "samples_per_step": sum(LEVEL_SAMPLES) * world,
+            "rel_tol": REL, "abs_tol": ABS, "max_iter": MAXIT,
+            "l2_policy": "batched working set per level >> 126 MB L2 (level 0: ~2 GB of vectors per batch); no flush",
+            "parallelism": f"samples sharded over {world} GPU(s), one allreduce of 3x9 sums per step"}
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def run_product(args):
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from common import make_context
+    p = build_problem()
+    ctx = make_context(p, True, REL, ABS, MAXIT, device=local)
+    stream = torch.cuda.current_stream()
+    ctx.set_stream(stream.cuda_stream)
+    nl = p["nlevels"]
+    pos = stream_positions(p, LEVEL_SAMPLES, rank, world)
+    dev = torch.device("cuda", local)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    lev_events = []
+
+    def step(record=False):
+        """One InitRun on the device path: sums[level] accumulated by the fused level loop, then one allreduce."""
+        sums = np.zeros((nl, 9))
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(nl + 1)] if record else None
+        if record:
+            evs[0].record(stream)
+        its = 0
+        for i, lev in enumerate(range(nl - 1, -1, -1)):
+            _, _, it = ctx.mlmc_level_batch(lev, LEVEL_SAMPLES[lev], pos[lev], sums=sums[lev])
+            its += it
+            if record:
+                evs[i + 1].record(stream)
+        if dist is not None:
+            t = torch.from_numpy(sums).to(dev)
+            dist.all_reduce(t)
+            sums = t.cpu().numpy()
+        if record:
+            lev_events.append(evs)
+        return sums, its
+
+    # ---- warm-up (un-instrumented) ----
+    solve_classes = ["saddle_apply", "lanczos_update", "solution_update", "mass_smooth", "schur_smooth", "transfer"]
+    ctx.profile([])
+    for _ in range(args.warmup):
+        step()
+    # ---- timed region: no per-kernel instrumentation, CUDA events on the launching stream ----
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    ctx.reset_stats()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    its_total = 0
+    for _ in range(args.steps):
+        sums, its = step(record=True)
+        its_total += its
+    e1.record(stream)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    st_timed = ctx.kernel_stats()
+    clk = clocks.stop() if rank == 0 else None
+    if dist is not None:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    # ---- per-kernel CUDA-event timing: the same step repeated with every launch of the solve kernels bracketed
+    #      by events on the launching stream (kept out of the timed region above because ~15k event pairs per
+    #      step perturb the small-level launches) ----
+    ctx.profile(solve_classes)
+    ctx.reset_stats()
+    barrier()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record(stream)
+    step()
+    e3.record(stream)
+    barrier()
+    ms_instr = e2.elapsed_time(e3)
+    st = ctx.kernel_stats()
+    ctx.profile([])
+    dominant = max(solve_classes, key=lambda n: st[n]["ms"])
+    class_ms = {n: round(st[n]["ms"], 3) for n in solve_classes}
+    class_gbs = {n: round(st[n]["algo_bytes"] / max(st[n]["ms"], 1e-9) / 1e6, 1) for n in solve_classes}
+    total_samples = sum(LEVEL_SAMPLES) * world * args.steps
+    value = total_samples / (ms * 1e-3)
+    per_level = {}
+    for i, lev in enumerate(range(nl - 1, -1, -1)):
+        lms = sum(ev[i].elapsed_time(ev[i + 1]) for ev in lev_events)
+        per_level[f"level{lev}"] = LEVEL_SAMPLES[lev] * world * args.steps / (lms * 1e-3)
+    launches = int(sum(v["launches"] for v in st_timed.values())) // max(1, args.steps)
+    dom = st[dominant]
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    achieved = dom["algo_bytes"] / max(dom["ms"] * 1e-3, 1e-12) / 1e9 if dom["timed_launches"] else None
+    roofline = {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": (achieved / peak) if achieved else None, "traffic": None,
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
+                "launches": int(dom["timed_launches"]), "avg_launch_us": 1e3 * dom["ms"] / max(1, dom["timed_launches"]),
+                "algo_bytes_per_launch": dom["algo_bytes"] / max(1, dom["launches"]),
+                "share_of_step": dom["ms"] / ms_instr, "class_ms_per_step": class_ms, "class_achieved_gbs": class_gbs,
+                "timing": "CUDA events around every launch of the solve kernels during one repeat of the timed step "
+                          f"({ms_instr:.1f} ms instrumented vs {ms / args.steps:.1f} ms un-instrumented)"}
+
+    # ---- e2e: the same InitRun through the host-buffer plugin API (Sample / Eval / SolveFwd, batched) ----
+    ctx.profile([])
+    h2d = d2h = 0
+
+    def step_e2e():
+        nonlocal h2d, d2h
+        h2d = d2h = 0
+        sums = np.zeros((nl, 9))
+        for lev in range(nl - 1, -1, -1):
+            n = LEVEL_SAMPLES[lev]
+            xi = ctx.sampler_sample_batch(lev, n, pos[lev])                       # Sample(level, xi)
+            d2h += xi.nbytes
+            if lev == nl - 1:
+                s, _, _ = ctx.sampler_eval_batch(lev, xi, xi_level=lev, want_embed=False)   # Eval(level, xi, s)
+                h2d += xi.nbytes
+                d2h += s.nbytes
+                q, c, _, _ = ctx.darcy_solve_batch(lev, s)                        # SolveFwd(level, s, q, c)
+                h2d += s.nbytes
+                d2h += q.nbytes
+                y = q
+            else:
+                sc, emb, _ = ctx.sampler_eval_batch(lev + 1, xi, xi_level=lev, use_init=0)   # Eval(l+1, xi, s, init, false)
+                h2d += xi.nbytes
+                d2h += sc.nbytes + emb.nbytes
+                qc, cc, _, _ = ctx.darcy_solve_batch(lev + 1, sc)
+                h2d += sc.nbytes
+                d2h += qc.nbytes
+                sf, _, _ = ctx.sampler_eval_batch(lev, xi, xi_level=lev, init_s=emb, init_level=lev + 1, use_init=1,
+                                                  want_embed=False)               # Eval(l, xi, s, init, true)
+                h2d += xi.nbytes + emb.nbytes
+                d2h += sf.nbytes
+                q, c, _, _ = ctx.darcy_solve_batch(lev, sf)
+                h2d += sf.nbytes
+                d2h += q.nbytes
+                y = q - qc
+                c = c + cc
+            sums[lev] = [np.sum(y * y), np.sum(y), np.sum(np.abs(y)), np.sum(q * q), np.sum(q), np.sum(np.abs(q)),
+                         np.sum(c), np.sum(y ** 3), np.sum(y ** 4)]
+        if dist is not None:
+            t = torch.from_numpy(sums).to(dev)
+            dist.all_reduce(t)
+            sums = t.cpu().numpy()
+        return sums
+
+    e2e_steps = max(1, min(args.steps, 3))
+    step_e2e()
+    barrier()
+    e0.record(stream)
+    for _ in range(e2e_steps):
+        sums_e2e = step_e2e()
+    e1.record(stream)
+    barrier()
+    ms_e = e0.elapsed_time(e1)
+    if dist is not None:
+        t = torch.tensor([ms_e], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_e = float(t.item())
+    e2e_value = sum(LEVEL_SAMPLES) * world * e2e_steps / (ms_e * 1e-3)
+
+    # ---- CPU baseline (rank 0, N = 1 only): the oracle port on a bounded sample ----
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        threads = os.cpu_count() or 1
+        smp = bounded_sample(p, threads, 12.0)
+        tcpu = cpu_reference_run(p, smp, threads, stream_positions(p, smp, 0, 1))
+        cpu = {"value": sum(smp) / tcpu, "unit": "samples/s", "cores": threads, "kind": "port",
+               "sample": f"{smp[0]}/{smp[1]}/{smp[2]} samples on levels 0/1/2 (1:3:6 like the workload), "
+                         f"{tcpu:.1f} s, {threads} OpenMP threads over samples, same tolerances"}
+    if rank == 0:
+        mean_y = sums[:, 1] / (np.array(LEVEL_SAMPLES) * world)
+        out = {"metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
+               "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+               "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(world),
+               "per_level_samples_per_s": per_level, "minres_iterations_per_step": its_total / args.steps,
+               "mlmc_estimate": float(mean_y.sum()),
+               "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": int(h2d),
+                       "d2h_bytes_per_step": int(d2h), "steps": e2e_steps,
+                       "api": "sampler_sample_batch / sampler_eval_batch / darcy_solve_batch with host buffers",
+                       "mlmc_estimate": float((sums_e2e[:, 1] / (np.array(LEVEL_SAMPLES) * world)).sum())},
+               "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "clocks": clk}
+        print(json.dumps(out), flush=True)
+    ctx.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="product", choices=["product", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_product(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -66,6 +66,11 @@ int pmc_set_tolerances(pmc_handle h, double rel_tol, double abs_tol, int max_ite
  * Values <= 0 keep the current setting. */
 int pmc_set_preconditioner(pmc_handle h, int mass_degree, int schur_degree, double schur_ratio,
                            int coarse_degree, double coarse_ratio);
+/* Fine-grained options, to be set before the first solve / pmc_prepare.  Keys "sampler.<k>" / "darcy.<k>" with
+ * <k> in {mass_degree, schur_degree, schur_ratio, coarse_degree, coarse_ratio, omega (over-correction factor of the
+ * coarse-grid correction), max_vlevels (depth of the Schur V-cycle; 0 = full hierarchy, -1 = decide from the mass
+ * term, sampler only)}; and "max_batch", "check_every". */
+int pmc_set_option(pmc_handle h, const char *key, double value);
 /* Largest number of realisations processed per kernel launch (0 = choose from free device memory), and
  * how many MINRES iterations are queued between convergence checks. */
 int pmc_set_batch(pmc_handle h, int max_batch, int check_every);

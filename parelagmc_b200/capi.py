@@ -22,7 +22,7 @@ K_CLASSES = ["saddle_apply", "lanczos_update", "solution_update", "mass_smooth",
 # every symbol include/pmc_b200.h declares (checked by tests/test_abi.py against the header text)
 SYMBOLS = [
     "pmc_create", "pmc_destroy", "pmc_last_error", "pmc_set_stream", "pmc_synchronize", "pmc_set_tolerances",
-    "pmc_set_preconditioner", "pmc_set_batch", "pmc_upload_sampler_level", "pmc_upload_darcy_level", "pmc_prepare",
+    "pmc_set_preconditioner", "pmc_set_option", "pmc_set_batch", "pmc_upload_sampler_level", "pmc_upload_darcy_level", "pmc_prepare",
     "pmc_rng_init", "pmc_rng_fill_int", "pmc_rng_fill", "pmc_sampler_sample_batch", "pmc_sampler_eval_batch",
     "pmc_darcy_solve_batch", "pmc_darcy_apply_batch", "pmc_mlmc_level_batch", "pmc_mc_level_batch", "pmc_profile",
     "pmc_reset_stats", "pmc_kernel_stats",
@@ -75,6 +75,7 @@ def load():
     L.pmc_synchronize.argtypes = [vp]
     L.pmc_set_tolerances.argtypes = [vp, C.c_double, C.c_double, C.c_int]
     L.pmc_set_preconditioner.argtypes = [vp, C.c_int, C.c_int, C.c_double, C.c_int, C.c_double]
+    L.pmc_set_option.argtypes = [vp, C.c_char_p, C.c_double]
     L.pmc_set_batch.argtypes = [vp, C.c_int, C.c_int]
     L.pmc_upload_sampler_level.argtypes = [vp, C.c_int, C.c_int, C.c_int, _ip, _ip, _dp, _ip, _ip, _dp, _dp,
                                            C.c_int, _ip, _ip, _dp, C.c_double, C.c_double, C.c_int]
@@ -160,6 +161,9 @@ class Context:
     def set_preconditioner(self, mass_degree=0, schur_degree=0, schur_ratio=0.0, coarse_degree=0, coarse_ratio=0.0):
         self._ck(self._L.pmc_set_preconditioner(self._h, mass_degree, schur_degree, schur_ratio, coarse_degree,
                                                 coarse_ratio))
+
+    def set_option(self, key: str, value: float):
+        self._ck(self._L.pmc_set_option(self._h, key.encode(), float(value)))
 
     def set_batch(self, max_batch: int = 0, check_every: int = 0):
         self._ck(self._L.pmc_set_batch(self._h, max_batch, check_every))

@@ -66,10 +66,11 @@ struct SpmmArgs {
     const double *r;     // EP_RESID, EP_CHEB
     double *d;           // EP_CHEB direction (in/out)
     const double *dinv;  // EP_CHEB: [n] (fixed) or [n][ld] (batched)
-    double ca, cb;       // EP_CHEB: d = ca d + cb dinv (r - A x);  z_out = x + d
+    double ca, cb;       // EP_CHEB: d = ca d + cb dinv (r - A x);  z_out = x + d.   EP_ADD: y += ca (A x)
     const double *dotw;  // DOT: partial += out_row * dotw_row
     double *partial;
     int partial_off;
+    const int *perm;     // optional processing order: the CTA's i-th row is perm[i] (storage order is unchanged)
 };
 
 template <int EP, bool WEIGHTED, bool BDINV, bool DOT>
@@ -84,7 +85,8 @@ __global__ void __launch_bounds__(TX *TY) k_spmm(const SpmmArgs a)
     const int r1 = min(a.n, r0 + a.rows_per_cta);
     double2 acc = make_double2(0.0, 0.0);
     if (live) {
-        for (int row = r0 + threadIdx.y; row < r1; row += TY) {
+        for (int ri = r0 + threadIdx.y; ri < r1; ri += TY) {
+            const int row = a.perm ? __ldg(a.perm + ri) : ri;
             double2 s = make_double2(0.0, 0.0);
             if (WEIGHTED) {
                 const int p0 = __ldg(a.rowptr + 2 * row), p1 = __ldg(a.rowptr + 2 * row + 1),
@@ -123,7 +125,7 @@ __global__ void __launch_bounds__(TX *TY) k_spmm(const SpmmArgs a)
                 out = make_double2(rv.x - s.x, rv.y - s.y);
             } else if (EP == EP_ADD) {
                 const double2 yv = ld2w(a.y + o);
-                out = make_double2(yv.x + s.x, yv.y + s.y);
+                out = make_double2(fma(a.ca, s.x, yv.x), fma(a.ca, s.y, yv.y));  // y += ca * (A x)
             } else {  // EP_CHEB
                 const double2 rv = ld2(a.r + o);
                 double2 di;
@@ -249,10 +251,20 @@ enum {
 
 __device__ __forceinline__ double safe_inv(double x) { return x != 0.0 ? 1.0 / x : 0.0; }
 
+// Sum of the row-block partials of one realisation, in block order (deterministic); loads are issued eight at a
+// time so the loop is not bound by one memory latency per term.
 __device__ __forceinline__ double sum_partials(const double *partial, int nblk, int ld, int s)
 {
     double d = 0.0;
-    for (int b = 0; b < nblk; ++b) d += partial[(size_t)b * ld + s];
+    int b = 0;
+    for (; b + 8 <= nblk; b += 8) {
+        double t[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) t[k] = partial[(size_t)(b + k) * ld + s];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) d += t[k];
+    }
+    for (; b < nblk; ++b) d += partial[(size_t)b * ld + s];
     return d;
 }
 

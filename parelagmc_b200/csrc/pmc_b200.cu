@@ -92,8 +92,21 @@ struct VLevel {
     DevCsr L;                       // Darcy: l1_m = L |V_m|
 };
 
+// Shape of the block-diagonal preconditioner of one system kind (sampler / Darcy).
+struct PrecCfg {
+    int mass_degree = 2;       // Chebyshev-Jacobi steps on the RT mass block
+    int schur_degree = 2;      // Chebyshev steps of the V-cycle smoother on the Schur complement levels
+    double schur_ratio = 4.0;  // smoother targets the eigenvalues in [1/ratio, 1] of the l1-scaled operator
+    int coarse_degree = 8;     // Chebyshev steps on the coarsest V-cycle level
+    double coarse_ratio = 30.0;
+    double omega = 1.0;        // over-correction factor of the piecewise-constant coarse-grid correction
+    int max_vlevels = 0;       // 0: as deep as the hierarchy allows; -1 (sampler): decide from the mass term
+};
+
 struct SaddleSys {
     bool ready = false, weighted = false;
+    PrecCfg cfg;               // frozen at prepare time
+    int *perm = nullptr;       // processing order of the block operator's rows (locality of the u-p coupling)
     int Nf = 0, Ne = 0, N = 0;
     DevCsr A;                       // block operator over N rows
     DevCsr Muu;                     // RT mass block (Nf rows)
@@ -158,8 +171,7 @@ struct pmc_context_s {
     std::string err;
     double rel = 1e-6, abs_ = 1e-12;
     int maxit = 300;
-    int mass_degree = 2, schur_degree = 2, coarse_degree = 8;
-    double schur_ratio = 4.0, coarse_ratio = 30.0;
+    PrecCfg cfg_sampler, cfg_darcy;
     int max_batch = 0, check_every = 4;
     std::vector<SamplerLevel> s;
     std::vector<DarcyLevel> d;
@@ -378,6 +390,32 @@ static HCsr symmetrize_pattern(const HCsr &S)
     return csr_from_coo(S.rows, S.rows, e);
 }
 
+// Processing order of the saddle operator's rows: every element row (Nf + e) is preceded by the face rows it
+// "owns" (faces whose lowest-numbered adjacent element is e).  Storage order is unchanged; a CTA's row block then
+// touches u and p entries that were fetched recently, so the gathers hit L2 instead of re-reading HBM.
+static std::vector<int> saddle_row_order(const HCsr &B, int Nf, int Ne)
+{
+    std::vector<int> owner(Nf, -1);
+    for (int e = 0; e < Ne; ++e)
+        for (int p = B.rowptr[e]; p < B.rowptr[e + 1]; ++p) {
+            const int f = B.col[p];
+            if (f >= 0 && f < Nf && owner[f] < 0) owner[f] = e;
+        }
+    std::vector<int> cnt(Ne + 2, 0);
+    for (int f = 0; f < Nf; ++f) cnt[(owner[f] < 0 ? Ne : owner[f]) + 1]++;
+    for (int e = 0; e <= Ne; ++e) cnt[e + 1] += cnt[e];
+    std::vector<int> faces(Nf), pos(cnt.begin(), cnt.end() - 1);
+    for (int f = 0; f < Nf; ++f) faces[pos[owner[f] < 0 ? Ne : owner[f]]++] = f;
+    std::vector<int> perm;
+    perm.reserve(Nf + Ne);
+    for (int e = 0; e < Ne; ++e) {
+        for (int q = cnt[e]; q < cnt[e + 1]; ++q) perm.push_back(faces[q]);
+        perm.push_back(Nf + e);
+    }
+    for (int q = cnt[Ne]; q < cnt[Ne + 1]; ++q) perm.push_back(faces[q]);
+    return perm;
+}
+
 // ---- sampler system (everything fixed across samples) ---------------------------------------------------
 static int prepare_sampler(Ctx *c, int level)
 {
@@ -389,6 +427,12 @@ static int prepare_sampler(Ctx *c, int level)
     sys.Nf = Nf;
     sys.Ne = Ne;
     sys.N = N;
+    sys.cfg = c->cfg_sampler;
+    {
+        std::vector<int> perm = saddle_row_order(L.B, Nf, Ne);
+        int rcp = to_device(c, perm, &sys.perm);
+        if (rcp) return rcp;
+    }
     HCsr Bt = csr_transpose(L.B);
     {  // block operator [[M, B^T], [B, -alpha W]]   (/root/reference/src/PDESampler.cpp:279-284)
         std::vector<Coo> e;
@@ -428,6 +472,23 @@ static int prepare_sampler(Ctx *c, int level)
     }
     std::vector<const HCsr *> Ps;
     for (int m = level; m < c->nlevels - 1 && c->s[m].set && c->s[m].hasP; ++m) Ps.push_back(&c->s[m].P);
+    if (sys.cfg.max_vlevels < 0) {
+        // lambda_min of the l1-scaled Schur complement is at least min_e alpha W_e / l1_e: when that is not small the
+        // -alpha W block makes S well conditioned and one Chebyshev sweep over [lambda_min, 1] replaces the V-cycle
+        double lmin = 1.0;
+        for (int i = 0; i < Ne; ++i) {
+            double t = 0;
+            for (int p = S.rowptr[i]; p < S.rowptr[i + 1]; ++p) t += std::fabs(S.val[p]);
+            if (t > 0) lmin = std::min(lmin, L.alpha * L.Wdiag[i] / t);
+        }
+        if (lmin >= 1.0 / 20.0) {
+            sys.cfg.max_vlevels = 1;
+            sys.cfg.coarse_ratio = std::max(2.0, 1.0 / lmin);
+            sys.cfg.coarse_degree = sys.cfg.coarse_ratio <= 8.0 ? 3 : 4;
+        } else
+            sys.cfg.max_vlevels = 0;
+    }
+    if (sys.cfg.max_vlevels > 0 && (int)Ps.size() > sys.cfg.max_vlevels - 1) Ps.resize(sys.cfg.max_vlevels - 1);
     sys.v.resize(Ps.size() + 1);
     for (size_t m = 0; m < sys.v.size(); ++m) {
         VLevel &V = sys.v[m];
@@ -463,6 +524,12 @@ static int prepare_darcy(Ctx *c, int level)
     sys.Nf = Nf;
     sys.Ne = Ne;
     sys.N = N;
+    sys.cfg = c->cfg_darcy;
+    {
+        std::vector<int> perm = saddle_row_order(L.B, Nf, Ne);
+        int rcp = to_device(c, perm, &sys.perm);
+        if (rcp) return rcp;
+    }
     const std::vector<int> &ess = L.ess_u;
     // Be: essential columns removed
     HCsr Be;
@@ -549,6 +616,7 @@ static int prepare_darcy(Ctx *c, int level)
     // Schur complement S(k) = Be diag(M(k))^-1 Be^T: pattern, unique-value map T_0 and the Galerkin chain
     std::vector<const HCsr *> Ps;
     for (int m = level; m < c->nlevels - 1 && c->d[m].set && c->d[m].hasP; ++m) Ps.push_back(&c->d[m].Pp);
+    if (sys.cfg.max_vlevels > 0 && (int)Ps.size() > sys.cfg.max_vlevels - 1) Ps.resize(sys.cfg.max_vlevels - 1);
     sys.v.resize(Ps.size() + 1);
     HCsr Spat;
     {
@@ -695,10 +763,11 @@ static double spmm_bytes(const DevCsr &A, int ld, double vec_rows)
 // generic fused SpMM dispatch
 static void spmm(Ctx *c, int kclass, int ep, const DevCsr &A, const double *V, int ld, const double *x, double *y,
                  const double *r, double *d, const double *dinv, bool bdinv, double ca, double cb, const double *dotw,
-                 double *partial, int partial_off, double vec_rows)
+                 double *partial, int partial_off, double vec_rows, const int *perm = nullptr)
 {
     const Shape sh = shape_for(A.rows, ld);
     SpmmArgs a;
+    a.perm = perm;
     a.n = A.rows; a.ld = ld; a.rows_per_cta = sh.rows_per_cta;
     a.rowptr = A.rowptr; a.col = A.col; a.val = A.val; a.widx = A.widx; a.V = V;
     a.x = x; a.y = y; a.r = r; a.d = d; a.dinv = dinv; a.ca = ca; a.cb = cb;
@@ -800,13 +869,14 @@ static void vcycle(Solver &sv, int m, const double *r, double *zout, double *ztm
     op.vrows = sys.weighted ? L.nU : 0;
     op.kclass = PMC_K_SCHUR_SMOOTH;
     const bool last = (m + 1 == (int)sys.v.size());
+    const PrecCfg &cfg = sys.cfg;
     if (last) {
-        op.lo = 1.0 / c->coarse_ratio;
-        cheb_run(c, op, ld, r, ws.vd[m], c->coarse_degree, true, zout, ztmp, dot, ws.partial, partial_off);
+        op.lo = 1.0 / cfg.coarse_ratio;
+        cheb_run(c, op, ld, r, ws.vd[m], cfg.coarse_degree, true, zout, ztmp, dot, ws.partial, partial_off);
         return;
     }
-    op.lo = 1.0 / c->schur_ratio;
-    const int s = c->schur_degree;
+    op.lo = 1.0 / cfg.schur_ratio;
+    const int s = cfg.schur_degree;
     double *E = (s % 2 == 0) ? zout : ztmp, *O = (s % 2 == 0) ? ztmp : zout;
     cheb_run(c, op, ld, r, ws.vd[m], s, true, E, O, false, nullptr, 0);
     spmm(c, PMC_K_SCHUR_SMOOTH, EP_RESID, L.S, op.V, ld, E, ws.vres[m], r, nullptr, nullptr, false, 0, 0, nullptr,
@@ -814,8 +884,8 @@ static void vcycle(Solver &sv, int m, const double *r, double *zout, double *ztm
     spmm(c, PMC_K_TRANSFER, EP_AX, L.Pt, nullptr, ld, ws.vres[m], ws.vr[m + 1], nullptr, nullptr, nullptr, false, 0, 0,
          nullptr, nullptr, 0, (double)L.n + sys.v[m + 1].n);
     vcycle(sv, m + 1, ws.vr[m + 1], ws.vzA[m + 1], ws.vzB[m + 1], false, 0);
-    spmm(c, PMC_K_TRANSFER, EP_ADD, L.P, nullptr, ld, ws.vzA[m + 1], E, nullptr, nullptr, nullptr, false, 0, 0, nullptr,
-         nullptr, 0, 2.0 * L.n + sys.v[m + 1].n);
+    spmm(c, PMC_K_TRANSFER, EP_ADD, L.P, nullptr, ld, ws.vzA[m + 1], E, nullptr, nullptr, nullptr, false, cfg.omega, 0,
+         nullptr, nullptr, 0, 2.0 * L.n + sys.v[m + 1].n);
     cheb_run(c, op, ld, r, ws.vd[m], s, false, E, O, dot, ws.partial, partial_off);
 }
 
@@ -835,7 +905,7 @@ static int apply_prec(Solver &sv, const double *r, double *z, bool dot)
     op.hi = sys.m_hi;
     op.vrows = sys.weighted ? sys.Ne : 0;
     op.kclass = PMC_K_MASS_SMOOTH;
-    cheb_run(c, op, ld, r, ws.mu_d, c->mass_degree, true, z, ws.mu_z, dot, ws.partial, 0);
+    cheb_run(c, op, ld, r, ws.mu_d, sys.cfg.mass_degree, true, z, ws.mu_z, dot, ws.partial, 0);
     const int nbu = shape_for(sys.Nf, ld).nblk;
     vcycle(sv, 0, r + po, z + po, ws.vzB[0], dot, nbu);
     return nbu + shape_for(sys.Ne, ld).nblk;
@@ -845,7 +915,7 @@ static void saddle_apply(Solver &sv, int ep, const double *x, double *y, const d
 {
     SaddleSys &sys = *sv.sys;
     spmm(sv.c, kclass, ep, sys.A, sv.k_ext, sv.ld, x, y, r, nullptr, nullptr, false, 0, 0, dot ? x : nullptr,
-         sv.ws->partial, 0, (ep == EP_RESID ? 3.0 : 2.0) * sys.N + (sys.weighted ? sys.Ne : 0));
+         sv.ws->partial, 0, (ep == EP_RESID ? 3.0 : 2.0) * sys.N + (sys.weighted ? sys.Ne : 0), sys.perm);
 }
 
 static void fill(Ctx *c, double *p, size_t n, double v)
@@ -1092,6 +1162,8 @@ int pmc_create(int device, int nlevels, pmc_handle *out)
     Ctx *c = new Ctx();
     c->device = device;
     c->nlevels = nlevels;
+    c->cfg_sampler.max_vlevels = -1;  // single-level Schur smoother when alpha*W dominates (short correlation length)
+    c->cfg_darcy.omega = 2.0;         // aggregation-type coarse spaces under-correct the pressure Laplacian
     c->s.resize(nlevels);
     c->d.resize(nlevels);
     memset(&c->stats, 0, sizeof c->stats);
@@ -1157,11 +1229,40 @@ int pmc_set_preconditioner(pmc_handle c, int mass_degree, int schur_degree, doub
                            double coarse_ratio)
 {
     if (!c) return PMC_ERR_ARG;
-    if (mass_degree > 0) c->mass_degree = mass_degree;
-    if (schur_degree > 0) c->schur_degree = schur_degree;
-    if (schur_ratio > 1.0) c->schur_ratio = schur_ratio;
-    if (coarse_degree > 0) c->coarse_degree = coarse_degree;
-    if (coarse_ratio > 1.0) c->coarse_ratio = coarse_ratio;
+    for (PrecCfg *g : {&c->cfg_sampler, &c->cfg_darcy}) {
+        if (mass_degree > 0) g->mass_degree = mass_degree;
+        if (schur_degree > 0) g->schur_degree = schur_degree;
+        if (schur_ratio > 1.0) g->schur_ratio = schur_ratio;
+        if (coarse_degree > 0) g->coarse_degree = coarse_degree;
+        if (coarse_ratio > 1.0) g->coarse_ratio = coarse_ratio;
+    }
+    return PMC_OK;
+}
+
+int pmc_set_option(pmc_handle c, const char *key, double value)
+{
+    if (!c || !key) return PMC_ERR_ARG;
+    std::string k(key);
+    PrecCfg *g = nullptr;
+    if (k.rfind("sampler.", 0) == 0) { g = &c->cfg_sampler; k = k.substr(8); }
+    else if (k.rfind("darcy.", 0) == 0) { g = &c->cfg_darcy; k = k.substr(6); }
+    if (g) {
+        for (int l = 0; l < c->nlevels; ++l)
+            if ((g == &c->cfg_sampler ? c->s[l].sys.ready : c->d[l].sys.ready))
+                return fail(c, PMC_ERR_STATE, "pmc_set_option(%s): preconditioner already built; set options before the first solve / pmc_prepare", key);
+        if (k == "mass_degree" && value >= 1) g->mass_degree = (int)value;
+        else if (k == "schur_degree" && value >= 1) g->schur_degree = (int)value;
+        else if (k == "schur_ratio" && value > 1) g->schur_ratio = value;
+        else if (k == "coarse_degree" && value >= 1) g->coarse_degree = (int)value;
+        else if (k == "coarse_ratio" && value > 1) g->coarse_ratio = value;
+        else if (k == "omega" && value > 0) g->omega = value;
+        else if (k == "max_vlevels") g->max_vlevels = (int)value;
+        else return fail(c, PMC_ERR_ARG, "pmc_set_option: bad key or value '%s' = %g", key, value);
+        return PMC_OK;
+    }
+    if (k == "max_batch" && value >= 0) c->max_batch = (int)value;
+    else if (k == "check_every" && value >= 1) c->check_every = (int)value;
+    else return fail(c, PMC_ERR_ARG, "pmc_set_option: unknown key '%s'", key);
     return PMC_OK;
 }
 
