@@ -841,8 +841,18 @@ int po_sampler_eval(po_problem *p, int level, int xi_level, const double *xi, do
         free(cur);
         iterative = 1;
     }
-    saddle_t A = {Nf, Ne, &sl->M, &sl->B, &sl->Bt, sl->negaW, &sl->mg, 3};
+    /* the level's multigrid hierarchy is shared and read-only; its scratch vectors are per call so that
+     * concurrent samples (OpenMP threads of po_mlmc_level) do not share work space */
+    mg_t mgl = sl->mg;
+    for (int m = 0; m < mgl.nlev; ++m) {
+        size_t n = (size_t)mgl.S[m].rows;
+        mgl.r[m] = (double *)malloc(sizeof(double) * n);
+        mgl.x[m] = (double *)malloc(sizeof(double) * n);
+        mgl.t[m] = (double *)malloc(sizeof(double) * n);
+    }
+    saddle_t A = {Nf, Ne, &sl->M, &sl->B, &sl->Bt, sl->negaW, &mgl, 3};
     int it = minres(&A, b, x, iterative, p->rel, p->abs_, p->maxit);
+    for (int m = 0; m < mgl.nlev; ++m) { free(mgl.r[m]); free(mgl.x[m]); free(mgl.t[m]); }
     if (iters) *iters = it;
     if (embed_s) memcpy(embed_s, x + Nf, sizeof(double) * (size_t)Ne); /* :527 */
     for (int i = 0; i < Ne; ++i) s_out[i] = sl->lognormal ? exp(x[Nf + i]) : x[Nf + i]; /* :529-533 */

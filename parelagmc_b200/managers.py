@@ -1,0 +1,369 @@
+"""Host-side Monte-Carlo managers, mirroring the reference's `MLMC_Manager` / `MC_Manager` over the batched C ABI.
+
+Same names, arguments and behaviour as `/root/reference/src/MLMC_Manager.{hpp,cpp}` and
+`/root/reference/src/MC_Manager.{hpp,cpp}` (`Run`, `InitRun`, `ShowMe`, `wallTime`), except that the inner sample
+loop (`MLMC_Manager.cpp:110-175`, `MC_Manager.cpp:82-116`) is ONE batched call per level into the GPU library and
+that realisations are sharded over the ranks of `comm` (a `torch.distributed` process group or `None`): each rank
+processes a contiguous slice of every level's sample budget and the per-level sums are combined with one
+all-reduce per `InitRun` (there is no other communication).  The C++ twin of this file, used by the reference-style
+drivers, is `parelagmc_b200/host/`.
+"""
+from __future__ import annotations
+
+import math
+import sys
+import time
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+# enum of /root/reference/src/MLMC_Manager.hpp:65
+Y2, Y, ABSY, Q2, Q, ABSQ, C, Y3, Y4, NVAR = range(10)
+# enum of /root/reference/src/MC_Manager.hpp:61
+SL_Q2, SL_Q, SL_ABSQ, SL_C, SL_NVAR = range(5)  # SL_NVAR == 4 sums
+
+
+def expWRegression(y: Sequence[float], x: Sequence[float], skip_n_last: int) -> float:
+    """`/root/reference/src/Utilities.cpp:257-283`: weighted log-log regression slope, weights 0.5^i."""
+    n = len(y) - 1 - skip_n_last
+    if n < 1:
+        return 0.0
+    num = den = 0.0
+    for i in range(n):
+        logdy = math.log(abs(y[i] / y[i + 1]))
+        logdx = math.log(x[i] / x[i + 1])
+        w = 0.5 ** i
+        num += logdy * w * logdx
+        den += logdx * w * logdx
+    return num / den
+
+
+def split_samples(n: int, rank: int, world: int):
+    """Contiguous slice [first, first+count) of n realisations owned by `rank`."""
+    base, rem = divmod(n, world)
+    count = base + (1 if rank < rem else 0)
+    first = rank * base + min(rank, rem)
+    return first, count
+
+
+class _Comm:
+    """Thin wrapper: torch.distributed group (any backend) or single process."""
+
+    def __init__(self, group=None, use_dist: bool = False, device=None):
+        self.use_dist = use_dist
+        self.group = group
+        self.device = device
+        if use_dist:
+            import torch.distributed as dist
+            self.dist = dist
+            self.rank = dist.get_rank(group)
+            self.size = dist.get_world_size(group)
+        else:
+            self.rank, self.size = 0, 1
+
+    def allreduce_sum(self, a: np.ndarray) -> np.ndarray:
+        if not self.use_dist or self.size == 1:
+            return a
+        import torch
+        t = torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64))
+        if self.device is not None:
+            t = t.to(self.device)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, group=self.group)
+        return t.cpu().numpy()
+
+
+class MLMC_Manager:
+    """`parelagmc::MLMC_Manager` (`/root/reference/src/MLMC_Manager.hpp:30-61`).
+
+    backend: object with `mlmc_level_batch(level, nsamples, pos0, nlevels=..., want_rows=..., sums=...)`,
+    `Ne[level]` and `Nf[level]` (a `capi.Context`).  params: the "Problem parameters" keys read at
+    `MLMC_Manager.cpp:29-36`."""
+
+    def __init__(self, comm: Optional[_Comm], nlevels: int, backend, params: Optional[dict] = None, out=sys.stdout):
+        params = params or {}
+        self.wallTime = True
+        self.comm = comm or _Comm()
+        self.nlevels = nlevels
+        self.backend = backend
+        self.eps2 = float(params.get("Mean square error", 0.001))
+        self.auto_eps2 = self.eps2 < 0
+        self.ratio = float(params.get("MSE splitting ratio", 0.5))
+        self.file_name = params.get("Output filename for MC managers", "MLMC.dat")
+        self.init_nsamples = int(params.get("Number of samples", 10))
+        self.use_array_samples = bool(params.get("Use array samples", False))
+        self.v_init_nsamples = list(params.get("Array number of samples", []))
+        if self.use_array_samples and len(self.v_init_nsamples) != nlevels:
+            self.use_array_samples = False
+        if not self.use_array_samples:
+            self.v_init_nsamples = [self.init_nsamples] * nlevels
+        self.out = out
+        self.pid = self.comm.rank
+        self.M = np.array([backend.Ne[i] + backend.Nf[i] for i in range(nlevels)], dtype=np.float64)
+        self.logger = open(self.file_name, "w") if (self.pid == 0 and self.file_name) else None
+        self.stream_pos = 0            # absolute yarn5 position of the next unused draw (all ranks agree)
+        self._reset()
+        if self.pid == 0 and out is not None:
+            print("\n" + "*" * 50 + "\n*  MLMC_Manager \n*    MSE: %g\n*    MSE splitting ratio: %g\n"
+                  "*    Number of Initial Samples: %s \n*    Output filename: %s\n" % (
+                      self.eps2, self.ratio, " ".join(map(str, self.v_init_nsamples)), self.file_name) + "*" * 50,
+                  file=out)
+
+    def _reset(self):
+        L = self.nlevels
+        self.sums = np.zeros((L, NVAR))
+        self.level_nsamples = np.zeros(L, dtype=np.int64)
+        self.level_nsamples_missing = np.zeros(L, dtype=np.int64)
+        self.level_time = np.zeros(L)
+        self.ml_estimator_variance = math.inf
+        self.expected_discretization_error2 = math.inf
+        self.actualMSE = math.inf
+        self.total_iters = 0
+        for n in ("eY", "eABSY", "eQ", "eABSQ", "eC", "varY", "varQ", "consistency", "kurtosis", "VC"):
+            setattr(self, n, np.zeros(L))
+        self.alpha = self.alphaABS = self.beta = self.gamma = 0.0
+
+    # --------------------------------------------------------------------------------------------
+    def InitRun(self, level_nsamples_init: Sequence[int]):
+        """`MLMC_Manager.cpp:103-179`: coarsest level first, then nlevels-2 .. 0; sums accumulate."""
+        first_call = self.level_nsamples.max() == 0
+        if first_call and self.logger:
+            self.logger.write("%" + "level ".rjust(13) + "Y(xi) ".rjust(14) + "Q(xi)".rjust(14) + "Q_c(xi)".rjust(14)
+                              + "c \n".rjust(14))
+        local = np.zeros((self.nlevels, NVAR))
+        for ilevel in range(self.nlevels - 1, -1, -1):
+            n = int(level_nsamples_init[ilevel])
+            Ne = self.backend.Ne[ilevel]
+            first, count = split_samples(n, self.comm.rank, self.comm.size)
+            t0 = time.perf_counter()
+            want_rows = self.logger is not None and self.comm.size == 1
+            if count > 0:
+                _, rows, its = self.backend.mlmc_level_batch(ilevel, count, self.stream_pos + first * Ne,
+                                                             nlevels=self.nlevels, want_rows=want_rows,
+                                                             sums=local[ilevel])
+                self.total_iters += its
+                if want_rows:
+                    for r in rows:
+                        self.logger.write(f"{ilevel:14d}{r[0]:14.6g}{r[1]:14.6g}{r[2]:14.6g}{r[3]:14.6g}\n")
+            self.level_time[ilevel] += time.perf_counter() - t0
+            self.stream_pos += n * Ne
+            self.level_nsamples[ilevel] += n
+        self.sums += self.comm.allreduce_sum(local)
+        if self.logger:
+            self.logger.flush()
+        self.computeNSamplesMSE()
+
+    def Run(self):
+        """`MLMC_Manager.cpp:181-214`."""
+        self._reset()
+        self.InitRun(self.v_init_nsamples)
+        grain = [0] * self.nlevels
+        while self.ml_estimator_variance > self.ratio * self.eps2:
+            for i in range(self.nlevels):
+                grain[i] = min(int(self.level_nsamples_missing[i]),
+                               self.v_init_nsamples[i] + grain[i] + int(self.level_nsamples_missing[i]) // 10)
+            if sum(grain) == 0:
+                break
+            self.InitRun(grain)
+        if self.pid == 0 and self.out is not None:
+            print("FINAL MLMC ERRORS", file=self.out)
+        self.ShowMe()
+
+    # --------------------------------------------------------------------------------------------
+    def computeNSamplesMSE(self):
+        """`MLMC_Manager.cpp:300-401`."""
+        L = self.nlevels
+        n = self.level_nsamples.astype(np.float64)
+        e = self.sums / n[:, None]
+        self.eY, self.eABSY, self.eQ, self.eABSQ, self.eC = (e[:, Y].copy(), e[:, ABSY].copy(), e[:, Q].copy(),
+                                                             e[:, ABSQ].copy(), e[:, C].copy())
+        varY, varQ, kurt = e[:, Y2].copy(), e[:, Q2].copy(), e[:, Y4].copy()
+        with np.errstate(divide="ignore", invalid="ignore"):
+            kurt = kurt / (varY * varY)          # note: before the mean is subtracted (:318-319)
+            varY = (varY - self.eY ** 2) * n / (n - 1.0)
+            varQ = (varQ - self.eQ ** 2) * n / (n - 1.0)
+        self.varY, self.varQ, self.kurtosis = varY, varQ, kurt
+        self.consistency = np.zeros(L)
+        for l in range(L - 1):
+            with np.errstate(divide="ignore", invalid="ignore"):
+                self.consistency[l] = abs(self.eQ[l] - self.eQ[l + 1] + self.eY[l]) / (
+                    3 * (math.sqrt(max(varQ[l], 0)) + math.sqrt(max(varQ[l + 1], 0)) + math.sqrt(max(varY[l], 0))))
+        M = self.M
+        self.alpha = expWRegression(self.eY, M, 1)
+        self.alphaABS = expWRegression(self.eABSY, M, 1)
+        self.beta = expWRegression(varY, M, 1)
+        if L == 1:
+            bias2 = 0.0
+        else:
+            m = M[0] / M[1]
+            if L > 3:
+                bias2 = max(m ** (2.0 * self.alphaABS) * self.eABSY[1] ** 2, self.eABSY[0] ** 2) / (
+                    (m ** (-2.0 * self.alphaABS) - 1.0) ** 2)
+            elif L == 3:
+                bias2 = self.eABSY[0] ** 2 / ((m ** (-self.alphaABS) - 1.0) ** 2)
+            else:
+                bias2 = self.eABSY[0] ** 2
+        self.expected_discretization_error2 = bias2
+        if self.auto_eps2:
+            self.eps2 = bias2 / (1.0 - self.ratio)
+        self.ml_estimator_variance = float(np.sum(varY / n))
+        self.actualMSE = bias2 + self.ml_estimator_variance
+        cost = (self.level_time / n) if self.wallTime else self.eC
+        self.cost = np.asarray(cost, dtype=np.float64)
+        self.gamma = expWRegression(self.cost, M, 0)
+        prop = float(np.sum(np.sqrt(np.maximum(varY, 0) * self.cost))) / (self.ratio * self.eps2)
+        for i in range(L):
+            missings = prop * math.sqrt(max(varY[i], 0) / self.cost[i]) - n[i]
+            self.level_nsamples_missing[i] = max(int(math.ceil(missings)), 0)
+            self.VC[i] = varY[i] * self.cost[i]
+        self.ShowMe()
+
+    def ShowMe(self, os=None):
+        """`MLMC_Manager.cpp:216-297` (same labels, widths and order)."""
+        os = os or self.out
+        if self.pid != 0 or os is None:
+            return
+        W, NW = 79, 42
+
+        def row(name, v):
+            os.write(name.ljust(NW) + ("%.8g" % v).ljust(18) + "\n")
+
+        def vec(name, v, fmt="%.8g"):
+            os.write(name.ljust(NW) + "  ".join(fmt % x for x in v) + "\n")
+
+        os.write("=" * W + "\nMLMC Manager Errors: \n" + "-" * W + "\n")
+        row("Estimate", float(np.sum(self.eY)))
+        row("Target MSE", self.eps2)
+        row("Actual MSE", self.actualMSE)
+        row("ML Estimator Variance", self.ml_estimator_variance)
+        row("Estimator Bias", self.expected_discretization_error2)
+        row("Alpha", self.alpha)
+        row("AlphaAbs", self.alphaABS)
+        row("Beta", self.beta)
+        row("Gamma", self.gamma)
+        os.write("\n")
+        vec("DOFS in Forward Problem", self.M)
+        vec("C_l ", self.eC)
+        os.write("\n")
+        vec("NumSamples ", self.level_nsamples, "%d")
+        os.write("\n")
+        vec("E[Y_l] ", self.eY)
+        vec("E[|Y_l|] ", self.eABSY)
+        vec("Var[Y_l] ", self.varY)
+        vec("E[Q_l] ", self.eQ)
+        vec("E[|Q_l|] ", self.eABSQ)
+        vec("Var[Q_l] ", self.varQ)
+        vec("V[Y_l]*C_l ", self.VC)
+        vec("Consistency ", self.consistency)
+        vec("Kurtosis", self.kurtosis)
+        os.write("=" * W + "\n")
+        os.flush()
+
+
+class MC_Manager:
+    """`parelagmc::MC_Manager` (`/root/reference/src/MC_Manager.hpp:28-57`): single level (level 0)."""
+
+    def __init__(self, comm: Optional[_Comm], backend, params: Optional[dict] = None, out=sys.stdout, level: int = 0):
+        params = params or {}
+        self.wallTime = True
+        self.comm = comm or _Comm()
+        self.backend = backend
+        self.level = level
+        self.eps2 = float(params.get("Mean square error", 0.001))
+        self.auto_eps2 = self.eps2 < 0
+        self.ratio = float(params.get("MSE splitting ratio", 0.5))
+        self.file_name = params.get("Output filename for MC managers", "MLMC.dat")
+        self.init_nsamples = int(params.get("Number of samples", 10))
+        self.out = out
+        self.pid = self.comm.rank
+        self.M = float(backend.Ne[level] + backend.Nf[level])
+        self.logger = open(self.file_name, "w") if (self.pid == 0 and self.file_name) else None
+        self.stream_pos = 0
+        self._reset()
+
+    def _reset(self):
+        self.sums = np.zeros(SL_NVAR)[:4].copy()
+        self.level_nsamples = 0
+        self.level_nsamples_missing = 0
+        self.time = 0.0
+        self.ml_estimator_variance = math.inf
+        self.expected_discretization_error2 = math.inf
+        self.actualMSE = math.inf
+        self.eQ = self.eABSQ = self.eC = self.varQ = 0.0
+
+    def InitRun(self, nsamples: int):
+        """`MC_Manager.cpp:82-116`."""
+        Ne = self.backend.Ne[self.level]
+        first, count = split_samples(int(nsamples), self.comm.rank, self.comm.size)
+        local = np.zeros(4)
+        t0 = time.perf_counter()
+        if count > 0:
+            want_rows = self.logger is not None and self.comm.size == 1
+            _, rows, _ = self.backend.mc_level_batch(self.level, count, self.stream_pos + first * Ne,
+                                                     want_rows=want_rows, sums=local)
+            if want_rows:
+                for r in rows:
+                    self.logger.write(f"{r[0]:14.6g}{r[1]:14.6g}\n")
+        self.time += time.perf_counter() - t0
+        self.stream_pos += int(nsamples) * Ne
+        self.level_nsamples += int(nsamples)
+        self.sums += self.comm.allreduce_sum(local)
+        self.computeNSamplesMSE()
+
+    def Run(self):
+        """`MC_Manager.cpp:118-146`."""
+        self._reset()
+        grain = self.init_nsamples
+        self.InitRun(grain)
+        grain = 0
+        while self.ml_estimator_variance > self.ratio * self.eps2:
+            grain = min(self.level_nsamples_missing, self.init_nsamples + grain + self.level_nsamples_missing // 10)
+            if grain == 0:
+                break
+            self.InitRun(grain)
+        if self.pid == 0 and self.out is not None:
+            print("FINAL SLMC ERRORS", file=self.out)
+        self.ShowMe()
+
+    def computeNSamplesMSE(self):
+        """`MC_Manager.cpp:194-239`."""
+        nl = float(self.level_nsamples)
+        self.eQ = self.sums[SL_Q] / nl
+        self.eABSQ = self.sums[SL_ABSQ] / nl
+        self.eC = self.sums[SL_C] / nl
+        self.varQ = (self.sums[SL_Q2] / nl - self.eQ ** 2) * nl / (nl - 1.0) if nl > 1 else math.inf
+        self.expected_discretization_error2 = 0.0
+        if self.auto_eps2:
+            self.eps2 = self.expected_discretization_error2 / (1.0 - self.ratio)
+        self.ml_estimator_variance = self.varQ / nl
+        self.actualMSE = self.expected_discretization_error2 + self.ml_estimator_variance
+        cost = (self.time / nl) if self.wallTime else self.eC
+        prop = math.sqrt(self.varQ * cost) / (self.ratio * self.eps2)
+        missings = prop * math.sqrt(self.varQ / cost) - nl
+        self.level_nsamples_missing = max(int(math.ceil(missings)), 0)
+        self.ShowMe()
+
+    def ShowMe(self, os=None):
+        """`MC_Manager.cpp:148-192`."""
+        os = os or self.out
+        if self.pid != 0 or os is None:
+            return
+        W, NW = 79, 42
+
+        def row(name, v):
+            os.write(name.ljust(NW) + ("%.8g" % v).ljust(18) + "\n")
+
+        os.write("=" * W + "\nSLMC Manager Errors: \n" + "-" * W + "\n")
+        row("Estimate", self.eQ)
+        row("Target MSE", self.eps2)
+        row("Actual MSE", self.actualMSE)
+        row("SL Estimator Variance", self.ml_estimator_variance)
+        row("Estimator Bias", self.expected_discretization_error2)
+        row("Target Bias Error", math.sqrt(max(self.eps2, 0)) / math.sqrt(2))
+        row("DOFS in Forward Problem", self.M)
+        row("C_l ", self.eC)
+        os.write("\n" + "NumSamples ".ljust(NW) + str(self.level_nsamples) + "\n")
+        row("E[Q_l] ", self.eQ)
+        row("E[|Q_l|] ", self.eABSQ)
+        row("Var[Q_l] ", self.varQ)
+        os.write("=" * W + "\n")
+        os.flush()

@@ -54,3 +54,31 @@ def rel_l2(a, b):
     a = np.asarray(a, dtype=np.float64)
     b = np.asarray(b, dtype=np.float64)
     return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300))
+
+
+class OracleBackend:
+    """Test double with the `capi.Context` manager-facing surface, computed by the CPU oracle.  Lets the host-side
+    manager logic (sample sharding, stream positions, all-reduce, statistics) be tested without a GPU."""
+
+    def __init__(self, p, rel=1e-8, abs_=1e-30, maxit=1000, threads=4):
+        self.o = make_oracle(p, True, rel, abs_, maxit)
+        self.nlevels = p["nlevels"]
+        self.Ne = [s.Ne for s in p["sampler"]]
+        self.Nf = [s.Nf for s in p["sampler"]]
+        self.threads = threads
+        self.calls = []
+
+    def mlmc_level_batch(self, level, nsamples, pos0, nlevels=None, want_rows=False, sums=None):
+        s, rows, its = self.o.mlmc_level(level, nsamples, pos0, nthreads=self.threads, nlevels=nlevels)
+        self.calls.append((level, nsamples, pos0))
+        if sums is None:
+            sums = np.zeros(9)
+        sums += s
+        return sums, (rows if want_rows else None), its
+
+    def mc_level_batch(self, level, nsamples, pos0, want_rows=False, sums=None):
+        s, rows, its = self.o.mlmc_level(level, nsamples, pos0, nthreads=self.threads, nlevels=level + 1)
+        if sums is None:
+            sums = np.zeros(4)
+        sums += np.array([s[3], s[4], s[5], s[6]])
+        return sums, (rows[:, [1, 3]] if want_rows else None), its

@@ -230,3 +230,69 @@ def test_empty_and_error_paths(ctx, prob):
     # zero noise -> zero field, converges in 0 iterations
     s, emb, it = ctx.sampler_eval_batch(1, np.zeros((2, prob["sampler"][1].Ne)))
     assert np.all(emb == 0) and np.all(it == 0) and np.all(s == 1.0)
+
+
+def test_committed_golden_fixtures():
+    """CUDA path against tests/golden/oracle_golden.json (tools/make_golden.py)."""
+    import json, os
+    from oracle.binding import Yarn5
+    G = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "oracle_golden.json")))
+    p = hex_problem(4, 2)
+    c = make_context(p)
+    try:
+        for pos, v in G["yarn5_ints"].items():
+            assert c.rng_fill_int(int(pos), len(v)).tolist() == v
+        c.rng_init(0.0, 1.0, 4, 3)
+        assert c.rng_fill_int(0, 8).tolist() == G["yarn5_split_4_3"]
+        c.rng_init(0.0, 1.0, 1, 0)
+        g = G["hex4"]
+        for lev in range(2):
+            Ne = p["darcy"][lev].Ne
+            k = np.stack([np.ones(Ne), np.exp(np.sin(np.arange(Ne, dtype=float)))])
+            Q, _, _, _ = c.darcy_solve_batch(lev, k)
+            assert abs(Q[0] - g["Q_k1"][lev]) <= 1e-9 * abs(g["Q_k1"][lev])
+            assert abs(Q[1] - g["Q_ksin"][lev]) <= 1e-9 * abs(g["Q_ksin"][lev])
+        xi = c.sampler_sample_batch(0, 1, 0)
+        _, e0, _ = c.sampler_eval_batch(0, xi)
+        _, e1, _ = c.sampler_eval_batch(1, xi, xi_level=0, use_init=0)
+        assert rel_l2(e0[0], g["field_l0"]) < FIELD_TOL
+        assert rel_l2(e1[0], g["field_l1_from_l0_noise"]) < FIELD_TOL
+        for lev, ns in [(1, 4), (0, 3)]:
+            sums, rows, _ = c.mlmc_level_batch(lev, ns, 1234, want_rows=True)
+            assert np.allclose(rows, g[f"mlmc_rows_l{lev}"], rtol=1e-7, atol=1e-9)
+            assert np.allclose(sums, g[f"mlmc_sums_l{lev}"], rtol=1e-6, atol=1e-9)
+    finally:
+        c.close()
+
+
+def test_managers_on_gpu_match_oracle_backend(tmp_path):
+    """MLMC_Manager / MC_Manager (host mirror of the reference managers) driving the CUDA library, against the same
+    managers driving the oracle: estimates and variances within 1e-6 relative."""
+    from common import OracleBackend
+    from parelagmc_b200 import managers as MG
+    p = hex_problem(4, 3)
+    c = make_context(p, rel=1e-10)
+    try:
+        params = {"Use array samples": True, "Array number of samples": [6, 10, 16], "Mean square error": 1e6,
+                  "Output filename for MC managers": ""}
+        mg = MG.MLMC_Manager(None, 3, c, params, out=None)
+        mg.wallTime = False
+        mg.Run()
+        mo = MG.MLMC_Manager(None, 3, OracleBackend(p, rel=1e-10), params, out=None)
+        mo.wallTime = False
+        mo.Run()
+        assert np.allclose(mg.eY, mo.eY, rtol=MOMENT_TOL, atol=1e-12)
+        assert np.allclose(mg.varY, mo.varY, rtol=MOMENT_TOL, atol=1e-14)
+        assert np.allclose(mg.eQ, mo.eQ, rtol=MOMENT_TOL) and np.allclose(mg.varQ, mo.varQ, rtol=MOMENT_TOL)
+        assert np.array_equal(mg.level_nsamples, mo.level_nsamples)
+        sl = MG.MC_Manager(None, c, {"Number of samples": 8, "Mean square error": 1e6,
+                                     "Output filename for MC managers": ""}, out=None)
+        sl.wallTime = False
+        sl.Run()
+        so = MG.MC_Manager(None, OracleBackend(p, rel=1e-10), {"Number of samples": 8, "Mean square error": 1e6,
+                                                                 "Output filename for MC managers": ""}, out=None)
+        so.wallTime = False
+        so.Run()
+        assert abs(sl.eQ - so.eQ) <= MOMENT_TOL * abs(so.eQ) and abs(sl.varQ - so.varQ) <= MOMENT_TOL * abs(so.varQ)
+    finally:
+        c.close()

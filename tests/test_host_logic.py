@@ -1,0 +1,187 @@
+"""CPU tests of the host side: the hierarchy provider (stand-in for ParELAG), the managers' logic (sample sharding,
+stream positions, statistics, report) and the N>1 path with world_size 2 over gloo."""
+import io
+import os
+import sys
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from common import hex_problem, quad_problem, OracleBackend
+from parelagmc_b200 import hierarchy as H
+from parelagmc_b200 import managers as MG
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_hierarchy_counts_and_identities():
+    L = H.build_box_hierarchy([16] * 3, [2.0] * 3, 3)
+    assert [(l.Ne, l.Nf) for l in L] == [(4096, 13056), (512, 1728), (64, 240)]
+    for l in L:
+        assert np.isclose(l.Wdiag.sum(), 8.0)
+        M = l.assemble_M()
+        assert abs(M - M.T).max() < 1e-15
+        # B = W D, rows sum to zero on interior-only... every element has net zero incidence
+        assert np.allclose(np.asarray(l.B.sum(axis=1)).ravel(), 0.0)
+    for f, c in zip(L[:-1], L[1:]):
+        assert np.allclose(np.asarray(f.P_s.sum(axis=1)).ravel(), 1.0)           # aggregation: partition of unity
+        # commuting diagram: the divergence of a prolongated coarse flux is the prolongated coarse divergence
+        rng = np.random.default_rng(0)
+        uc = rng.standard_normal(c.Nf)
+        assert np.allclose(f.D @ (f.P_u @ uc), f.P_s @ (c.D @ uc), atol=1e-12)
+        # Galerkin mass: P_u^T M_f P_u == M_c (nested RT0 spaces)
+        assert abs(f.P_u.T @ f.assemble_M() @ f.P_u - c.assemble_M()).max() < 1e-12
+
+
+def test_darcy_levels_rhs_obs():
+    p = hex_problem(8, 3)
+    for lev, d in enumerate(p["darcy"]):
+        n = 8 >> lev
+        assert d.ess_u.sum() == 4 * n * n                       # four lateral faces
+        # flux dofs are total face fluxes: one unit entry per inflow / observation face on every level
+        assert np.isclose(np.abs(d.rhs).sum(), n * n) and np.isclose(np.abs(d.obs).sum(), n * n)
+    q = quad_problem(4, 2)
+    assert q["sampler"][0].ess_u.sum() == 16
+
+
+def test_split_samples_partition():
+    for n in (0, 1, 7, 10, 1000):
+        for w in (1, 2, 3, 8):
+            parts = [MG.split_samples(n, r, w) for r in range(w)]
+            assert sum(c for _, c in parts) == n
+            pos = 0
+            for f, c in parts:
+                assert f == pos
+                pos += c
+
+
+def test_expwregression_matches_oracle():
+    from oracle.binding import exp_w_regression
+    rng = np.random.default_rng(1)
+    x = np.array([17152.0, 2240.0, 304.0, 40.0])
+    y = np.abs(rng.standard_normal(4)) + 0.1
+    for skip in (0, 1):
+        assert MG.expWRegression(y, x, skip) == pytest.approx(exp_w_regression(y, x, skip), rel=1e-13)
+
+
+def test_mlmc_manager_matches_reference_formulas(tmp_path):
+    """InitRun order / stream positions (MLMC_Manager.cpp:110,140) and computeNSamplesMSE against the oracle's
+    restatement of :300-401."""
+    from oracle.binding import mlmc_compute
+    p = hex_problem(4, 3)
+    be = OracleBackend(p)
+    out = io.StringIO()
+    params = {"Use array samples": True, "Array number of samples": [4, 6, 8], "Mean square error": 1e6,
+              "Output filename for MC managers": str(tmp_path / "MLMC.dat")}
+    m = MG.MLMC_Manager(None, 3, be, params, out=out)
+    m.wallTime = False
+    m.Run()
+    # coarsest level first; every level starts where the previous one stopped
+    assert [c[0] for c in be.calls] == [2, 1, 0]
+    assert be.calls[0][2] == 0 and be.calls[1][2] == 8 * be.Ne[2] and be.calls[2][2] == 8 * be.Ne[2] + 6 * be.Ne[1]
+    r = mlmc_compute(m.sums, m.level_nsamples, m.M, cost=None, eps2=1e6, ratio=0.5)
+    assert np.allclose(m.eY, r["eY"]) and np.allclose(m.varY, r["varY"]) and np.allclose(m.varQ, r["varQ"])
+    assert np.allclose(m.kurtosis, r["kurtosis"]) and np.allclose(m.consistency, r["consistency"])
+    assert m.alpha == pytest.approx(r["alpha"]) and m.alphaABS == pytest.approx(r["alpha_abs"])
+    assert m.gamma == pytest.approx(r["gamma"])
+    assert m.expected_discretization_error2 == pytest.approx(r["bias2"])
+    assert m.ml_estimator_variance == pytest.approx(r["ml_estimator_variance"])
+    assert np.array_equal(m.level_nsamples_missing, r["missing"])
+    txt = out.getvalue()
+    for label in ("MLMC Manager Errors:", "Estimate", "Target MSE", "ML Estimator Variance", "DOFS in Forward Problem",
+                  "NumSamples", "E[Y_l]", "Var[Q_l]", "Consistency", "Kurtosis", "FINAL MLMC ERRORS"):
+        assert label in txt
+    log = open(tmp_path / "MLMC.dat").read().splitlines()
+    assert len(log) == 1 + 4 + 6 + 8                              # header + one row per sample (:134-135,:171-172)
+
+
+def test_mlmc_manager_adaptive_loop(tmp_path):
+    """Run() keeps adding samples until the estimator variance meets ratio * eps2 (:202-209)."""
+    p = hex_problem(4, 2)
+    be = OracleBackend(p)
+    params = {"Number of samples": 6, "Mean square error": 4e-3, "Output filename for MC managers": ""}
+    m = MG.MLMC_Manager(None, 2, be, params, out=None)
+    m.wallTime = False
+    m.Run()
+    assert m.ml_estimator_variance <= 0.5 * m.eps2
+    assert m.level_nsamples.sum() > 12
+
+
+def test_mc_manager(tmp_path):
+    from oracle.binding import mc_compute
+    p = hex_problem(4, 2)
+    be = OracleBackend(p)
+    out = io.StringIO()
+    m = MG.MC_Manager(None, be, {"Number of samples": 12, "Mean square error": 1e6,
+                                 "Output filename for MC managers": ""}, out=out)
+    m.wallTime = False
+    m.Run()
+    r = mc_compute(m.sums, m.level_nsamples, eps2=1e6, ratio=0.5)
+    assert m.eQ == pytest.approx(r["eQ"]) and m.varQ == pytest.approx(r["varQ"])
+    assert "FINAL SLMC ERRORS" in out.getvalue() and "SLMC Manager Errors:" in out.getvalue()
+
+
+def _gloo_worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from common import hex_problem, OracleBackend
+    from parelagmc_b200 import managers as MG
+    p = hex_problem(4, 2)
+    be = OracleBackend(p, threads=1)
+    m = MG.MLMC_Manager(MG._Comm(None, True), 2, be, {"Use array samples": True, "Array number of samples": [5, 9],
+                                                      "Mean square error": 1e6,
+                                                      "Output filename for MC managers": ""}, out=None)
+    m.wallTime = False
+    m.Run()
+    q.put((rank, m.sums.copy(), m.level_nsamples.copy(), list(be.calls), float(np.sum(m.eY))))
+    dist.destroy_process_group()
+
+
+def test_sharded_run_world2_gloo():
+    """N > 1 path on CPU: two ranks shard every level's budget; the all-reduced sums equal the 1-rank sums and the
+    union of the ranks' stream slices is the 1-rank stream."""
+    import socket
+    import torch.multiprocessing as mp
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    for pr in procs:
+        pr.start()
+    res = sorted([q.get(timeout=300) for _ in range(2)], key=lambda t: t[0])
+    for pr in procs:
+        pr.join(timeout=60)
+        assert pr.exitcode == 0
+    p = hex_problem(4, 2)
+    be = OracleBackend(p, threads=1)
+    m = MG.MLMC_Manager(None, 2, be, {"Use array samples": True, "Array number of samples": [5, 9],
+                                      "Mean square error": 1e6, "Output filename for MC managers": ""}, out=None)
+    m.wallTime = False
+    m.Run()
+    for rank, sums, ns, calls, est in res:
+        assert np.allclose(sums, m.sums, rtol=1e-12, atol=1e-14)
+        assert np.array_equal(ns, m.level_nsamples)
+        assert est == pytest.approx(float(np.sum(m.eY)), rel=1e-12)
+    # rank slices: level 1 (9 samples): 5 + 4, level 0 (5 samples): 3 + 2, contiguous in the stream
+    Ne = be.Ne
+    c0, c1 = res[0][3], res[1][3]
+    assert c0[0] == (1, 5, 0) and c1[0] == (1, 4, 5 * Ne[1])
+    assert c0[1] == (0, 3, 9 * Ne[1]) and c1[1] == (0, 2, 9 * Ne[1] + 3 * Ne[0])
+
+
+def test_bench_stream_positions():
+    sys.path.insert(0, ROOT)
+    import bench
+    p = hex_problem(4, 2)
+    Ne = [s.Ne for s in p["sampler"]]
+    pos0 = bench.stream_positions(p, [10, 20], 0, 2)
+    pos1 = bench.stream_positions(p, [10, 20], 1, 2)
+    assert pos0[1] == 0 and pos1[1] == 20 * Ne[1]
+    assert pos0[0] == 2 * 20 * Ne[1] and pos1[0] == 2 * 20 * Ne[1] + 10 * Ne[0]
