@@ -50,6 +50,8 @@ def build(force: bool = False) -> str:
     stale = (not os.path.exists(LIB_PATH)) or any(os.path.getmtime(s) > os.path.getmtime(LIB_PATH) for s in srcs)
     if force or stale:
         subprocess.check_call(["make", "-C", CSRC], stdout=subprocess.DEVNULL)
+    # the C++ host layer (reference-style classes and drivers over the C ABI)
+    subprocess.check_call(["make", "-C", os.path.join(_HERE, "host")], stdout=subprocess.DEVNULL)
     return LIB_PATH
 
 

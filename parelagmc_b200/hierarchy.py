@@ -431,3 +431,52 @@ def build_darcy_levels(levels: List[LevelData], ess_attr: Sequence[int], obs_att
 MLMC_DEFAULT_BC = dict(ess_attr=[0, 1, 1, 1, 1, 0], obs_attr=[1, 0, 0, 0, 0, 0], inflow_attr=[0, 0, 0, 0, 0, 1])
 # SPE10 XML (`examples/SPE10/spe10_3D_parameters.xml:45-49`)
 SPE10_BC = dict(ess_attr=[1, 0, 1, 0, 1, 1], obs_attr=[0, 1, 0, 0, 0, 0], inflow_attr=[0, 0, 0, 1, 0, 0])
+
+
+# --------------------------------------------------------------------------------------
+# binary dump read by the C++ host layer (parelagmc_b200/host/HierarchyData.cpp)
+# --------------------------------------------------------------------------------------
+def dump_problem(path: str, sampler_levels: List[SamplerLevel], darcy_levels: List[DarcyLevel], dim: int,
+                 corlen: float) -> None:
+    """Write the host-once hierarchy data in the "PMCH1" layout of `HierarchyData::Load`."""
+    import struct
+
+    def ivec(f, a):
+        a = np.ascontiguousarray(a, dtype=np.int32)
+        f.write(struct.pack("<q", a.size))
+        f.write(a.tobytes())
+
+    def dvec(f, a):
+        a = np.ascontiguousarray(a, dtype=np.float64)
+        f.write(struct.pack("<q", a.size))
+        f.write(a.tobytes())
+
+    def csr(f, m):
+        if m is None:
+            f.write(struct.pack("<i", 0))
+            return
+        m = _csr(m)
+        f.write(struct.pack("<iii", 1, m.shape[0], m.shape[1]))
+        ivec(f, m.indptr)
+        ivec(f, m.indices)
+        dvec(f, m.data)
+
+    with open(path, "wb") as f:
+        f.write(b"PMCH1\0\0\0")
+        f.write(struct.pack("<iid", len(sampler_levels), dim, corlen))
+        for s, d in zip(sampler_levels, darcy_levels):
+            f.write(struct.pack("<ii", s.Ne, s.Nf))
+            csr(f, s.M)
+            csr(f, s.B)
+            csr(f, s.P)
+            dvec(f, s.Wdiag)
+            f.write(struct.pack("<ii", d.Ne, d.Nf))
+            ivec(f, d.elem_ptr)
+            ivec(f, d.elem_dofs)
+            dvec(f, d.elem_mat)
+            csr(f, d.B)
+            csr(f, d.P_p)
+            ivec(f, d.ess_u)
+            dvec(f, d.ess_data)
+            dvec(f, d.rhs)
+            dvec(f, d.obs)

@@ -1,0 +1,31 @@
+// B200Device.hpp -- one pmc_handle (include/pmc_b200.h) shared by the sampler and the solver of a run, plus the
+// error convention of the host layer: C-ABI status codes become std::runtime_error, which the reference drivers
+// catch in main (/root/reference/examples/MLMC.cpp:277-282).
+#pragma once
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include "../../include/pmc_b200.h"
+
+namespace parelagmc {
+class B200Device {
+public:
+    B200Device(int device, int nlevels) : nlevels_(nlevels)
+    {
+        if (pmc_create(device, nlevels, &h_) != PMC_OK)
+            throw std::runtime_error(std::string("pmc_create: ") + pmc_last_error(nullptr));
+    }
+    ~B200Device() { pmc_destroy(h_); }
+    B200Device(const B200Device &) = delete;
+    B200Device &operator=(const B200Device &) = delete;
+    pmc_handle handle() const { return h_; }
+    int nlevels() const { return nlevels_; }
+    void check(int rc, const char *what) const
+    {
+        if (rc != PMC_OK) throw std::runtime_error(std::string(what) + ": " + pmc_last_error(h_));
+    }
+private:
+    pmc_handle h_ = nullptr;
+    int nlevels_;
+};
+}  // namespace parelagmc

@@ -1,0 +1,34 @@
+#include "NormalDistributionSampler.hpp"
+
+#include <cmath>
+
+namespace parelagmc {
+
+NormalDistributionSampler::NormalDistributionSampler(double mu, double sigma2, std::shared_ptr<B200Device> dev)
+    : dev_(std::move(dev)), mu_(mu), sigma_(std::sqrt(sigma2))  // d(mu, sqrt(sigma2)), reference .cpp:17-19
+{
+    dev_->check(pmc_rng_init(dev_->handle(), mu_, sigma_, 1, 0), "pmc_rng_init");
+}
+
+void NormalDistributionSampler::Split(int nparts, int mypart)
+{
+    // rng.split(nparts, mypart) (reference .cpp:21-24); the sub-stream restarts at its own position 0
+    dev_->check(pmc_rng_init(dev_->handle(), mu_, sigma_, nparts, mypart), "pmc_rng_init");
+    pos_ = 0;
+}
+
+double NormalDistributionSampler::operator()()
+{
+    double v = 0.0;
+    dev_->check(pmc_rng_fill(dev_->handle(), pos_, 1, &v), "pmc_rng_fill");
+    pos_ += 1;
+    return v;
+}
+
+void NormalDistributionSampler::operator()(mfem::Vector &x)
+{
+    // for( ; it != end; ++it) *it = d(rng);   (reference .cpp:31-37): x.Size() consecutive draws, in order
+    dev_->check(pmc_rng_fill(dev_->handle(), pos_, x.Size(), x.GetData()), "pmc_rng_fill");
+    pos_ += (uint64_t)x.Size();
+}
+}  // namespace parelagmc

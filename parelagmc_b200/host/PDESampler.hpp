@@ -1,0 +1,50 @@
+// PDESampler.hpp -- SPDE sampler with the public interface of /root/reference/src/PDESampler.hpp:45-206 for the
+// methods on the hot path; the saddle solve [M B^T; B -alpha W] runs batched on the GPU through include/pmc_b200.h.
+#pragma once
+#include <memory>
+#include <vector>
+#include "HierarchyData.hpp"
+#include "MLSampler.hpp"
+#include "NormalDistributionSampler.hpp"
+
+namespace parelagmc {
+class PDESampler : public MLSampler {
+public:
+    /// The reference takes the ParMesh (src/PDESampler.hpp:52-55) and builds the hierarchy with ParELAG; here the
+    /// already-built hierarchy data is handed over (see INTEGRATION.md for the ParELAG-side extraction).
+    PDESampler(std::shared_ptr<const HierarchyData> hier, NormalDistributionSampler &dist_sampler,
+               parelag::ParameterList &master_list);
+    virtual ~PDESampler() = default;
+    PDESampler(PDESampler const &) = delete;
+    PDESampler &operator=(PDESampler const &) = delete;
+
+    /// Uploads the per-level operators (end of src/PDESampler.cpp:177-334).
+    void BuildHierarchy() override;
+    void Sample(const int level, mfem::Vector &xi) override;
+    void Eval(const int level, const mfem::Vector &xi, mfem::Vector &s) override;
+    void Eval(const int level, const mfem::Vector &xi, mfem::Vector &s, mfem::Vector &u, bool use_init) override;
+    int SampleSize(int level) const override { return level_size_[level]; }
+    int GlobalSampleSize(int level) const { return level_size_[level]; }
+    size_t GetNNZ(int level) const override { return nnz_[level]; }
+    int GetNumberOfDofs(int level) const { return hier_->sampler[level].Ne + hier_->sampler[level].Nf; }
+    int GetNumIters() const { return -1; }  // as the reference (src/PDESampler.hpp:141-145)
+
+    NormalDistributionSampler &Distribution() { return dist_sampler_; }
+    const std::shared_ptr<B200Device> &Device() const { return dist_sampler_.Device(); }
+    bool Lognormal() const { return lognormal_; }
+
+private:
+    int FindLevel(int size) const;  // level_size.Find(xi.Size()) (src/PDESampler.cpp:349,419)
+    std::shared_ptr<const HierarchyData> hier_;
+    NormalDistributionSampler &dist_sampler_;
+    parelag::ParameterList &prob_list_;
+    bool lognormal_;
+    double corlen_, alpha_, matern_coeff_;
+    std::vector<int> level_size_;
+    std::vector<size_t> nnz_;
+    bool built_ = false;
+};
+
+/// ComputeScalingCoefficientForSPDE (/root/reference/src/Utilities.hpp:188-200)
+double ComputeScalingCoefficientForSPDE(double corlen, int myDim);
+}  // namespace parelagmc

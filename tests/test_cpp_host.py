@@ -1,0 +1,78 @@
+"""The C++ host layer (parelagmc_b200/host): the reference's class interfaces over the C ABI and reference-style
+drivers.  CPU: it builds and links.  GPU: the drivers reproduce the reference's ctest output (DarcyDeterministicTest)
+and the C++ MLMC_Manager agrees with the Python twin."""
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from common import hex_problem, make_context
+from parelagmc_b200 import hierarchy as H
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LIB = os.path.join(ROOT, "parelagmc_b200", "lib")
+
+
+def _dump(tmp_path, n, nl):
+    p = hex_problem(n, nl)
+    path = str(tmp_path / f"hex{n}_{nl}.pmch")
+    H.dump_problem(path, p["sampler"], p["darcy"], 3, 0.1)
+    return p, path
+
+
+def test_host_layer_builds_and_roundtrips_dump(tmp_path):
+    from parelagmc_b200 import capi
+    capi.build()
+    for f in ("libparelagmc_b200_host.so", "MLMC.exe", "SLMC.exe", "DarcyTest.exe"):
+        assert os.path.exists(os.path.join(LIB, f))
+    p, path = _dump(tmp_path, 4, 2)
+    assert os.path.getsize(path) > 1000
+    # without a GPU the driver must fail loudly through the reference's error convention (message, exit 0)
+    import torch
+    if not torch.cuda.is_available():
+        out = subprocess.run([os.path.join(LIB, "DarcyTest.exe"), "--hierarchy", path], capture_output=True, text=True)
+        assert out.returncode == 0 and "no CPU fallback" in out.stdout
+
+
+@pytest.mark.gpu
+def test_darcy_deterministic_ctest_regex(tmp_path):
+    """PASS_REGULAR_EXPRESSION of DarcyDeterministicTest (/root/reference/examples/CMakeLists.txt:62-66)."""
+    p, path = _dump(tmp_path, 16, 3)
+    out = subprocess.run([os.path.join(LIB, "DarcyTest.exe"), "--hierarchy", path, "--rel-tol", "1e-10"],
+                         capture_output=True, text=True, timeout=600).stdout
+    assert re.search(r"0  2         17152", out), out
+    assert re.search(r"1  2         2240", out), out
+    assert re.search(r"2  2         304", out), out
+
+
+@pytest.mark.gpu
+def test_cpp_mlmc_manager_matches_python_twin(tmp_path):
+    from parelagmc_b200 import managers as MG
+    p, path = _dump(tmp_path, 8, 3)
+    log = str(tmp_path / "MLMC.dat")
+    out = subprocess.run([os.path.join(LIB, "MLMC.exe"), "--hierarchy", path, "--samples", "6,12,20", "--mse", "1e6",
+                          "--rel-tol", "1e-10", "--dof-cost", "--log", log], capture_output=True, text=True,
+                         timeout=600).stdout
+    assert "FINAL MLMC ERRORS" in out                    # first alternative of the MLMC_PDESampler ctest regex
+    est = float(re.findall(r"Estimate\s+([-0-9.e+]+)", out)[-1])
+    c = make_context(p, rel=1e-10)
+    try:
+        m = MG.MLMC_Manager(None, 3, c, {"Use array samples": True, "Array number of samples": [6, 12, 20],
+                                         "Mean square error": 1e6, "Output filename for MC managers": ""}, out=None)
+        m.wallTime = False
+        m.Run()
+    finally:
+        c.close()
+    assert est == pytest.approx(float(np.sum(m.eY)), rel=1e-6)
+    rows = [l.split() for l in open(log).read().splitlines()[1:]]
+    assert len(rows) == 38 and [int(r[0]) for r in rows[:20]] == [2] * 20
+
+
+@pytest.mark.gpu
+def test_cpp_slmc_driver(tmp_path):
+    p, path = _dump(tmp_path, 4, 2)
+    out = subprocess.run([os.path.join(LIB, "SLMC.exe"), "--hierarchy", path, "--nsamples", "16", "--mse", "1e6",
+                          "--log", str(tmp_path / "SLMC.dat")], capture_output=True, text=True, timeout=600).stdout
+    assert "FINAL SLMC ERRORS" in out and "SLMC Manager Errors:" in out
