@@ -55,15 +55,16 @@ class ClockSampler:
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index):
+    def __init__(self, index, period_ms=100):
         self.index = index
+        self.period_ms = period_ms
         self.proc = None
         self.lines = []
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                          "--format=csv,noheader,nounits", "-lms", str(self.period_ms)], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -214,14 +215,13 @@ def run_product(args):
             lev_events.append(evs)
         return sums, its
 
-    # ---- warm-up (un-instrumented) ----
-    solve_classes = ["saddle_apply", "lanczos_update", "solution_update", "mass_smooth", "schur_smooth", "transfer"]
-    ctx.profile([])
+    # ---- warm-up ----
     for _ in range(args.warmup):
         step()
-    # ---- timed region: no per-kernel instrumentation, CUDA events on the launching stream ----
-    clocks = ClockSampler(local)
-    if rank == 0:
+    # ---- timed region: CUDA events on the launching stream; the library also brackets every launch of its
+    #      persistent solver kernel (one per level batch, 3 per step) with events on the same stream ----
+    clocks = ClockSampler(local, args.clock_ms)
+    if rank == 0 and not args.no_clocks:
         clocks.start()
     ctx.reset_stats()
     barrier()
@@ -234,55 +234,39 @@ def run_product(args):
     e1.record(stream)
     barrier()
     ms = e0.elapsed_time(e1)
-    st_timed = ctx.kernel_stats()
+    st = ctx.kernel_stats()
     clk = clocks.stop() if rank == 0 else None
     if dist is not None:
         t = torch.tensor([ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
-    # ---- per-kernel CUDA-event timing: the same step repeated with every launch of the solve kernels bracketed
-    #      by events on the launching stream (kept out of the timed region above because ~15k event pairs per
-    #      step perturb the small-level launches) ----
-    ctx.profile(solve_classes)
-    ctx.reset_stats()
-    barrier()
-    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e2.record(stream)
-    step()
-    e3.record(stream)
-    barrier()
-    ms_instr = e2.elapsed_time(e3)
-    st = ctx.kernel_stats()
-    ctx.profile([])
-    dominant = max(solve_classes, key=lambda n: st[n]["ms"])
-    class_ms = {n: round(st[n]["ms"], 3) for n in solve_classes}
-    class_gbs = {n: round(st[n]["algo_bytes"] / max(st[n]["ms"], 1e-9) / 1e6, 1) for n in solve_classes}
     total_samples = sum(LEVEL_SAMPLES) * world * args.steps
     value = total_samples / (ms * 1e-3)
     per_level = {}
     for i, lev in enumerate(range(nl - 1, -1, -1)):
         lms = sum(ev[i].elapsed_time(ev[i + 1]) for ev in lev_events)
         per_level[f"level{lev}"] = LEVEL_SAMPLES[lev] * world * args.steps / (lms * 1e-3)
-    launches = int(sum(v["launches"] for v in st_timed.values())) // max(1, args.steps)
-    dom = st[dominant]
+    kst = st["kernel"]
+    launches = int(kst["launches"] + kst["other_launches"]) // max(1, args.steps)
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
-    achieved = dom["algo_bytes"] / max(dom["ms"] * 1e-3, 1e-12) / 1e9 if dom["timed_launches"] else None
-    roofline = {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": (achieved / peak) if achieved else None, "traffic": None,
+    achieved = kst["algo_bytes"] / max(kst["ms"] * 1e-3, 1e-12) / 1e9
+    classes = [n for n in st if n != "kernel"]
+    roofline = {"bound": "hbm", "kernel": "k_run_program (tile-persistent solver: the whole level batch in one launch)",
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
-                "launches": int(dom["timed_launches"]), "avg_launch_us": 1e3 * dom["ms"] / max(1, dom["timed_launches"]),
-                "algo_bytes_per_launch": dom["algo_bytes"] / max(1, dom["launches"]),
-                "share_of_step": dom["ms"] / ms_instr, "class_ms_per_step": class_ms, "class_achieved_gbs": class_gbs,
-                "timing": "CUDA events around every launch of the solve kernels during one repeat of the timed step "
-                          f"({ms_instr:.1f} ms instrumented vs {ms / args.steps:.1f} ms un-instrumented)"}
+                "launches": int(kst["launches"]), "avg_launch_us": 1e3 * kst["ms"] / max(1, kst["launches"]),
+                "algo_bytes_per_launch": kst["algo_bytes"] / max(1, kst["launches"]),
+                "share_of_step": kst["ms"] / ms,
+                "class_cycle_share": {n: round(st[n]["cycle_share"], 4) for n in classes if st[n]["ops"]},
+                "class_algo_gb_per_step": {n: round(st[n]["algo_bytes"] / 1e9 / args.steps, 3) for n in classes if st[n]["ops"]},
+                "timing": "CUDA events on the launching stream around every launch of the kernel, inside the timed region"}
 
     # ---- e2e: the same InitRun through the host-buffer plugin API (Sample / Eval / SolveFwd, batched) ----
-    ctx.profile([])
     h2d = d2h = 0
 
     def step_e2e():
@@ -374,6 +358,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="product", choices=["product", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-clocks", action="store_true", help="do not poll nvidia-smi during the timed region")
+    ap.add_argument("--clock-ms", type=int, default=100, help="nvidia-smi polling period")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -170,12 +170,19 @@ enum {
     PMC_K_COUNT
 };
 typedef struct {
-    int64_t launches[PMC_K_COUNT];      /* launches since pmc_reset_stats                            */
-    double algo_bytes[PMC_K_COUNT];     /* algorithmic bytes of those launches (DESIGN.md formulas)  */
-    double ms[PMC_K_COUNT];             /* CUDA-event time of the launches of classes in the profile mask */
-    int64_t timed_launches[PMC_K_COUNT];
+    int64_t launches[PMC_K_COUNT];        /* kernel launches outside the persistent solver kernel, per class          */
+    double algo_bytes[PMC_K_COUNT];       /* algorithmic bytes per class (DESIGN.md formulas), in-kernel ops included   */
+    double ms[PMC_K_COUNT];               /* kernel_ms split by the in-kernel cycle share of each operation class       */
+    int64_t timed_launches[PMC_K_COUNT];  /* operations of each class executed inside the persistent kernel (x tiles)   */
+    double class_cycle_share[PMC_K_COUNT];/* fraction of the persistent kernel's CTA cycles spent in each class         */
+    int64_t kernel_launches;              /* launches of the persistent solver kernel (one per level batch)             */
+    int64_t other_launches;               /* all other kernel launches (layout conversion, RNG fills, moment sums)      */
+    double kernel_ms;                     /* CUDA-event time of the persistent kernel launches (always measured)        */
+    double kernel_algo_bytes;             /* algorithmic bytes moved by the operations executed inside them             */
+    int64_t ops_executed;                 /* operations executed inside them, summed over tiles                         */
+    int64_t minres_iterations;            /* MINRES iterations, summed over realisations and solves                     */
 } pmc_kernel_stats_t;
-/* Bit k of mask set: every launch of class k is bracketed by CUDA events on the handle's stream. */
+/* Kept for ABI stability: the persistent kernel always accounts time and bytes per operation class. */
 int pmc_profile(pmc_handle h, unsigned mask);
 int pmc_reset_stats(pmc_handle h);
 int pmc_kernel_stats(pmc_handle h, pmc_kernel_stats_t *out);

@@ -37,7 +37,9 @@ class PmcError(RuntimeError):
 
 class KernelStats(C.Structure):
     _fields_ = [("launches", C.c_int64 * 10), ("algo_bytes", C.c_double * 10), ("ms", C.c_double * 10),
-                ("timed_launches", C.c_int64 * 10)]
+                ("timed_launches", C.c_int64 * 10), ("class_cycle_share", C.c_double * 10),
+                ("kernel_launches", C.c_int64), ("other_launches", C.c_int64), ("kernel_ms", C.c_double),
+                ("kernel_algo_bytes", C.c_double), ("ops_executed", C.c_int64), ("minres_iterations", C.c_int64)]
 
 
 _dp = C.POINTER(C.c_double)
@@ -297,5 +299,9 @@ class Context:
     def kernel_stats(self) -> dict:
         st = KernelStats()
         self._ck(self._L.pmc_kernel_stats(self._h, C.byref(st)))
-        return {n: dict(launches=st.launches[i], algo_bytes=st.algo_bytes[i], ms=st.ms[i],
-                        timed_launches=st.timed_launches[i]) for i, n in enumerate(K_CLASSES)}
+        out = {n: dict(launches=st.launches[i], algo_bytes=st.algo_bytes[i], ms=st.ms[i], ops=st.timed_launches[i],
+                       cycle_share=st.class_cycle_share[i]) for i, n in enumerate(K_CLASSES)}
+        out["kernel"] = dict(launches=st.kernel_launches, ms=st.kernel_ms, algo_bytes=st.kernel_algo_bytes,
+                             ops_executed=st.ops_executed, minres_iterations=st.minres_iterations,
+                             other_launches=st.other_launches)
+        return out

@@ -1,7 +1,8 @@
 // pmc_b200.cu -- context, host-once uploads, batched solver driver and the C ABI of include/pmc_b200.h.
 //
-// Product path: there is no CPU fallback in this file.  Every compute entry point launches the kernels of
-// kernels.cuh / rng.cuh on the handle's stream and fails with PMC_ERR_CUDA if that is not possible.
+// Product path: there is no CPU fallback in this file.  Every compute entry point records a program of operations
+// and runs it with the tile-persistent kernel of program.cuh (plus a few layout-conversion kernels) on the handle's
+// stream, and fails with PMC_ERR_CUDA if that is not possible.
 #include "../../include/pmc_b200.h"
 
 #include <cuda_runtime.h>
@@ -14,8 +15,7 @@
 #include <vector>
 
 #include "host_sparse.hpp"
-#include "kernels.cuh"
-#include "rng.cuh"
+#include "program.cuh"
 
 namespace pmc {
 
@@ -24,9 +24,14 @@ namespace pmc {
 // --------------------------------------------------------------------------------------------------
 struct DevCsr {
     int rows = 0, cols = 0, nnz = 0;
-    bool weighted = false;  // rowptr has 2*rows+1 entries, widx valid
-    int *rowptr = nullptr, *col = nullptr, *widx = nullptr;
+    bool weighted = false;
+    // plain CSR (plain operators only; used by the per-solve set-up maps)
+    int *rowptr = nullptr, *col = nullptr;
     double *val = nullptr;
+    // sliced ELL (SLICE rows per slice, per-slice width, zero padding): the apply format.  Weighted operators keep
+    // their weighted entries in s* (with widx) and their fixed entries in f*.
+    int *soff = nullptr, *scol = nullptr, *swidx = nullptr, *foff = nullptr, *fcol = nullptr;
+    double *sval = nullptr, *fval = nullptr;
     double matrix_bytes() const
     {
         return (double)nnz * (weighted ? 16.0 : 12.0) + (double)((weighted ? 2 : 1) * rows + 1) * 4.0;
@@ -106,7 +111,6 @@ struct PrecCfg {
 struct SaddleSys {
     bool ready = false, weighted = false;
     PrecCfg cfg;               // frozen at prepare time
-    int *perm = nullptr;       // processing order of the block operator's rows (locality of the u-p coupling)
     int Nf = 0, Ne = 0, N = 0;
     DevCsr A;                       // block operator over N rows
     DevCsr Muu;                     // RT mass block (Nf rows)
@@ -157,7 +161,6 @@ struct Arena {
 
 struct EventPair {
     cudaEvent_t a, b;
-    int kclass;
 };
 
 }  // namespace pmc
@@ -172,7 +175,7 @@ struct pmc_context_s {
     double rel = 1e-6, abs_ = 1e-12;
     int maxit = 300;
     PrecCfg cfg_sampler, cfg_darcy;
-    int max_batch = 0, check_every = 4;
+    int max_batch = 0, force_nt = 0;
     std::vector<SamplerLevel> s;
     std::vector<DarcyLevel> d;
     // rng
@@ -182,14 +185,15 @@ struct pmc_context_s {
     // memory
     Arena arena;
     std::vector<void *> owned;
-    int *d_nactive = nullptr;
-    int *h_nactive = nullptr;  // pinned
-    unsigned long long *d_iters_total = nullptr;
+    Op *d_ops = nullptr, *h_ops = nullptr;  // program buffer (device / pinned staging)
+    size_t ops_cap = 0;
+    ProgStats *d_pstats = nullptr;
     double *h_pinned = nullptr;  // pinned scratch for small results
     size_t h_pinned_count = 0;
     // stats
-    unsigned profile_mask = 0;
     pmc_kernel_stats_t stats;
+    double kernel_ms = 0.0;
+    int64_t kernel_launches = 0, other_launches = 0;
     std::vector<EventPair> ev_pending;
     std::vector<EventPair> ev_free;
     cudaError_t cuda_status = cudaSuccess;
@@ -219,83 +223,17 @@ static int fail(Ctx *c, int code, const char *fmt, ...)
     } while (0)
 
 // --------------------------------------------------------------------------------------------------
-// launch helper with per-class statistics
+// launch helper (the few kernels outside the persistent program: layout conversion, RNG fills, moment sums)
 // --------------------------------------------------------------------------------------------------
-static void ev_begin(Ctx *c, int kclass, EventPair &ep, bool &timed)
-{
-    timed = (c->profile_mask >> kclass) & 1u;
-    if (!timed) return;
-    if (!c->ev_free.empty()) {
-        ep = c->ev_free.back();
-        c->ev_free.pop_back();
-    } else {
-        cudaEventCreate(&ep.a);
-        cudaEventCreate(&ep.b);
-    }
-    ep.kclass = kclass;
-    cudaEventRecord(ep.a, c->stream);
-}
-static void ev_end(Ctx *c, EventPair &ep, bool timed)
-{
-    if (!timed) return;
-    cudaEventRecord(ep.b, c->stream);
-    c->ev_pending.push_back(ep);
-}
-
 template <typename... KArgs, typename... Args>
 static void launch(Ctx *c, int kclass, double bytes, void (*kernel)(KArgs...), dim3 grid, dim3 block, Args... args)
 {
-    EventPair ep;
-    bool timed;
-    ev_begin(c, kclass, ep, timed);
     kernel<<<grid, block, 0, c->stream>>>(args...);
-    ev_end(c, ep, timed);
     c->stats.launches[kclass]++;
     c->stats.algo_bytes[kclass] += bytes;
+    c->other_launches++;
     cudaError_t e = cudaPeekAtLastError();
     if (e != cudaSuccess && c->cuda_status == cudaSuccess) c->cuda_status = e;
-}
-
-static void resolve_events(Ctx *c)
-{
-    if (c->ev_pending.empty()) return;
-    cudaStreamSynchronize(c->stream);
-    for (auto &ep : c->ev_pending) {
-        float ms = 0;
-        if (cudaEventElapsedTime(&ms, ep.a, ep.b) == cudaSuccess) {
-            c->stats.ms[ep.kclass] += ms;
-            c->stats.timed_launches[ep.kclass]++;
-        }
-        c->ev_free.push_back(ep);
-    }
-    c->ev_pending.clear();
-}
-
-// --------------------------------------------------------------------------------------------------
-// grid shapes
-// --------------------------------------------------------------------------------------------------
-struct Shape {
-    dim3 grid, block;
-    int rows_per_cta, nblk;
-};
-static Shape shape_for(int n, int ld)
-{
-    Shape s;
-    const int sblocks = (ld / 2 + TX - 1) / TX;
-    int want = (148 * 16 + sblocks - 1) / sblocks;  // ~2 waves of 8 resident CTAs per SM
-    int maxblk = (n + TY - 1) / TY;
-    if (maxblk < 1) maxblk = 1;
-    if (want > 512) want = 512;
-    if (want > maxblk) want = maxblk;
-    if (want < 1) want = 1;
-    int rpc = (n + want - 1) / want;
-    rpc = ((rpc + TY - 1) / TY) * TY;
-    if (rpc < TY) rpc = TY;
-    s.rows_per_cta = rpc;
-    s.nblk = n > 0 ? (n + rpc - 1) / rpc : 1;
-    s.grid = dim3(sblocks, s.nblk);
-    s.block = dim3(TX, TY);
-    return s;
 }
 
 // --------------------------------------------------------------------------------------------------
@@ -314,6 +252,38 @@ static int to_device(Ctx *c, const std::vector<T> &h, T **out)
     return PMC_OK;
 }
 
+// Sliced-ELL conversion of rows given as [begin, end) ranges into (col, val, widx) arrays.
+struct HSell {
+    std::vector<int> off, col, widx;
+    std::vector<double> val;
+};
+static HSell make_sell(int rows, const std::vector<int> &beg, const std::vector<int> &end, const std::vector<int> &col,
+                       const std::vector<double> &val, const std::vector<int> *widx)
+{
+    HSell S;
+    const int nsl = (rows + SLICE - 1) / SLICE;
+    S.off.assign(nsl + 1, 0);
+    for (int sl = 0; sl < nsl; ++sl) {
+        int w = 0;
+        for (int r = sl * SLICE; r < std::min(rows, (sl + 1) * SLICE); ++r) w = std::max(w, end[r] - beg[r]);
+        S.off[sl + 1] = S.off[sl] + w;
+    }
+    const size_t total = (size_t)S.off[nsl] * SLICE;
+    S.col.assign(total, 0);
+    S.val.assign(total, 0.0);
+    if (widx) S.widx.assign(total, 0);
+    for (int r = 0; r < rows; ++r) {
+        const int sl = r / SLICE, rs = r % SLICE;
+        for (int p = beg[r], k = 0; p < end[r]; ++p, ++k) {
+            const size_t idx = (size_t)(S.off[sl] + k) * SLICE + rs;
+            S.col[idx] = col[p];
+            S.val[idx] = val[p];
+            if (widx) S.widx[idx] = (*widx)[p];
+        }
+    }
+    return S;
+}
+
 static int upload_csr(Ctx *c, const HCsr &A, DevCsr &D)
 {
     D.rows = A.rows;
@@ -324,6 +294,11 @@ static int upload_csr(Ctx *c, const HCsr &A, DevCsr &D)
     if ((rc = to_device(c, A.rowptr, &D.rowptr))) return rc;
     if ((rc = to_device(c, A.col, &D.col))) return rc;
     if ((rc = to_device(c, A.val, &D.val))) return rc;
+    std::vector<int> beg(A.rowptr.begin(), A.rowptr.end() - 1), end(A.rowptr.begin() + 1, A.rowptr.end());
+    HSell S = make_sell(A.rows, beg, end, A.col, A.val, nullptr);
+    if ((rc = to_device(c, S.off, &D.soff))) return rc;
+    if ((rc = to_device(c, S.col, &D.scol))) return rc;
+    if ((rc = to_device(c, S.val, &D.sval))) return rc;
     return PMC_OK;
 }
 
@@ -334,10 +309,21 @@ static int upload_wcsr(Ctx *c, const HWCsr &A, DevCsr &D)
     D.nnz = (int)A.col.size();
     D.weighted = true;
     int rc;
-    if ((rc = to_device(c, A.rowptr2, &D.rowptr))) return rc;
-    if ((rc = to_device(c, A.col, &D.col))) return rc;
-    if ((rc = to_device(c, A.widx, &D.widx))) return rc;
-    if ((rc = to_device(c, A.val, &D.val))) return rc;
+    std::vector<int> wb(A.rows), we(A.rows), fb(A.rows), fe(A.rows);
+    for (int r = 0; r < A.rows; ++r) {
+        wb[r] = A.rowptr2[2 * r];
+        we[r] = fb[r] = A.rowptr2[2 * r + 1];
+        fe[r] = A.rowptr2[2 * r + 2];
+    }
+    HSell W = make_sell(A.rows, wb, we, A.col, A.val, &A.widx);
+    HSell F = make_sell(A.rows, fb, fe, A.col, A.val, nullptr);
+    if ((rc = to_device(c, W.off, &D.soff))) return rc;
+    if ((rc = to_device(c, W.col, &D.scol))) return rc;
+    if ((rc = to_device(c, W.widx, &D.swidx))) return rc;
+    if ((rc = to_device(c, W.val, &D.sval))) return rc;
+    if ((rc = to_device(c, F.off, &D.foff))) return rc;
+    if ((rc = to_device(c, F.col, &D.fcol))) return rc;
+    if ((rc = to_device(c, F.val, &D.fval))) return rc;
     return PMC_OK;
 }
 
@@ -390,32 +376,6 @@ static HCsr symmetrize_pattern(const HCsr &S)
     return csr_from_coo(S.rows, S.rows, e);
 }
 
-// Processing order of the saddle operator's rows: every element row (Nf + e) is preceded by the face rows it
-// "owns" (faces whose lowest-numbered adjacent element is e).  Storage order is unchanged; a CTA's row block then
-// touches u and p entries that were fetched recently, so the gathers hit L2 instead of re-reading HBM.
-static std::vector<int> saddle_row_order(const HCsr &B, int Nf, int Ne)
-{
-    std::vector<int> owner(Nf, -1);
-    for (int e = 0; e < Ne; ++e)
-        for (int p = B.rowptr[e]; p < B.rowptr[e + 1]; ++p) {
-            const int f = B.col[p];
-            if (f >= 0 && f < Nf && owner[f] < 0) owner[f] = e;
-        }
-    std::vector<int> cnt(Ne + 2, 0);
-    for (int f = 0; f < Nf; ++f) cnt[(owner[f] < 0 ? Ne : owner[f]) + 1]++;
-    for (int e = 0; e <= Ne; ++e) cnt[e + 1] += cnt[e];
-    std::vector<int> faces(Nf), pos(cnt.begin(), cnt.end() - 1);
-    for (int f = 0; f < Nf; ++f) faces[pos[owner[f] < 0 ? Ne : owner[f]]++] = f;
-    std::vector<int> perm;
-    perm.reserve(Nf + Ne);
-    for (int e = 0; e < Ne; ++e) {
-        for (int q = cnt[e]; q < cnt[e + 1]; ++q) perm.push_back(faces[q]);
-        perm.push_back(Nf + e);
-    }
-    for (int q = cnt[Ne]; q < cnt[Ne + 1]; ++q) perm.push_back(faces[q]);
-    return perm;
-}
-
 // ---- sampler system (everything fixed across samples) ---------------------------------------------------
 static int prepare_sampler(Ctx *c, int level)
 {
@@ -428,11 +388,6 @@ static int prepare_sampler(Ctx *c, int level)
     sys.Ne = Ne;
     sys.N = N;
     sys.cfg = c->cfg_sampler;
-    {
-        std::vector<int> perm = saddle_row_order(L.B, Nf, Ne);
-        int rcp = to_device(c, perm, &sys.perm);
-        if (rcp) return rcp;
-    }
     HCsr Bt = csr_transpose(L.B);
     {  // block operator [[M, B^T], [B, -alpha W]]   (/root/reference/src/PDESampler.cpp:279-284)
         std::vector<Coo> e;
@@ -525,11 +480,6 @@ static int prepare_darcy(Ctx *c, int level)
     sys.Ne = Ne;
     sys.N = N;
     sys.cfg = c->cfg_darcy;
-    {
-        std::vector<int> perm = saddle_row_order(L.B, Nf, Ne);
-        int rcp = to_device(c, perm, &sys.perm);
-        if (rcp) return rcp;
-    }
     const std::vector<int> &ess = L.ess_u;
     // Be: essential columns removed
     HCsr Be;
@@ -690,45 +640,155 @@ static int prepare_darcy(Ctx *c, int level)
 }
 
 // --------------------------------------------------------------------------------------------------
-// solve workspace
+// program builder: the host records the operations of a level batch once; k_run_program executes them per tile
 // --------------------------------------------------------------------------------------------------
-struct SolveWs {
-    int ld = 0;
-    double *v0, *v1, *w0, *w1, *u1, *q, *x, *b;  // MINRES, N x ld each
-    double *mu_d, *mu_z;                         // mass-block Chebyshev scratch, Nf x ld
-    double *dinvM;                               // Darcy: batched 1/diag M(k), Nf x ld
-    std::vector<double *> vr, vzA, vzB, vd, vres, vV, vl1;  // per V-level
-    double *partial;                                          // [npart][ld]
-    double *st;                                               // ST_COUNT x ld
-    int *active, *iters;
-    int npart = 0;
+typedef long long Off;  // offset (in doubles) inside a tile chunk; < 0: none
+static VecRef vr(Off off, int /*nrows*/ = 0, int row_off = 0)
+{
+    VecRef v;
+    v.off = off >= 0 ? off + (Off)row_off * TW : -1;
+    return v;
+}
+static const VecRef VNULL = {-1};
+
+// Row allocator of the tile chunk: every tile owns `peak` doubles laid out identically.
+struct Rows {
+    Off top = 0, peak = 0;
+    Off alloc(long long nrows)
+    {
+        const Off o = top;
+        top += nrows * TW;
+        if (top > peak) peak = top;
+        return o;
+    }
 };
 
-static void carve_solve(Arena &ar, const SaddleSys &sys, int ld, SolveWs &ws)
-{
-    const size_t N = sys.N, Nf = sys.Nf, S = ld;
-    ws.ld = ld;
-    ws.v0 = ar.alloc(N * S); ws.v1 = ar.alloc(N * S); ws.w0 = ar.alloc(N * S); ws.w1 = ar.alloc(N * S);
-    ws.u1 = ar.alloc(N * S); ws.q = ar.alloc(N * S); ws.x = ar.alloc(N * S); ws.b = ar.alloc(N * S);
-    ws.mu_d = ar.alloc(Nf * S);
-    ws.mu_z = ar.alloc(Nf * S);
-    ws.dinvM = sys.weighted ? ar.alloc(Nf * S) : nullptr;
-    const size_t nv = sys.v.size();
-    ws.vr.assign(nv, nullptr); ws.vzA.assign(nv, nullptr); ws.vzB.assign(nv, nullptr); ws.vd.assign(nv, nullptr);
-    ws.vres.assign(nv, nullptr); ws.vV.assign(nv, nullptr); ws.vl1.assign(nv, nullptr);
-    for (size_t m = 0; m < nv; ++m) {
-        const size_t n = sys.v[m].n;
-        if (m > 0) { ws.vr[m] = ar.alloc(n * S); ws.vzA[m] = ar.alloc(n * S); }
-        ws.vzB[m] = ar.alloc(n * S);
-        ws.vd[m] = ar.alloc(n * S);
-        if (m + 1 < nv) ws.vres[m] = ar.alloc(n * S);
-        if (sys.weighted) { ws.vV[m] = ar.alloc((size_t)sys.v[m].nU * S); ws.vl1[m] = ar.alloc(n * S); }
+struct Program {
+    std::vector<Op> ops;
+    int pc() const { return (int)ops.size(); }
+    Op &add(int kind, int kclass, int n, double rows_moved, double matrix_bytes = 0.0)
+    {
+        Op o;
+        memset(&o, 0, sizeof o);
+        o.kind = kind;
+        o.kclass = kclass;
+        o.n = n;
+        o.bytes = rows_moved * TW * 8.0;  // batched-vector traffic of one tile; the shared matrices stay in L2
+        (void)matrix_bytes;
+        o.x = o.y = o.r = o.d = o.w = o.v = VNULL;
+        ops.push_back(o);
+        return ops.back();
     }
-    ws.npart = shape_for(sys.N, ld).nblk + shape_for(sys.Nf, ld).nblk + shape_for(sys.Ne, ld).nblk + 4;
-    ws.partial = ar.alloc((size_t)ws.npart * S);
-    ws.st = ar.alloc((size_t)ST_COUNT * S);
-    ws.active = ar.alloc_int(S);
-    ws.iters = ar.alloc_int(S);
+};
+
+static void emit_spmm(Program &pg, int kclass, int ep, const DevCsr &A, VecRef V, VecRef x, VecRef y, VecRef r, VecRef d,
+                      const double *dinv_fixed, VecRef dinv_b, double ca, double cb, int dot_slot, bool dot_acc,
+                      bool dot_with_r, double rows_moved)
+{
+    Op &o = pg.add(OP_SPMM, kclass, A.rows, rows_moved, A.matrix_bytes());
+    o.flags = (ep << F_EP_SHIFT) | (A.weighted ? F_WEIGHTED : 0) | ((ep == EP_CHEB && A.weighted) ? F_BDINV : 0) |
+              (dot_slot >= 0 ? F_DOT : 0) | (dot_acc ? F_DOT_ACC : 0) | (dot_with_r ? F_DOT_WITH_R : 0);
+    o.rowptr = A.soff; o.col = A.scol; o.widx = A.swidx; o.val = A.sval;
+    o.foff = A.foff; o.fcol = A.fcol; o.fval = A.fval;
+    o.fixed = dinv_fixed;
+    o.x = x; o.y = y; o.r = r; o.d = d; o.w = dinv_b; o.v = V;
+    o.ca = ca; o.cb = cb;
+    o.slot = dot_slot < 0 ? 0 : dot_slot;
+}
+
+static void emit_fill(Program &pg, VecRef y, int n, double v)
+{
+    Op &o = pg.add(OP_FILL, KC_MISC, n, n);
+    o.y = y;
+    o.ca = v;
+}
+static void emit_copy(Program &pg, VecRef x, VecRef y, int n)
+{
+    Op &o = pg.add(OP_COPY, KC_MISC, n, 2.0 * n);
+    o.x = x;
+    o.y = y;
+}
+
+struct ChebOp {
+    const DevCsr *A;
+    VecRef V;               // weights (weighted operators)
+    const double *dinv_f;   // fixed [n]   (plain operators)
+    VecRef dinv_b;          // batched     (weighted operators)
+    double lo, hi;
+    double vrows;           // weight rows read per apply
+    int kclass;
+};
+
+// `deg` Chebyshev steps for A z = r.  from_zero: z_0 = 0 and the result ends in `cur`.  Otherwise the current iterate
+// lives in `cur` and the result ends in (deg even ? cur : other).  Returns the buffer holding the result.
+static VecRef emit_cheb(Program &pg, const ChebOp &op, VecRef r, VecRef d, int deg, bool from_zero, VecRef cur, VecRef other,
+                        int dot_slot, bool dot_acc)
+{
+    const int n = op.A->rows;
+    const bool bd = op.A->weighted;
+    const double theta = 0.5 * (op.hi + op.lo), delta = 0.5 * (op.hi - op.lo), sigma = theta / delta;
+    double rho = 1.0 / sigma;
+    VecRef zin = cur, zout = other;
+    int j0 = 0;
+    if (from_zero) {
+        zout = (deg % 2 == 1) ? cur : other;
+        Op &o = pg.add(OP_CHEB_FIRST, op.kclass, n, n * (3.0 + (bd ? 1 : 0)));
+        o.flags = (bd ? F_BDINV : 0) | ((dot_slot >= 0 && deg == 1) ? F_DOT : 0) | (dot_acc ? F_DOT_ACC : 0);
+        o.r = r; o.d = d; o.y = zout; o.w = op.dinv_b; o.fixed = op.dinv_f;
+        o.cb = 1.0 / theta;
+        o.slot = dot_slot < 0 ? 0 : dot_slot;
+        zin = zout;
+        zout = (zin.off == cur.off) ? other : cur;
+        j0 = 1;
+    }
+    for (int j = j0; j < deg; ++j) {
+        double ca, cb;
+        if (j == 0) { ca = 0.0; cb = 1.0 / theta; }
+        else {
+            const double rho_new = 1.0 / (2.0 * sigma - rho);
+            ca = rho_new * rho;
+            cb = 2.0 * rho_new / delta;
+            rho = rho_new;
+        }
+        const bool dl = dot_slot >= 0 && j == deg - 1;
+        emit_spmm(pg, op.kclass, EP_CHEB, *op.A, op.V, zin, zout, r, d, op.dinv_f, op.dinv_b, ca, cb, dl ? dot_slot : -1,
+                  dl && dot_acc, true, n * (5.0 + (bd ? 1 : 0)) + op.vrows);
+        VecRef t = zin; zin = zout; zout = t;
+    }
+    return zin;
+}
+
+// --------------------------------------------------------------------------------------------------
+// solve workspace (tile-major batched vectors: n rows -> n * ld doubles, ld = ntiles * TW)
+// --------------------------------------------------------------------------------------------------
+struct SolveWs {
+    Off v0, v1, w0, w1, u1, q, x, b;  // MINRES, N rows each
+    Off mu_d, mu_z;                   // mass-block Chebyshev scratch, Nf rows
+    Off dinvM;                        // Darcy: batched 1/diag M(k), Nf rows
+    std::vector<Off> vr_, vzA, vzB, vd, vres, vV, vl1;  // per V-level
+    Off iters;                        // one row: iteration counts of the tile's samples (as doubles)
+};
+
+static void carve_solve(Rows &ar, const SaddleSys &sys, SolveWs &ws)
+{
+    const long long N = sys.N, Nf = sys.Nf;
+    ws.v0 = ar.alloc(N); ws.v1 = ar.alloc(N); ws.w0 = ar.alloc(N); ws.w1 = ar.alloc(N);
+    ws.u1 = ar.alloc(N); ws.q = ar.alloc(N); ws.x = ar.alloc(N); ws.b = ar.alloc(N);
+    ws.mu_d = ar.alloc(Nf);
+    ws.mu_z = ar.alloc(Nf);
+    ws.dinvM = sys.weighted ? ar.alloc(Nf) : -1;
+    const size_t nv = sys.v.size();
+    ws.vr_.assign(nv, -1); ws.vzA.assign(nv, -1); ws.vzB.assign(nv, -1); ws.vd.assign(nv, -1);
+    ws.vres.assign(nv, -1); ws.vV.assign(nv, -1); ws.vl1.assign(nv, -1);
+    for (size_t m = 0; m < nv; ++m) {
+        const long long n = sys.v[m].n;
+        if (m > 0) { ws.vr_[m] = ar.alloc(n); ws.vzA[m] = ar.alloc(n); }
+        ws.vzB[m] = ar.alloc(n);
+        ws.vd[m] = ar.alloc(n);
+        if (m + 1 < nv) ws.vres[m] = ar.alloc(n);
+        if (sys.weighted) { ws.vV[m] = ar.alloc(sys.v[m].nU); ws.vl1[m] = ar.alloc(n); }
+    }
+    ws.iters = ar.alloc(1);
 }
 
 static int ensure_arena(Ctx *c, size_t bytes)
@@ -752,309 +812,185 @@ static int ensure_arena(Ctx *c, size_t bytes)
     return PMC_OK;
 }
 
-// --------------------------------------------------------------------------------------------------
-// operator applies
-// --------------------------------------------------------------------------------------------------
-static double spmm_bytes(const DevCsr &A, int ld, double vec_rows)
-{
-    return A.matrix_bytes() + (double)ld * vec_rows * 8.0;
-}
-
-// generic fused SpMM dispatch
-static void spmm(Ctx *c, int kclass, int ep, const DevCsr &A, const double *V, int ld, const double *x, double *y,
-                 const double *r, double *d, const double *dinv, bool bdinv, double ca, double cb, const double *dotw,
-                 double *partial, int partial_off, double vec_rows, const int *perm = nullptr)
-{
-    const Shape sh = shape_for(A.rows, ld);
-    SpmmArgs a;
-    a.perm = perm;
-    a.n = A.rows; a.ld = ld; a.rows_per_cta = sh.rows_per_cta;
-    a.rowptr = A.rowptr; a.col = A.col; a.val = A.val; a.widx = A.widx; a.V = V;
-    a.x = x; a.y = y; a.r = r; a.d = d; a.dinv = dinv; a.ca = ca; a.cb = cb;
-    a.dotw = dotw; a.partial = partial; a.partial_off = partial_off;
-    const bool dot = dotw != nullptr;
-    const double bytes = spmm_bytes(A, ld, vec_rows);
-    const bool w = A.weighted;
-#define PMC_SPMM_CASE(EP_, W_, BD_, DOT_) \
-    launch(c, kclass, bytes, k_spmm<EP_, W_, BD_, DOT_>, sh.grid, sh.block, a)
-    if (ep == EP_AX) {
-        if (w) { if (dot) PMC_SPMM_CASE(EP_AX, true, false, true); else PMC_SPMM_CASE(EP_AX, true, false, false); }
-        else   { if (dot) PMC_SPMM_CASE(EP_AX, false, false, true); else PMC_SPMM_CASE(EP_AX, false, false, false); }
-    } else if (ep == EP_RESID) {
-        if (w) PMC_SPMM_CASE(EP_RESID, true, false, false); else PMC_SPMM_CASE(EP_RESID, false, false, false);
-    } else if (ep == EP_ADD) {
-        if (w) PMC_SPMM_CASE(EP_ADD, true, false, false); else PMC_SPMM_CASE(EP_ADD, false, false, false);
-    } else {
-        if (w) { if (dot) PMC_SPMM_CASE(EP_CHEB, true, true, true); else PMC_SPMM_CASE(EP_CHEB, true, true, false); }
-        else   { if (dot) PMC_SPMM_CASE(EP_CHEB, false, false, true); else PMC_SPMM_CASE(EP_CHEB, false, false, false); }
-        (void)bdinv;
-    }
-#undef PMC_SPMM_CASE
-}
-
-struct ChebOp {
-    const DevCsr *A;
-    const double *V;     // weights (weighted operators)
-    const double *dinv;  // fixed [n] or batched [n][ld] (batched iff A->weighted)
-    double lo, hi;
-    double vrows;        // weight rows read per apply (for the byte count)
-    int kclass;
-};
-
-// `deg` Chebyshev steps for A z = r.  from_zero: z_0 = 0, the result ends in `end_buf`.  Otherwise the current
-// iterate lives in `cur` and the result ends in (deg even ? cur : other).  Returns the buffer holding the result.
-static double *cheb_run(Ctx *c, const ChebOp &op, int ld, const double *r, double *d, int deg, bool from_zero,
-                        double *cur, double *other, bool dot, double *partial, int partial_off)
-{
-    const int n = op.A->rows;
-    const bool bd = op.A->weighted;
-    const double theta = 0.5 * (op.hi + op.lo), delta = 0.5 * (op.hi - op.lo), sigma = theta / delta;
-    double rho = 1.0 / sigma;
-    double *zin = cur, *zout = other;
-    int j0 = 0;
-    if (from_zero) {
-        // writes alternate; the last of `deg` writes must hit end_buf == cur
-        zout = (deg % 2 == 1) ? cur : other;
-        const Shape sh = shape_for(n, ld);
-        const bool d0 = dot && deg == 1;
-        const double bytes = (double)ld * n * (3 + (bd ? 1 : 0)) * 8.0;
-        if (bd) {
-            if (d0) launch(c, op.kclass, bytes, k_cheb_first<true, true>, sh.grid, sh.block, n, ld, sh.rows_per_cta, r, op.dinv, 1.0 / theta, d, zout, partial, partial_off);
-            else launch(c, op.kclass, bytes, k_cheb_first<true, false>, sh.grid, sh.block, n, ld, sh.rows_per_cta, r, op.dinv, 1.0 / theta, d, zout, partial, partial_off);
-        } else {
-            if (d0) launch(c, op.kclass, bytes, k_cheb_first<false, true>, sh.grid, sh.block, n, ld, sh.rows_per_cta, r, op.dinv, 1.0 / theta, d, zout, partial, partial_off);
-            else launch(c, op.kclass, bytes, k_cheb_first<false, false>, sh.grid, sh.block, n, ld, sh.rows_per_cta, r, op.dinv, 1.0 / theta, d, zout, partial, partial_off);
-        }
-        zin = zout;
-        zout = (zin == cur) ? other : cur;
-        j0 = 1;
-    }
-    for (int j = j0; j < deg; ++j) {
-        double ca, cb;
-        if (j == 0) { ca = 0.0; cb = 1.0 / theta; }
-        else {
-            const double rho_new = 1.0 / (2.0 * sigma - rho);
-            ca = rho_new * rho;
-            cb = 2.0 * rho_new / delta;
-            rho = rho_new;
-        }
-        const bool dl = dot && j == deg - 1;
-        spmm(c, op.kclass, EP_CHEB, *op.A, op.V, ld, zin, zout, r, d, op.dinv, bd, ca, cb, dl ? r : nullptr, partial,
-             partial_off, n * (5.0 + (bd ? 1 : 0)) + op.vrows);
-        double *t = zin; zin = zout; zout = t;
-    }
-    return zin;
-}
-
 struct Solver {
-    Ctx *c;
     SaddleSys *sys;
     SolveWs *ws;
-    const double *k_ext;  // Darcy weights [Ne+1][ld] or null
-    int ld;
+    VecRef k_ext;  // Darcy weights [Ne+1 rows] or null
 };
 
-static void vcycle(Solver &sv, int m, const double *r, double *zout, double *ztmp, bool dot, int partial_off)
+static void emit_vcycle(Program &pg, Solver &sv, int m, VecRef r, VecRef zout, VecRef ztmp, int dot_slot)
 {
-    Ctx *c = sv.c;
     SaddleSys &sys = *sv.sys;
     SolveWs &ws = *sv.ws;
     VLevel &L = sys.v[m];
-    const int ld = sv.ld;
+    const PrecCfg &cfg = sys.cfg;
     ChebOp op;
     op.A = &L.S;
-    op.V = sys.weighted ? ws.vV[m] : nullptr;
-    op.dinv = sys.weighted ? ws.vl1[m] : L.l1inv_fixed;
+    op.V = sys.weighted ? vr(ws.vV[m], L.nU) : VNULL;
+    op.dinv_f = sys.weighted ? nullptr : L.l1inv_fixed;
+    op.dinv_b = sys.weighted ? vr(ws.vl1[m], L.n) : VNULL;
     op.hi = 1.0;
     op.vrows = sys.weighted ? L.nU : 0;
-    op.kclass = PMC_K_SCHUR_SMOOTH;
+    op.kclass = KC_SCHUR;
+    VecRef d = vr(ws.vd[m], L.n);
     const bool last = (m + 1 == (int)sys.v.size());
-    const PrecCfg &cfg = sys.cfg;
     if (last) {
         op.lo = 1.0 / cfg.coarse_ratio;
-        cheb_run(c, op, ld, r, ws.vd[m], cfg.coarse_degree, true, zout, ztmp, dot, ws.partial, partial_off);
+        emit_cheb(pg, op, r, d, cfg.coarse_degree, true, zout, ztmp, dot_slot, dot_slot >= 0);
         return;
     }
     op.lo = 1.0 / cfg.schur_ratio;
     const int s = cfg.schur_degree;
-    double *E = (s % 2 == 0) ? zout : ztmp, *O = (s % 2 == 0) ? ztmp : zout;
-    cheb_run(c, op, ld, r, ws.vd[m], s, true, E, O, false, nullptr, 0);
-    spmm(c, PMC_K_SCHUR_SMOOTH, EP_RESID, L.S, op.V, ld, E, ws.vres[m], r, nullptr, nullptr, false, 0, 0, nullptr,
-         nullptr, 0, 3.0 * L.n + op.vrows);
-    spmm(c, PMC_K_TRANSFER, EP_AX, L.Pt, nullptr, ld, ws.vres[m], ws.vr[m + 1], nullptr, nullptr, nullptr, false, 0, 0,
-         nullptr, nullptr, 0, (double)L.n + sys.v[m + 1].n);
-    vcycle(sv, m + 1, ws.vr[m + 1], ws.vzA[m + 1], ws.vzB[m + 1], false, 0);
-    spmm(c, PMC_K_TRANSFER, EP_ADD, L.P, nullptr, ld, ws.vzA[m + 1], E, nullptr, nullptr, nullptr, false, cfg.omega, 0,
-         nullptr, nullptr, 0, 2.0 * L.n + sys.v[m + 1].n);
-    cheb_run(c, op, ld, r, ws.vd[m], s, false, E, O, dot, ws.partial, partial_off);
+    VecRef E = (s % 2 == 0) ? zout : ztmp, O = (s % 2 == 0) ? ztmp : zout;
+    emit_cheb(pg, op, r, d, s, true, E, O, -1, false);
+    VLevel &Lc = sys.v[m + 1];
+    VecRef res = vr(ws.vres[m], L.n), rc = vr(ws.vr_[m + 1], Lc.n), zc = vr(ws.vzA[m + 1], Lc.n), zct = vr(ws.vzB[m + 1], Lc.n);
+    emit_spmm(pg, KC_SCHUR, EP_RESID, L.S, op.V, E, res, r, VNULL, nullptr, VNULL, 0, 0, -1, false, false, 3.0 * L.n + op.vrows);
+    emit_spmm(pg, KC_TRANSFER, EP_AX, L.Pt, VNULL, res, rc, VNULL, VNULL, nullptr, VNULL, 0, 0, -1, false, false, (double)L.n + Lc.n);
+    emit_vcycle(pg, sv, m + 1, rc, zc, zct, -1);
+    emit_spmm(pg, KC_TRANSFER, EP_ADD, L.P, VNULL, zc, E, VNULL, VNULL, nullptr, VNULL, cfg.omega, 0, -1, false, false,
+              2.0 * L.n + Lc.n);
+    emit_cheb(pg, op, r, d, s, false, E, O, dot_slot, dot_slot >= 0);
 }
 
-// z = Prec r (block diagonal); if dot, partial[0..nblk) receives the row-block partial sums of r.z.  Returns nblk.
-static int apply_prec(Solver &sv, const double *r, double *z, bool dot)
+// z = Prec r (block diagonal: Chebyshev-Jacobi on the RT mass block, V-cycle on the Schur complement); if dot_slot >= 0
+// the slot receives r . z (mass part assigns, Schur part accumulates).
+static void emit_prec(Program &pg, Solver &sv, Off r, Off z, int dot_slot)
 {
-    Ctx *c = sv.c;
     SaddleSys &sys = *sv.sys;
     SolveWs &ws = *sv.ws;
-    const int ld = sv.ld;
-    const size_t po = (size_t)sys.Nf * ld;
     ChebOp op;
     op.A = &sys.Muu;
     op.V = sv.k_ext;
-    op.dinv = sys.weighted ? ws.dinvM : sys.dinvM_fixed;
+    op.dinv_f = sys.weighted ? nullptr : sys.dinvM_fixed;
+    op.dinv_b = sys.weighted ? vr(ws.dinvM, sys.Nf) : VNULL;
     op.lo = sys.m_lo;
     op.hi = sys.m_hi;
     op.vrows = sys.weighted ? sys.Ne : 0;
-    op.kclass = PMC_K_MASS_SMOOTH;
-    cheb_run(c, op, ld, r, ws.mu_d, sys.cfg.mass_degree, true, z, ws.mu_z, dot, ws.partial, 0);
-    const int nbu = shape_for(sys.Nf, ld).nblk;
-    vcycle(sv, 0, r + po, z + po, ws.vzB[0], dot, nbu);
-    return nbu + shape_for(sys.Ne, ld).nblk;
+    op.kclass = KC_MASS;
+    emit_cheb(pg, op, vr(r, sys.N), vr(ws.mu_d, sys.Nf), sys.cfg.mass_degree, true, vr(z, sys.N), vr(ws.mu_z, sys.Nf), dot_slot,
+              false);
+    emit_vcycle(pg, sv, 0, vr(r, sys.N, sys.Nf), vr(z, sys.N, sys.Nf), vr(ws.vzB[0], sys.Ne), dot_slot);
 }
 
-static void saddle_apply(Solver &sv, int ep, const double *x, double *y, const double *r, bool dot, int kclass)
+static void emit_saddle(Program &pg, Solver &sv, int ep, Off x, Off y, Off r, int dot_slot)
 {
     SaddleSys &sys = *sv.sys;
-    spmm(sv.c, kclass, ep, sys.A, sv.k_ext, sv.ld, x, y, r, nullptr, nullptr, false, 0, 0, dot ? x : nullptr,
-         sv.ws->partial, 0, (ep == EP_RESID ? 3.0 : 2.0) * sys.N + (sys.weighted ? sys.Ne : 0), sys.perm);
-}
-
-static void fill(Ctx *c, double *p, size_t n, double v)
-{
-    if (n == 0) return;
-    int blocks = (int)std::min<size_t>((n + 255) / 256, 148 * 16);
-    launch(c, PMC_K_MISC, (double)n * 8.0, k_fill, dim3(blocks), dim3(256), p, n, v);
+    emit_spmm(pg, KC_SADDLE, ep, sys.A, sv.k_ext, vr(x, sys.N), vr(y, sys.N), r >= 0 ? vr(r, sys.N) : VNULL, VNULL, nullptr, VNULL, 0,
+              0, dot_slot, false, false, (ep == EP_RESID ? 3.0 : 2.0) * sys.N + (sys.weighted ? sys.Ne : 0));
 }
 
 // Darcy per-solve values: 1/diag M(k), Schur values on every V-level, l1 norms.
-static void darcy_setup_values(Solver &sv)
+static void emit_darcy_setup(Program &pg, Solver &sv)
 {
-    Ctx *c = sv.c;
     SaddleSys &sys = *sv.sys;
     SolveWs &ws = *sv.ws;
-    const int ld = sv.ld;
     {
-        const Shape sh = shape_for(sys.Nf, ld);
-        launch(c, PMC_K_SETUP, spmm_bytes(sys.Dm, ld, sys.Ne + sys.Nf), k_spmm_setup<false, true>, sh.grid, sh.block,
-               sys.Nf, ld, sh.rows_per_cta, sys.Dm.rowptr, sys.Dm.col, sys.Dm.val, sv.k_ext, ws.dinvM);
+        Op &o = pg.add(OP_SETUP_SPMM, KC_SETUP, sys.Nf, (double)sys.Ne + sys.Nf, sys.Dm.matrix_bytes());
+        o.flags = F_RECIP;
+        o.rowptr = sys.Dm.rowptr; o.col = sys.Dm.col; o.val = sys.Dm.val;
+        o.x = sv.k_ext;
+        o.y = vr(ws.dinvM, sys.Nf);
     }
-    const double *prev = ws.dinvM;
+    VecRef prev = vr(ws.dinvM, sys.Nf);
     int prev_rows = sys.Nf;
     for (size_t m = 0; m < sys.v.size(); ++m) {
         VLevel &L = sys.v[m];
-        Shape sh = shape_for(L.nU, ld);
-        launch(c, PMC_K_SETUP, spmm_bytes(L.T, ld, prev_rows + L.nU), k_spmm_setup<false, false>, sh.grid, sh.block,
-               L.nU, ld, sh.rows_per_cta, L.T.rowptr, L.T.col, L.T.val, prev, ws.vV[m]);
-        sh = shape_for(L.n, ld);
-        launch(c, PMC_K_SETUP, spmm_bytes(L.L, ld, L.nU + L.n), k_spmm_setup<true, true>, sh.grid, sh.block, L.n, ld,
-               sh.rows_per_cta, L.L.rowptr, L.L.col, L.L.val, ws.vV[m], ws.vl1[m]);
-        prev = ws.vV[m];
+        {
+            Op &o = pg.add(OP_SETUP_SPMM, KC_SETUP, L.nU, (double)prev_rows + L.nU, L.T.matrix_bytes());
+            o.rowptr = L.T.rowptr; o.col = L.T.col; o.val = L.T.val;
+            o.x = prev;
+            o.y = vr(ws.vV[m], L.nU);
+        }
+        {
+            Op &o = pg.add(OP_SETUP_SPMM, KC_SETUP, L.n, (double)L.nU + L.n, L.L.matrix_bytes());
+            o.flags = F_ABSX | F_RECIP;
+            o.rowptr = L.L.rowptr; o.col = L.L.col; o.val = L.L.val;
+            o.x = vr(ws.vV[m], L.nU);
+            o.y = vr(ws.vl1[m], L.n);
+        }
+        prev = vr(ws.vV[m], L.nU);
         prev_rows = L.nU;
     }
 }
 
-// Preconditioned MINRES on the batch; ws.b and ws.x are set by the caller (x_nonzero: x holds an initial guess).
-static int minres_batch(Solver &sv, int nsamples, bool x_nonzero)
+// Preconditioned MINRES; ws.b and ws.x are set by earlier operations (x_nonzero: x holds an initial guess).
+static void emit_minres(Program &pg, Solver &sv, bool x_nonzero, bool store_iters)
 {
-    Ctx *c = sv.c;
     SaddleSys &sys = *sv.sys;
     SolveWs &ws = *sv.ws;
-    const int ld = sv.ld, N = sys.N;
-    const size_t NS = (size_t)N * ld;
-    const Shape shN = shape_for(N, ld);
-    const int sthreads = 128, sblocks = (ld + sthreads - 1) / sthreads;
-    if (x_nonzero) saddle_apply(sv, EP_RESID, ws.x, ws.v1, ws.b, false, PMC_K_SADDLE_APPLY);
-    else CK(cudaMemcpyAsync(ws.v1, ws.b, NS * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
-    fill(c, ws.v0, NS, 0.0);
-    fill(c, ws.w0, NS, 0.0);
-    fill(c, ws.w1, NS, 0.0);
-    CK(cudaMemsetAsync(c->d_nactive, 0, sizeof(int), c->stream));
-    int nblk = apply_prec(sv, ws.v1, ws.u1, true);
-    launch(c, PMC_K_SCALAR, 0.0, k_minres_init, dim3(sblocks), dim3(sthreads), ld, nsamples, nblk, ws.partial, c->rel,
-           c->abs_, ws.st, ws.active, ws.iters, c->d_nactive);
-    CK(cudaMemcpyAsync(c->h_nactive, c->d_nactive, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaStreamSynchronize(c->stream));
-    double *v0 = ws.v0, *v1 = ws.v1, *w0 = ws.w0, *w1 = ws.w1, *u1 = ws.u1, *q = ws.q;
-    double *st = ws.st;
-    int it = 0;
-    while (*c->h_nactive > 0 && it < c->maxit) {
-        const int chunk = std::min(c->check_every, c->maxit - it);
-        for (int k = 0; k < chunk; ++k, ++it) {
-            saddle_apply(sv, EP_AX, u1, q, nullptr, true, PMC_K_SADDLE_APPLY);
-            launch(c, PMC_K_SCALAR, 0.0, k_minres_alpha, dim3(sblocks), dim3(sthreads), ld, shN.nblk, ws.partial, st,
-                   ws.active, c->d_nactive);
-            launch(c, PMC_K_LANCZOS_UPDATE, (double)ld * N * 4 * 8.0, k_lincomb3, shN.grid, shN.block, N, ld,
-                   shN.rows_per_cta, st + (size_t)ST_CQ * ld, q, st + (size_t)ST_CV1 * ld, v1,
-                   st + (size_t)ST_CV0 * ld, v0);
-            nblk = apply_prec(sv, v0, q, true);
-            launch(c, PMC_K_SCALAR, 0.0, k_minres_beta, dim3(sblocks), dim3(sthreads), ld, nblk, ws.partial, c->maxit,
-                   st, ws.active, ws.iters, c->d_nactive);
-            launch(c, PMC_K_SOLUTION_UPDATE, (double)ld * N * 6 * 8.0, k_solution_update, shN.grid, shN.block, N, ld,
-                   shN.rows_per_cta, st + (size_t)ST_CW0 * ld, st + (size_t)ST_CW1 * ld, st + (size_t)ST_CU * ld,
-                   st + (size_t)ST_CX * ld, w0, w1, u1, ws.x);
-            std::swap(u1, q);
-            std::swap(v0, v1);
-            std::swap(w0, w1);
-        }
-        CK(cudaMemcpyAsync(c->h_nactive, c->d_nactive, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-        CK(cudaStreamSynchronize(c->stream));
+    const int N = sys.N;
+    if (x_nonzero) emit_saddle(pg, sv, EP_RESID, ws.x, ws.v1, ws.b, -1);
+    else emit_copy(pg, vr(ws.b, N), vr(ws.v1, N), N);
+    emit_fill(pg, vr(ws.v0, N), N, 0.0);
+    emit_fill(pg, vr(ws.w0, N), N, 0.0);
+    emit_fill(pg, vr(ws.w1, N), N, 0.0);
+    emit_prec(pg, sv, ws.v1, ws.u1, 1);
+    { Op &o = pg.add(OP_SC_INIT, KC_SCALAR, 0, 0); o.slot = 1; }
+    std::vector<int> exits;
+    exits.push_back(pg.pc());
+    pg.add(OP_CHECK, KC_SCALAR, 0, 0);
+    const int loop_start = pg.pc();
+    Off v0 = ws.v0, v1 = ws.v1, w0 = ws.w0, w1 = ws.w1, u1 = ws.u1, q = ws.q;
+    for (int parity = 0; parity < 2; ++parity) {
+        emit_saddle(pg, sv, EP_AX, u1, q, -1, 0);
+        { Op &o = pg.add(OP_SC_ALPHA, KC_SCALAR, 0, 0); o.slot = 0; }
+        { Op &o = pg.add(OP_LINCOMB3, KC_LANCZOS, N, 4.0 * N); o.x = vr(q, N); o.r = vr(v1, N); o.y = vr(v0, N); }
+        emit_prec(pg, sv, v0, q, 1);
+        { Op &o = pg.add(OP_SC_BETA, KC_SCALAR, 0, 0); o.slot = 1; }
+        { Op &o = pg.add(OP_SOL_UPDATE, KC_SOLUPD, N, 6.0 * N); o.y = vr(w0, N); o.r = vr(w1, N); o.x = vr(u1, N); o.d = vr(ws.x, N); }
+        exits.push_back(pg.pc());
+        pg.add(OP_CHECK, KC_SCALAR, 0, 0);
+        std::swap(u1, q);
+        std::swap(v0, v1);
+        std::swap(w0, w1);
     }
-    launch(c, PMC_K_MISC, 0.0, k_sum_int, dim3(1), dim3(256), nsamples, ws.iters, c->d_iters_total);
-    if (c->cuda_status != cudaSuccess)
-        return fail(c, PMC_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(c->cuda_status));
-    return PMC_OK;
+    { Op &o = pg.add(OP_JUMP, KC_SCALAR, 0, 0); o.a0 = loop_start; }
+    const int exit_pc = pg.pc();
+    for (int e : exits) pg.ops[e].a0 = exit_pc;
+    { Op &o = pg.add(OP_STORE_ITERS, KC_SCALAR, 0, 0); o.y = store_iters ? vr(ws.iters) : VNULL; }
 }
 
-// Sampler solve on the device: rhs_p = batched [Ne][ld] right-hand side at `level`; x0_p (nullable) batched initial
-// guess of the Gaussian field.  The field is left in ws.x + Nf*ld.
-static int sampler_solve_dev(Ctx *c, int level, int ld, int nsamples, const double *rhs_p, const double *x0_p,
-                             SolveWs &ws)
+// Sampler solve: rhs_p = batched right-hand side at `level` (Ne rows); x0_p (nullable) initial guess of the Gaussian
+// field.  The field is left in rows [Nf, N) of ws.x.
+static void emit_sampler_solve(Program &pg, Ctx *c, int level, Off rhs_p, Off x0_p, SolveWs &ws, bool store_iters)
 {
     SaddleSys &sys = c->s[level].sys;
-    Solver sv{c, &sys, &ws, nullptr, ld};
-    const size_t po = (size_t)sys.Nf * ld, pn = (size_t)sys.Ne * ld;
-    fill(c, ws.b, po, 0.0);  // rhs_u = 0 (/root/reference/src/PDESampler.cpp:441-442)
-    CK(cudaMemcpyAsync(ws.b + po, rhs_p, pn * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
-    fill(c, ws.x, po, 0.0);
-    if (x0_p) CK(cudaMemcpyAsync(ws.x + po, x0_p, pn * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
-    else fill(c, ws.x + po, pn, 0.0);
-    return minres_batch(sv, nsamples, x0_p != nullptr);
+    Solver sv{&sys, &ws, VNULL};
+    emit_fill(pg, vr(ws.b, sys.N), sys.Nf, 0.0);  // rhs_u = 0 (/root/reference/src/PDESampler.cpp:441-442)
+    emit_copy(pg, vr(rhs_p, sys.Ne), vr(ws.b, sys.N, sys.Nf), sys.Ne);
+    emit_fill(pg, vr(ws.x, sys.N), sys.Nf, 0.0);
+    if (x0_p >= 0) emit_copy(pg, vr(x0_p, sys.Ne), vr(ws.x, sys.N, sys.Nf), sys.Ne);
+    else emit_fill(pg, vr(ws.x, sys.N, sys.Nf), sys.Ne, 0.0);
+    emit_minres(pg, sv, x0_p >= 0, store_iters);
 }
 
-// Darcy solve on the device: k_ext = batched [Ne+1][ld] (row Ne = 1).  Q_dev[ld] receives obs . sol.
-static int darcy_solve_dev(Ctx *c, int level, int ld, int nsamples, const double *k_ext, SolveWs &ws, double *Q_dev)
+// Darcy solve: k_ext = batched [Ne+1 rows] (row Ne = 1).  Q_dev[sample] receives obs . sol.
+static void emit_darcy_solve(Program &pg, Ctx *c, int level, Off k_ext, SolveWs &ws, Off Q_row, bool store_iters)
 {
     DarcyLevel &L = c->d[level];
     SaddleSys &sys = L.sys;
-    Solver sv{c, &sys, &ws, k_ext, ld};
+    Solver sv{&sys, &ws, vr(k_ext, sys.Ne + 1)};
     const int N = sys.N;
-    darcy_setup_values(sv);
-    const Shape shN = shape_for(N, ld);
-    launch(c, PMC_K_MISC, (double)ld * N * 8.0, k_broadcast, shN.grid, shN.block, N, ld, shN.rows_per_cta, nsamples,
-           L.d_rhs_bc, ws.b);
+    emit_darcy_setup(pg, sv);
+    { Op &o = pg.add(OP_BROADCAST, KC_MISC, N, N); o.fixed = L.d_rhs_bc; o.y = vr(ws.b, N); }
     if (L.ess_nonzero) {
         // rhs_bc -= M(k)[:, ess] ess_data  (BlockMatrix::EliminateRowCol, /root/reference/src/DarcySolver.cpp:498)
-        const Shape shF = shape_for(sys.Nf, ld);
-        launch(c, PMC_K_MISC, (double)ld * sys.Nf * 8.0, k_broadcast, shF.grid, shF.block, sys.Nf, ld, shF.rows_per_cta,
-               nsamples, L.d_ess_u_data, ws.mu_z);
-        spmm(c, PMC_K_SADDLE_APPLY, EP_RESID, L.Mbc, k_ext, ld, ws.mu_z, ws.b, ws.b, nullptr, nullptr, false, 0, 0,
-             nullptr, nullptr, 0, 3.0 * sys.Nf + sys.Ne);
+        { Op &o = pg.add(OP_BROADCAST, KC_MISC, sys.Nf, sys.Nf); o.fixed = L.d_ess_u_data; o.y = vr(ws.mu_z, sys.Nf); }
+        emit_spmm(pg, KC_SADDLE, EP_RESID, L.Mbc, sv.k_ext, vr(ws.mu_z, sys.Nf), vr(ws.b, N), vr(ws.b, N), VNULL, nullptr, VNULL, 0,
+                  0, -1, false, false, 3.0 * sys.Nf + sys.Ne);
     }
-    fill(c, ws.x, (size_t)N * ld, 0.0);  // p_sol = 0 (:629)
-    int rc = minres_batch(sv, nsamples, false);
-    if (rc) return rc;
-    if (Q_dev) {
-        launch(c, PMC_K_MISC, (double)ld * N * 8.0, k_dot_fixed, shN.grid, shN.block, N, ld, shN.rows_per_cta, L.d_obs,
-               ws.x, ws.partial);
-        launch(c, PMC_K_MISC, 0.0, k_finish_sum, dim3((ld + 127) / 128), dim3(128), ld, shN.nblk, ws.partial, Q_dev);
+    emit_fill(pg, vr(ws.x, N), N, 0.0);  // p_sol = 0 (:629)
+    emit_minres(pg, sv, false, store_iters);
+    if (Q_row >= 0) {
+        Op &o = pg.add(OP_DOT_FIXED, KC_MISC, N, N);  // Q = obs . sol (:427)
+        o.fixed = L.d_obs;
+        o.x = vr(ws.x, N);
+        o.y = vr(Q_row);
     }
-    return PMC_OK;
 }
 
-static int pad_ld(int nsamples)
-{
-    if (nsamples >= 64) return ((nsamples + 63) / 64) * 64;
-    return ((nsamples + 1) / 2) * 2;
-}
+static int pad_ld(int nsamples) { return ((nsamples + TW - 1) / TW) * TW; }
 
 static int pick_batch(Ctx *c, size_t bytes_per_sample, int nsamples)
 {
@@ -1065,21 +1001,12 @@ static int pick_batch(Ctx *c, size_t bytes_per_sample, int nsamples)
         free_b += c->arena.cap;
         const size_t usable = (size_t)(0.80 * (double)free_b);
         size_t nb = usable / std::max<size_t>(bytes_per_sample, 1);
-        if (nb > 4096) nb = 4096;
+        if (nb > 16384) nb = 16384;
         b = (int)nb;
     }
-    if (b >= 64) b = (b / 64) * 64;
+    if (b >= TW) b = (b / TW) * TW;
     if (b < 1) b = 1;
     return std::min(b, std::max(nsamples, 1));
-}
-
-static size_t solve_bytes_per_sample(const SaddleSys &sys)
-{
-    Arena dry;
-    dry.dry = true;
-    SolveWs ws;
-    carve_solve(dry, sys, 64, ws);
-    return dry.peak / 64 + 64;
 }
 
 static int check_level(Ctx *c, int level, bool sampler, bool darcy)
@@ -1120,6 +1047,70 @@ static int finish(Ctx *c)
     return PMC_OK;
 }
 
+// Upload the program and run it: one CTA per tile, one launch.
+static int run_program(Ctx *c, Program &pg, int nsamples, Off chunk, int max_rows)
+{
+    const int ntiles = (nsamples + TW - 1) / TW;
+    if (ntiles == 0 || pg.ops.empty()) return PMC_OK;
+    const size_t bytes = pg.ops.size() * sizeof(Op);
+    if (bytes > c->ops_cap) {
+        if (c->d_ops) { cudaStreamSynchronize(c->stream); cudaFree(c->d_ops); cudaFreeHost(c->h_ops); }
+        c->ops_cap = bytes * 2;
+        CK(cudaMalloc((void **)&c->d_ops, c->ops_cap));
+        CK(cudaMallocHost((void **)&c->h_ops, c->ops_cap));
+    } else {
+        CK(cudaStreamSynchronize(c->stream));  // the pinned staging buffer may still be in use by the previous copy
+    }
+    memcpy(c->h_ops, pg.ops.data(), bytes);
+    CK(cudaMemcpyAsync(c->d_ops, c->h_ops, bytes, cudaMemcpyHostToDevice, c->stream));
+    ProgParams P;
+    P.ops = c->d_ops;
+    P.nops = (int)pg.ops.size();
+    P.ntiles = ntiles;
+    P.nsamples = nsamples;
+    P.max_iter = c->maxit;
+    P.rel = c->rel;
+    P.abs_ = c->abs_;
+    P.mu = c->mu;
+    P.sigma = c->sigma;
+    P.tab = c->d_tab;
+    P.stats = c->d_pstats;
+    P.base = (double *)c->arena.base;
+    P.chunk = chunk;
+    EventPair ep;
+    if (!c->ev_free.empty()) { ep = c->ev_free.back(); c->ev_free.pop_back(); }
+    else { cudaEventCreate(&ep.a); cudaEventCreate(&ep.b); }
+    cudaEventRecord(ep.a, c->stream);
+    // CTA size: at most ~32 rows per row lane on the largest operand, enlarged while the tiles of the batch would not fill the
+    // machine; every variant keeps 1024 threads per SM resident (64 registers per thread)
+    int nt = 64;
+    while (nt < 512 && max_rows / (nt / LPR) > 32) nt *= 2;
+    while (nt < 512 && (long long)ntiles * nt * 2 <= 148LL * 1024) nt *= 2;
+    if (c->force_nt == 64 || c->force_nt == 128 || c->force_nt == 256 || c->force_nt == 512) nt = c->force_nt;
+    if (nt == 512) k_run_program<512, 2><<<ntiles, 512, 0, c->stream>>>(P);
+    else if (nt == 256) k_run_program<256, 4><<<ntiles, 256, 0, c->stream>>>(P);
+    else if (nt == 128) k_run_program<128, 8><<<ntiles, 128, 0, c->stream>>>(P);
+    else k_run_program<64, 16><<<ntiles, 64, 0, c->stream>>>(P);
+    cudaEventRecord(ep.b, c->stream);
+    c->ev_pending.push_back(ep);
+    c->kernel_launches++;
+    cudaError_t e = cudaPeekAtLastError();
+    if (e != cudaSuccess && c->cuda_status == cudaSuccess) c->cuda_status = e;
+    return PMC_OK;
+}
+
+static void resolve_events(Ctx *c)
+{
+    if (c->ev_pending.empty()) return;
+    cudaStreamSynchronize(c->stream);
+    for (auto &ep : c->ev_pending) {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, ep.a, ep.b) == cudaSuccess) c->kernel_ms += ms;
+        c->ev_free.push_back(ep);
+    }
+    c->ev_pending.clear();
+}
+
 static int rng_launch(Ctx *c, int mode, uint64_t pos0, uint64_t pstride, uint64_t limit, int64_t nj, int64_t ni,
                       int64_t si, int64_t sj, int T, double neg_g, const double *w_sqrt, double *out, int32_t *out_i)
 {
@@ -1135,6 +1126,32 @@ static int rng_launch(Ctx *c, int mode, uint64_t pos0, uint64_t pstride, uint64_
     if (mode == 0) launch(c, PMC_K_RNG, bytes, k_rng<0>, grid, block, a, (const RngTables *)c->d_tab);
     else if (mode == 1) launch(c, PMC_K_RNG, bytes, k_rng<1>, grid, block, a, (const RngTables *)c->d_tab);
     else launch(c, PMC_K_RNG, bytes, k_rng<2>, grid, block, a, (const RngTables *)c->d_tab);
+    return PMC_OK;
+}
+
+static dim3 grid1d(size_t n) { return dim3((unsigned)std::min<size_t>((n + 255) / 256, 148 * 16)); }
+
+// host [ns][n] -> tile-major batched (via the staging buffer `stage`)
+static int upload_rows(Ctx *c, const double *host, int ns, int n, double *stage, Off dst, Off chunk, int mode, double neg_g,
+                       const double *w_sqrt)
+{
+    const int ntiles = (ns + TW - 1) / TW;
+    double *d = (double *)c->arena.base + dst;
+    CK(cudaMemcpyAsync(stage, host, (size_t)ns * n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    const size_t total = (size_t)ntiles * n * TW;
+    if (mode == 1) launch(c, PMC_K_MISC, (double)total * 16.0, k_to_tiles<1>, grid1d(total), dim3(256), n, chunk, ntiles, ns, (const double *)stage, d, neg_g, w_sqrt);
+    else launch(c, PMC_K_MISC, (double)total * 16.0, k_to_tiles<0>, grid1d(total), dim3(256), n, chunk, ntiles, ns, (const double *)stage, d, neg_g, w_sqrt);
+    return PMC_OK;
+}
+
+// tile-major batched view -> host [ns][n]
+static int download_rows(Ctx *c, Off src_off, Off chunk, int ns, int n, double *stage, double *host, bool do_exp)
+{
+    const size_t total = (size_t)ns * n;
+    const double *src = (const double *)c->arena.base + src_off;
+    if (do_exp) launch(c, PMC_K_MISC, (double)total * 16.0, k_from_tiles<1>, grid1d(total), dim3(256), n, chunk, ns, src, stage);
+    else launch(c, PMC_K_MISC, (double)total * 16.0, k_from_tiles<0>, grid1d(total), dim3(256), n, chunk, ns, src, stage);
+    CK(cudaMemcpyAsync(host, stage, total * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     return PMC_OK;
 }
 
@@ -1168,14 +1185,12 @@ int pmc_create(int device, int nlevels, pmc_handle *out)
     c->d.resize(nlevels);
     memset(&c->stats, 0, sizeof c->stats);
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaMalloc((void **)&c->d_nactive, sizeof(int)) != cudaSuccess ||
-        cudaMalloc((void **)&c->d_iters_total, sizeof(unsigned long long)) != cudaSuccess ||
-        cudaMalloc((void **)&c->d_tab, sizeof(RngTables)) != cudaSuccess ||
-        cudaMallocHost((void **)&c->h_nactive, sizeof(int)) != cudaSuccess) {
+        cudaMalloc((void **)&c->d_pstats, sizeof(ProgStats)) != cudaSuccess ||
+        cudaMalloc((void **)&c->d_tab, sizeof(RngTables)) != cudaSuccess) {
         delete c;
         return fail(nullptr, PMC_ERR_CUDA, "pmc_create: CUDA resource allocation failed");
     }
-    cudaMemset(c->d_iters_total, 0, sizeof(unsigned long long));
+    cudaMemset(c->d_pstats, 0, sizeof(ProgStats));
     *out = c;
     return PMC_OK;
 }
@@ -1187,10 +1202,10 @@ void pmc_destroy(pmc_handle c)
     cudaStreamSynchronize(c->stream);
     for (void *p : c->owned) cudaFree(p);
     if (c->arena.base) cudaFree(c->arena.base);
-    cudaFree(c->d_nactive);
-    cudaFree(c->d_iters_total);
+    cudaFree(c->d_pstats);
     cudaFree(c->d_tab);
-    cudaFreeHost(c->h_nactive);
+    if (c->d_ops) cudaFree(c->d_ops);
+    if (c->h_ops) cudaFreeHost(c->h_ops);
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
     for (auto &ep : c->ev_pending) { cudaEventDestroy(ep.a); cudaEventDestroy(ep.b); }
     for (auto &ep : c->ev_free) { cudaEventDestroy(ep.a); cudaEventDestroy(ep.b); }
@@ -1203,6 +1218,7 @@ const char *pmc_last_error(pmc_handle c) { return c ? c->err.c_str() : g_create_
 int pmc_set_stream(pmc_handle c, void *cuda_stream)
 {
     if (!c) return PMC_ERR_ARG;
+    resolve_events(c);
     cudaStreamSynchronize(c->stream);
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
     c->stream = (cudaStream_t)cuda_stream;
@@ -1261,7 +1277,7 @@ int pmc_set_option(pmc_handle c, const char *key, double value)
         return PMC_OK;
     }
     if (k == "max_batch" && value >= 0) c->max_batch = (int)value;
-    else if (k == "check_every" && value >= 1) c->check_every = (int)value;
+    else if (k == "cta_threads") c->force_nt = (int)value;
     else return fail(c, PMC_ERR_ARG, "pmc_set_option: unknown key '%s'", key);
     return PMC_OK;
 }
@@ -1270,7 +1286,7 @@ int pmc_set_batch(pmc_handle c, int max_batch, int check_every)
 {
     if (!c) return PMC_ERR_ARG;
     if (max_batch >= 0) c->max_batch = max_batch;
-    if (check_every > 0) c->check_every = check_every;
+    (void)check_every;  // convergence is checked on the device after every iteration; kept for ABI stability
     return PMC_OK;
 }
 
@@ -1356,6 +1372,7 @@ int pmc_rng_init(pmc_handle c, double mu, double sigma, int nparts, int mypart)
     if (!c) return PMC_ERR_ARG;
     if (nparts > 1 && (mypart < 0 || mypart >= nparts)) return fail(c, PMC_ERR_ARG, "pmc_rng_init: mypart out of range");
     CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
     RngTables *t = new RngTables();
     h_build_rng_tables(*t, nparts, mypart);
     cudaError_t e = cudaMemcpy(c->d_tab, t, sizeof(RngTables), cudaMemcpyHostToDevice);
@@ -1396,26 +1413,28 @@ int pmc_sampler_sample_batch(pmc_handle c, int level, int nsamples, uint64_t pos
 }
 
 // ---- sampler Eval ---------------------------------------------------------------------------------
-// Restrict a batched right-hand side from xi_level to level (Ps^T chain, /root/reference/src/PDESampler.cpp:361-368).
-// bufs: two batched buffers large enough for Ne(xi_level); returns the buffer holding the result.
-static double *restrict_rhs(Ctx *c, int xi_level, int level, int ld, double *cur, double *other)
+// Restrict a batched right-hand side from xi_level to level (Ps^T chain, /root/reference/src/PDESampler.cpp:361-368);
+// returns the buffer holding the result.
+static Off emit_restrict(Program &pg, Ctx *c, int xi_level, int level, Off cur, Off other)
 {
     for (int l = xi_level; l < level; ++l) {
         SamplerLevel &L = c->s[l];
-        spmm(c, PMC_K_TRANSFER, EP_AX, L.dPt, nullptr, ld, cur, other, nullptr, nullptr, nullptr, false, 0, 0, nullptr,
-             nullptr, 0, (double)L.Ne + c->s[l + 1].Ne);
+        const int nc = c->s[l + 1].Ne;
+        emit_spmm(pg, KC_TRANSFER, EP_AX, L.dPt, VNULL, vr(cur, L.Ne), vr(other, nc), VNULL, VNULL, nullptr, VNULL, 0, 0, -1, false,
+                  false, (double)L.Ne + nc);
         std::swap(cur, other);
     }
     return cur;
 }
 
-// Prolongate a batched Gaussian field from init_level down to level (finer) (:496-508).
-static double *prolong_field(Ctx *c, int init_level, int level, int ld, double *cur, double *other)
+// Prolongate a batched Gaussian field from init_level to the finer `level` (:496-508).
+static Off emit_prolong(Program &pg, Ctx *c, int init_level, int level, Off cur, Off other)
 {
     for (int l = init_level; l > level; --l) {
         SamplerLevel &L = c->s[l - 1];
-        spmm(c, PMC_K_TRANSFER, EP_AX, L.dP, nullptr, ld, cur, other, nullptr, nullptr, nullptr, false, 0, 0, nullptr,
-             nullptr, 0, (double)L.Ne + c->s[l].Ne);
+        const int nc = c->s[l].Ne;
+        emit_spmm(pg, KC_TRANSFER, EP_AX, L.dP, VNULL, vr(cur, nc), vr(other, L.Ne), VNULL, VNULL, nullptr, VNULL, 0, 0, -1, false,
+                  false, (double)L.Ne + nc);
         std::swap(cur, other);
     }
     return cur;
@@ -1443,47 +1462,40 @@ int pmc_sampler_eval_batch(pmc_handle c, int level, int xi_level, int nsamples, 
     SaddleSys &sys = L.sys;
     const int Ne = L.Ne, Nex = c->s[xi_level].Ne, Nei = warm ? c->s[init_level].Ne : 0;
     const int nmax = std::max(Nex, std::max(Ne, Nei));
-    const size_t per_sample = solve_bytes_per_sample(sys) + (size_t)(4 * nmax) * 8 + 64;
+    // the program (identical for every batch): restrict, optional prolongated initial guess, solve
+    Rows ar;
+    SolveWs ws;
+    carve_solve(ar, sys, ws);
+    const Off bufA = ar.alloc(nmax), bufB = ar.alloc(nmax), bufC = ar.alloc(nmax);
+    Program pg;
+    const Off rhs = emit_restrict(pg, c, xi_level, level, bufA, bufB);
+    const Off t1 = (rhs == bufA) ? bufB : bufA;
+    Off x0 = -1;
+    if (warm) x0 = emit_prolong(pg, c, init_level, level, t1, bufC);
+    emit_sampler_solve(pg, c, level, rhs, x0, ws, true);
+    const Off chunk = ar.peak;
+    const size_t per_sample = (size_t)chunk * 8 / TW + (size_t)nmax * 8 + 64;
     const int B = pick_batch(c, per_sample, nsamples);
-    const int ldB = pad_ld(B);
-    if ((rc = ensure_arena(c, per_sample * (size_t)ldB + (1 << 16)))) return rc;
+    if ((rc = ensure_arena(c, per_sample * (size_t)pad_ld(B) + (1 << 16)))) return rc;
+    std::vector<double> itbuf;
     for (int s0 = 0; s0 < nsamples; s0 += B) {
         const int ns = std::min(B, nsamples - s0);
         const int ld = pad_ld(ns);
-        Arena &ar = c->arena;
-        ar.top = 0;
-        SolveWs ws;
-        carve_solve(ar, sys, ld, ws);
-        double *stage = ar.alloc((size_t)ns * nmax);
-        double *bufA = ar.alloc((size_t)nmax * ld), *bufB = ar.alloc((size_t)nmax * ld);
-        double *bufC = ar.alloc((size_t)nmax * ld);
-        if (ar.overflow) return finish(c);
-        // rhs_s = -g * xi * w_sqrt at xi_level (:352-358 / :423-428), then restrict
-        CK(cudaMemcpyAsync(stage, xi + (size_t)s0 * Nex, (size_t)ns * Nex * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-        launch(c, PMC_K_MISC, (double)ns * Nex * 16.0, k_transpose_in<1>, dim3((Nex + 31) / 32, (ld + 31) / 32),
-               dim3(32, 8), Nex, ld, ns, (const double *)stage, bufA, -c->s[xi_level].g, (const double *)c->s[xi_level].w_sqrt);
-        double *rhs = restrict_rhs(c, xi_level, level, ld, bufA, bufB);
-        double *x0 = nullptr;
-        if (warm) {
-            double *t1 = (rhs == bufA) ? bufB : bufA;
-            CK(cudaMemcpyAsync(stage, init_s + (size_t)s0 * Nei, (size_t)ns * Nei * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-            launch(c, PMC_K_MISC, (double)ns * Nei * 16.0, k_transpose_in<0>, dim3((Nei + 31) / 32, (ld + 31) / 32),
-                   dim3(32, 8), Nei, ld, ns, (const double *)stage, t1, 0.0, (const double *)nullptr);
-            x0 = prolong_field(c, init_level, level, ld, t1, bufC);
+        double *stage = (double *)c->arena.base + (size_t)(ld / TW) * (size_t)chunk;
+        // rhs_s = -g * xi * w_sqrt at xi_level (:352-358 / :423-428)
+        if ((rc = upload_rows(c, xi + (size_t)s0 * Nex, ns, Nex, stage, bufA, chunk, 1, -c->s[xi_level].g, c->s[xi_level].w_sqrt))) return rc;
+        if (warm && (rc = upload_rows(c, init_s + (size_t)s0 * Nei, ns, Nei, stage, t1, chunk, 0, 0.0, nullptr))) return rc;
+        if ((rc = run_program(c, pg, ns, chunk, sys.N))) return rc;
+        const Off field = ws.x + (Off)sys.Nf * TW;  // rows [Nf, N) of the solution
+        if ((rc = download_rows(c, field, chunk, ns, Ne, stage, s_out + (size_t)s0 * Ne, L.lognormal != 0))) return rc;
+        if (embed_s_out && (rc = download_rows(c, field, chunk, ns, Ne, stage, embed_s_out + (size_t)s0 * Ne, false))) return rc;
+        if (iters_out) {
+            itbuf.resize(ns);
+            if ((rc = download_rows(c, ws.iters, chunk, ns, 1, stage, itbuf.data(), false))) return rc;
         }
-        if ((rc = sampler_solve_dev(c, level, ld, ns, rhs, x0, ws))) return rc;
-        const double *field = ws.x + (size_t)sys.Nf * ld;
-        dim3 tg((Ne + 31) / 32, (ld + 31) / 32), tb(32, 8);
-        if (L.lognormal) launch(c, PMC_K_MISC, (double)ns * Ne * 16.0, k_transpose_out<1>, tg, tb, Ne, ld, ns, field, stage);
-        else launch(c, PMC_K_MISC, (double)ns * Ne * 16.0, k_transpose_out<0>, tg, tb, Ne, ld, ns, field, stage);
-        CK(cudaMemcpyAsync(s_out + (size_t)s0 * Ne, stage, (size_t)ns * Ne * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-        if (embed_s_out) {
-            CK(cudaStreamSynchronize(c->stream));
-            launch(c, PMC_K_MISC, (double)ns * Ne * 16.0, k_transpose_out<0>, tg, tb, Ne, ld, ns, field, stage);
-            CK(cudaMemcpyAsync(embed_s_out + (size_t)s0 * Ne, stage, (size_t)ns * Ne * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-        }
-        if (iters_out) CK(cudaMemcpyAsync(iters_out + s0, ws.iters, (size_t)ns * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
         if ((rc = finish(c))) return rc;
+        if (iters_out)
+            for (int j = 0; j < ns; ++j) iters_out[s0 + j] = (int)itbuf[j];
     }
     return PMC_OK;
 }
@@ -1500,47 +1512,48 @@ static int darcy_host_batch(Ctx *c, int level, int nsamples, const double *k, co
     DarcyLevel &L = c->d[level];
     SaddleSys &sys = L.sys;
     const int Ne = L.Ne, N = sys.N;
-    const size_t per_sample = solve_bytes_per_sample(sys) + (size_t)(Ne + 1 + 2 * N) * 8 + 64;
+    Rows ar;
+    SolveWs ws;
+    carve_solve(ar, sys, ws);
+    const Off k_ext = ar.alloc(Ne + 1), Qrow = ar.alloc(1);
+    Program pg;
+    if (apply_only) {
+        Solver sv{&sys, &ws, vr(k_ext, Ne + 1)};
+        emit_fill(pg, vr(k_ext, Ne + 1, Ne), 1, 1.0);  // weight of the fixed entries
+        emit_saddle(pg, sv, EP_AX, ws.x, ws.q, -1, -1);
+    } else {
+        emit_fill(pg, vr(k_ext, Ne + 1, Ne), 1, 1.0);
+        emit_darcy_solve(pg, c, level, k_ext, ws, Qrow, true);
+    }
+    const Off chunk = ar.peak;
+    const size_t per_sample = (size_t)chunk * 8 / TW + (size_t)N * 8 + 64;
     const int B = pick_batch(c, per_sample, nsamples);
-    const int ldB = pad_ld(B);
-    if ((rc = ensure_arena(c, per_sample * (size_t)ldB + (1 << 16)))) return rc;
+    if ((rc = ensure_arena(c, per_sample * (size_t)pad_ld(B) + (1 << 16)))) return rc;
+    std::vector<double> itbuf;
     for (int s0 = 0; s0 < nsamples; s0 += B) {
         const int ns = std::min(B, nsamples - s0);
         const int ld = pad_ld(ns);
-        Arena &ar = c->arena;
-        ar.top = 0;
-        SolveWs ws;
-        carve_solve(ar, sys, ld, ws);
-        double *stage = ar.alloc((size_t)ns * N);
-        double *k_ext = ar.alloc((size_t)(Ne + 1) * ld);
-        double *Qd = ar.alloc(ld);
-        if (ar.overflow) return finish(c);
-        CK(cudaMemcpyAsync(stage, k + (size_t)s0 * Ne, (size_t)ns * Ne * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-        launch(c, PMC_K_MISC, (double)ns * Ne * 16.0, k_transpose_in<0>, dim3((Ne + 31) / 32, (ld + 31) / 32), dim3(32, 8),
-               Ne, ld, ns, (const double *)stage, k_ext, 0.0, (const double *)nullptr);
-        fill(c, k_ext + (size_t)Ne * ld, ld, 1.0);
-        dim3 tgN((N + 31) / 32, (ld + 31) / 32), tb(32, 8);
+        double *stage = (double *)c->arena.base + (size_t)(ld / TW) * (size_t)chunk;
+        if ((rc = upload_rows(c, k + (size_t)s0 * Ne, ns, Ne, stage, k_ext, chunk, 0, 0.0, nullptr))) return rc;
         if (apply_only) {
-            Solver sv{c, &sys, &ws, k_ext, ld};
-            CK(cudaMemcpyAsync(stage, xin + (size_t)s0 * N, (size_t)ns * N * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-            launch(c, PMC_K_MISC, (double)ns * N * 16.0, k_transpose_in<0>, tgN, tb, N, ld, ns, (const double *)stage, ws.x,
-                   0.0, (const double *)nullptr);
-            saddle_apply(sv, EP_AX, ws.x, ws.q, nullptr, false, PMC_K_SADDLE_APPLY);
-            launch(c, PMC_K_MISC, (double)ns * N * 16.0, k_transpose_out<0>, tgN, tb, N, ld, ns, (const double *)ws.q, stage);
-            CK(cudaMemcpyAsync(sol_out + (size_t)s0 * N, stage, (size_t)ns * N * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+            if ((rc = upload_rows(c, xin + (size_t)s0 * N, ns, N, stage, ws.x, chunk, 0, 0.0, nullptr))) return rc;
+            if ((rc = run_program(c, pg, ns, chunk, N))) return rc;
+            if ((rc = download_rows(c, ws.q, chunk, ns, N, stage, sol_out + (size_t)s0 * N, false))) return rc;
             if ((rc = finish(c))) return rc;
             continue;
         }
-        if ((rc = darcy_solve_dev(c, level, ld, ns, k_ext, ws, Qd))) return rc;
-        if (Q_out) CK(cudaMemcpyAsync(Q_out + s0, Qd, (size_t)ns * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        if ((rc = run_program(c, pg, ns, chunk, N))) return rc;
+        if (Q_out && (rc = download_rows(c, Qrow, chunk, ns, 1, stage, Q_out + s0, false))) return rc;
         if (C_out)
             for (int j = 0; j < ns; ++j) C_out[s0 + j] = (double)N;  // /root/reference/src/DarcySolver.cpp:429
-        if (sol_out) {
-            launch(c, PMC_K_MISC, (double)ns * N * 16.0, k_transpose_out<0>, tgN, tb, N, ld, ns, (const double *)ws.x, stage);
-            CK(cudaMemcpyAsync(sol_out + (size_t)s0 * N, stage, (size_t)ns * N * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        if (sol_out && (rc = download_rows(c, ws.x, chunk, ns, N, stage, sol_out + (size_t)s0 * N, false))) return rc;
+        if (iters_out) {
+            itbuf.resize(ns);
+            if ((rc = download_rows(c, ws.iters, chunk, ns, 1, stage, itbuf.data(), false))) return rc;
         }
-        if (iters_out) CK(cudaMemcpyAsync(iters_out + s0, ws.iters, (size_t)ns * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
         if ((rc = finish(c))) return rc;
+        if (iters_out)
+            for (int j = 0; j < ns; ++j) iters_out[s0 + j] = (int)itbuf[j];
     }
     return PMC_OK;
 }
@@ -1560,7 +1573,7 @@ int pmc_darcy_apply_batch(pmc_handle c, int level, int nsamples, const double *k
 }
 
 // ---- fused manager loops --------------------------------------------------------------------------
-// mode 0: MLMC level pair (or coarsest single), sums[9]; mode 1: MC single level, sums[4].
+// One level of the manager loop as ONE program / one kernel launch per batch.
 static int level_batch(Ctx *c, int level, int nlevels, int nsamples, uint64_t pos0, double *sums, double *rows,
                        int64_t *total_iters, bool mc)
 {
@@ -1582,83 +1595,81 @@ static int level_batch(Ctx *c, int level, int nlevels, int nsamples, uint64_t po
     DarcyLevel &DF = c->d[level];
     const int Ne = SF.Ne, Nec = coarsest ? 0 : c->s[level + 1].Ne;
     const double cost = (double)DF.sys.N + (coarsest ? 0.0 : (double)c->d[level + 1].sys.N);
-    size_t solve_ps = std::max(solve_bytes_per_sample(SF.sys), solve_bytes_per_sample(DF.sys));
-    const size_t per_sample = solve_ps + (size_t)(2 * Ne + 2 * Nec + (Ne + 1) + 8) * 8 + 64;
+    // ---- record the program of the level (the same for every batch except the stream position) ----
+    Rows ar;
+    const Off rhs_f = ar.alloc(Ne);
+    const Off rhs_c = coarsest ? -1 : ar.alloc(Nec), s_c = coarsest ? -1 : ar.alloc(Nec), x0_f = coarsest ? -1 : ar.alloc(Ne);
+    const Off k_ext = ar.alloc(Ne + 1), Qf = ar.alloc(1), Qc = ar.alloc(1);
+    const Off mark = ar.top;
+    Program pg;
+    // Sample(level, xi) fused with rhs_s = -g W^{1/2} xi  (/root/reference/src/PDESampler.cpp:336-340, :352-358)
+    {
+        Op &o = pg.add(OP_RNG, KC_RNG, Ne, Ne);
+        o.y = vr(rhs_f, Ne);
+        o.fixed = SF.w_sqrt;
+        o.ca = -SF.g;
+    }
+    const int rng_op = 0;
+    if (!coarsest) {
+        SamplerLevel &SC = c->s[level + 1];
+        DarcyLevel &DC = c->d[level + 1];
+        // Eval(level+1, xi, ., init_s, false): restrict the right-hand side, solve from zero (:431-438)
+        emit_spmm(pg, KC_TRANSFER, EP_AX, SF.dPt, VNULL, vr(rhs_f, Ne), vr(rhs_c, Nec), VNULL, VNULL, nullptr, VNULL, 0, 0, -1,
+                  false, false, (double)Ne + Nec);
+        {
+            ar.top = mark;
+            SolveWs ws;
+            carve_solve(ar, SC.sys, ws);
+            emit_sampler_solve(pg, c, level + 1, rhs_c, -1, ws, false);
+            emit_copy(pg, vr(ws.x, SC.sys.N, SC.sys.Nf), vr(s_c, Nec), Nec);
+            if (SC.lognormal) { Op &o = pg.add(OP_MAP_EXP, KC_MISC, Nec, 2.0 * Nec); o.x = vr(s_c, Nec); o.y = vr(k_ext, Nec + 1); }
+            else emit_copy(pg, vr(s_c, Nec), vr(k_ext, Nec + 1), Nec);
+            emit_fill(pg, vr(k_ext, Nec + 1, Nec), 1, 1.0);
+        }
+        {
+            ar.top = mark;
+            SolveWs ws;
+            carve_solve(ar, DC.sys, ws);
+            emit_darcy_solve(pg, c, level + 1, k_ext, ws, Qc, false);
+        }
+        // initial guess for the fine solve: prolongated coarse Gaussian field (:496-511)
+        emit_spmm(pg, KC_TRANSFER, EP_AX, SF.dP, VNULL, vr(s_c, Nec), vr(x0_f, Ne), VNULL, VNULL, nullptr, VNULL, 0, 0, -1, false,
+                  false, (double)Ne + Nec);
+    }
+    {
+        ar.top = mark;
+        SolveWs ws;
+        carve_solve(ar, SF.sys, ws);
+        emit_sampler_solve(pg, c, level, rhs_f, x0_f, ws, false);
+        if (SF.lognormal) { Op &o = pg.add(OP_MAP_EXP, KC_MISC, Ne, 2.0 * Ne); o.x = vr(ws.x, SF.sys.N, SF.sys.Nf); o.y = vr(k_ext, Ne + 1); }
+        else emit_copy(pg, vr(ws.x, SF.sys.N, SF.sys.Nf), vr(k_ext, Ne + 1), Ne);
+        emit_fill(pg, vr(k_ext, Ne + 1, Ne), 1, 1.0);
+    }
+    {
+        ar.top = mark;
+        SolveWs ws;
+        carve_solve(ar, DF.sys, ws);
+        emit_darcy_solve(pg, c, level, k_ext, ws, Qf, false);
+    }
+    const Off chunk = ar.peak;
+    const size_t per_sample = (size_t)chunk * 8 / TW + 64 + 40;
     const int B = pick_batch(c, per_sample, nsamples);
-    const int ldB = pad_ld(B);
-    if ((rc = ensure_arena(c, per_sample * (size_t)ldB + (size_t)B * 32 + (1 << 16)))) return rc;
+    if ((rc = ensure_arena(c, per_sample * (size_t)pad_ld(B) + (size_t)B * 32 + (1 << 16)))) return rc;
     if ((rc = ensure_pinned(c, 16 + (rows ? (size_t)B * 4 : 0)))) return rc;
-    CK(cudaMemsetAsync(c->d_iters_total, 0, sizeof(unsigned long long), c->stream));
+    unsigned long long it0 = 0, it1 = 0;
+    if (total_iters) {
+        CK(cudaStreamSynchronize(c->stream));
+        CK(cudaMemcpy(&it0, &c->d_pstats->iters_total, sizeof it0, cudaMemcpyDeviceToHost));
+    }
     for (int s0 = 0; s0 < nsamples; s0 += B) {
         const int ns = std::min(B, nsamples - s0);
         const int ld = pad_ld(ns);
-        Arena &ar = c->arena;
-        ar.top = 0;
-        double *rhs_f = ar.alloc((size_t)Ne * ld);
-        double *rhs_c = coarsest ? nullptr : ar.alloc((size_t)Nec * ld);
-        double *s_c = coarsest ? nullptr : ar.alloc((size_t)Nec * ld);
-        double *x0_f = coarsest ? nullptr : ar.alloc((size_t)Ne * ld);
-        double *k_ext = ar.alloc((size_t)(Ne + 1) * ld);
-        double *Qf = ar.alloc(ld), *Qc = ar.alloc(ld), *out9 = ar.alloc(16);
-        double *rows_d = rows ? ar.alloc((size_t)ns * 4) : nullptr;
-        const size_t mark = ar.top;
-        if (ar.overflow) return finish(c);
-        // Sample(level, xi) fused with rhs_s = -g W^{1/2} xi  (/root/reference/src/PDESampler.cpp:336-340, :352-358)
-        fill(c, rhs_f, (size_t)Ne * ld, 0.0);
-        if ((rc = rng_launch(c, 2, pos0 + (uint64_t)s0 * (uint64_t)Ne, (uint64_t)Ne, ~0ull, ns, Ne, ld, 1, 32, -SF.g,
-                             SF.w_sqrt, rhs_f, nullptr)))
-            return rc;
-        if (!coarsest) {
-            SamplerLevel &SC = c->s[level + 1];
-            DarcyLevel &DC = c->d[level + 1];
-            // Eval(level+1, xi, ., init_s, false): restrict the right-hand side, solve from zero (:431-438)
-            spmm(c, PMC_K_TRANSFER, EP_AX, SF.dPt, nullptr, ld, rhs_f, rhs_c, nullptr, nullptr, nullptr, false, 0, 0,
-                 nullptr, nullptr, 0, (double)Ne + Nec);
-            {
-                ar.top = mark;
-                SolveWs ws;
-                carve_solve(ar, SC.sys, ld, ws);
-                if (ar.overflow) return finish(c);
-                if ((rc = sampler_solve_dev(c, level + 1, ld, ns, rhs_c, nullptr, ws))) return rc;
-                const double *field = ws.x + (size_t)SC.sys.Nf * ld;
-                CK(cudaMemcpyAsync(s_c, field, (size_t)Nec * ld * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
-                const Shape sh = shape_for(Nec, ld);
-                if (SC.lognormal) launch(c, PMC_K_MISC, (double)ld * Nec * 16.0, k_map_rows<1>, sh.grid, sh.block, Nec, ld, sh.rows_per_cta, (const double *)s_c, k_ext);
-                else launch(c, PMC_K_MISC, (double)ld * Nec * 16.0, k_map_rows<0>, sh.grid, sh.block, Nec, ld, sh.rows_per_cta, (const double *)s_c, k_ext);
-                fill(c, k_ext + (size_t)Nec * ld, ld, 1.0);
-            }
-            {
-                ar.top = mark;
-                SolveWs ws;
-                carve_solve(ar, DC.sys, ld, ws);
-                if (ar.overflow) return finish(c);
-                if ((rc = darcy_solve_dev(c, level + 1, ld, ns, k_ext, ws, Qc))) return rc;
-            }
-            // initial guess for the fine solve: prolongated coarse Gaussian field (:496-511)
-            spmm(c, PMC_K_TRANSFER, EP_AX, SF.dP, nullptr, ld, s_c, x0_f, nullptr, nullptr, nullptr, false, 0, 0, nullptr,
-                 nullptr, 0, (double)Ne + Nec);
-        }
-        {
-            ar.top = mark;
-            SolveWs ws;
-            carve_solve(ar, SF.sys, ld, ws);
-            if (ar.overflow) return finish(c);
-            if ((rc = sampler_solve_dev(c, level, ld, ns, rhs_f, x0_f, ws))) return rc;
-            const double *field = ws.x + (size_t)SF.sys.Nf * ld;
-            const Shape sh = shape_for(Ne, ld);
-            if (SF.lognormal) launch(c, PMC_K_MISC, (double)ld * Ne * 16.0, k_map_rows<1>, sh.grid, sh.block, Ne, ld, sh.rows_per_cta, field, k_ext);
-            else launch(c, PMC_K_MISC, (double)ld * Ne * 16.0, k_map_rows<0>, sh.grid, sh.block, Ne, ld, sh.rows_per_cta, field, k_ext);
-            fill(c, k_ext + (size_t)Ne * ld, ld, 1.0);
-        }
-        {
-            ar.top = mark;
-            SolveWs ws;
-            carve_solve(ar, DF.sys, ld, ws);
-            if (ar.overflow) return finish(c);
-            if ((rc = darcy_solve_dev(c, level, ld, ns, k_ext, ws, Qf))) return rc;
-        }
-        launch(c, PMC_K_MISC, (double)ns * 16.0, k_mlmc_accumulate, dim3(1), dim3(256), ns, (const double *)Qf,
-               (const double *)(coarsest ? nullptr : Qc), cost, out9, rows_d);
+        double *out9 = (double *)c->arena.base + (size_t)(ld / TW) * (size_t)chunk;
+        double *rows_d = rows ? out9 + 16 : nullptr;
+        pg.ops[rng_op].u0 = pos0 + (uint64_t)s0 * (uint64_t)Ne;
+        if ((rc = run_program(c, pg, ns, chunk, DF.sys.N))) return rc;
+        launch(c, PMC_K_MISC, (double)ns * 16.0, k_mlmc_accumulate, dim3(1), dim3(256), ns, (const double *)c->arena.base, chunk,
+               Qf, coarsest ? (Off)-1 : Qc, cost, out9, rows_d);
         CK(cudaMemcpyAsync(c->h_pinned, out9, 9 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
         if (rows) CK(cudaMemcpyAsync(c->h_pinned + 16, rows_d, (size_t)ns * 4 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
         if ((rc = finish(c))) return rc;
@@ -1677,9 +1688,8 @@ static int level_batch(Ctx *c, int level, int nlevels, int nsamples, uint64_t po
         }
     }
     if (total_iters) {
-        unsigned long long t = 0;
-        CK(cudaMemcpy(&t, c->d_iters_total, sizeof t, cudaMemcpyDeviceToHost));
-        *total_iters = (int64_t)t;
+        CK(cudaMemcpy(&it1, &c->d_pstats->iters_total, sizeof it1, cudaMemcpyDeviceToHost));
+        *total_iters = (int64_t)(it1 - it0);
     }
     return PMC_OK;
 }
@@ -1700,8 +1710,7 @@ int pmc_mc_level_batch(pmc_handle c, int level, int nsamples, uint64_t pos0, dou
 int pmc_profile(pmc_handle c, unsigned mask)
 {
     if (!c) return PMC_ERR_ARG;
-    resolve_events(c);
-    c->profile_mask = mask;
+    (void)mask;  // the persistent kernel always accounts time and bytes per operation class; nothing to switch on
     return PMC_OK;
 }
 
@@ -1710,6 +1719,11 @@ int pmc_reset_stats(pmc_handle c)
     if (!c) return PMC_ERR_ARG;
     resolve_events(c);
     memset(&c->stats, 0, sizeof c->stats);
+    c->kernel_ms = 0.0;
+    c->kernel_launches = 0;
+    c->other_launches = 0;
+    CK(cudaMemsetAsync(c->d_pstats, 0, sizeof(ProgStats), c->stream));
+    CK(cudaStreamSynchronize(c->stream));
     return PMC_OK;
 }
 
@@ -1717,7 +1731,24 @@ int pmc_kernel_stats(pmc_handle c, pmc_kernel_stats_t *out)
 {
     if (!c || !out) return PMC_ERR_ARG;
     resolve_events(c);
-    *out = c->stats;
+    ProgStats ps;
+    CK(cudaMemcpy(&ps, c->d_pstats, sizeof ps, cudaMemcpyDeviceToHost));
+    pmc_kernel_stats_t st = c->stats;
+    unsigned long long cyc = 0;
+    for (int k = 0; k < KC_COUNT; ++k) cyc += ps.class_cycles[k];
+    for (int k = 0; k < KC_COUNT; ++k) {
+        st.class_cycle_share[k] = cyc ? (double)ps.class_cycles[k] / (double)cyc : 0.0;
+        st.ms[k] = c->kernel_ms * st.class_cycle_share[k];
+        st.algo_bytes[k] += ps.class_bytes[k];
+        st.timed_launches[k] = (int64_t)ps.class_ops[k];
+    }
+    st.kernel_launches = c->kernel_launches;
+    st.other_launches = c->other_launches;
+    st.kernel_ms = c->kernel_ms;
+    st.kernel_algo_bytes = ps.bytes;
+    st.ops_executed = (int64_t)ps.ops_executed;
+    st.minres_iterations = (int64_t)ps.iters_total;
+    *out = st;
     return PMC_OK;
 }
 

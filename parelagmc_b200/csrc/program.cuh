@@ -1,0 +1,664 @@
+// program.cuh -- the tile-persistent solver kernel.
+//
+// EXECUTION MODEL.  The realisations of a batch are grouped into TILES of TW = 4 consecutive samples.  One CTA owns
+// one tile for the whole life of a level batch: it runs a host-recorded PROGRAM (a flat list of operations: noise
+// generation, restriction, per-solve value set-up, the preconditioned MINRES loop with its Chebyshev / V-cycle
+// preconditioner, exp, QoI) from the first operation to the last, with only CTA-local barriers between operations
+// and with the per-sample Krylov scalars, convergence flags and dot products living in shared memory.  There is one
+// kernel launch per level batch, no grid-wide synchronisation and no host round trip inside a solve; a tile whose
+// four realisations have converged leaves the Krylov loop on its own (no lock-step with the slowest sample of the
+// batch).  Realisations never interact, so nothing is exchanged between CTAs.
+//
+// DATA LAYOUT.  Everything a tile touches lives in one contiguous chunk; inside it a batched vector with n rows is
+// stored as X[row * TW + j], j = sample within the tile, i.e. n rows of 32 bytes.  Two adjacent threads share a row
+// (one 128-bit access each), so a warp touches 16 consecutive rows = 512 contiguous bytes per access, the CTA
+// streams each vector linearly, and the gathers of a sparse operator apply stay within a band of the tile's vector
+// that lives in the SM's L1.  The sparse operators (CSR, weighted CSR) are shared by all tiles and stay in L2.  All
+// traffic of the batched vectors goes to HBM once per operation (ncu: dram bytes = 1.03 x algorithmic bytes): the
+// kernel is bound by HBM bandwidth and, per CTA, by memory latency -- hence CTA sizes chosen per level so that about
+// 1024 threads per SM are resident.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "rng.cuh"
+
+namespace pmc {
+
+constexpr int TW = 4;     // samples per tile (32-byte rows)
+constexpr int LPR = 2;    // lanes per row: two adjacent threads share a row, 16 bytes (one double2) each
+constexpr int PW = TW / LPR;
+constexpr int SLICE = 32 / LPR;  // rows per sliced-ELL slice = rows one warp covers per pass
+constexpr int MAXWARP = 16;  // largest CTA: 512 threads
+
+enum { EP_AX = 0, EP_RESID = 1, EP_CHEB = 2, EP_ADD = 3 };
+
+enum {
+    ST_BETA = 0, ST_IB, ST_IBPREV, ST_G0, ST_G1, ST_S0, ST_S1, ST_ETA, ST_GOAL, ST_ALPHA,
+    ST_CQ, ST_CV1, ST_CV0, ST_CW0, ST_CW1, ST_CU, ST_CX, ST_COUNT
+};
+
+enum OpKind {
+    OP_SPMM = 0,      // y = epilogue(A x)       flags: ep | weighted | bdinv | dot
+    OP_CHEB_FIRST,    // d = z = cb * dinv * r   flags: bdinv | dot
+    OP_LINCOMB3,      // y = cq x + cv1 r + cv0 y          (per-sample coefficients from the Krylov state)
+    OP_SOL_UPDATE,    // y = cw0 y + cw1 r + cu x ; d += cx y   (y = w0, r = w1, x = u1, d = solution)
+    OP_SETUP_SPMM,    // y = f(A g(x))           flags: absx | recip
+    OP_FILL,          // y = ca
+    OP_COPY,          // y = x
+    OP_BROADCAST,     // y[row][j] = sample valid ? fixed[row] : 0
+    OP_MAP_EXP,       // y = exp(x)
+    OP_DOT_FIXED,     // y[0][j] = sum_row fixed[row] * x[row][j]   (one chunk row of per-sample results)
+    OP_SC_INIT,       // Krylov state from dots[slot]
+    OP_SC_ALPHA,
+    OP_SC_BETA,
+    OP_CHECK,         // if no sample of the tile is active: pc = a0
+    OP_JUMP,          // pc = a0
+    OP_STORE_ITERS,   // y[0][j] = iterations of sample j (as double) ; total += iterations
+    OP_RNG,           // y[row][j] = (-g * N(mu,sigma)) * w_sqrt[row]  at stream position u0 + sample * n + row
+    OP_KIND_COUNT
+};
+
+enum {
+    F_WEIGHTED = 1, F_BDINV = 2, F_DOT = 4, F_DOT_ACC = 8, F_DOT_WITH_R = 16, F_ABSX = 32, F_RECIP = 64,
+    F_EP_SHIFT = 8  // ep stored in bits 8..9
+};
+
+// kernel classes for the in-kernel time/byte accounting (same meaning as PMC_K_* in include/pmc_b200.h)
+enum { KC_SADDLE = 0, KC_LANCZOS, KC_SOLUPD, KC_MASS, KC_SCHUR, KC_TRANSFER, KC_SETUP, KC_SCALAR, KC_RNG, KC_MISC, KC_COUNT };
+
+// A batched operand: offset (in doubles) of the first row of the view inside the tile's CHUNK.  Everything a tile
+// touches -- Krylov vectors, preconditioner scratch, right-hand sides, per-sample outputs -- lives in one contiguous
+// chunk of `ProgParams::chunk` doubles at base + tile * chunk, so workspace reuse between the consecutive solves of a
+// program is private to the tile (tiles progress independently of one another).  off < 0: no operand.
+struct VecRef {
+    long long off;
+};
+
+struct Op {
+    int kind, flags, n, slot;
+    int a0, a1, kclass, pad;
+    // OP_SPMM: sliced-ELL arrays (slice = 16 rows = one warp pass; entry k of slice s, row r: index (k * 16 + r) with
+    // k in [rowptr[s], rowptr[s+1])); for weighted operators these hold the WEIGHTED entries and f* the FIXED entries.
+    // OP_SETUP_SPMM: plain CSR arrays.
+    const int *rowptr;
+    const int *col;
+    const int *widx;
+    const double *val;
+    const int *foff;
+    const int *fcol;
+    const double *fval;
+    const double *fixed;  // fixed (sample-independent) vector: 1/diag, obs, rhs, w_sqrt
+    VecRef x, y, r, d, w, v;
+    double ca, cb, bytes;  // bytes: algorithmic bytes this op moves per tile
+    unsigned long long u0;
+};
+
+struct ProgStats {
+    unsigned long long class_cycles[KC_COUNT];  // summed over CTAs
+    double class_bytes[KC_COUNT];               // algorithmic bytes per class, summed over tiles
+    unsigned long long class_ops[KC_COUNT];
+    unsigned long long ops_executed;
+    unsigned long long iters_total;
+    double bytes;                               // algorithmic bytes of the executed ops, summed over tiles
+    unsigned long long cta_cycles;              // summed over CTAs
+};
+
+struct ProgParams {
+    const Op *ops;
+    int nops, ntiles, nsamples, max_iter;
+    double rel, abs_, mu, sigma;
+    const RngTables *tab;
+    ProgStats *stats;
+    double *base;      // tile chunks
+    long long chunk;   // doubles per tile chunk
+};
+
+struct Smem {
+    double st[ST_COUNT][TW];
+    double dots[4][TW];
+    double red[MAXWARP][TW];
+    int active[TW];
+    int iters[TW];
+    unsigned long long cyc[KC_COUNT];
+    double cbytes[KC_COUNT];
+    unsigned int cops[KC_COUNT];
+};
+
+typedef double2 D2;
+__device__ __forceinline__ D2 ld2c(const double *p) { return *reinterpret_cast<const double2 *>(p); }
+__device__ __forceinline__ void st2(double *p, D2 v) { *reinterpret_cast<double2 *>(p) = v; }
+__device__ __forceinline__ double *tp(const VecRef &v, double *chunk) { return v.off >= 0 ? chunk + v.off : nullptr; }
+__device__ __forceinline__ double safe_inv(double x) { return x != 0.0 ? 1.0 / x : 0.0; }
+
+// Deterministic CTA reduction.  Every thread holds the partial sums of its PW samples (lane parity selects which
+// samples); xor-butterfly over lanes of equal parity, then the warp results are added in warp order.  Result lands
+// in sm.dots[slot] (= or +=).
+template <int NTt>
+__device__ __forceinline__ void block_dot(D2 acc, Smem &sm, int slot, bool accumulate)
+{
+#pragma unroll
+    for (int o = 16; o >= LPR; o >>= 1) {
+        acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o);
+        acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane < LPR) {
+        sm.red[warp][lane * PW + 0] = acc.x;
+        sm.red[warp][lane * PW + 1] = acc.y;
+    }
+    __syncthreads();
+    if (threadIdx.x < TW) {
+        double s = accumulate ? sm.dots[slot][threadIdx.x] : 0.0;
+#pragma unroll
+        for (int w = 0; w < NTt / 32; ++w) s += sm.red[w][threadIdx.x];
+        sm.dots[slot][threadIdx.x] = s;
+    }
+}
+
+// ---- sparse operator apply with fused epilogue ------------------------------------------------------------
+//   plain CSR   : row i: p in [rowptr[i], rowptr[i+1])              sum += val[p] * x[col[p]]
+//   weighted CSR: row i: p in [rowptr[2i], rowptr[2i+1])            sum += val[p] * V[widx[p]] * x[col[p]]
+//                        p in [rowptr[2i+1], rowptr[2i+2])          sum += val[p] * x[col[p]]
+//   V = per-sample weights: the permeability k_e for M(k) = sum_e k_e R_e^T M_e R_e (the element reassembly of
+//   DarcySolver::assemble, /root/reference/src/DarcySolver.cpp:479, never materialised) or the Schur values.
+template <int NTt, int EP, bool WEIGHTED, bool BDINV, bool DOT>
+__device__ __forceinline__ void op_spmm(const Op &o, double *chunk, Smem &sm)
+{
+    const int sub = (threadIdx.x % LPR) * PW;  // first sample of this thread inside the row
+    const double *__restrict__ x = tp(o.x, chunk) + sub;
+    double *__restrict__ y = tp(o.y, chunk) + sub;
+    const double *__restrict__ r = (EP == EP_RESID || EP == EP_CHEB) ? tp(o.r, chunk) + sub : nullptr;
+    double *__restrict__ d = (EP == EP_CHEB) ? tp(o.d, chunk) + sub : nullptr;
+    const double *__restrict__ V = WEIGHTED ? tp(o.v, chunk) + sub : nullptr;
+    const double *__restrict__ dinvb = (EP == EP_CHEB && BDINV) ? tp(o.w, chunk) + sub : nullptr;
+    const int *__restrict__ rowptr = o.rowptr;
+    const int *__restrict__ col = o.col;
+    const int *__restrict__ widx = o.widx;
+    const double *__restrict__ val = o.val;
+    const double ca = o.ca, cb = o.cb;
+    const bool dot_r = (o.flags & F_DOT_WITH_R) != 0;
+    D2 acc = make_double2(0.0, 0.0);
+    const int *__restrict__ foff = o.foff;
+    const int *__restrict__ fcol = o.fcol;
+    const double *__restrict__ fval = o.fval;
+    const int npad = (o.n + SLICE - 1) & ~(SLICE - 1);  // whole warps stay converged through the slice loops
+    for (int row = threadIdx.x / LPR; row < npad; row += NTt / LPR) {
+        const int sl = row / SLICE, rs = row % SLICE;
+        D2 s = make_double2(0.0, 0.0);
+        if (WEIGHTED) {
+            const int k0 = __ldg(rowptr + sl), k1 = __ldg(rowptr + sl + 1);
+            const int f0 = __ldg(foff + sl), f1 = __ldg(foff + sl + 1);
+#pragma unroll 4
+            for (int k = k0; k < k1; ++k) {
+                const int idx = k * SLICE + rs;
+                const double c = __ldg(val + idx);
+                const D2 wv = ld2c(V + (size_t)__ldg(widx + idx) * TW);
+                const D2 xv = ld2c(x + (size_t)__ldg(col + idx) * TW);
+                s.x = fma(c * wv.x, xv.x, s.x);
+                s.y = fma(c * wv.y, xv.y, s.y);
+            }
+#pragma unroll 4
+            for (int k = f0; k < f1; ++k) {
+                const int idx = k * SLICE + rs;
+                const double c = __ldg(fval + idx);
+                const D2 xv = ld2c(x + (size_t)__ldg(fcol + idx) * TW);
+                s.x = fma(c, xv.x, s.x);
+                s.y = fma(c, xv.y, s.y);
+            }
+        } else {
+            const int k0 = __ldg(rowptr + sl), k1 = __ldg(rowptr + sl + 1);
+#pragma unroll 4
+            for (int k = k0; k < k1; ++k) {
+                const int idx = k * SLICE + rs;
+                const double c = __ldg(val + idx);
+                const D2 xv = ld2c(x + (size_t)__ldg(col + idx) * TW);
+                s.x = fma(c, xv.x, s.x);
+                s.y = fma(c, xv.y, s.y);
+            }
+        }
+        if (row >= o.n) continue;
+        const size_t ro = (size_t)row * TW;
+        D2 out;
+        if (EP == EP_AX) {
+            out = s;
+        } else if (EP == EP_RESID) {
+            const D2 rv = ld2c(r + ro);
+            out = make_double2(rv.x - s.x, rv.y - s.y);
+        } else if (EP == EP_ADD) {
+            const D2 yv = ld2c(y + ro);
+            out = make_double2(fma(ca, s.x, yv.x), fma(ca, s.y, yv.y));
+        } else {  // EP_CHEB: d = ca d + cb dinv (r - A z);  z_out = z + d
+            const D2 rv = ld2c(r + ro);
+            D2 di;
+            if (BDINV) di = ld2c(dinvb + ro);
+            else { const double t = __ldg(o.fixed + row); di = make_double2(t, t); }
+            D2 dn = make_double2(cb * di.x * (rv.x - s.x), cb * di.y * (rv.y - s.y));
+            if (ca != 0.0) {
+                const D2 dv = ld2c(d + ro);
+                dn.x = fma(ca, dv.x, dn.x);
+                dn.y = fma(ca, dv.y, dn.y);
+            }
+            st2(d + ro, dn);
+            const D2 zv = ld2c(x + ro);
+            out = make_double2(zv.x + dn.x, zv.y + dn.y);
+            if (DOT && dot_r) {
+                acc.x = fma(out.x, rv.x, acc.x);
+                acc.y = fma(out.y, rv.y, acc.y);
+            }
+        }
+        st2(y + ro, out);
+        if (DOT && !dot_r) {
+            const D2 wv = ld2c(x + ro);
+            acc.x = fma(out.x, wv.x, acc.x);
+            acc.y = fma(out.y, wv.y, acc.y);
+        }
+    }
+    if (DOT) block_dot<NTt>(acc, sm, o.slot, (o.flags & F_DOT_ACC) != 0);
+}
+
+template <int NTt, bool BDINV>
+__device__ __forceinline__ void op_cheb_first(const Op &o, double *chunk, Smem &sm)
+{
+    const int sub = (threadIdx.x % LPR) * PW;
+    const double *__restrict__ r = tp(o.r, chunk) + sub;
+    double *__restrict__ d = tp(o.d, chunk) + sub;
+    double *__restrict__ z = tp(o.y, chunk) + sub;
+    const double *__restrict__ dinvb = BDINV ? tp(o.w, chunk) + sub : nullptr;
+    const bool dot = (o.flags & F_DOT) != 0;
+    D2 acc = make_double2(0.0, 0.0);
+#pragma unroll 4
+    for (int row = threadIdx.x / LPR; row < o.n; row += NTt / LPR) {
+        const size_t ro = (size_t)row * TW;
+        const D2 rv = ld2c(r + ro);
+        D2 di;
+        if (BDINV) di = ld2c(dinvb + ro);
+        else { const double t = __ldg(o.fixed + row); di = make_double2(t, t); }
+        const D2 dn = make_double2(o.cb * di.x * rv.x, o.cb * di.y * rv.y);
+        acc.x = fma(dn.x, rv.x, acc.x);
+        acc.y = fma(dn.y, rv.y, acc.y);
+        st2(d + ro, dn);
+        st2(z + ro, dn);
+    }
+    if (dot) block_dot<NTt>(acc, sm, o.slot, (o.flags & F_DOT_ACC) != 0);
+}
+
+template <int NTt>
+__device__ __forceinline__ void op_lincomb3(const Op &o, double *chunk, Smem &sm)
+{
+    const int sub = (threadIdx.x % LPR) * PW;
+    const double *__restrict__ q = tp(o.x, chunk) + sub;
+    const double *__restrict__ v1 = tp(o.r, chunk) + sub;
+    double *__restrict__ v0 = tp(o.y, chunk) + sub;
+    const D2 a = make_double2(sm.st[ST_CQ][sub], sm.st[ST_CQ][sub + 1]);
+    const D2 b = make_double2(sm.st[ST_CV1][sub], sm.st[ST_CV1][sub + 1]);
+    const D2 c = make_double2(sm.st[ST_CV0][sub], sm.st[ST_CV0][sub + 1]);
+    const bool anyc = c.x != 0.0 || c.y != 0.0;
+#pragma unroll 4
+    for (int row = threadIdx.x / LPR; row < o.n; row += NTt / LPR) {
+        const size_t ro = (size_t)row * TW;
+        const D2 qv = ld2c(q + ro), vv = ld2c(v1 + ro);
+        D2 cv = make_double2(0.0, 0.0);
+        if (anyc) cv = ld2c(v0 + ro);
+        st2(v0 + ro, make_double2(fma(a.x, qv.x, fma(b.x, vv.x, c.x * cv.x)), fma(a.y, qv.y, fma(b.y, vv.y, c.y * cv.y))));
+    }
+}
+
+template <int NTt>
+__device__ __forceinline__ void op_sol_update(const Op &o, double *chunk, Smem &sm)
+{
+    const int sub = (threadIdx.x % LPR) * PW;
+    double *__restrict__ w0 = tp(o.y, chunk) + sub;
+    const double *__restrict__ w1 = tp(o.r, chunk) + sub;
+    const double *__restrict__ u1 = tp(o.x, chunk) + sub;
+    double *__restrict__ xs = tp(o.d, chunk) + sub;
+    const D2 a = make_double2(sm.st[ST_CW0][sub], sm.st[ST_CW0][sub + 1]);
+    const D2 b = make_double2(sm.st[ST_CW1][sub], sm.st[ST_CW1][sub + 1]);
+    const D2 c = make_double2(sm.st[ST_CU][sub], sm.st[ST_CU][sub + 1]);
+    const D2 e = make_double2(sm.st[ST_CX][sub], sm.st[ST_CX][sub + 1]);
+#pragma unroll 4
+    for (int row = threadIdx.x / LPR; row < o.n; row += NTt / LPR) {
+        const size_t ro = (size_t)row * TW;
+        const D2 w0v = ld2c(w0 + ro), w1v = ld2c(w1 + ro), uv = ld2c(u1 + ro);
+        D2 xv = ld2c(xs + ro);
+        const D2 wn = make_double2(fma(a.x, w0v.x, fma(b.x, w1v.x, c.x * uv.x)), fma(a.y, w0v.y, fma(b.y, w1v.y, c.y * uv.y)));
+        if (e.x != 0.0) xv.x = fma(e.x, wn.x, xv.x);
+        if (e.y != 0.0) xv.y = fma(e.y, wn.y, xv.y);
+        st2(w0 + ro, wn);
+        st2(xs + ro, xv);
+    }
+}
+
+template <int NTt>
+__device__ __forceinline__ void op_setup_spmm(const Op &o, double *chunk)
+{
+    const int sub = (threadIdx.x % LPR) * PW;
+    const double *__restrict__ x = tp(o.x, chunk) + sub;
+    double *__restrict__ y = tp(o.y, chunk) + sub;
+    const bool absx = (o.flags & F_ABSX) != 0, recip = (o.flags & F_RECIP) != 0;
+    for (int row = threadIdx.x / LPR; row < o.n; row += NTt / LPR) {
+        D2 s = make_double2(0.0, 0.0);
+        const int p0 = __ldg(o.rowptr + row), p1 = __ldg(o.rowptr + row + 1);
+#pragma unroll 4
+        for (int p = p0; p < p1; ++p) {
+            const double c = __ldg(o.val + p);
+            D2 xv = ld2c(x + (size_t)__ldg(o.col + p) * TW);
+            if (absx) { xv.x = fabs(xv.x); xv.y = fabs(xv.y); }
+            s.x = fma(c, xv.x, s.x);
+            s.y = fma(c, xv.y, s.y);
+        }
+        if (recip) { s.x = safe_inv(s.x); s.y = safe_inv(s.y); }
+        st2(y + (size_t)row * TW, s);
+    }
+}
+
+// ---- per-sample scalar recurrences of preconditioned MINRES (mfem::MINRESSolver::Mult structure, reached by the
+// reference through ParELAG's Krylov wrapper at /root/reference/src/PDESampler.cpp:517-522 and
+// src/DarcySolver.cpp:629-631), with lazily normalised Lanczos vectors.  Thread j < TW owns sample j of the tile.
+__device__ __forceinline__ void sc_init(const Op &o, int tile, Smem &sm, const ProgParams &P)
+{
+    const int j = threadIdx.x;
+    if (j >= TW) return;
+    const double eta = sqrt(fmax(sm.dots[o.slot][j], 0.0));
+    const double goal = fmax(P.rel * eta, P.abs_);
+    const int sample = tile * TW + j;
+    sm.st[ST_BETA][j] = eta;
+    sm.st[ST_IB][j] = safe_inv(eta);
+    sm.st[ST_IBPREV][j] = 0.0;
+    sm.st[ST_G0][j] = 1.0;
+    sm.st[ST_G1][j] = 1.0;
+    sm.st[ST_S0][j] = 0.0;
+    sm.st[ST_S1][j] = 0.0;
+    sm.st[ST_ETA][j] = eta;
+    sm.st[ST_GOAL][j] = goal;
+    sm.active[j] = (sample < P.nsamples) && (eta > goal);
+    sm.iters[j] = 0;
+}
+
+__device__ __forceinline__ void sc_alpha(const Op &o, Smem &sm)
+{
+    const int j = threadIdx.x;
+    if (j >= TW) return;
+    double cq = 0.0, cv1 = 0.0, cv0 = 0.0;
+    if (sm.active[j]) {
+        const double ib = sm.st[ST_IB][j];
+        const double alpha = sm.dots[o.slot][j] * ib * ib;
+        sm.st[ST_ALPHA][j] = alpha;
+        cq = ib;
+        cv1 = -alpha * ib;
+        cv0 = -sm.st[ST_BETA][j] * sm.st[ST_IBPREV][j];
+    }
+    sm.st[ST_CQ][j] = cq;
+    sm.st[ST_CV1][j] = cv1;
+    sm.st[ST_CV0][j] = cv0;
+}
+
+__device__ __forceinline__ void sc_beta(const Op &o, Smem &sm, const ProgParams &P)
+{
+    const int j = threadIdx.x;
+    if (j >= TW) return;
+    double cw0 = 0.0, cw1 = 0.0, cu = 0.0, cx = 0.0;
+    if (sm.active[j]) {
+        const double beta_new = sqrt(fmax(sm.dots[o.slot][j], 0.0));
+        const double beta = sm.st[ST_BETA][j], alpha = sm.st[ST_ALPHA][j], ib = sm.st[ST_IB][j];
+        double g0 = sm.st[ST_G0][j], g1 = sm.st[ST_G1][j], s0 = sm.st[ST_S0][j], s1 = sm.st[ST_S1][j];
+        double eta = sm.st[ST_ETA][j];
+        const double delta = g1 * alpha - g0 * s1 * beta;
+        const double rho3 = s0 * beta;
+        const double rho2 = s1 * alpha + g0 * g1 * beta;
+        const double rho1 = hypot(delta, beta_new);
+        const double ir = safe_inv(rho1);
+        cw0 = -rho3 * ir;
+        cw1 = -rho2 * ir;
+        cu = ib * ir;
+        g0 = g1;
+        g1 = delta * ir;
+        cx = g1 * eta;
+        s0 = s1;
+        s1 = beta_new * ir;
+        eta = -s1 * eta;
+        const int it = sm.iters[j] + 1;
+        sm.iters[j] = it;
+        sm.st[ST_G0][j] = g0;
+        sm.st[ST_G1][j] = g1;
+        sm.st[ST_S0][j] = s0;
+        sm.st[ST_S1][j] = s1;
+        sm.st[ST_ETA][j] = eta;
+        sm.st[ST_IBPREV][j] = ib;
+        sm.st[ST_BETA][j] = beta_new;
+        sm.st[ST_IB][j] = safe_inv(beta_new);
+        if (fabs(eta) <= sm.st[ST_GOAL][j] || it >= P.max_iter || beta_new == 0.0) sm.active[j] = 0;
+    }
+    sm.st[ST_CW0][j] = cw0;
+    sm.st[ST_CW1][j] = cw1;
+    sm.st[ST_CU][j] = cu;
+    sm.st[ST_CX][j] = cx;
+}
+
+// Noise generation fused with the SPDE right-hand-side scaling: thread (chunk c, sample j) jumps to stream position
+// u0 + sample * n + c * T and steps T times (PDESampler::Sample + :352-358 of src/PDESampler.cpp).
+template <int NTt>
+__device__ __forceinline__ void op_rng(const Op &o, int tile, double *chunk, const ProgParams &P)
+{
+    double *__restrict__ y = tp(o.y, chunk);
+    const int j = threadIdx.x & (TW - 1), c = threadIdx.x / TW;
+    constexpr int NCH = NTt / TW;
+    const int T = (o.n + NCH - 1) / NCH;
+    const int i0 = c * T, i1 = min(o.n, i0 + T);
+    const int sample = tile * TW + j;
+    if (i0 >= i1) return;
+    if (sample >= P.nsamples) {
+        for (int i = i0; i < i1; ++i) y[(size_t)i * TW + j] = 0.0;
+        return;
+    }
+    uint32_t r[5], co[5];
+#pragma unroll
+    for (int k = 0; k < 5; ++k) { r[k] = P.tab->r0[k]; co[k] = P.tab->a[k]; }
+    yarn5_jump(r, o.u0 + (uint64_t)sample * (uint64_t)o.n + (uint64_t)i0, P.tab->jump);
+    for (int i = i0; i < i1; ++i) {
+        yarn5_step(r, co);
+        const uint32_t v = yarn5_output(r[0], P.tab->powtab);
+        const double u = dm((double)v + 1.0, 1.0 / 2147483648.0);
+        const double z = da(dm(dev_inv_Phi(u), P.sigma), P.mu);
+        y[(size_t)i * TW + j] = dm(dm(o.ca, z), __ldg(o.fixed + i));
+    }
+}
+
+template <int NTt, int MINB>
+__global__ void __launch_bounds__(NTt, MINB) k_run_program(const ProgParams P)
+{
+    __shared__ Smem sm;
+    const int tile = blockIdx.x;
+    if (tile >= P.ntiles) return;
+    double *const chunk = P.base + (size_t)tile * (size_t)P.chunk;
+    if (threadIdx.x < KC_COUNT) { sm.cyc[threadIdx.x] = 0ull; sm.cbytes[threadIdx.x] = 0.0; sm.cops[threadIdx.x] = 0u; }
+    if (threadIdx.x < TW) { sm.active[threadIdx.x] = 0; sm.iters[threadIdx.x] = 0; }
+    __syncthreads();
+    const long long t_begin = clock64();
+    int pc = 0;
+    while (pc < P.nops) {
+        const Op &o = P.ops[pc];
+        const int kind = o.kind, flags = o.flags;
+        int next = pc + 1;
+        const long long t0 = clock64();
+        switch (kind) {
+        case OP_SPMM: {
+            const int ep = (flags >> F_EP_SHIFT) & 3;
+            const bool w = flags & F_WEIGHTED, dot = flags & F_DOT;
+            if (ep == EP_AX) {
+                if (w) { if (dot) op_spmm<NTt, EP_AX, true, false, true>(o, chunk, sm); else op_spmm<NTt, EP_AX, true, false, false>(o, chunk, sm); }
+                else   { if (dot) op_spmm<NTt, EP_AX, false, false, true>(o, chunk, sm); else op_spmm<NTt, EP_AX, false, false, false>(o, chunk, sm); }
+            } else if (ep == EP_RESID) {
+                if (w) op_spmm<NTt, EP_RESID, true, false, false>(o, chunk, sm); else op_spmm<NTt, EP_RESID, false, false, false>(o, chunk, sm);
+            } else if (ep == EP_ADD) {
+                op_spmm<NTt, EP_ADD, false, false, false>(o, chunk, sm);
+            } else {
+                if (w) { if (dot) op_spmm<NTt, EP_CHEB, true, true, true>(o, chunk, sm); else op_spmm<NTt, EP_CHEB, true, true, false>(o, chunk, sm); }
+                else   { if (dot) op_spmm<NTt, EP_CHEB, false, false, true>(o, chunk, sm); else op_spmm<NTt, EP_CHEB, false, false, false>(o, chunk, sm); }
+            }
+        } break;
+        case OP_CHEB_FIRST:
+            if (flags & F_BDINV) op_cheb_first<NTt, true>(o, chunk, sm); else op_cheb_first<NTt, false>(o, chunk, sm);
+            break;
+        case OP_LINCOMB3: op_lincomb3<NTt>(o, chunk, sm); break;
+        case OP_SOL_UPDATE: op_sol_update<NTt>(o, chunk, sm); break;
+        case OP_SETUP_SPMM: op_setup_spmm<NTt>(o, chunk); break;
+        case OP_FILL: {
+            double *y = tp(o.y, chunk);
+            const double v = o.ca;
+            for (int i = threadIdx.x; i < o.n * (TW / 2); i += NTt) reinterpret_cast<double2 *>(y)[i] = make_double2(v, v);
+        } break;
+        case OP_COPY: {
+            const double2 *x = reinterpret_cast<const double2 *>(tp(o.x, chunk));
+            double2 *y = reinterpret_cast<double2 *>(tp(o.y, chunk));
+#pragma unroll 4
+            for (int i = threadIdx.x; i < o.n * (TW / 2); i += NTt) y[i] = x[i];
+        } break;
+        case OP_BROADCAST: {
+            double *y = tp(o.y, chunk);
+            const int sub = (threadIdx.x % LPR) * PW;
+            for (int row = threadIdx.x / LPR; row < o.n; row += NTt / LPR) {
+                const double v = __ldg(o.fixed + row);
+                st2(y + (size_t)row * TW + sub, make_double2((tile * TW + sub < P.nsamples) ? v : 0.0,
+                                                              (tile * TW + sub + 1 < P.nsamples) ? v : 0.0));
+            }
+        } break;
+        case OP_MAP_EXP: {
+            const double *x = tp(o.x, chunk);
+            double *y = tp(o.y, chunk);
+            for (int i = threadIdx.x; i < o.n * TW; i += NTt) y[i] = exp(x[i]);
+        } break;
+        case OP_DOT_FIXED: {
+            const int sub = (threadIdx.x % LPR) * PW;
+            const double *x = tp(o.x, chunk) + sub;
+            D2 acc = make_double2(0.0, 0.0);
+            for (int row = threadIdx.x / LPR; row < o.n; row += NTt / LPR) {
+                const double w = __ldg(o.fixed + row);
+                if (w != 0.0) {
+                    const D2 xv = ld2c(x + (size_t)row * TW);
+                    acc.x = fma(w, xv.x, acc.x);
+                    acc.y = fma(w, xv.y, acc.y);
+                }
+            }
+            block_dot<NTt>(acc, sm, 3, false);
+            __syncthreads();
+            if (threadIdx.x < TW) tp(o.y, chunk)[threadIdx.x] = sm.dots[3][threadIdx.x];
+        } break;
+        case OP_SC_INIT: sc_init(o, tile, sm, P); break;
+        case OP_SC_ALPHA: sc_alpha(o, sm); break;
+        case OP_SC_BETA: sc_beta(o, sm, P); break;
+        case OP_CHECK: {
+            int any = 0;
+#pragma unroll
+            for (int j = 0; j < TW; ++j) any |= sm.active[j];
+            if (!any) next = o.a0;
+        } break;
+        case OP_JUMP: next = o.a0; break;
+        case OP_STORE_ITERS:
+            if (threadIdx.x < TW) {
+                const int sample = tile * TW + threadIdx.x;
+                if (o.y.off >= 0) tp(o.y, chunk)[threadIdx.x] = (double)sm.iters[threadIdx.x];
+                if (sample < P.nsamples) atomicAdd(&P.stats->iters_total, (unsigned long long)sm.iters[threadIdx.x]);
+            }
+            break;
+        case OP_RNG: op_rng<NTt>(o, tile, chunk, P); break;
+        default: break;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            sm.cyc[o.kclass] += (unsigned long long)(clock64() - t0);
+            sm.cbytes[o.kclass] += o.bytes;
+            sm.cops[o.kclass] += 1u;
+        }
+        pc = next;
+    }
+    __syncthreads();
+    if (threadIdx.x < KC_COUNT && sm.cops[threadIdx.x]) {
+        atomicAdd(&P.stats->class_cycles[threadIdx.x], sm.cyc[threadIdx.x]);
+        atomicAdd(&P.stats->class_bytes[threadIdx.x], sm.cbytes[threadIdx.x]);
+        atomicAdd(&P.stats->class_ops[threadIdx.x], (unsigned long long)sm.cops[threadIdx.x]);
+        atomicAdd(&P.stats->bytes, sm.cbytes[threadIdx.x]);
+        atomicAdd(&P.stats->ops_executed, (unsigned long long)sm.cops[threadIdx.x]);
+    }
+    if (threadIdx.x == 0) atomicAdd(&P.stats->cta_cycles, (unsigned long long)(clock64() - t_begin));
+}
+
+// ---- layout conversion and small reductions (separate launches; not on the per-iteration path) ----------------
+// Host layout [nsamples][n] (sample-major) -> rows of the tile chunks (dst = base + operand offset);  MODE 1 applies the SPDE right-hand-side scaling
+// out = (-g * xi) * w_sqrt[row] (/root/reference/src/PDESampler.cpp:352-358).
+template <int MODE>
+__global__ void k_to_tiles(int n, long long chunk, int ntiles, int nsamples, const double *__restrict__ src,
+                           double *__restrict__ dst, double neg_g, const double *__restrict__ w_sqrt)
+{
+    const size_t total = (size_t)ntiles * n * TW;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int j = (int)(i % TW);
+        const size_t t = i / TW;
+        const int row = (int)(t % n), tile = (int)(t / n);
+        const int s = tile * TW + j;
+        double v = s < nsamples ? src[(size_t)s * n + row] : 0.0;
+        if (MODE == 1) v = __dmul_rn(__dmul_rn(neg_g, v), __ldg(w_sqrt + row));
+        dst[(size_t)tile * (size_t)chunk + (size_t)row * TW + j] = v;
+    }
+}
+
+// rows of the tile chunks (src = base + operand offset) -> host layout [nsamples][n];  MODE 1 applies exp.
+template <int MODE>
+__global__ void k_from_tiles(int n, long long chunk, int nsamples, const double *__restrict__ src, double *__restrict__ dst)
+{
+    const size_t total = (size_t)nsamples * n;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int row = (int)(i % n), s = (int)(i / n);
+        const int tile = s / TW, j = s % TW;
+        double v = src[(size_t)tile * (size_t)chunk + (size_t)row * TW + j];
+        if (MODE == 1) v = exp(v);
+        dst[i] = v;
+    }
+}
+
+__global__ void k_fill(double *p, size_t n, double v)
+{
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) p[i] = v;
+}
+
+// Per-level moment sums of MLMC_Manager::InitRun (/root/reference/src/MLMC_Manager.cpp:123-131,:158-168), order
+// {Y2, Y, ABSY, Q2, Q, ABSQ, C, Y3, Y4}.  One CTA, fixed reduction tree => deterministic.
+__global__ void __launch_bounds__(256)
+    k_mlmc_accumulate(int nsamples, const double *__restrict__ base, long long chunk, long long offQ, long long offQc,
+                      double cost, double *__restrict__ out9, double *__restrict__ rows)
+{
+    __shared__ double red[9][256];
+    double a[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    for (int j = threadIdx.x; j < nsamples; j += 256) {
+        const size_t to = (size_t)(j / TW) * (size_t)chunk + (size_t)(j % TW);
+        const double q = base[to + offQ], qc = offQc >= 0 ? base[to + offQc] : 0.0;
+        const double y = offQc >= 0 ? q - qc : q;
+        a[7] += y * y * y;
+        a[8] += y * y * y * y;
+        a[0] += y * y;
+        a[1] += y;
+        a[2] += fabs(y);
+        a[3] += q * q;
+        a[4] += q;
+        a[5] += fabs(q);
+        a[6] += cost;
+        if (rows) {
+            rows[4 * (size_t)j + 0] = y;
+            rows[4 * (size_t)j + 1] = q;
+            rows[4 * (size_t)j + 2] = qc;
+            rows[4 * (size_t)j + 3] = cost;
+        }
+    }
+    for (int k = 0; k < 9; ++k) red[k][threadIdx.x] = a[k];
+    __syncthreads();
+    for (int w = 128; w > 0; w >>= 1) {
+        if (threadIdx.x < w)
+            for (int k = 0; k < 9; ++k) red[k][threadIdx.x] += red[k][threadIdx.x + w];
+        __syncthreads();
+    }
+    if (threadIdx.x < 9) out9[threadIdx.x] = red[threadIdx.x][0];
+}
+
+}  // namespace pmc

@@ -17,5 +17,6 @@ p = hex_problem(a.n, 3)
 ctx = make_context(p, True, 1e-6, 1e-12, a.maxit)
 sums, rows, its = (ctx.mc_level_batch if a.mc else ctx.mlmc_level_batch)(a.level, a.samples, 0)
 st = ctx.kernel_stats()
-print("launches", {k: v["launches"] for k, v in st.items()}, "iters", its)
+print("kernel", st["kernel"], "iters", its)
+print({k: (round(v["cycle_share"], 3), round(v["algo_bytes"] / 1e9, 2)) for k, v in st.items() if k != "kernel"})
 ctx.close()
