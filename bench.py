@@ -180,11 +180,15 @@ def run_product(args):
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     from common import make_context
+    from concurrent.futures import ThreadPoolExecutor
     p = build_problem()
-    ctx = make_context(p, True, REL, ABS, MAXIT, device=local)
-    stream = torch.cuda.current_stream()
-    ctx.set_stream(stream.cuda_stream)
     nl = p["nlevels"]
+    # One handle (own stream, own workspace) per level: the level batches of an InitRun are independent, so they are
+    # launched from one host thread each and their persistent kernels share the GPU (the finest level alone cannot
+    # fill it with 1000 realisations = 250 tiles).
+    ctxs = [make_context(p, True, REL, ABS, MAXIT, device=local) for _ in range(nl)]
+    pool = ThreadPoolExecutor(max_workers=nl)
+    stream = torch.cuda.current_stream()
     pos = stream_positions(p, LEVEL_SAMPLES, rank, world)
     dev = torch.device("cuda", local)
 
@@ -193,26 +197,16 @@ def run_product(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    lev_events = []
-
-    def step(record=False):
-        """One InitRun on the device path: sums[level] accumulated by the fused level loop, then one allreduce."""
+    def step():
+        """One InitRun on the device path: every level's fused loop (one kernel launch each), then one allreduce."""
         sums = np.zeros((nl, 9))
-        evs = [torch.cuda.Event(enable_timing=True) for _ in range(nl + 1)] if record else None
-        if record:
-            evs[0].record(stream)
-        its = 0
-        for i, lev in enumerate(range(nl - 1, -1, -1)):
-            _, _, it = ctx.mlmc_level_batch(lev, LEVEL_SAMPLES[lev], pos[lev], sums=sums[lev])
-            its += it
-            if record:
-                evs[i + 1].record(stream)
+        futs = [pool.submit(ctxs[lev].mlmc_level_batch, lev, LEVEL_SAMPLES[lev], pos[lev], None, False, sums[lev])
+                for lev in range(nl)]
+        its = sum(f.result()[2] for f in futs)
         if dist is not None:
             t = torch.from_numpy(sums).to(dev)
             dist.all_reduce(t)
             sums = t.cpu().numpy()
-        if record:
-            lev_events.append(evs)
         return sums, its
 
     # ---- warm-up ----
@@ -223,18 +217,19 @@ def run_product(args):
     clocks = ClockSampler(local, args.clock_ms)
     if rank == 0 and not args.no_clocks:
         clocks.start()
-    ctx.reset_stats()
+    for c in ctxs:
+        c.reset_stats()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     its_total = 0
     for _ in range(args.steps):
-        sums, its = step(record=True)
+        sums, its = step()
         its_total += its
     e1.record(stream)
     barrier()
     ms = e0.elapsed_time(e1)
-    st = ctx.kernel_stats()
+    stats = [c.kernel_stats() for c in ctxs]
     clk = clocks.stop() if rank == 0 else None
     if dist is not None:
         t = torch.tensor([ms], device=dev, dtype=torch.float64)
@@ -242,67 +237,95 @@ def run_product(args):
         ms = float(t.item())
     total_samples = sum(LEVEL_SAMPLES) * world * args.steps
     value = total_samples / (ms * 1e-3)
-    per_level = {}
-    for i, lev in enumerate(range(nl - 1, -1, -1)):
-        lms = sum(ev[i].elapsed_time(ev[i + 1]) for ev in lev_events)
-        per_level[f"level{lev}"] = LEVEL_SAMPLES[lev] * world * args.steps / (lms * 1e-3)
-    kst = st["kernel"]
-    launches = int(kst["launches"] + kst["other_launches"]) // max(1, args.steps)
+    launches = int(sum(st["kernel"]["launches"] + st["kernel"]["other_launches"] for st in stats)) // max(1, args.steps)
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
-    achieved = kst["algo_bytes"] / max(kst["ms"] * 1e-3, 1e-12) / 1e9
+    total_bytes = sum(x["kernel"]["algo_bytes"] for x in stats)
+    n_launch = int(sum(x["kernel"]["launches"] for x in stats))
+    # The three level batches of a step are three concurrent launches of the same kernel; their CUDA-event durations
+    # overlap, so the honest denominator is the device time of the timed region itself (which also contains the
+    # host-side gaps between steps): achieved is a lower bound.
+    achieved = total_bytes / (ms * 1e-3) / 1e9
+    # solo pass (outside the timed region): each level's launch alone on the GPU -> per-level throughput and the
+    # bandwidth of the dominant launch without co-runners
+    solo = {}
+    for lev in range(nl):
+        ctxs[lev].reset_stats()
+        ctxs[lev].mlmc_level_batch(lev, LEVEL_SAMPLES[lev], pos[lev])
+        k = ctxs[lev].kernel_stats()
+        solo[lev] = k
+    per_level = {f"level{lev}": LEVEL_SAMPLES[lev] * world / max(solo[lev]["kernel"]["ms"] * 1e-3, 1e-12) for lev in range(nl)}
+    dom = max(range(nl), key=lambda l: solo[l]["kernel"]["algo_bytes"])
+    st = solo[dom]
+    kst = st["kernel"]
     classes = [n for n in st if n != "kernel"]
-    roofline = {"bound": "hbm", "kernel": "k_run_program (tile-persistent solver: the whole level batch in one launch)",
+    roofline = {"bound": "hbm",
+                "kernel": "k_run_program (tile-persistent solver: a whole level batch per launch; the 3 level batches of a "
+                          "step run as 3 concurrent launches)",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
-                "launches": int(kst["launches"]), "avg_launch_us": 1e3 * kst["ms"] / max(1, kst["launches"]),
-                "algo_bytes_per_launch": kst["algo_bytes"] / max(1, kst["launches"]),
-                "share_of_step": kst["ms"] / ms,
-                "class_cycle_share": {n: round(st[n]["cycle_share"], 4) for n in classes if st[n]["ops"]},
-                "class_algo_gb_per_step": {n: round(st[n]["algo_bytes"] / 1e9 / args.steps, 3) for n in classes if st[n]["ops"]},
-                "timing": "CUDA events on the launching stream around every launch of the kernel, inside the timed region"}
+                "launches": n_launch, "algo_bytes_per_launch": total_bytes / max(1, n_launch),
+                "avg_launch_us": 1e3 * sum(x["kernel"]["ms"] for x in stats) / max(1, n_launch),
+                "definition": "algorithmic bytes of all launches in the timed region / CUDA-event time of the timed region "
+                              "(launches overlap; lower bound)",
+                "share_of_step": 1.0,
+                f"solo_level{dom}_launch": {"achieved": kst["algo_bytes"] / max(kst["ms"] * 1e-3, 1e-12) / 1e9,
+                                            "frac": kst["algo_bytes"] / max(kst["ms"] * 1e-3, 1e-12) / 1e9 / peak,
+                                            "ms": kst["ms"], "algo_gb": kst["algo_bytes"] / 1e9,
+                                            "class_cycle_share": {n: round(st[n]["cycle_share"], 4) for n in classes if st[n]["ops"]},
+                                            "class_algo_gb": {n: round(st[n]["algo_bytes"] / 1e9, 3) for n in classes if st[n]["ops"]}},
+                "timing": "CUDA events on the launching streams; in-kernel clock64 accounting for the class shares"}
 
     # ---- e2e: the same InitRun through the host-buffer plugin API (Sample / Eval / SolveFwd, batched) ----
     h2d = d2h = 0
 
+    def level_e2e(lev):
+        """One level of InitRun through the host-buffer API (the reference managers' call sequence, batched)."""
+        ctx = ctxs[lev]
+        n = LEVEL_SAMPLES[lev]
+        hi = ho = 0
+        xi = ctx.sampler_sample_batch(lev, n, pos[lev])                       # Sample(level, xi)
+        ho += xi.nbytes
+        if lev == nl - 1:
+            s, _, _ = ctx.sampler_eval_batch(lev, xi, xi_level=lev, want_embed=False)   # Eval(level, xi, s)
+            hi += xi.nbytes
+            ho += s.nbytes
+            q, c, _, _ = ctx.darcy_solve_batch(lev, s)                        # SolveFwd(level, s, q, c)
+            hi += s.nbytes
+            ho += q.nbytes
+            y = q
+        else:
+            sc, emb, _ = ctx.sampler_eval_batch(lev + 1, xi, xi_level=lev, use_init=0)   # Eval(l+1, xi, s, init, false)
+            hi += xi.nbytes
+            ho += sc.nbytes + emb.nbytes
+            qc, cc, _, _ = ctx.darcy_solve_batch(lev + 1, sc)
+            hi += sc.nbytes
+            ho += qc.nbytes
+            sf, _, _ = ctx.sampler_eval_batch(lev, xi, xi_level=lev, init_s=emb, init_level=lev + 1, use_init=1,
+                                              want_embed=False)               # Eval(l, xi, s, init, true)
+            hi += xi.nbytes + emb.nbytes
+            ho += sf.nbytes
+            q, c, _, _ = ctx.darcy_solve_batch(lev, sf)
+            hi += sf.nbytes
+            ho += q.nbytes
+            y = q - qc
+            c = c + cc
+        row = [np.sum(y * y), np.sum(y), np.sum(np.abs(y)), np.sum(q * q), np.sum(q), np.sum(np.abs(q)),
+               np.sum(c), np.sum(y ** 3), np.sum(y ** 4)]
+        return row, hi, ho
+
     def step_e2e():
         nonlocal h2d, d2h
-        h2d = d2h = 0
         sums = np.zeros((nl, 9))
-        for lev in range(nl - 1, -1, -1):
-            n = LEVEL_SAMPLES[lev]
-            xi = ctx.sampler_sample_batch(lev, n, pos[lev])                       # Sample(level, xi)
-            d2h += xi.nbytes
-            if lev == nl - 1:
-                s, _, _ = ctx.sampler_eval_batch(lev, xi, xi_level=lev, want_embed=False)   # Eval(level, xi, s)
-                h2d += xi.nbytes
-                d2h += s.nbytes
-                q, c, _, _ = ctx.darcy_solve_batch(lev, s)                        # SolveFwd(level, s, q, c)
-                h2d += s.nbytes
-                d2h += q.nbytes
-                y = q
-            else:
-                sc, emb, _ = ctx.sampler_eval_batch(lev + 1, xi, xi_level=lev, use_init=0)   # Eval(l+1, xi, s, init, false)
-                h2d += xi.nbytes
-                d2h += sc.nbytes + emb.nbytes
-                qc, cc, _, _ = ctx.darcy_solve_batch(lev + 1, sc)
-                h2d += sc.nbytes
-                d2h += qc.nbytes
-                sf, _, _ = ctx.sampler_eval_batch(lev, xi, xi_level=lev, init_s=emb, init_level=lev + 1, use_init=1,
-                                                  want_embed=False)               # Eval(l, xi, s, init, true)
-                h2d += xi.nbytes + emb.nbytes
-                d2h += sf.nbytes
-                q, c, _, _ = ctx.darcy_solve_batch(lev, sf)
-                h2d += sf.nbytes
-                d2h += q.nbytes
-                y = q - qc
-                c = c + cc
-            sums[lev] = [np.sum(y * y), np.sum(y), np.sum(np.abs(y)), np.sum(q * q), np.sum(q), np.sum(np.abs(q)),
-                         np.sum(c), np.sum(y ** 3), np.sum(y ** 4)]
+        res = [f.result() for f in [pool.submit(level_e2e, lev) for lev in range(nl)]]
+        h2d = sum(r[1] for r in res)
+        d2h = sum(r[2] for r in res)
+        for lev in range(nl):
+            sums[lev] = res[lev][0]
         if dist is not None:
             t = torch.from_numpy(sums).to(dev)
             dist.all_reduce(t)
@@ -338,7 +361,7 @@ def run_product(args):
         out = {"metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
                "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
                "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(world),
-               "per_level_samples_per_s": per_level, "minres_iterations_per_step": its_total / args.steps,
+               "per_level_samples_per_s_solo": per_level, "minres_iterations_per_step": its_total / args.steps,
                "mlmc_estimate": float(mean_y.sum()),
                "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": int(h2d),
                        "d2h_bytes_per_step": int(d2h), "steps": e2e_steps,
@@ -346,7 +369,9 @@ def run_product(args):
                        "mlmc_estimate": float((sums_e2e[:, 1] / (np.array(LEVEL_SAMPLES) * world)).sum())},
                "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "clocks": clk}
         print(json.dumps(out), flush=True)
-    ctx.close()
+    for c in ctxs:
+        c.close()
+    pool.shutdown()
     if dist is not None:
         dist.destroy_process_group()
 

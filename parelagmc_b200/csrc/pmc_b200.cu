@@ -194,6 +194,7 @@ struct pmc_context_s {
     pmc_kernel_stats_t stats;
     double kernel_ms = 0.0;
     int64_t kernel_launches = 0, other_launches = 0;
+    unsigned long long iters_seen = 0;  // host mirror of the device iteration counter
     std::vector<EventPair> ev_pending;
     std::vector<EventPair> ev_free;
     cudaError_t cuda_status = cudaSuccess;
@@ -995,6 +996,7 @@ static int pad_ld(int nsamples) { return ((nsamples + TW - 1) / TW) * TW; }
 static int pick_batch(Ctx *c, size_t bytes_per_sample, int nsamples)
 {
     int b = c->max_batch;
+    if (b <= 0 && c->arena.cap >= bytes_per_sample * (size_t)pad_ld(nsamples) + (size_t)nsamples * 32 + (1 << 16)) b = nsamples;
     if (b <= 0) {
         size_t free_b = 0, total_b = 0;
         cudaMemGetInfo(&free_b, &total_b);
@@ -1180,7 +1182,9 @@ int pmc_create(int device, int nlevels, pmc_handle *out)
     c->device = device;
     c->nlevels = nlevels;
     c->cfg_sampler.max_vlevels = -1;  // single-level Schur smoother when alpha*W dominates (short correlation length)
-    c->cfg_darcy.omega = 2.0;         // aggregation-type coarse spaces under-correct the pressure Laplacian
+    c->cfg_darcy.omega = 2.5;         // aggregation-type coarse spaces under-correct the pressure Laplacian
+    c->cfg_darcy.mass_degree = 1;     // plain Jacobi on the RT mass block: fewest bytes per unit of convergence
+    c->cfg_sampler.mass_degree = 1;   // (measured on the bench hierarchy, tools/tune_prec.py)
     c->s.resize(nlevels);
     c->d.resize(nlevels);
     memset(&c->stats, 0, sizeof c->stats);
@@ -1656,11 +1660,7 @@ static int level_batch(Ctx *c, int level, int nlevels, int nsamples, uint64_t po
     const int B = pick_batch(c, per_sample, nsamples);
     if ((rc = ensure_arena(c, per_sample * (size_t)pad_ld(B) + (size_t)B * 32 + (1 << 16)))) return rc;
     if ((rc = ensure_pinned(c, 16 + (rows ? (size_t)B * 4 : 0)))) return rc;
-    unsigned long long it0 = 0, it1 = 0;
-    if (total_iters) {
-        CK(cudaStreamSynchronize(c->stream));
-        CK(cudaMemcpy(&it0, &c->d_pstats->iters_total, sizeof it0, cudaMemcpyDeviceToHost));
-    }
+    const unsigned long long it0 = c->iters_seen;
     for (int s0 = 0; s0 < nsamples; s0 += B) {
         const int ns = std::min(B, nsamples - s0);
         const int ld = pad_ld(ns);
@@ -1671,9 +1671,11 @@ static int level_batch(Ctx *c, int level, int nlevels, int nsamples, uint64_t po
         launch(c, PMC_K_MISC, (double)ns * 16.0, k_mlmc_accumulate, dim3(1), dim3(256), ns, (const double *)c->arena.base, chunk,
                Qf, coarsest ? (Off)-1 : Qc, cost, out9, rows_d);
         CK(cudaMemcpyAsync(c->h_pinned, out9, 9 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaMemcpyAsync(c->h_pinned + 10, &c->d_pstats->iters_total, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
         if (rows) CK(cudaMemcpyAsync(c->h_pinned + 16, rows_d, (size_t)ns * 4 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
         if ((rc = finish(c))) return rc;
         const double *o = c->h_pinned;
+        memcpy(&c->iters_seen, c->h_pinned + 10, sizeof(unsigned long long));
         if (mc) {
             // MC_Manager enum {Q2, Q, ABSQ, C} (/root/reference/src/MC_Manager.hpp:61)
             sums[0] += o[3]; sums[1] += o[4]; sums[2] += o[5]; sums[3] += o[6];
@@ -1687,10 +1689,7 @@ static int level_batch(Ctx *c, int level, int nlevels, int nsamples, uint64_t po
             if (rows) memcpy(rows + 4 * (size_t)s0, c->h_pinned + 16, (size_t)ns * 4 * sizeof(double));
         }
     }
-    if (total_iters) {
-        CK(cudaMemcpy(&it1, &c->d_pstats->iters_total, sizeof it1, cudaMemcpyDeviceToHost));
-        *total_iters = (int64_t)(it1 - it0);
-    }
+    if (total_iters) *total_iters = (int64_t)(c->iters_seen - it0);
     return PMC_OK;
 }
 
@@ -1722,6 +1721,7 @@ int pmc_reset_stats(pmc_handle c)
     c->kernel_ms = 0.0;
     c->kernel_launches = 0;
     c->other_launches = 0;
+    c->iters_seen = 0;
     CK(cudaMemsetAsync(c->d_pstats, 0, sizeof(ProgStats), c->stream));
     CK(cudaStreamSynchronize(c->stream));
     return PMC_OK;

@@ -32,7 +32,7 @@ def test_library_is_sm100a_cuda_not_a_cpu_stub():
     out = subprocess.run(["cuobjdump", "-lelf", capi.LIB_PATH], capture_output=True, text=True).stdout
     assert "sm_100a" in out
     sass = subprocess.run(["cuobjdump", "-sass", capi.LIB_PATH], capture_output=True, text=True).stdout
-    assert "k_spmm" in sass and "k_rng" in sass
+    assert "k_run_program" in sass and "k_rng" in sass
     assert "LDG.E.128" in sass, "128-bit vector loads expected in the batched kernels"
 
 
