@@ -186,7 +186,8 @@ def run_product(args):
     # One handle (own stream, own workspace) per level: the level batches of an InitRun are independent, so they are
     # launched from one host thread each and their persistent kernels share the GPU (the finest level alone cannot
     # fill it with 1000 realisations = 250 tiles).
-    ctxs = [make_context(p, True, REL, ABS, MAXIT, device=local) for _ in range(nl)]
+    ctxs = [make_context(p, True, REL, ABS, MAXIT, device=local)]
+    ctxs += [ctxs[0].clone() for _ in range(nl - 1)]          # pmc_clone: same hierarchy, own stream and workspace
     pool = ThreadPoolExecutor(max_workers=nl)
     stream = torch.cuda.current_stream()
     pos = stream_positions(p, LEVEL_SAMPLES, rank, world)
@@ -283,15 +284,28 @@ def run_product(args):
     # ---- e2e: the same InitRun through the host-buffer plugin API (Sample / Eval / SolveFwd, batched) ----
     h2d = d2h = 0
 
+    from parelagmc_b200.capi import pinned_empty
+    Ne_l = [p["sampler"][l].Ne for l in range(nl)]
+    # page-locked host buffers of the per-level vectors the managers hold (xi, sparam, init_s): allocated once
+    hb = []
+    for lev in range(nl):
+        n = LEVEL_SAMPLES[lev]
+        d = {"xi": pinned_empty((n, Ne_l[lev])), "s": pinned_empty((n, Ne_l[lev]))}
+        if lev < nl - 1:
+            d["sc"] = pinned_empty((n, Ne_l[lev + 1]))
+            d["emb"] = pinned_empty((n, Ne_l[lev + 1]))
+        hb.append(d)
+
     def level_e2e(lev):
         """One level of InitRun through the host-buffer API (the reference managers' call sequence, batched)."""
         ctx = ctxs[lev]
         n = LEVEL_SAMPLES[lev]
+        b = hb[lev]
         hi = ho = 0
-        xi = ctx.sampler_sample_batch(lev, n, pos[lev])                       # Sample(level, xi)
+        xi = ctx.sampler_sample_batch(lev, n, pos[lev], out=b["xi"])          # Sample(level, xi)
         ho += xi.nbytes
         if lev == nl - 1:
-            s, _, _ = ctx.sampler_eval_batch(lev, xi, xi_level=lev, want_embed=False)   # Eval(level, xi, s)
+            s, _, _ = ctx.sampler_eval_batch(lev, xi, xi_level=lev, want_embed=False, out_s=b["s"])   # Eval(level, xi, s)
             hi += xi.nbytes
             ho += s.nbytes
             q, c, _, _ = ctx.darcy_solve_batch(lev, s)                        # SolveFwd(level, s, q, c)
@@ -299,14 +313,15 @@ def run_product(args):
             ho += q.nbytes
             y = q
         else:
-            sc, emb, _ = ctx.sampler_eval_batch(lev + 1, xi, xi_level=lev, use_init=0)   # Eval(l+1, xi, s, init, false)
+            sc, emb, _ = ctx.sampler_eval_batch(lev + 1, xi, xi_level=lev, use_init=0, out_s=b["sc"],
+                                                out_embed=b["emb"])            # Eval(l+1, xi, s, init, false)
             hi += xi.nbytes
             ho += sc.nbytes + emb.nbytes
             qc, cc, _, _ = ctx.darcy_solve_batch(lev + 1, sc)
             hi += sc.nbytes
             ho += qc.nbytes
             sf, _, _ = ctx.sampler_eval_batch(lev, xi, xi_level=lev, init_s=emb, init_level=lev + 1, use_init=1,
-                                              want_embed=False)               # Eval(l, xi, s, init, true)
+                                              want_embed=False, out_s=b["s"])  # Eval(l, xi, s, init, true)
             hi += xi.nbytes + emb.nbytes
             ho += sf.nbytes
             q, c, _, _ = ctx.darcy_solve_batch(lev, sf)
@@ -365,7 +380,7 @@ def run_product(args):
                "mlmc_estimate": float(mean_y.sum()),
                "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": int(h2d),
                        "d2h_bytes_per_step": int(d2h), "steps": e2e_steps,
-                       "api": "sampler_sample_batch / sampler_eval_batch / darcy_solve_batch with host buffers",
+                       "api": "sampler_sample_batch / sampler_eval_batch / darcy_solve_batch with page-locked host buffers, levels concurrent",
                        "mlmc_estimate": float((sums_e2e[:, 1] / (np.array(LEVEL_SAMPLES) * world)).sum())},
                "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "clocks": clk}
         print(json.dumps(out), flush=True)

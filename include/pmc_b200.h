@@ -27,6 +27,7 @@
 #ifndef PMC_B200_H
 #define PMC_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -54,6 +55,11 @@ const char *pmc_last_error(pmc_handle h);
 int pmc_set_stream(pmc_handle h, void *cuda_stream);
 /* Synchronise the handle's stream. */
 int pmc_synchronize(pmc_handle h);
+
+/* Page-locked host buffers (cudaMallocHost) for the batched host-side vectors: with them the host<->device copies of the
+ * *_batch entry points run at full PCIe rate and asynchronously; any host pointer is accepted, pinned or not. */
+int pmc_host_alloc(size_t bytes, void **out);
+void pmc_host_free(void *p);
 
 /* ---- solver configuration ---------------------------------------------------------------------- */
 /* Krylov stopping rule of the reference's "MINRES-BJ-GS" entry: relative/absolute tolerance on the
@@ -100,6 +106,12 @@ int pmc_upload_darcy_level(pmc_handle h, int level, int Ne, int Nf,
                            const int *B_rowptr, const int *B_col, const double *B_val,
                            const int *ess_u, const double *ess_data, const double *rhs, const double *obs,
                            int Pp_cols, const int *Pp_rowptr, const int *Pp_col, const double *Pp_val);
+
+/* A second handle on the same device with the same uploaded levels, options, tolerances and random stream but its own
+ * CUDA stream and workspace.  The level loops of one InitRun are independent of one another, so a manager keeps one
+ * handle per level and issues the level batches from one host thread each: their kernels then share the GPU (a single
+ * fine-level batch of ~1000 realisations does not fill it). */
+int pmc_clone(pmc_handle src, pmc_handle *out);
 
 /* Build every derived device structure now (Schur-complement hierarchies, block operators) instead of on
  * first use, so that set-up time stays out of timed regions. */

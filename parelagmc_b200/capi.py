@@ -21,8 +21,8 @@ K_CLASSES = ["saddle_apply", "lanczos_update", "solution_update", "mass_smooth",
 
 # every symbol include/pmc_b200.h declares (checked by tests/test_abi.py against the header text)
 SYMBOLS = [
-    "pmc_create", "pmc_destroy", "pmc_last_error", "pmc_set_stream", "pmc_synchronize", "pmc_set_tolerances",
-    "pmc_set_preconditioner", "pmc_set_option", "pmc_set_batch", "pmc_upload_sampler_level", "pmc_upload_darcy_level", "pmc_prepare",
+    "pmc_create", "pmc_destroy", "pmc_last_error", "pmc_host_alloc", "pmc_host_free", "pmc_set_stream", "pmc_synchronize", "pmc_set_tolerances",
+    "pmc_set_preconditioner", "pmc_set_option", "pmc_set_batch", "pmc_upload_sampler_level", "pmc_upload_darcy_level", "pmc_clone", "pmc_prepare",
     "pmc_rng_init", "pmc_rng_fill_int", "pmc_rng_fill", "pmc_sampler_sample_batch", "pmc_sampler_eval_batch",
     "pmc_darcy_solve_batch", "pmc_darcy_apply_batch", "pmc_mlmc_level_batch", "pmc_mc_level_batch", "pmc_profile",
     "pmc_reset_stats", "pmc_kernel_stats",
@@ -75,6 +75,9 @@ def load():
     L.pmc_destroy.restype = None
     L.pmc_last_error.argtypes = [vp]
     L.pmc_last_error.restype = C.c_char_p
+    L.pmc_host_alloc.argtypes = [C.c_size_t, C.POINTER(vp)]
+    L.pmc_host_free.argtypes = [vp]
+    L.pmc_host_free.restype = None
     L.pmc_set_stream.argtypes = [vp, vp]
     L.pmc_synchronize.argtypes = [vp]
     L.pmc_set_tolerances.argtypes = [vp, C.c_double, C.c_double, C.c_int]
@@ -85,6 +88,7 @@ def load():
                                            C.c_int, _ip, _ip, _dp, C.c_double, C.c_double, C.c_int]
     L.pmc_upload_darcy_level.argtypes = [vp, C.c_int, C.c_int, C.c_int, _ip, _ip, _dp, _ip, _ip, _dp, _ip, _dp,
                                          _dp, _dp, C.c_int, _ip, _ip, _dp]
+    L.pmc_clone.argtypes = [vp, C.POINTER(vp)]
     L.pmc_prepare.argtypes = [vp]
     L.pmc_rng_init.argtypes = [vp, C.c_double, C.c_double, C.c_int, C.c_int]
     L.pmc_rng_fill_int.argtypes = [vp, C.c_uint64, C.c_int64, C.POINTER(C.c_int32)]
@@ -100,7 +104,7 @@ def load():
     L.pmc_kernel_stats.argtypes = [vp, C.POINTER(KernelStats)]
     for name in SYMBOLS:
         f = getattr(L, name)
-        if name not in ("pmc_destroy", "pmc_last_error"):
+        if name not in ("pmc_destroy", "pmc_last_error", "pmc_host_free"):
             f.restype = C.c_int
     _lib = L
     return L
@@ -123,15 +127,42 @@ def _csr(m):
     return _i(rp), _i(ci), _d(v), (rp, ci, v)
 
 
+class _PinnedBlock:
+    def __init__(self, ptr, lib):
+        self.ptr, self.lib = ptr, lib
+
+    def __del__(self):
+        try:
+            self.lib.pmc_host_free(self.ptr)
+        except Exception:
+            pass
+
+
+def pinned_empty(shape, dtype=np.float64) -> np.ndarray:
+    """numpy array over page-locked host memory (`pmc_host_alloc`); freed with the array."""
+    L = load()
+    n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+    p = C.c_void_p()
+    rc = L.pmc_host_alloc(n, C.byref(p))
+    if rc != 0:
+        raise PmcError(rc, (L.pmc_last_error(None) or b"").decode())
+    buf = (C.c_char * max(n, 1)).from_address(p.value)
+    buf._owner = _PinnedBlock(p, L)
+    return np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+
+
 class Context:
     """One `pmc_handle`: a GPU-resident hierarchy plus the batched per-sample path on it."""
 
-    def __init__(self, nlevels: int, device: int = 0):
+    def __init__(self, nlevels: int, device: int = 0, _handle=None):
         self._L = load()
         self._h = C.c_void_p()
-        rc = self._L.pmc_create(device, nlevels, C.byref(self._h))
-        if rc != 0:
-            raise PmcError(rc, (self._L.pmc_last_error(None) or b"").decode())
+        if _handle is not None:
+            self._h = _handle
+        else:
+            rc = self._L.pmc_create(device, nlevels, C.byref(self._h))
+            if rc != 0:
+                raise PmcError(rc, (self._L.pmc_last_error(None) or b"").decode())
         self.nlevels = nlevels
         self.device = device
         self.Ne = [0] * nlevels
@@ -200,6 +231,14 @@ class Context:
                                                 0 if d.P_p is None else d.P_p.shape[1], pr, pc, pv))
         self.Ne[level], self.Nf[level] = d.Ne, d.Nf
 
+    def clone(self) -> "Context":
+        """`pmc_clone`: same hierarchy, options and stream of random numbers; own CUDA stream and workspace."""
+        h = C.c_void_p()
+        self._ck(self._L.pmc_clone(self._h, C.byref(h)))
+        c = Context(self.nlevels, self.device, _handle=h)
+        c.Ne, c.Nf = list(self.Ne), list(self.Nf)
+        return c
+
     def prepare(self):
         self._ck(self._L.pmc_prepare(self._h))
 
@@ -218,14 +257,16 @@ class Context:
         return out
 
     # -- sampler -----------------------------------------------------------------------------------
-    def sampler_sample_batch(self, level: int, nsamples: int, pos0: int) -> np.ndarray:
-        out = np.empty((nsamples, self.Ne[level]), dtype=np.float64)
+    def sampler_sample_batch(self, level: int, nsamples: int, pos0: int, out: Optional[np.ndarray] = None) -> np.ndarray:
+        out = np.empty((nsamples, self.Ne[level]), dtype=np.float64) if out is None else out
+        assert out.shape == (nsamples, self.Ne[level]) and out.flags.c_contiguous
         self._ck(self._L.pmc_sampler_sample_batch(self._h, level, nsamples, C.c_uint64(pos0), _d(out)))
         return out
 
     def sampler_eval_batch(self, level: int, xi: np.ndarray, xi_level: Optional[int] = None,
                            init_s: Optional[np.ndarray] = None, init_level: int = 0, use_init: int = -1,
-                           want_embed: bool = True):
+                           want_embed: bool = True, out_s: Optional[np.ndarray] = None,
+                           out_embed: Optional[np.ndarray] = None):
         """Returns (s [n, Ne], embed_s [n, Ne] | None, iters [n])."""
         xi = np.ascontiguousarray(xi, dtype=np.float64)
         if xi.ndim == 1:
@@ -237,8 +278,9 @@ class Context:
         if init_s is not None:
             init_s = np.ascontiguousarray(init_s, dtype=np.float64).reshape(n, -1)
             assert init_s.shape[1] == self.Ne[init_level]
-        s = np.empty((n, self.Ne[level]))
-        emb = np.empty((n, self.Ne[level])) if want_embed else None
+        s = np.empty((n, self.Ne[level])) if out_s is None else out_s
+        emb = (np.empty((n, self.Ne[level])) if out_embed is None else out_embed) if want_embed else None
+        assert s.shape == (n, self.Ne[level]) and s.flags.c_contiguous
         it = np.zeros(n, dtype=np.int32)
         self._ck(self._L.pmc_sampler_eval_batch(self._h, level, xi_level, n, _d(xi), _d(init_s), init_level,
                                                 use_init, _d(s), _d(emb), _i(it)))

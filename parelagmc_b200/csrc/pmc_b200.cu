@@ -181,6 +181,7 @@ struct pmc_context_s {
     // rng
     bool rng_ready = false;
     double mu = 0.0, sigma = 1.0;
+    int rng_nparts = 1, rng_mypart = 0;
     RngTables *d_tab = nullptr;
     // memory
     Arena arena;
@@ -1358,6 +1359,57 @@ int pmc_upload_darcy_level(pmc_handle c, int level, int Ne, int Nf, const int *e
     return PMC_OK;
 }
 
+int pmc_host_alloc(size_t bytes, void **out)
+{
+    if (!out) return PMC_ERR_ARG;
+    *out = nullptr;
+    cudaError_t e = cudaMallocHost(out, bytes ? bytes : 1);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(nullptr, PMC_ERR_NOMEM, "pmc_host_alloc(%zu): %s", bytes, cudaGetErrorString(e));
+    }
+    return PMC_OK;
+}
+
+void pmc_host_free(void *p)
+{
+    if (p) cudaFreeHost(p);
+}
+
+int pmc_clone(pmc_handle src, pmc_handle *out)
+{
+    if (!src || !out) return PMC_ERR_ARG;
+    *out = nullptr;
+    pmc_handle c = nullptr;
+    int rc = pmc_create(src->device, src->nlevels, &c);
+    if (rc) return fail(src, rc, "pmc_clone: %s", pmc_last_error(nullptr));
+    c->rel = src->rel; c->abs_ = src->abs_; c->maxit = src->maxit;
+    c->cfg_sampler = src->cfg_sampler; c->cfg_darcy = src->cfg_darcy;
+    c->max_batch = src->max_batch; c->force_nt = src->force_nt;
+    for (int l = 0; l < src->nlevels && !rc; ++l) {
+        const SamplerLevel &S = src->s[l];
+        if (S.set)
+            rc = pmc_upload_sampler_level(c, l, S.Ne, S.Nf, S.M.rowptr.data(), S.M.col.data(), S.M.val.data(), S.B.rowptr.data(),
+                                          S.B.col.data(), S.B.val.data(), S.Wdiag.data(), S.hasP ? S.P.cols : 0,
+                                          S.hasP ? S.P.rowptr.data() : nullptr, S.hasP ? S.P.col.data() : nullptr,
+                                          S.hasP ? S.P.val.data() : nullptr, S.alpha, S.g, S.lognormal);
+        const DarcyLevel &D = src->d[l];
+        if (!rc && D.set)
+            rc = pmc_upload_darcy_level(c, l, D.Ne, D.Nf, D.elem_ptr.data(), D.elem_dofs.data(), D.elem_mat.data(),
+                                        D.B.rowptr.data(), D.B.col.data(), D.B.val.data(), D.ess_u.data(), D.ess_data.data(),
+                                        D.rhs.data(), D.obs.data(), D.hasP ? D.Pp.cols : 0, D.hasP ? D.Pp.rowptr.data() : nullptr,
+                                        D.hasP ? D.Pp.col.data() : nullptr, D.hasP ? D.Pp.val.data() : nullptr);
+    }
+    if (!rc && src->rng_ready) rc = pmc_rng_init(c, src->mu, src->sigma, src->rng_nparts, src->rng_mypart);
+    if (rc) {
+        fail(src, rc, "pmc_clone: %s", pmc_last_error(c));
+        pmc_destroy(c);
+        return rc;
+    }
+    *out = c;
+    return PMC_OK;
+}
+
 int pmc_prepare(pmc_handle c)
 {
     if (!c) return PMC_ERR_ARG;
@@ -1384,6 +1436,8 @@ int pmc_rng_init(pmc_handle c, double mu, double sigma, int nparts, int mypart)
     if (e != cudaSuccess) return fail(c, PMC_ERR_CUDA, "rng table upload failed: %s", cudaGetErrorString(e));
     c->mu = mu;
     c->sigma = sigma;
+    c->rng_nparts = nparts;
+    c->rng_mypart = mypart;
     c->rng_ready = true;
     return PMC_OK;
 }

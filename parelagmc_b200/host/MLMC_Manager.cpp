@@ -5,6 +5,8 @@
 #include <cmath>
 #include <iomanip>
 #include <limits>
+#include <stdexcept>
+#include <thread>
 
 #include "DarcySolver.hpp"
 #include "PDESampler.hpp"
@@ -63,6 +65,11 @@ MLMC_Manager::MLMC_Manager(MPI_Comm comm_, const int nlevels_, PhysicalMLSolver 
     }
 }
 
+MLMC_Manager::~MLMC_Manager()
+{
+    for (auto h : clones) pmc_destroy(h);
+}
+
 void MLMC_Manager::accumulate(int l, double y, double q, double c)
 {
     double *s = &sums[l * NVAR];
@@ -86,28 +93,60 @@ void MLMC_Manager::InitRun(std::vector<int> &level_nsamples_init)
     PDESampler *bs = dynamic_cast<PDESampler *>(&sampler);
     DarcySolver *bd = dynamic_cast<DarcySolver *>(&pSolver);
     const bool batched = bs && bd && bs->Device().get() == bd->Device().get();
-    // coarsest level first, then nlevels-2 .. 0 (src/MLMC_Manager.cpp:110,140)
-    for (int ilevel = nlevels - 1; ilevel >= 0; --ilevel) {
-        const int nsamples = level_nsamples_init[ilevel];
-        const bool coarsest = (ilevel == nlevels - 1);
-        const auto t0 = std::chrono::steady_clock::now();
-        if (batched && nsamples > 0) {
-            // the whole loop body for all samples of this level in one device call; the stream positions are the
-            // ones the sequential Sample() calls would have consumed
-            const uint64_t pos0 = bs->Distribution().Advance((uint64_t)nsamples * (uint64_t)bs->SampleSize(ilevel));
-            std::vector<double> rows(logger.is_open() ? (size_t)nsamples * 4 : 0);
-            bs->Device()->check(pmc_mlmc_level_batch(bs->Device()->handle(), ilevel, nlevels, nsamples, pos0,
-                                                     &sums[ilevel * NVAR], rows.empty() ? nullptr : rows.data(), nullptr),
-                                "pmc_mlmc_level_batch");
+    if (batched) {
+        // The level loops of an InitRun are independent of one another: every level gets its own device handle
+        // (pmc_clone: own stream and workspace) and its own host thread, so the levels' kernels share the GPU.  The
+        // stream positions are the ones the reference's sequential Sample() calls would have consumed: coarsest level
+        // first, then nlevels-2 .. 0 (src/MLMC_Manager.cpp:110,140).
+        pmc_handle main_h = bs->Device()->handle();
+        while ((int)clones.size() < nlevels - 1) {
+            pmc_handle h = nullptr;
+            bs->Device()->check(pmc_clone(main_h, &h), "pmc_clone");
+            clones.push_back(h);
+        }
+        std::vector<uint64_t> pos0(nlevels);
+        for (int ilevel = nlevels - 1; ilevel >= 0; --ilevel)
+            pos0[ilevel] = bs->Distribution().Advance((uint64_t)level_nsamples_init[ilevel] * (uint64_t)bs->SampleSize(ilevel));
+        std::vector<std::vector<double>> rows(nlevels);
+        std::vector<int> rcs(nlevels, 0);
+        std::vector<double> secs(nlevels, 0.0);
+        std::vector<std::thread> workers;
+        for (int ilevel = 0; ilevel < nlevels; ++ilevel) {
+            const int nsamples = level_nsamples_init[ilevel];
+            if (nsamples <= 0) continue;
+            if (logger.is_open()) rows[ilevel].resize((size_t)nsamples * 4);
+            pmc_handle h = ilevel == 0 ? main_h : clones[ilevel - 1];
+            workers.emplace_back([&, ilevel, nsamples, h]() {
+                const auto t0 = std::chrono::steady_clock::now();
+                rcs[ilevel] = pmc_mlmc_level_batch(h, ilevel, nlevels, nsamples, pos0[ilevel], &sums[ilevel * NVAR],
+                                                   rows[ilevel].empty() ? nullptr : rows[ilevel].data(), nullptr);
+                secs[ilevel] = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+            });
+        }
+        for (auto &w : workers) w.join();
+        for (int ilevel = nlevels - 1; ilevel >= 0; --ilevel) {
+            const int nsamples = level_nsamples_init[ilevel];
+            if (rcs[ilevel] != 0)
+                throw std::runtime_error(std::string("pmc_mlmc_level_batch: ") +
+                                         pmc_last_error(ilevel == 0 ? main_h : clones[ilevel - 1]));
+            const bool coarsest = (ilevel == nlevels - 1);
             if (!pid && logger.is_open())
                 for (int j = 0; j < nsamples; ++j) {
-                    logger << std::setw(width) << ilevel << std::setw(width) << rows[4 * j] << std::setw(width)
-                           << rows[4 * j + 1] << std::setw(width);
-                    if (coarsest) logger << "0"; else logger << rows[4 * j + 2];
-                    logger << std::setw(width) << rows[4 * j + 3] << "\n";
+                    const double *r = &rows[ilevel][4 * (size_t)j];
+                    logger << std::setw(width) << ilevel << std::setw(width) << r[0] << std::setw(width) << r[1]
+                           << std::setw(width);
+                    if (coarsest) logger << "0"; else logger << r[2];
+                    logger << std::setw(width) << r[3] << "\n";
                 }
-        } else {
-            // reference loop through the abstract interfaces (src/MLMC_Manager.cpp:113-136 / :144-173)
+            level_time[ilevel] += secs[ilevel];
+            level_nsamples[ilevel] += nsamples;
+        }
+    } else {
+        // reference loop through the abstract interfaces (src/MLMC_Manager.cpp:113-136 / :144-173)
+        for (int ilevel = nlevels - 1; ilevel >= 0; --ilevel) {
+            const int nsamples = level_nsamples_init[ilevel];
+            const bool coarsest = (ilevel == nlevels - 1);
+            const auto t0 = std::chrono::steady_clock::now();
             mfem::Vector xi, sparam, init_s;
             for (int isample = 0; isample < nsamples; ++isample) {
                 double q = 0, c = 0, qc = 0, cc = 0, y;
@@ -132,9 +171,9 @@ void MLMC_Manager::InitRun(std::vector<int> &level_nsamples_init)
                     logger << std::setw(width) << c << "\n";
                 }
             }
+            level_time[ilevel] += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+            level_nsamples[ilevel] += nsamples;
         }
-        level_time[ilevel] += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-        level_nsamples[ilevel] += nsamples;
     }
     if (pid == 0 && logger.is_open()) logger << std::flush;
     computeNSamplesMSE();

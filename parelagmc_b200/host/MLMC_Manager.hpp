@@ -10,12 +10,14 @@
 #include "MLSampler.hpp"
 #include "PhysicalMLSolver.hpp"
 
+struct pmc_context_s;
+
 namespace parelagmc {
 class MLMC_Manager {
 public:
     MLMC_Manager(MPI_Comm comm, const int nlevels, PhysicalMLSolver &pSolver, MLSampler &sampler,
                  parelag::ParameterList &master_list);
-    ~MLMC_Manager() = default;
+    ~MLMC_Manager();
     MLMC_Manager(MLMC_Manager const &) = delete;
     MLMC_Manager &operator=(MLMC_Manager const &) = delete;
 
@@ -59,6 +61,7 @@ private:
     double alpha, alphaABS, beta, gamma;
     std::vector<int> level_nsamples, level_nsamples_missing;
     std::ofstream logger;
+    std::vector<pmc_context_s *> clones;  // one extra device handle per level > 0 (concurrent level loops)
 };
 
 /// expWRegression (/root/reference/src/Utilities.cpp:257-283)

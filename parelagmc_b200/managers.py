@@ -101,12 +101,24 @@ class MLMC_Manager:
         self.M = np.array([backend.Ne[i] + backend.Nf[i] for i in range(nlevels)], dtype=np.float64)
         self.logger = open(self.file_name, "w") if (self.pid == 0 and self.file_name) else None
         self.stream_pos = 0            # absolute yarn5 position of the next unused draw (all ranks agree)
+        self.concurrent_levels = True  # run the level loops of an InitRun concurrently (one cloned handle per level)
+        self._clones = {}
+        self._pool = None
         self._reset()
         if self.pid == 0 and out is not None:
             print("\n" + "*" * 50 + "\n*  MLMC_Manager \n*    MSE: %g\n*    MSE splitting ratio: %g\n"
                   "*    Number of Initial Samples: %s \n*    Output filename: %s\n" % (
                       self.eps2, self.ratio, " ".join(map(str, self.v_init_nsamples)), self.file_name) + "*" * 50,
                   file=out)
+
+    def _level_backend(self, ilevel):
+        if not (self.concurrent_levels and self.nlevels > 1 and hasattr(self.backend, "clone")):
+            return self.backend
+        if ilevel == 0:
+            return self.backend
+        if ilevel not in self._clones:
+            self._clones[ilevel] = self.backend.clone()
+        return self._clones[ilevel]
 
     def _reset(self):
         L = self.nlevels
@@ -130,23 +142,41 @@ class MLMC_Manager:
             self.logger.write("%" + "level ".rjust(13) + "Y(xi) ".rjust(14) + "Q(xi)".rjust(14) + "Q_c(xi)".rjust(14)
                               + "c \n".rjust(14))
         local = np.zeros((self.nlevels, NVAR))
+        want_rows = self.logger is not None and self.comm.size == 1
+        # stream positions in the reference's order: coarsest level first, every level after the previous one
+        jobs = []
         for ilevel in range(self.nlevels - 1, -1, -1):
             n = int(level_nsamples_init[ilevel])
             Ne = self.backend.Ne[ilevel]
             first, count = split_samples(n, self.comm.rank, self.comm.size)
-            t0 = time.perf_counter()
-            want_rows = self.logger is not None and self.comm.size == 1
-            if count > 0:
-                _, rows, its = self.backend.mlmc_level_batch(ilevel, count, self.stream_pos + first * Ne,
-                                                             nlevels=self.nlevels, want_rows=want_rows,
-                                                             sums=local[ilevel])
-                self.total_iters += its
-                if want_rows:
-                    for r in rows:
-                        self.logger.write(f"{ilevel:14d}{r[0]:14.6g}{r[1]:14.6g}{r[2]:14.6g}{r[3]:14.6g}\n")
-            self.level_time[ilevel] += time.perf_counter() - t0
+            jobs.append((ilevel, count, self.stream_pos + first * Ne))
             self.stream_pos += n * Ne
             self.level_nsamples[ilevel] += n
+
+        def run(job):
+            ilevel, count, pos = job
+            t0 = time.perf_counter()
+            rows, its = None, 0
+            if count > 0:
+                be = self._level_backend(ilevel)
+                _, rows, its = be.mlmc_level_batch(ilevel, count, pos, nlevels=self.nlevels, want_rows=want_rows,
+                                                   sums=local[ilevel])
+            return ilevel, rows, its, time.perf_counter() - t0
+
+        if self.concurrent_levels and self.nlevels > 1 and hasattr(self.backend, "clone"):
+            # the level loops are independent: one handle (own stream and workspace) and one host thread per level
+            from concurrent.futures import ThreadPoolExecutor
+            if self._pool is None:
+                self._pool = ThreadPoolExecutor(max_workers=self.nlevels)
+            results = list(self._pool.map(run, jobs))
+        else:
+            results = [run(j) for j in jobs]
+        for ilevel, rows, its, dt in results:
+            self.total_iters += its
+            self.level_time[ilevel] += dt
+            if want_rows and rows is not None:
+                for r in rows:
+                    self.logger.write(f"{ilevel:14d}{r[0]:14.6g}{r[1]:14.6g}{r[2]:14.6g}{r[3]:14.6g}\n")
         self.sums += self.comm.allreduce_sum(local)
         if self.logger:
             self.logger.flush()
