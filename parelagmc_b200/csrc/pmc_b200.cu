@@ -857,10 +857,14 @@ static void emit_vcycle(Program &pg, Solver &sv, int m, VecRef r, VecRef zout, V
 
 // z = Prec r (block diagonal: Chebyshev-Jacobi on the RT mass block, V-cycle on the Schur complement); if dot_slot >= 0
 // the slot receives r . z (mass part assigns, Schur part accumulates).
-static void emit_prec(Program &pg, Solver &sv, Off r, Off z, int dot_slot)
+static void emit_prec(Program &pg, Solver &sv, Off r, Off z, int dot_slot, bool mass_done = false)
 {
     SaddleSys &sys = *sv.sys;
     SolveWs &ws = *sv.ws;
+    if (mass_done) {  // the mass-block Jacobi (and its share of the dot) was fused into the Lanczos update
+        emit_vcycle(pg, sv, 0, vr(r, sys.N, sys.Nf), vr(z, sys.N, sys.Nf), vr(ws.vzB[0], sys.Ne), dot_slot);
+        return;
+    }
     ChebOp op;
     op.A = &sys.Muu;
     op.V = sv.k_ext;
@@ -937,8 +941,23 @@ static void emit_minres(Program &pg, Solver &sv, bool x_nonzero, bool store_iter
     for (int parity = 0; parity < 2; ++parity) {
         emit_saddle(pg, sv, EP_AX, u1, q, -1, 0);
         { Op &o = pg.add(OP_SC_ALPHA, KC_SCALAR, 0, 0); o.slot = 0; }
-        { Op &o = pg.add(OP_LINCOMB3, KC_LANCZOS, N, 4.0 * N); o.x = vr(q, N); o.r = vr(v1, N); o.y = vr(v0, N); }
-        emit_prec(pg, sv, v0, q, 1);
+        const bool fuse_jacobi = sys.cfg.mass_degree == 1;
+        {
+            Op &o = pg.add(OP_LINCOMB3, KC_LANCZOS, N, 4.0 * N + (fuse_jacobi ? (sys.weighted ? 2.0 : 1.0) * sys.Nf : 0.0));
+            o.x = vr(q, N); o.r = vr(v1, N); o.y = vr(v0, N);
+            if (fuse_jacobi) {
+                // z_u = dinvM v0_u / theta written straight into the u block of q (q's own rows are read first)
+                const double theta = 0.5 * (sys.m_hi + sys.m_lo);
+                o.flags = F_DOT | (sys.weighted ? F_BDINV : 0);
+                o.d = vr(q, N);
+                o.w = sys.weighted ? vr(ws.dinvM, sys.Nf) : VNULL;
+                o.fixed = sys.weighted ? nullptr : sys.dinvM_fixed;
+                o.cb = 1.0 / theta;
+                o.a0 = sys.Nf;
+                o.slot = 1;
+            }
+        }
+        emit_prec(pg, sv, v0, q, 1, fuse_jacobi);
         { Op &o = pg.add(OP_SC_BETA, KC_SCALAR, 0, 0); o.slot = 1; }
         { Op &o = pg.add(OP_SOL_UPDATE, KC_SOLUPD, N, 6.0 * N); o.y = vr(w0, N); o.r = vr(w1, N); o.x = vr(u1, N); o.d = vr(ws.x, N); }
         exits.push_back(pg.pc());

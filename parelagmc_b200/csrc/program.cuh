@@ -41,7 +41,8 @@ enum {
 enum OpKind {
     OP_SPMM = 0,      // y = epilogue(A x)       flags: ep | weighted | bdinv | dot
     OP_CHEB_FIRST,    // d = z = cb * dinv * r   flags: bdinv | dot
-    OP_LINCOMB3,      // y = cq x + cv1 r + cv0 y          (per-sample coefficients from the Krylov state)
+    OP_LINCOMB3,      // y = cq x + cv1 r + cv0 y  (per-sample coefficients); with F_DOT: fused mass-block Jacobi
+                      //   d[row < a0] = cb * dinv * y, dots[slot] = y . d over those rows
     OP_SOL_UPDATE,    // y = cw0 y + cw1 r + cu x ; d += cx y   (y = w0, r = w1, x = u1, d = solution)
     OP_SETUP_SPMM,    // y = f(A g(x))           flags: absx | recip
     OP_FILL,          // y = ca
@@ -283,25 +284,43 @@ __device__ __forceinline__ void op_cheb_first(const Op &o, double *chunk, Smem &
     if (dot) block_dot<NTt>(acc, sm, o.slot, (o.flags & F_DOT_ACC) != 0);
 }
 
-template <int NTt>
+// Lanczos update v0 = cq q + cv1 v1 + cv0 v0, optionally fused with the Jacobi preconditioner of the RT mass block
+// (rows < a0): z = cb * dinv * v0 written to o.d, and the partial dot v0 . z of those rows.
+template <int NTt, bool JACOBI, bool BDINV>
 __device__ __forceinline__ void op_lincomb3(const Op &o, double *chunk, Smem &sm)
 {
     const int sub = (threadIdx.x % LPR) * PW;
     const double *__restrict__ q = tp(o.x, chunk) + sub;
     const double *__restrict__ v1 = tp(o.r, chunk) + sub;
     double *__restrict__ v0 = tp(o.y, chunk) + sub;
+    double *__restrict__ z = JACOBI ? tp(o.d, chunk) + sub : nullptr;
+    const double *__restrict__ dinvb = (JACOBI && BDINV) ? tp(o.w, chunk) + sub : nullptr;
     const D2 a = make_double2(sm.st[ST_CQ][sub], sm.st[ST_CQ][sub + 1]);
     const D2 b = make_double2(sm.st[ST_CV1][sub], sm.st[ST_CV1][sub + 1]);
     const D2 c = make_double2(sm.st[ST_CV0][sub], sm.st[ST_CV0][sub + 1]);
     const bool anyc = c.x != 0.0 || c.y != 0.0;
+    const int nj = o.a0;
+    const double cb = o.cb;
+    D2 acc = make_double2(0.0, 0.0);
 #pragma unroll 4
     for (int row = threadIdx.x / LPR; row < o.n; row += NTt / LPR) {
         const size_t ro = (size_t)row * TW;
         const D2 qv = ld2c(q + ro), vv = ld2c(v1 + ro);
         D2 cv = make_double2(0.0, 0.0);
         if (anyc) cv = ld2c(v0 + ro);
-        st2(v0 + ro, make_double2(fma(a.x, qv.x, fma(b.x, vv.x, c.x * cv.x)), fma(a.y, qv.y, fma(b.y, vv.y, c.y * cv.y))));
+        const D2 vn = make_double2(fma(a.x, qv.x, fma(b.x, vv.x, c.x * cv.x)), fma(a.y, qv.y, fma(b.y, vv.y, c.y * cv.y)));
+        st2(v0 + ro, vn);
+        if (JACOBI && row < nj) {
+            D2 di;
+            if (BDINV) di = ld2c(dinvb + ro);
+            else { const double t = __ldg(o.fixed + row); di = make_double2(t, t); }
+            const D2 zn = make_double2(cb * di.x * vn.x, cb * di.y * vn.y);
+            st2(z + ro, zn);
+            acc.x = fma(zn.x, vn.x, acc.x);
+            acc.y = fma(zn.y, vn.y, acc.y);
+        }
     }
+    if (JACOBI) block_dot<NTt>(acc, sm, o.slot, false);
 }
 
 template <int NTt>
@@ -500,7 +519,10 @@ __global__ void __launch_bounds__(NTt, MINB) k_run_program(const ProgParams P)
         case OP_CHEB_FIRST:
             if (flags & F_BDINV) op_cheb_first<NTt, true>(o, chunk, sm); else op_cheb_first<NTt, false>(o, chunk, sm);
             break;
-        case OP_LINCOMB3: op_lincomb3<NTt>(o, chunk, sm); break;
+        case OP_LINCOMB3:
+            if (flags & F_DOT) { if (flags & F_BDINV) op_lincomb3<NTt, true, true>(o, chunk, sm); else op_lincomb3<NTt, true, false>(o, chunk, sm); }
+            else op_lincomb3<NTt, false, false>(o, chunk, sm);
+            break;
         case OP_SOL_UPDATE: op_sol_update<NTt>(o, chunk, sm); break;
         case OP_SETUP_SPMM: op_setup_spmm<NTt>(o, chunk); break;
         case OP_FILL: {
