@@ -296,3 +296,64 @@ def test_managers_on_gpu_match_oracle_backend(tmp_path):
         assert abs(sl.eQ - so.eQ) <= MOMENT_TOL * abs(so.eQ) and abs(sl.varQ - so.varQ) <= MOMENT_TOL * abs(so.varQ)
     finally:
         c.close()
+
+
+def _custom_problem(n, lengths, nlevels, bc, ess_value=0.0, corlen=0.2):
+    """Anisotropic box, other boundary conditions, optionally non-zero essential data."""
+    from parelagmc_b200 import hierarchy as H
+    L = H.build_box_hierarchy(n, lengths, nlevels)
+    SL = H.build_sampler_levels(L)
+    DL = H.build_darcy_levels(L, **bc)
+    if ess_value != 0.0:
+        # prescribed outward flux ess_value per essential face (non-zero ess_data exercises the right-hand-side
+        # fix-up of BlockMatrix::EliminateRowCol, /root/reference/src/DarcySolver.cpp:498)
+        for lv, d in zip(L, DL):
+            on_ess = np.asarray(bc["ess_attr"])[lv.bdr_attr - 1] != 0
+            d.ess_data[lv.bdr_face[on_ess]] = ess_value * lv.bdr_sign[on_ess]
+    return dict(levels=L, sampler=SL, darcy=DL, alpha=H.spde_alpha(corlen),
+                g=H.matern_scaling_coefficient(corlen, len(n)), nlevels=nlevels)
+
+
+@pytest.mark.parametrize("case", ["spe10_bc", "anisotropic", "ess_data"])
+def test_other_problems_match_oracle(case):
+    from parelagmc_b200 import hierarchy as H
+    if case == "spe10_bc":
+        p = _custom_problem([8, 8, 8], [2.0, 2.0, 2.0], 3, H.SPE10_BC)
+    elif case == "anisotropic":
+        p = _custom_problem([8, 12, 4], [2.0, 1.0, 0.5], 2, H.MLMC_DEFAULT_BC)
+    else:
+        p = _custom_problem([8, 8, 8], [2.0, 2.0, 2.0], 2, H.MLMC_DEFAULT_BC, ess_value=0.01)
+    c = make_context(p)
+    o = make_oracle(p)
+    try:
+        rng = np.random.default_rng(5)
+        for lev in range(p["nlevels"]):
+            d = p["darcy"][lev]
+            k = np.exp(0.7 * rng.standard_normal((5, d.Ne)))
+            Q, C, sol, it = c.darcy_solve_batch(lev, k, want_sol=True)
+            for j in range(5):
+                q, _, s, _ = o.darcy_solve(lev, k[j], want_sol=True)
+                assert rel_l2(sol[j], s) < FIELD_TOL, (case, lev, j, rel_l2(sol[j], s))
+                assert abs(Q[j] - q) <= 1e-8 * max(abs(q), 1e-3)
+        lev = 0
+        sums, rows, _ = c.mlmc_level_batch(lev, 6, 17, want_rows=True)
+        osums, orows, _ = o.mlmc_level(lev, 6, 17, nthreads=4)
+        assert np.allclose(rows[:, :3], orows[:, :3], rtol=1e-7, atol=1e-9)
+    finally:
+        c.close()
+
+
+def test_clone_runs_levels_concurrently_with_identical_results(ctx, prob):
+    """pmc_clone: same hierarchy and stream of random numbers, own CUDA stream; results are bitwise those of the
+    original handle, also when the level batches run from concurrent host threads."""
+    from concurrent.futures import ThreadPoolExecutor
+    c2 = ctx.clone()
+    try:
+        ref = [ctx.mlmc_level_batch(lev, 20, 321, want_rows=True)[1] for lev in (1, 0)]
+        with ThreadPoolExecutor(max_workers=2) as pool:
+            f1 = pool.submit(ctx.mlmc_level_batch, 1, 20, 321, None, True)
+            f0 = pool.submit(c2.mlmc_level_batch, 0, 20, 321, None, True)
+            got = [f1.result()[1], f0.result()[1]]
+        assert np.array_equal(ref[0], got[0]) and np.array_equal(ref[1], got[1])
+    finally:
+        c2.close()
