@@ -107,6 +107,15 @@ int pmc_upload_darcy_level(pmc_handle h, int level, int Ne, int Nf,
                            const int *ess_u, const double *ess_data, const double *rhs, const double *obs,
                            int Pp_cols, const int *Pp_rowptr, const int *Pp_col, const double *Pp_val);
 
+/* Enlarged-domain samplers: the SPDE is solved on an enlarged mesh and the field is brought to the forward problem's
+ * mesh before exp, s = row_scale .* (T field).  EmbeddedPDESampler (src/EmbeddedPDESampler.cpp:63-89, applied at
+ * :426-435): T = meshP[level] (0/1 selection), row_scale = NULL.  L2ProjectionPDESampler
+ * (src/L2ProjectionPDESampler.cpp:488-514, applied at :595-611): T = Gt[level], row_scale = 1/diag(W_orig).
+ * T is n_out x Ne(level) in CSR; after this call the level's sampler outputs have n_out entries (= the Darcy level's
+ * Ne) while noise vectors and embed_s keep the enlarged size. */
+int pmc_upload_field_transfer(pmc_handle h, int level, int n_out, const int *T_rowptr, const int *T_col,
+                              const double *T_val, const double *row_scale);
+
 /* A second handle on the same device with the same uploaded levels, options, tolerances and random stream but its own
  * CUDA stream and workspace.  The level loops of one InitRun are independent of one another, so a manager keeps one
  * handle per level and issues the level batches from one host thread each: their kernels then share the GPU (a single

@@ -70,6 +70,7 @@ def lib():
                                            _dp, C.c_int, _ip, _ip, _dp, C.c_double, C.c_double, C.c_int]
         L.po_set_darcy_level.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, _ip, _ip, _dp, _ip, _ip, _dp,
                                          _ip, _dp, _dp, _dp, C.c_int, _ip, _ip, _dp]
+        L.po_set_field_transfer.argtypes = [C.c_void_p, C.c_int, C.c_int, _ip, _ip, _dp, _dp]
         L.po_sampler_eval.argtypes = [C.c_void_p, C.c_int, C.c_int, _dp, _dp, _dp, C.c_int, C.c_int, _ip]
         L.po_darcy_solve.argtypes = [C.c_void_p, C.c_int, _dp, _dp, _dp, _dp, _ip]
         L.po_mlmc_level.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_double, C.c_double,
@@ -141,6 +142,13 @@ class OracleProblem:
                                         0 if s.P is None else s.P.shape[1], pr, pc, pv, alpha, g,
                                         1 if lognormal else 0)
             assert rc == 0
+            if getattr(s, "T", None) is not None:
+                tr, tc, tv, k4 = _csr_args(s.T)
+                ts = None if s.Tscale is None else np.ascontiguousarray(s.Tscale, dtype=np.float64)
+                assert L.po_set_field_transfer(self.h, l, s.T.shape[0], tr, tc, tv, _d(ts)) == 0
+        self.Nout = [s.T.shape[0] if getattr(s, "T", None) is not None else s.Ne for s in sampler_levels]
+        self.dNe = [d.Ne for d in (darcy_levels or [])]
+        self.dNf = [d.Nf for d in (darcy_levels or [])]
         for l, d in enumerate(darcy_levels or []):
             br, bc, bv, k2 = _csr_args(d.B)
             pr, pc, pv, k3 = _csr_args(d.P_p)
@@ -173,7 +181,7 @@ class OracleProblem:
         if xi_level is None:
             xi_level = self.Ne.index(len(xi))
         xi = np.ascontiguousarray(xi, dtype=np.float64)
-        s = np.empty(self.Ne[level])
+        s = np.empty(self.Nout[level])
         emb = np.zeros(max(self.Ne[level], self.Ne[init_level] if embed_s is not None else 0))
         if embed_s is not None:
             emb[:len(embed_s)] = embed_s
@@ -189,7 +197,7 @@ class OracleProblem:
         q = C.c_double(0)
         c = C.c_double(0)
         it = C.c_int(0)
-        sol = np.empty(self.Ne[level] + self.Nf[level]) if want_sol else None
+        sol = np.empty(self.dNe[level] + self.dNf[level]) if want_sol else None
         rc = lib().po_darcy_solve(self.h, level, _d(k), C.byref(q), C.byref(c), _d(sol), C.byref(it))
         assert rc == 0, rc
         return q.value, c.value, sol, it.value

@@ -595,6 +595,11 @@ typedef struct {
     double alpha, g;
     mg_t mg;
     int mg_ready;
+    /* optional field transfer to the forward problem's mesh: s = tscale .* (T field)
+     * (EmbeddedPDESampler.cpp:426-435: T = meshP, no scale; L2ProjectionPDESampler.cpp:595-611: T = G^T, 1/diag(W)) */
+    int hasT, n_out;
+    csr_t T;
+    double *tscale;
 } sampler_level_t;
 
 typedef struct {
@@ -640,6 +645,7 @@ void po_destroy(po_problem *p)
             if (s->hasP) { csr_free(&s->P); csr_free(&s->Pt); }
             free(s->Wdiag); free(s->w_sqrt); free(s->negaW);
             if (s->mg_ready) mg_free(&s->mg);
+            if (s->hasT) { csr_free(&s->T); free(s->tscale); }
         }
         darcy_level_t *d = &p->d[l];
         if (d->set) {
@@ -691,6 +697,19 @@ int po_set_sampler_level(po_problem *p, int level, int Ne, int Nf,
         s->Pt = csr_transpose(&s->P);
     }
     s->set = 1;
+    return 0;
+}
+
+int po_set_field_transfer(po_problem *p, int level, int n_out, const int *T_rowptr, const int *T_col,
+                          const double *T_val, const double *row_scale)
+{
+    if (level < 0 || level >= p->nlevels || !p->s[level].set) return -1;
+    sampler_level_t *s = &p->s[level];
+    s->T = csr_copy_in(n_out, s->Ne, T_rowptr, T_col, T_val);
+    s->tscale = (double *)malloc(sizeof(double) * (size_t)n_out);
+    for (int i = 0; i < n_out; ++i) s->tscale[i] = row_scale ? row_scale[i] : 1.0;
+    s->n_out = n_out;
+    s->hasT = 1;
     return 0;
 }
 
@@ -855,7 +874,16 @@ int po_sampler_eval(po_problem *p, int level, int xi_level, const double *xi, do
     for (int m = 0; m < mgl.nlev; ++m) { free(mgl.r[m]); free(mgl.x[m]); free(mgl.t[m]); }
     if (iters) *iters = it;
     if (embed_s) memcpy(embed_s, x + Nf, sizeof(double) * (size_t)Ne); /* :527 */
-    for (int i = 0; i < Ne; ++i) s_out[i] = sl->lognormal ? exp(x[Nf + i]) : x[Nf + i]; /* :529-533 */
+    if (sl->hasT) { /* project to the original mesh, then exp (EmbeddedPDESampler.cpp:426-435) */
+        double *t = (double *)malloc(sizeof(double) * (size_t)sl->n_out);
+        csr_mult(&sl->T, x + Nf, t);
+        for (int i = 0; i < sl->n_out; ++i) {
+            const double v = t[i] * sl->tscale[i];
+            s_out[i] = sl->lognormal ? exp(v) : v;
+        }
+        free(t);
+    } else
+        for (int i = 0; i < Ne; ++i) s_out[i] = sl->lognormal ? exp(x[Nf + i]) : x[Nf + i]; /* :529-533 */
     free(rhs_s); free(b); free(x);
     return 0;
 }
@@ -935,15 +963,15 @@ int po_mlmc_level(po_problem *p, int level, int nlevels, int nsamples, uint64_t 
         double q = 0, c = 0, qc = 0, cc = 0;
         int it;
         if (coarsest) { /* MLMC_Manager.cpp:113-136 */
-            double *sp_ = (double *)malloc(sizeof(double) * (size_t)Ne);
+            double *sp_ = (double *)malloc(sizeof(double) * (size_t)(Ne + p->d[level].Ne));
             po_sampler_eval(p, level, level, xi, sp_, NULL, 0, -1, &it); its += it;
             po_darcy_solve(p, level, sp_, &q, &c, NULL, &it); its += it;
             free(sp_);
             loc[4 * j + 0] = q; loc[4 * j + 1] = q; loc[4 * j + 2] = 0.0; loc[4 * j + 3] = c;
         } else { /* :144-173 */
             int Nec = p->s[level + 1].Ne;
-            double *spc = (double *)malloc(sizeof(double) * (size_t)Nec);
-            double *spf = (double *)malloc(sizeof(double) * (size_t)Ne);
+            double *spc = (double *)malloc(sizeof(double) * (size_t)(Nec + p->d[level + 1].Ne));
+            double *spf = (double *)malloc(sizeof(double) * (size_t)(Ne + p->d[level].Ne));
             double *init = (double *)malloc(sizeof(double) * (size_t)(Ne > Nec ? Ne : Nec));
             po_sampler_eval(p, level + 1, level, xi, spc, init, 0, 0, &it); its += it;
             po_darcy_solve(p, level + 1, spc, &qc, &cc, NULL, &it); its += it;

@@ -66,6 +66,13 @@ int po_set_sampler_level(po_problem *p, int level, int Ne, int Nf,
                          int P_cols, const int *P_rowptr, const int *P_col, const double *P_val,
                          double alpha, double matern_coeff, int lognormal);
 
+/* Optional transfer of the sampled field to the forward problem's mesh, applied before exp:
+ * s = row_scale .* (T field).  EmbeddedPDESampler (/root/reference/src/EmbeddedPDESampler.cpp:426-435): T = meshP (0/1
+ * selection), row_scale = NULL.  L2ProjectionPDESampler (/root/reference/src/L2ProjectionPDESampler.cpp:595-611):
+ * T = G^T, row_scale = 1/diag(W_orig).  T is n_out x Ne(level). */
+int po_set_field_transfer(po_problem *p, int level, int n_out, const int *T_rowptr, const int *T_col,
+                          const double *T_val, const double *row_scale);
+
 /* DarcySolver level data (/root/reference/src/DarcySolver.cpp:60-414). B un-eliminated. */
 int po_set_darcy_level(po_problem *p, int level, int Ne, int Nf,
                        const int *elem_ptr, const int *elem_dofs, const double *elem_mat,

@@ -22,7 +22,7 @@ K_CLASSES = ["saddle_apply", "lanczos_update", "solution_update", "mass_smooth",
 # every symbol include/pmc_b200.h declares (checked by tests/test_abi.py against the header text)
 SYMBOLS = [
     "pmc_create", "pmc_destroy", "pmc_last_error", "pmc_host_alloc", "pmc_host_free", "pmc_set_stream", "pmc_synchronize", "pmc_set_tolerances",
-    "pmc_set_preconditioner", "pmc_set_option", "pmc_set_batch", "pmc_upload_sampler_level", "pmc_upload_darcy_level", "pmc_clone", "pmc_prepare",
+    "pmc_set_preconditioner", "pmc_set_option", "pmc_set_batch", "pmc_upload_sampler_level", "pmc_upload_darcy_level", "pmc_upload_field_transfer", "pmc_clone", "pmc_prepare",
     "pmc_rng_init", "pmc_rng_fill_int", "pmc_rng_fill", "pmc_sampler_sample_batch", "pmc_sampler_eval_batch",
     "pmc_darcy_solve_batch", "pmc_darcy_apply_batch", "pmc_mlmc_level_batch", "pmc_mc_level_batch", "pmc_profile",
     "pmc_reset_stats", "pmc_kernel_stats",
@@ -88,6 +88,7 @@ def load():
                                            C.c_int, _ip, _ip, _dp, C.c_double, C.c_double, C.c_int]
     L.pmc_upload_darcy_level.argtypes = [vp, C.c_int, C.c_int, C.c_int, _ip, _ip, _dp, _ip, _ip, _dp, _ip, _dp,
                                          _dp, _dp, C.c_int, _ip, _ip, _dp]
+    L.pmc_upload_field_transfer.argtypes = [vp, C.c_int, C.c_int, _ip, _ip, _dp, _dp]
     L.pmc_clone.argtypes = [vp, C.POINTER(vp)]
     L.pmc_prepare.argtypes = [vp]
     L.pmc_rng_init.argtypes = [vp, C.c_double, C.c_double, C.c_int, C.c_int]
@@ -165,8 +166,11 @@ class Context:
                 raise PmcError(rc, (self._L.pmc_last_error(None) or b"").decode())
         self.nlevels = nlevels
         self.device = device
-        self.Ne = [0] * nlevels
+        self.Ne = [0] * nlevels      # sampler sizes (noise / Gaussian field)
         self.Nf = [0] * nlevels
+        self.Nout = [0] * nlevels    # size of the sampler's output field (= Darcy Ne)
+        self.dNe = [0] * nlevels     # Darcy sizes
+        self.dNf = [0] * nlevels
 
     def close(self):
         if getattr(self, "_h", None):
@@ -214,6 +218,12 @@ class Context:
                                                   0 if s.P is None else s.P.shape[1], pr, pc, pv, alpha, g,
                                                   1 if lognormal else 0))
         self.Ne[level], self.Nf[level] = s.Ne, s.Nf
+        self.Nout[level] = s.Ne
+        if getattr(s, "T", None) is not None:
+            tr, tc, tv, k4 = _csr(s.T)
+            ts = None if s.Tscale is None else np.ascontiguousarray(s.Tscale, dtype=np.float64)
+            self._ck(self._L.pmc_upload_field_transfer(self._h, level, s.T.shape[0], tr, tc, tv, _d(ts)))
+            self.Nout[level] = s.T.shape[0]
 
     def upload_darcy_level(self, level: int, d):
         """`d`: a `hierarchy.DarcyLevel`-shaped object."""
@@ -229,14 +239,16 @@ class Context:
         self._ck(self._L.pmc_upload_darcy_level(self._h, level, d.Ne, d.Nf, _i(ep), _i(ed), _d(em), br, bc, bv,
                                                 _i(eu), _d(ev), _d(rh), _d(ob),
                                                 0 if d.P_p is None else d.P_p.shape[1], pr, pc, pv))
-        self.Ne[level], self.Nf[level] = d.Ne, d.Nf
+        self.dNe[level], self.dNf[level] = d.Ne, d.Nf
+        if self.Ne[level] == 0:
+            self.Ne[level], self.Nf[level], self.Nout[level] = d.Ne, d.Nf, d.Ne
 
     def clone(self) -> "Context":
         """`pmc_clone`: same hierarchy, options and stream of random numbers; own CUDA stream and workspace."""
         h = C.c_void_p()
         self._ck(self._L.pmc_clone(self._h, C.byref(h)))
         c = Context(self.nlevels, self.device, _handle=h)
-        c.Ne, c.Nf = list(self.Ne), list(self.Nf)
+        c.Ne, c.Nf, c.Nout, c.dNe, c.dNf = list(self.Ne), list(self.Nf), list(self.Nout), list(self.dNe), list(self.dNf)
         return c
 
     def prepare(self):
@@ -278,9 +290,9 @@ class Context:
         if init_s is not None:
             init_s = np.ascontiguousarray(init_s, dtype=np.float64).reshape(n, -1)
             assert init_s.shape[1] == self.Ne[init_level]
-        s = np.empty((n, self.Ne[level])) if out_s is None else out_s
+        s = np.empty((n, self.Nout[level])) if out_s is None else out_s
         emb = (np.empty((n, self.Ne[level])) if out_embed is None else out_embed) if want_embed else None
-        assert s.shape == (n, self.Ne[level]) and s.flags.c_contiguous
+        assert s.shape == (n, self.Nout[level]) and s.flags.c_contiguous
         it = np.zeros(n, dtype=np.int32)
         self._ck(self._L.pmc_sampler_eval_batch(self._h, level, xi_level, n, _d(xi), _d(init_s), init_level,
                                                 use_init, _d(s), _d(emb), _i(it)))
@@ -293,16 +305,16 @@ class Context:
         if k.ndim == 1:
             k = k[None, :]
         n = k.shape[0]
-        assert k.shape[1] == self.Ne[level]
+        assert k.shape[1] == self.dNe[level]
         Q = np.empty(n)
         Cc = np.empty(n)
-        sol = np.empty((n, self.Ne[level] + self.Nf[level])) if want_sol else None
+        sol = np.empty((n, self.dNe[level] + self.dNf[level])) if want_sol else None
         it = np.zeros(n, dtype=np.int32)
         self._ck(self._L.pmc_darcy_solve_batch(self._h, level, n, _d(k), _d(Q), _d(Cc), _d(sol), _i(it)))
         return Q, Cc, sol, it
 
     def darcy_apply_batch(self, level: int, k: np.ndarray, x: np.ndarray) -> np.ndarray:
-        k = np.ascontiguousarray(k, dtype=np.float64).reshape(-1, self.Ne[level])
+        k = np.ascontiguousarray(k, dtype=np.float64).reshape(-1, self.dNe[level])
         x = np.ascontiguousarray(x, dtype=np.float64).reshape(k.shape[0], -1)
         y = np.empty_like(x)
         self._ck(self._L.pmc_darcy_apply_batch(self._h, level, k.shape[0], _d(k), _d(x), _d(y)))

@@ -129,6 +129,12 @@ struct SamplerLevel {
     double *w_sqrt = nullptr;
     DevCsr dP, dPt;
     SaddleSys sys;
+    // optional transfer of the sampled field to the forward problem's mesh (row scale folded into the values)
+    bool hasT = false;
+    int n_out = 0;
+    HCsr T;
+    DevCsr dT;
+    int out_size() const { return hasT ? n_out : Ne; }
 };
 
 struct DarcyLevel {
@@ -1378,6 +1384,29 @@ int pmc_upload_darcy_level(pmc_handle c, int level, int Ne, int Nf, const int *e
     return PMC_OK;
 }
 
+int pmc_upload_field_transfer(pmc_handle c, int level, int n_out, const int *T_rowptr, const int *T_col, const double *T_val,
+                              const double *row_scale)
+{
+    if (!c) return PMC_ERR_ARG;
+    if (level < 0 || level >= c->nlevels || n_out < 1 || !T_rowptr || !T_col || !T_val)
+        return fail(c, PMC_ERR_ARG, "pmc_upload_field_transfer: bad arguments");
+    SamplerLevel &L = c->s[level];
+    if (!L.set) return fail(c, PMC_ERR_STATE, "pmc_upload_field_transfer: sampler level %d not uploaded", level);
+    if (L.hasT) return fail(c, PMC_ERR_STATE, "field transfer of level %d uploaded twice", level);
+    CK(cudaSetDevice(c->device));
+    L.T = csr_copy(n_out, L.Ne, T_rowptr, T_col, T_val);
+    for (int i = 0; i < n_out; ++i)
+        for (int p = L.T.rowptr[i]; p < L.T.rowptr[i + 1]; ++p) {
+            if (L.T.col[p] < 0 || L.T.col[p] >= L.Ne) return fail(c, PMC_ERR_ARG, "field transfer: column out of range");
+            if (row_scale) L.T.val[p] *= row_scale[i];
+        }
+    int rc = upload_csr(c, L.T, L.dT);
+    if (rc) return rc;
+    L.n_out = n_out;
+    L.hasT = true;
+    return PMC_OK;
+}
+
 int pmc_host_alloc(size_t bytes, void **out)
 {
     if (!out) return PMC_ERR_ARG;
@@ -1412,6 +1441,8 @@ int pmc_clone(pmc_handle src, pmc_handle *out)
                                           S.B.col.data(), S.B.val.data(), S.Wdiag.data(), S.hasP ? S.P.cols : 0,
                                           S.hasP ? S.P.rowptr.data() : nullptr, S.hasP ? S.P.col.data() : nullptr,
                                           S.hasP ? S.P.val.data() : nullptr, S.alpha, S.g, S.lognormal);
+        if (!rc && S.set && S.hasT)
+            rc = pmc_upload_field_transfer(c, l, S.n_out, S.T.rowptr.data(), S.T.col.data(), S.T.val.data(), nullptr);
         const DarcyLevel &D = src->d[l];
         if (!rc && D.set)
             rc = pmc_upload_darcy_level(c, l, D.Ne, D.Nf, D.elem_ptr.data(), D.elem_dofs.data(), D.elem_mat.data(),
@@ -1550,8 +1581,18 @@ int pmc_sampler_eval_batch(pmc_handle c, int level, int xi_level, int nsamples, 
     Off x0 = -1;
     if (warm) x0 = emit_prolong(pg, c, init_level, level, t1, bufC);
     emit_sampler_solve(pg, c, level, rhs, x0, ws, true);
+    const int Nout = L.out_size();
+    Off fout = ws.x + (Off)sys.Nf * TW;  // rows [Nf, N) of the solution: the Gaussian field
+    if (L.hasT) {
+        // project to the forward problem's mesh before exp (/root/reference/src/EmbeddedPDESampler.cpp:426-435,
+        // src/L2ProjectionPDESampler.cpp:595-611)
+        const Off buf = ar.alloc(Nout);
+        emit_spmm(pg, KC_TRANSFER, EP_AX, L.dT, VNULL, vr(fout), vr(buf), VNULL, VNULL, nullptr, VNULL, 0, 0, -1, false, false,
+                  (double)Ne + Nout);
+        fout = buf;
+    }
     const Off chunk = ar.peak;
-    const size_t per_sample = (size_t)chunk * 8 / TW + (size_t)nmax * 8 + 64;
+    const size_t per_sample = (size_t)chunk * 8 / TW + (size_t)std::max(nmax, Nout) * 8 + 64;
     const int B = pick_batch(c, per_sample, nsamples);
     if ((rc = ensure_arena(c, per_sample * (size_t)pad_ld(B) + (1 << 16)))) return rc;
     std::vector<double> itbuf;
@@ -1564,7 +1605,7 @@ int pmc_sampler_eval_batch(pmc_handle c, int level, int xi_level, int nsamples, 
         if (warm && (rc = upload_rows(c, init_s + (size_t)s0 * Nei, ns, Nei, stage, t1, chunk, 0, 0.0, nullptr))) return rc;
         if ((rc = run_program(c, pg, ns, chunk, sys.N))) return rc;
         const Off field = ws.x + (Off)sys.Nf * TW;  // rows [Nf, N) of the solution
-        if ((rc = download_rows(c, field, chunk, ns, Ne, stage, s_out + (size_t)s0 * Ne, L.lognormal != 0))) return rc;
+        if ((rc = download_rows(c, fout, chunk, ns, Nout, stage, s_out + (size_t)s0 * Nout, L.lognormal != 0))) return rc;
         if (embed_s_out && (rc = download_rows(c, field, chunk, ns, Ne, stage, embed_s_out + (size_t)s0 * Ne, false))) return rc;
         if (iters_out) {
             itbuf.resize(ns);
@@ -1671,12 +1712,16 @@ static int level_batch(Ctx *c, int level, int nlevels, int nsamples, uint64_t po
     SamplerLevel &SF = c->s[level];
     DarcyLevel &DF = c->d[level];
     const int Ne = SF.Ne, Nec = coarsest ? 0 : c->s[level + 1].Ne;
+    const int Nk = SF.out_size(), Nkc = coarsest ? 0 : c->s[level + 1].out_size();  // size of the coefficient vectors
+    if (Nk != DF.Ne || (!coarsest && Nkc != c->d[level + 1].Ne))
+        return fail(c, PMC_ERR_STATE, "sampler output size and Darcy coefficient size differ on level %d (missing field transfer?)", level);
     const double cost = (double)DF.sys.N + (coarsest ? 0.0 : (double)c->d[level + 1].sys.N);
     // ---- record the program of the level (the same for every batch except the stream position) ----
     Rows ar;
     const Off rhs_f = ar.alloc(Ne);
     const Off rhs_c = coarsest ? -1 : ar.alloc(Nec), s_c = coarsest ? -1 : ar.alloc(Nec), x0_f = coarsest ? -1 : ar.alloc(Ne);
-    const Off k_ext = ar.alloc(Ne + 1), Qf = ar.alloc(1), Qc = ar.alloc(1);
+    const Off k_ext = ar.alloc(std::max(Nk, Nkc) + 1), Qf = ar.alloc(1), Qc = ar.alloc(1);
+    const Off tbuf = (SF.hasT || (!coarsest && c->s[level + 1].hasT)) ? ar.alloc(std::max(Nk, Nkc)) : -1;
     const Off mark = ar.top;
     Program pg;
     // Sample(level, xi) fused with rhs_s = -g W^{1/2} xi  (/root/reference/src/PDESampler.cpp:336-340, :352-358)
@@ -1699,9 +1744,15 @@ static int level_batch(Ctx *c, int level, int nlevels, int nsamples, uint64_t po
             carve_solve(ar, SC.sys, ws);
             emit_sampler_solve(pg, c, level + 1, rhs_c, -1, ws, false);
             emit_copy(pg, vr(ws.x, SC.sys.N, SC.sys.Nf), vr(s_c, Nec), Nec);
-            if (SC.lognormal) { Op &o = pg.add(OP_MAP_EXP, KC_MISC, Nec, 2.0 * Nec); o.x = vr(s_c, Nec); o.y = vr(k_ext, Nec + 1); }
-            else emit_copy(pg, vr(s_c, Nec), vr(k_ext, Nec + 1), Nec);
-            emit_fill(pg, vr(k_ext, Nec + 1, Nec), 1, 1.0);
+            Off fsrc = s_c;
+            if (SC.hasT) {  // to the forward problem's mesh, before exp
+                emit_spmm(pg, KC_TRANSFER, EP_AX, SC.dT, VNULL, vr(s_c), vr(tbuf), VNULL, VNULL, nullptr, VNULL, 0, 0, -1, false,
+                          false, (double)Nec + Nkc);
+                fsrc = tbuf;
+            }
+            if (SC.lognormal) { Op &o = pg.add(OP_MAP_EXP, KC_MISC, Nkc, 2.0 * Nkc); o.x = vr(fsrc); o.y = vr(k_ext); }
+            else emit_copy(pg, vr(fsrc), vr(k_ext), Nkc);
+            emit_fill(pg, vr(k_ext, 0, Nkc), 1, 1.0);
         }
         {
             ar.top = mark;
@@ -1718,9 +1769,15 @@ static int level_batch(Ctx *c, int level, int nlevels, int nsamples, uint64_t po
         SolveWs ws;
         carve_solve(ar, SF.sys, ws);
         emit_sampler_solve(pg, c, level, rhs_f, x0_f, ws, false);
-        if (SF.lognormal) { Op &o = pg.add(OP_MAP_EXP, KC_MISC, Ne, 2.0 * Ne); o.x = vr(ws.x, SF.sys.N, SF.sys.Nf); o.y = vr(k_ext, Ne + 1); }
-        else emit_copy(pg, vr(ws.x, SF.sys.N, SF.sys.Nf), vr(k_ext, Ne + 1), Ne);
-        emit_fill(pg, vr(k_ext, Ne + 1, Ne), 1, 1.0);
+        VecRef fsrc = vr(ws.x, SF.sys.N, SF.sys.Nf);
+        if (SF.hasT) {
+            emit_spmm(pg, KC_TRANSFER, EP_AX, SF.dT, VNULL, fsrc, vr(tbuf), VNULL, VNULL, nullptr, VNULL, 0, 0, -1, false, false,
+                      (double)Ne + Nk);
+            fsrc = vr(tbuf);
+        }
+        if (SF.lognormal) { Op &o = pg.add(OP_MAP_EXP, KC_MISC, Nk, 2.0 * Nk); o.x = fsrc; o.y = vr(k_ext); }
+        else emit_copy(pg, fsrc, vr(k_ext), Nk);
+        emit_fill(pg, vr(k_ext, 0, Nk), 1, 1.0);
     }
     {
         ar.top = mark;

@@ -337,6 +337,10 @@ class SamplerLevel:
     ess_u: np.ndarray       # int32 0/1 mask over RT dofs
     P: Optional[sp.csr_matrix]  # Ne x Ne_coarse  (Ps[i], `PDESampler.cpp:189-193`)
     nnz: int
+    # optional transfer of the sampled field to the forward problem's mesh (applied before exp):
+    # s = Tscale .* (T field);  T is n_out x Ne
+    T: Optional[sp.csr_matrix] = None
+    Tscale: Optional[np.ndarray] = None
 
 
 def _eliminate_rowcol(M: sp.csr_matrix, ess: np.ndarray) -> sp.csr_matrix:
@@ -427,6 +431,49 @@ def build_darcy_levels(levels: List[LevelData], ess_attr: Sequence[int], obs_att
     return out
 
 
+# --------------------------------------------------------------------------------------
+# enlarged-domain samplers
+# --------------------------------------------------------------------------------------
+def embedded_selection(orig: List[LevelData], embed: List[LevelData], pad_cells: int) -> List[sp.csr_matrix]:
+    """meshP of `EmbeddedPDESampler` (`/root/reference/src/EmbeddedPDESampler.cpp:63-89`, applied at `:426-435`) for a
+    MATCHING enlarged box: the original n^d box sits `pad_cells` fine cells inside the enlarged one on every side; on
+    level l the offset is pad_cells / 2^l.  Row e of level l selects the embedded element that coincides with e."""
+    out = []
+    for l, (lo, le) in enumerate(zip(orig, embed)):
+        pad = pad_cells >> l
+        assert pad << l == pad_cells, "padding must survive the coarsening"
+        idx = lo.grid.elem_grid()
+        j = le.grid.elem_index([i + pad for i in idx])
+        out.append(_csr(sp.coo_matrix((np.ones(lo.Ne), (np.arange(lo.Ne), j)), shape=(lo.Ne, le.Ne))))
+    return out
+
+
+def _overlap_1d(a: np.ndarray, b: np.ndarray) -> sp.csr_matrix:
+    """|[a_i, a_i+1] n [b_j, b_j+1]| as a sparse (len(a)-1) x (len(b)-1) matrix."""
+    lo = np.maximum(a[:-1, None], b[None, :-1])
+    hi = np.minimum(a[1:, None], b[None, 1:])
+    return sp.csr_matrix(np.maximum(hi - lo, 0.0))
+
+
+def l2_projection_transfers(orig: List[LevelData], embed: List[LevelData]):
+    """Mortar matrices of `L2ProjectionPDESampler` for two (possibly non-matching) box hierarchies: on level 0
+    Gt[i, j] = |e_i n ebar_j| (piecewise constants; what ParMortarAssembler + L2MortarIntegrator assemble,
+    `/root/reference/src/L2ProjectionPDESampler.cpp:488-505`), on coarser levels the Galerkin product
+    Gt_{l+1} = P_orig^T Gt_l P_embed (`:507-514`); the apply is s = W_orig^-1 Gt s_bar (`:595-611`).
+    Returns [(Gt_l, 1/diag W_orig_l)]."""
+    go, ge = orig[0].grid, embed[0].grid
+    G = None
+    for a in range(go.dim):          # element numbering is x fastest => kron(last axis, ..., first axis)
+        O = _overlap_1d(go.nodes[a], ge.nodes[a])
+        G = O if G is None else sp.kron(O, G, format="csr")
+    out = []
+    for l in range(len(orig)):
+        out.append((_csr(G), 1.0 / orig[l].Wdiag))
+        if l + 1 < len(orig):
+            G = (orig[l].P_s.T @ G @ embed[l].P_s).tocsr()
+    return out
+
+
 # The reference's default MLMC problem (`examples/example_helpers/CreateMLMCParameterList.hpp:27-41`)
 MLMC_DEFAULT_BC = dict(ess_attr=[0, 1, 1, 1, 1, 0], obs_attr=[1, 0, 0, 0, 0, 0], inflow_attr=[0, 0, 0, 0, 0, 1])
 # SPE10 XML (`examples/SPE10/spe10_3D_parameters.xml:45-49`)
@@ -438,7 +485,7 @@ SPE10_BC = dict(ess_attr=[1, 0, 1, 0, 1, 1], obs_attr=[0, 1, 0, 0, 0, 0], inflow
 # --------------------------------------------------------------------------------------
 def dump_problem(path: str, sampler_levels: List[SamplerLevel], darcy_levels: List[DarcyLevel], dim: int,
                  corlen: float) -> None:
-    """Write the host-once hierarchy data in the "PMCH1" layout of `HierarchyData::Load`."""
+    """Write the host-once hierarchy data in the "PMCH2" layout of `HierarchyData::Load`."""
     import struct
 
     def ivec(f, a):
@@ -462,7 +509,7 @@ def dump_problem(path: str, sampler_levels: List[SamplerLevel], darcy_levels: Li
         dvec(f, m.data)
 
     with open(path, "wb") as f:
-        f.write(b"PMCH1\0\0\0")
+        f.write(b"PMCH2\0\0\0")
         f.write(struct.pack("<iid", len(sampler_levels), dim, corlen))
         for s, d in zip(sampler_levels, darcy_levels):
             f.write(struct.pack("<ii", s.Ne, s.Nf))
@@ -470,6 +517,8 @@ def dump_problem(path: str, sampler_levels: List[SamplerLevel], darcy_levels: Li
             csr(f, s.B)
             csr(f, s.P)
             dvec(f, s.Wdiag)
+            csr(f, getattr(s, "T", None))                       # enlarged-domain samplers: field transfer (or absent)
+            dvec(f, s.Tscale if getattr(s, "Tscale", None) is not None else np.zeros(0))
             f.write(struct.pack("<ii", d.Ne, d.Nf))
             ivec(f, d.elem_ptr)
             ivec(f, d.elem_dofs)

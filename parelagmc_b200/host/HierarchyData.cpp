@@ -51,7 +51,7 @@ HierarchyData HierarchyData::Load(const std::string &path)
     Reader r(path);
     char magic[8];
     r.raw(magic, 8);
-    if (memcmp(magic, "PMCH1\0\0\0", 8) != 0) throw std::runtime_error("HierarchyData::Load: bad magic in " + path);
+    if (memcmp(magic, "PMCH2\0\0\0", 8) != 0) throw std::runtime_error("HierarchyData::Load: bad magic in " + path);
     HierarchyData h;
     h.nlevels = r.i32();
     h.dim = r.i32();
@@ -64,6 +64,8 @@ HierarchyData HierarchyData::Load(const std::string &path)
         s.Ne = r.i32(); s.Nf = r.i32();
         s.M = r.csr(); s.B = r.csr(); s.P = r.csr();
         s.Wdiag = r.dvec();
+        s.T = r.csr();
+        s.Tscale = r.dvec();
         DarcyLevelData &d = h.darcy[l];
         d.Ne = r.i32(); d.Nf = r.i32();
         d.elem_ptr = r.ivec(); d.elem_dofs = r.ivec(); d.elem_mat = r.dvec();

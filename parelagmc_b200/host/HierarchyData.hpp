@@ -20,6 +20,10 @@ struct SamplerLevelData {
     int Ne = 0, Nf = 0;
     CsrData M, B, P;  // eliminated M, B (src/PDESampler.cpp:236-246); P = Ps[level] or empty
     std::vector<double> Wdiag;
+    // enlarged-domain samplers only: transfer of the field to the forward problem's mesh, s = Tscale .* (T field)
+    // (EmbeddedPDESampler: meshP, no scale; L2ProjectionPDESampler: G^T and 1/diag W_orig)
+    CsrData T;
+    std::vector<double> Tscale;
 };
 
 struct DarcyLevelData {
@@ -34,7 +38,7 @@ struct HierarchyData {
     double corlen = 0.1;
     std::vector<SamplerLevelData> sampler;
     std::vector<DarcyLevelData> darcy;
-    // Reads the binary dump (magic "PMCH1"); throws std::runtime_error on malformed input.
+    // Reads the binary dump (magic "PMCH2"); throws std::runtime_error on malformed input.
     static HierarchyData Load(const std::string &path);
 };
 

@@ -47,7 +47,7 @@ void MC_Manager::InitRun(int nsamples)
     const bool batched = bs && bd && bs->Device().get() == bd->Device().get();
     const auto t0 = std::chrono::steady_clock::now();
     if (batched && nsamples > 0) {
-        const uint64_t pos0 = bs->Distribution().Advance((uint64_t)nsamples * (uint64_t)bs->SampleSize(0));
+        const uint64_t pos0 = bs->Distribution().Advance((uint64_t)nsamples * (uint64_t)bs->NoiseSize(0));
         std::vector<double> rows(logger.is_open() ? (size_t)nsamples * 2 : 0);
         bs->Device()->check(pmc_mc_level_batch(bs->Device()->handle(), 0, nsamples, pos0, sums,
                                                rows.empty() ? nullptr : rows.data(), nullptr),

@@ -106,7 +106,7 @@ void MLMC_Manager::InitRun(std::vector<int> &level_nsamples_init)
         }
         std::vector<uint64_t> pos0(nlevels);
         for (int ilevel = nlevels - 1; ilevel >= 0; --ilevel)
-            pos0[ilevel] = bs->Distribution().Advance((uint64_t)level_nsamples_init[ilevel] * (uint64_t)bs->SampleSize(ilevel));
+            pos0[ilevel] = bs->Distribution().Advance((uint64_t)level_nsamples_init[ilevel] * (uint64_t)bs->NoiseSize(ilevel));
         std::vector<std::vector<double>> rows(nlevels);
         std::vector<int> rcs(nlevels, 0);
         std::vector<double> secs(nlevels, 0.0);

@@ -25,7 +25,7 @@ PDESampler::PDESampler(std::shared_ptr<const HierarchyData> hier, NormalDistribu
       alpha_(1. / (corlen_ * corlen_)),                           // :42
       matern_coeff_(ComputeScalingCoefficientForSPDE(corlen_, hier_->dim))
 {
-    for (const auto &s : hier_->sampler) level_size_.push_back(s.Ne);
+    for (const auto &s : hier_->sampler) { level_size_.push_back(s.Ne); out_size_.push_back(s.Ne); }
     nnz_.assign(hier_->nlevels, 0);
 }
 
@@ -43,6 +43,14 @@ void PDESampler::BuildHierarchy()
                                            matern_coeff_, lognormal_ ? 1 : 0),
                   "pmc_upload_sampler_level");
         nnz_[l] = s.M.nnz() + 2 * s.B.nnz() + (size_t)s.Ne;  // pM + pB + pBt + pW (src/PDESampler.cpp:260-265)
+        if (!s.T.empty()) {
+            // enlarged-domain variants: meshP (src/EmbeddedPDESampler.cpp:63-89) or Gt + 1/diag(W_orig)
+            // (src/L2ProjectionPDESampler.cpp:488-514)
+            dev.check(pmc_upload_field_transfer(dev.handle(), l, s.T.rows, s.T.rowptr.data(), s.T.col.data(), s.T.val.data(),
+                                                s.Tscale.empty() ? nullptr : s.Tscale.data()),
+                      "pmc_upload_field_transfer");
+            out_size_[l] = s.T.rows;
+        }
     }
     built_ = true;
 }
@@ -64,7 +72,7 @@ void PDESampler::Eval(const int level, const mfem::Vector &xi, mfem::Vector &s)
 {
     const int xi_level = FindLevel(xi.Size());  // :349
     if (xi_level > level) throw std::runtime_error("PDESampler::Eval: noise coarser than the evaluation level");
-    s.SetSize(level_size_[level]);
+    s.SetSize(out_size_[level]);
     auto &dev = *Device();
     dev.check(pmc_sampler_eval_batch(dev.handle(), level, xi_level, 1, xi.GetData(), nullptr, 0, -1, s.GetData(),
                                      nullptr, nullptr),
@@ -81,7 +89,7 @@ void PDESampler::Eval(const int level, const mfem::Vector &xi, mfem::Vector &s, 
         init_level = FindLevel(embed_s.Size());
         init = embed_s;
     }
-    s.SetSize(level_size_[level]);
+    s.SetSize(out_size_[level]);
     embed_s.SetSize(level_size_[level]);
     auto &dev = *Device();
     dev.check(pmc_sampler_eval_batch(dev.handle(), level, xi_level, 1, xi.GetData(), use_init ? init.GetData() : nullptr,

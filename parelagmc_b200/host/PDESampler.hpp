@@ -32,6 +32,8 @@ public:
     NormalDistributionSampler &Distribution() { return dist_sampler_; }
     const std::shared_ptr<B200Device> &Device() const { return dist_sampler_.Device(); }
     bool Lognormal() const { return lognormal_; }
+    int NoiseSize(int level) const { return level_size_[level]; }
+    int OutputSize(int level) const { return out_size_[level]; }
 
 private:
     int FindLevel(int size) const;  // level_size.Find(xi.Size()) (src/PDESampler.cpp:349,419)
@@ -40,9 +42,29 @@ private:
     parelag::ParameterList &prob_list_;
     bool lognormal_;
     double corlen_, alpha_, matern_coeff_;
-    std::vector<int> level_size_;
+    std::vector<int> level_size_;   // noise / Gaussian-field size per level (the enlarged mesh for the variants below)
+    std::vector<int> out_size_;     // size of the field handed to the forward solver
     std::vector<size_t> nnz_;
     bool built_ = false;
+};
+
+/// EmbeddedPDESampler (/root/reference/src/EmbeddedPDESampler.hpp:46): the SPDE is solved on an enlarged MATCHING mesh
+/// and the field is restricted to the original elements with the 0/1 selection meshP.  Same machinery as PDESampler;
+/// the transfer comes with the hierarchy data.  As in the reference, Sample draws the enlarged size while SampleSize
+/// reports the original-mesh size (src/EmbeddedPDESampler.hpp:126-129).
+class EmbeddedPDESampler : public PDESampler {
+public:
+    using PDESampler::PDESampler;
+    int SampleSize(int level) const override { return OutputSize(level); }
+};
+
+/// L2ProjectionPDESampler (/root/reference/src/L2ProjectionPDESampler.hpp:48): enlarged NON-matching mesh; the field is
+/// brought to the original mesh with s = W^-1 G^T s_bar (src/L2ProjectionPDESampler.cpp:595-611).  G itself (mortar
+/// assembly, ParMoonolith) stays a host-once input.
+class L2ProjectionPDESampler : public PDESampler {
+public:
+    using PDESampler::PDESampler;
+    int SampleSize(int level) const override { return OutputSize(level); }
 };
 
 /// ComputeScalingCoefficientForSPDE (/root/reference/src/Utilities.hpp:188-200)

@@ -98,7 +98,8 @@ class MLMC_Manager:
             self.v_init_nsamples = [self.init_nsamples] * nlevels
         self.out = out
         self.pid = self.comm.rank
-        self.M = np.array([backend.Ne[i] + backend.Nf[i] for i in range(nlevels)], dtype=np.float64)
+        dNe, dNf = getattr(backend, "dNe", backend.Ne), getattr(backend, "dNf", backend.Nf)
+        self.M = np.array([dNe[i] + dNf[i] for i in range(nlevels)], dtype=np.float64)   # pSolver.GetGlobalNumberOfDofs(i)
         self.logger = open(self.file_name, "w") if (self.pid == 0 and self.file_name) else None
         self.stream_pos = 0            # absolute yarn5 position of the next unused draw (all ranks agree)
         self.concurrent_levels = True  # run the level loops of an InitRun concurrently (one cloned handle per level)
@@ -305,7 +306,7 @@ class MC_Manager:
         self.init_nsamples = int(params.get("Number of samples", 10))
         self.out = out
         self.pid = self.comm.rank
-        self.M = float(backend.Ne[level] + backend.Nf[level])
+        self.M = float(getattr(backend, "dNe", backend.Ne)[level] + getattr(backend, "dNf", backend.Nf)[level])
         self.logger = open(self.file_name, "w") if (self.pid == 0 and self.file_name) else None
         self.stream_pos = 0
         self._reset()

@@ -29,6 +29,28 @@ def quad_problem(n=4, nlevels=2, corlen=0.1):
                 g=H.matern_scaling_coefficient(corlen, 2), nlevels=nlevels)
 
 
+@functools.lru_cache(maxsize=None)
+def enlarged_problem(kind="embedded", n=8, nlevels=2, corlen=0.3):
+    """Enlarged-domain samplers: the forward problem lives on the n^3 box [0,2]^3, the SPDE on a
+    larger box.  kind = "embedded": matching mesh, 2 cells of padding per side, meshP selection
+    (EmbeddedPDESampler); kind = "l2proj": NON-matching enlarged mesh (different h), mortar transfer W^-1 G^T
+    (L2ProjectionPDESampler)."""
+    import dataclasses
+    h = 2.0 / n
+    orig = H.build_box_hierarchy([n] * 3, [2.0] * 3, nlevels)
+    if kind == "embedded":
+        pad = 2
+        emb = H.build_box_hierarchy([n + 2 * pad] * 3, [2.0 + 2 * pad * h] * 3, nlevels)
+        T = [(m, None) for m in H.embedded_selection(orig, emb, pad)]
+    else:
+        emb = H.build_box_hierarchy([n + 2] * 3, [2.0] * 3, nlevels)   # same box, non-matching cells (h' = 2/(n+2))
+        T = H.l2_projection_transfers(orig, emb)
+    SL = [dataclasses.replace(s, T=t[0], Tscale=t[1]) for s, t in zip(H.build_sampler_levels(emb), T)]
+    DL = H.build_darcy_levels(orig, **H.MLMC_DEFAULT_BC)
+    return dict(levels=orig, embed_levels=emb, sampler=SL, darcy=DL, alpha=H.spde_alpha(corlen),
+                g=H.matern_scaling_coefficient(corlen, 3), nlevels=nlevels)
+
+
 def make_oracle(p, lognormal=True, rel=1e-12, abs_=1e-30, maxit=2000):
     from oracle.binding import OracleProblem
     op = OracleProblem(p["sampler"], p["darcy"], p["alpha"], p["g"], lognormal)
@@ -65,6 +87,8 @@ class OracleBackend:
         self.nlevels = p["nlevels"]
         self.Ne = [s.Ne for s in p["sampler"]]
         self.Nf = [s.Nf for s in p["sampler"]]
+        self.dNe = [d.Ne for d in p["darcy"]]
+        self.dNf = [d.Nf for d in p["darcy"]]
         self.threads = threads
         self.calls = []
 

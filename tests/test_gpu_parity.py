@@ -357,3 +357,30 @@ def test_clone_runs_levels_concurrently_with_identical_results(ctx, prob):
         assert np.array_equal(ref[0], got[0]) and np.array_equal(ref[1], got[1])
     finally:
         c2.close()
+
+
+@pytest.mark.parametrize("kind", ["embedded", "l2proj"])
+def test_enlarged_domain_samplers_match_oracle(kind):
+    """SURVEY 8f-1 (EmbeddedPDESampler, matching enlarged mesh + meshP selection) and 8f-2 (L2ProjectionPDESampler apply,
+    non-matching enlarged mesh + W^-1 G^T): sampler outputs on the forward mesh, and the fused MLMC level loop."""
+    from common import enlarged_problem
+    from oracle.binding import Yarn5
+    p = enlarged_problem(kind)
+    c = make_context(p)
+    o = make_oracle(p)
+    try:
+        for lev in range(p["nlevels"]):
+            Ne = p["sampler"][lev].Ne
+            xi = Yarn5().jump(5 * lev).normals(5 * Ne).reshape(5, Ne)
+            s, emb, it = c.sampler_eval_batch(lev, xi)
+            assert s.shape == (5, p["darcy"][lev].Ne) and emb.shape == (5, Ne)
+            for j in range(5):
+                so, eo, _ = o.sampler_eval(lev, xi[j])
+                assert rel_l2(emb[j], eo) < FIELD_TOL and rel_l2(s[j], so) < FIELD_TOL
+        for lev, ns in [(1, 9), (0, 6)]:
+            sums, rows, _ = c.mlmc_level_batch(lev, ns, 99, want_rows=True)
+            osums, orows, _ = o.mlmc_level(lev, ns, 99, nthreads=4)
+            assert np.allclose(rows[:, :3], orows[:, :3], rtol=1e-7, atol=1e-9), (kind, lev)
+            assert np.array_equal(rows[:, 3], orows[:, 3])
+    finally:
+        c.close()

@@ -181,3 +181,32 @@ def test_exp_w_regression_and_statistics():
     v = (s4[0] / 50 - (s4[1] / 50) ** 2) * 50 / 49
     assert r1["varQ"] == pytest.approx(v) and r1["estimate"] == pytest.approx(s4[1] / 50)
     assert r1["missing"] == max(int(math.ceil(v / (0.5 * 1e-3) - 50)), 0)
+
+
+@pytest.mark.parametrize("kind", ["embedded", "l2proj"])
+def test_enlarged_domain_sampler_oracle(kind):
+    """EmbeddedPDESampler / L2ProjectionPDESampler apply step: oracle against a direct solve on the
+    enlarged mesh followed by the transfer, and basic properties of the transfer matrices."""
+    from common import enlarged_problem
+    p = enlarged_problem(kind)
+    o = make_oracle(p, lognormal=True)
+    rng = np.random.default_rng(7)
+    for lev in range(p["nlevels"]):
+        s = p["sampler"][lev]
+        assert s.T.shape == (p["darcy"][lev].Ne, s.Ne)
+        if kind == "embedded":
+            assert np.all(s.T.data == 1.0) and np.all(np.diff(s.T.indptr) == 1)   # 0/1 selection
+        else:
+            assert np.allclose(s.Tscale * np.asarray(s.T.sum(axis=1)).ravel(), 1.0)   # averages: constants preserved
+        xi = rng.standard_normal(s.Ne)
+        A = sp.bmat([[s.M, s.B.T], [s.B, -p["alpha"] * sp.diags(s.Wdiag)]], format="csc")
+        x = spla.spsolve(A, np.concatenate([np.zeros(s.Nf), -p["g"] * xi * s.w_sqrt]))
+        ref = s.T @ x[s.Nf:]
+        if s.Tscale is not None:
+            ref = ref * s.Tscale
+        got, emb, _ = o.sampler_eval(lev, xi)
+        assert got.shape == (p["darcy"][lev].Ne,)
+        assert rel_l2(np.log(got), ref) < 1e-8
+        assert rel_l2(emb, x[s.Nf:]) < 1e-8
+    sums, rows, _ = o.mlmc_level(0, 3, 0)
+    assert np.all(np.isfinite(rows)) and np.all(rows[:, 1] > 0)
