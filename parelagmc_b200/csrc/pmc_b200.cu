@@ -1040,6 +1040,7 @@ static int pick_batch(Ctx *c, size_t bytes_per_sample, int nsamples)
 static int check_level(Ctx *c, int level, bool sampler, bool darcy)
 {
     if (!c) return PMC_ERR_ARG;
+    CK(cudaSetDevice(c->device));  // the current device is per host thread; callers may be pool threads
     if (level < 0 || level >= c->nlevels) return fail(c, PMC_ERR_ARG, "level %d out of range [0,%d)", level, c->nlevels);
     if (sampler && !c->s[level].set) return fail(c, PMC_ERR_STATE, "sampler level %d not uploaded", level);
     if (darcy && !c->d[level].set) return fail(c, PMC_ERR_STATE, "Darcy level %d not uploaded", level);
@@ -1248,6 +1249,7 @@ const char *pmc_last_error(pmc_handle c) { return c ? c->err.c_str() : g_create_
 int pmc_set_stream(pmc_handle c, void *cuda_stream)
 {
     if (!c) return PMC_ERR_ARG;
+    CK(cudaSetDevice(c->device));
     resolve_events(c);
     cudaStreamSynchronize(c->stream);
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
@@ -1259,6 +1261,7 @@ int pmc_set_stream(pmc_handle c, void *cuda_stream)
 int pmc_synchronize(pmc_handle c)
 {
     if (!c) return PMC_ERR_ARG;
+    CK(cudaSetDevice(c->device));
     return finish(c);
 }
 
@@ -1451,6 +1454,7 @@ int pmc_clone(pmc_handle src, pmc_handle *out)
                                         D.hasP ? D.Pp.col.data() : nullptr, D.hasP ? D.Pp.val.data() : nullptr);
     }
     if (!rc && src->rng_ready) rc = pmc_rng_init(c, src->mu, src->sigma, src->rng_nparts, src->rng_mypart);
+    if (!rc) rc = pmc_prepare(c);
     if (rc) {
         fail(src, rc, "pmc_clone: %s", pmc_last_error(c));
         pmc_destroy(c);
@@ -1846,6 +1850,7 @@ int pmc_profile(pmc_handle c, unsigned mask)
 int pmc_reset_stats(pmc_handle c)
 {
     if (!c) return PMC_ERR_ARG;
+    CK(cudaSetDevice(c->device));
     resolve_events(c);
     memset(&c->stats, 0, sizeof c->stats);
     c->kernel_ms = 0.0;
@@ -1860,6 +1865,7 @@ int pmc_reset_stats(pmc_handle c)
 int pmc_kernel_stats(pmc_handle c, pmc_kernel_stats_t *out)
 {
     if (!c || !out) return PMC_ERR_ARG;
+    CK(cudaSetDevice(c->device));
     resolve_events(c);
     ProgStats ps;
     CK(cudaMemcpy(&ps, c->d_pstats, sizeof ps, cudaMemcpyDeviceToHost));
