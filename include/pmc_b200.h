@@ -175,6 +175,21 @@ int pmc_mlmc_level_batch(pmc_handle h, int level, int nlevels, int nsamples, uin
 int pmc_mc_level_batch(pmc_handle h, int level, int nsamples, uint64_t pos0, double *sums, double *rows,
                        int64_t *total_iters);
 
+/* ---- BayesianInverseProblem + ratio-estimator managers ------------------------------------------------------ */
+/* BayesianInverseProblem set-up data for one level (src/BayesianInverseProblem.cpp:26-128): the m pressure functionals
+ * g_obs_func[i][level] (g: [m][Ne(level)], un-normalised as the reference holds them; ComputeG divides by their sums,
+ * :186-187), the observed data G_obs[m] (:130-175) and the noise variance ("Noise"). */
+int pmc_upload_observations(pmc_handle h, int level, int m, const double *g, const double *G_obs, double noise);
+/* One level of ML_BayesRatio_Manager::InitRun (src/ML_BayesRatio_Manager.hpp:313-424; the coarsest level is also the
+ * loop of SL_BayesRatio_Manager): per realisation two independent prior draws (zxi, then xi; stream positions
+ * pos0 + (2j) Ne and pos0 + (2j+1) Ne), Z = likelihood(zxi), R = Q * likelihood(xi)
+ * (BayesianInverseProblem::ComputeLikelihood / ComputeR, src/BayesianInverseProblem.cpp:190-218), on `level` and, unless
+ * it is the coarsest, on level + 1 with the 3-argument Eval.  sums[20] in the layout of the manager's enum
+ * (hpp:67-70) {YZ2, YZ, ABS_YZ, Z2, Z, ABS_Z, YR2, YR, ABS_YR, R2, R, ABS_R, -, -, -, -, -, -, C, -} is ACCUMULATED
+ * into; rows (may be NULL): [nsamples][5] = (R, Y_R, Z, Y_Z, c), the log row (:355-358). */
+int pmc_bayes_level_batch(pmc_handle h, int level, int nlevels, int nsamples, uint64_t pos0, double *sums,
+                          double *rows, int64_t *total_iters);
+
 /* ---- instrumentation ---------------------------------------------------------------------------- */
 /* Kernel classes for pmc_profile / pmc_kernel_stats. */
 enum {

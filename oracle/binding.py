@@ -75,6 +75,8 @@ def lib():
         L.po_darcy_solve.argtypes = [C.c_void_p, C.c_int, _dp, _dp, _dp, _dp, _ip]
         L.po_mlmc_level.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_double, C.c_double,
                                     _dp, _dp, C.c_int, C.POINTER(C.c_int64)]
+        L.po_set_observations.argtypes = [C.c_void_p, C.c_int, C.c_int, _dp, _dp, C.c_double]
+        L.po_bayes_level.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_double, C.c_double, _dp, _dp, C.c_int]
         L.po_exp_w_regression.restype = C.c_double
         L.po_exp_w_regression.argtypes = [_dp, _dp, C.c_int, C.c_int]
         L.po_mlmc_compute.argtypes = [C.c_int, _dp, _ip, _dp, _dp, C.c_double, C.c_double] + [_dp] * 10 + [
@@ -212,6 +214,27 @@ class OracleProblem:
                                  _d(sums), _d(rows), nthreads, C.byref(its))
         assert rc == 0, rc
         return sums, rows[:nsamples], its.value
+
+
+def _oracle_set_observations(self, level: int, g, G_obs, noise: float):
+    g = np.ascontiguousarray(g, dtype=np.float64).reshape(-1, self.dNe[level])
+    G_obs = np.ascontiguousarray(G_obs, dtype=np.float64)
+    assert lib().po_set_observations(self.h, level, g.shape[0], _d(g), _d(G_obs), float(noise)) == 0
+
+
+def _oracle_bayes_level(self, level: int, nsamples: int, pos0: int, mu: float = 0.0, sigma: float = 1.0,
+                        nthreads: int = 1, nlevels: Optional[int] = None):
+    """One level of ML_BayesRatio_Manager::InitRun.  Returns (sums[20], rows[nsamples,5])."""
+    sums = np.zeros(20)
+    rows = np.zeros((max(nsamples, 1), 5))
+    rc = lib().po_bayes_level(self.h, level, nlevels or self.nlevels, nsamples, C.c_uint64(pos0), mu, sigma, _d(sums),
+                              _d(rows), nthreads)
+    assert rc == 0, rc
+    return sums, rows[:nsamples]
+
+
+OracleProblem.set_observations = _oracle_set_observations
+OracleProblem.bayes_level = _oracle_bayes_level
 
 
 def exp_w_regression(y, x, skip_n_last: int) -> float:

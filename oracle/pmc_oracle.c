@@ -615,6 +615,9 @@ typedef struct {
     double *ess_data, *rhs, *obs;
     csr_t Pp;
     int hasP;
+    /* BayesianInverseProblem: m pressure functionals (un-normalised), observed data, noise variance */
+    int n_obs;
+    double *gobs_func, *Gobs, noise;
 } darcy_level_t;
 
 struct po_problem {
@@ -654,6 +657,7 @@ void po_destroy(po_problem *p)
             csr_free(&d->B); csr_free(&d->Be); csr_free(&d->Bet);
             free(d->ess_u); free(d->ess_data); free(d->rhs); free(d->obs);
             if (d->hasP) csr_free(&d->Pp);
+            free(d->gobs_func); free(d->Gobs);
         }
     }
     free(p->s); free(p->d); free(p);
@@ -996,6 +1000,92 @@ int po_mlmc_level(po_problem *p, int level, int nlevels, int nsamples, uint64_t 
     }
     if (rows) memcpy(rows, loc, sizeof(double) * 4 * (size_t)nsamples);
     if (total_iters) *total_iters = its;
+    free(loc);
+    return 0;
+}
+
+/* ---------------------------------------------------------------------------------------------- */
+/* BayesianInverseProblem + ML_BayesRatio_Manager                                                 */
+int po_set_observations(po_problem *p, int level, int m, const double *g, const double *G_obs, double noise)
+{
+    if (level < 0 || level >= p->nlevels || !p->d[level].set || m < 1) return -1;
+    darcy_level_t *d = &p->d[level];
+    d->n_obs = m;
+    d->gobs_func = dup_d(g, (size_t)m * (size_t)d->Ne);
+    d->Gobs = dup_d(G_obs, (size_t)m);
+    d->noise = noise;
+    return 0;
+}
+
+/* ComputeLikelihoodAndQ (/root/reference/src/BayesianInverseProblem.cpp:178-210): G_i = g_i . p / sum(g_i),
+ * likelihood = exp(-|G - G_obs|^2 / (2 noise)); Q = obs . sol */
+static void bayes_likelihood(po_problem *p, int level, const double *k, double *like, double *Q, int *iters)
+{
+    darcy_level_t *d = &p->d[level];
+    double C;
+    double *sol = (double *)malloc(sizeof(double) * (size_t)(d->Ne + d->Nf));
+    po_darcy_solve(p, level, k, Q, &C, sol, iters);
+    double n2 = 0.0;
+    for (int i = 0; i < d->n_obs; ++i) {
+        const double *g = d->gobs_func + (size_t)i * d->Ne;
+        double num = 0.0, den = 0.0;
+        for (int e = 0; e < d->Ne; ++e) { num += g[e] * sol[d->Nf + e]; den += g[e]; }
+        const double dl = num / den - d->Gobs[i];
+        n2 += dl * dl;
+    }
+    *like = exp((-1. / (d->noise * 2)) * n2);
+    free(sol);
+}
+
+int po_bayes_level(po_problem *p, int level, int nlevels, int nsamples, uint64_t pos0, double mu, double sigma,
+                   double *sums, double *rows, int nthreads)
+{
+    if (level < 0 || level >= nlevels || nlevels > p->nlevels) return -1;
+    const int coarsest = (level == nlevels - 1);
+    const int Ne = p->s[level].Ne;
+    double *loc = (double *)malloc(sizeof(double) * 5 * (size_t)(nsamples > 0 ? nsamples : 1));
+    sampler_prepare(p, level);
+    if (!coarsest) sampler_prepare(p, level + 1);
+#ifdef _OPENMP
+    if (nthreads < 1) nthreads = 1;
+#pragma omp parallel for schedule(dynamic, 1) num_threads(nthreads)
+#endif
+    for (int j = 0; j < nsamples; ++j) {
+        po_yarn5 g;
+        po_yarn5_init(&g);
+        po_yarn5_jump(&g, pos0 + (uint64_t)j * 2 * (uint64_t)Ne);
+        double *zxi = (double *)malloc(sizeof(double) * (size_t)Ne);
+        double *xi = (double *)malloc(sizeof(double) * (size_t)Ne);
+        po_normal_fill(&g, mu, sigma, Ne, zxi); /* problem.SamplePrior(ilevel, zxi)  (ML_BayesRatio_Manager.hpp:334) */
+        po_normal_fill(&g, mu, sigma, Ne, xi);  /* problem.SamplePrior(ilevel, xi)   (:339) */
+        int nk = p->d[level].Ne + Ne + (coarsest ? 0 : p->d[level + 1].Ne + p->s[level + 1].Ne);
+        double *par = (double *)malloc(sizeof(double) * (size_t)nk);
+        double z = 0, r = 0, zc = 0, rc = 0, q = 0, c_tot = 0;
+        int it;
+        po_sampler_eval(p, level, level, zxi, par, NULL, 0, -1, &it);   /* EvalPrior: 3-argument Eval */
+        bayes_likelihood(p, level, par, &z, &q, &it); c_tot += p->d[level].Ne + p->d[level].Nf;
+        po_sampler_eval(p, level, level, xi, par, NULL, 0, -1, &it);
+        bayes_likelihood(p, level, par, &r, &q, &it); r *= q; c_tot += p->d[level].Ne + p->d[level].Nf;   /* ComputeR */
+        if (!coarsest) {
+            po_sampler_eval(p, level + 1, level, zxi, par, NULL, 0, -1, &it);
+            bayes_likelihood(p, level + 1, par, &zc, &q, &it); c_tot += p->d[level + 1].Ne + p->d[level + 1].Nf;
+            po_sampler_eval(p, level + 1, level, xi, par, NULL, 0, -1, &it);
+            bayes_likelihood(p, level + 1, par, &rc, &q, &it); rc *= q; c_tot += p->d[level + 1].Ne + p->d[level + 1].Nf;
+        }
+        loc[5 * j + 0] = r; loc[5 * j + 1] = coarsest ? r : r - rc;
+        loc[5 * j + 2] = z; loc[5 * j + 3] = coarsest ? z : z - zc; loc[5 * j + 4] = c_tot;
+        free(zxi); free(xi); free(par);
+    }
+    /* enum {YZ2, YZ, ABS_YZ, Z2, Z, ABS_Z, YR2, YR, ABS_YR, R2, R, ABS_R, ..., C = 18} (ML_BayesRatio_Manager.hpp:67-70) */
+    for (int j = 0; j < nsamples; ++j) {
+        const double r = loc[5 * j], yr = loc[5 * j + 1], z = loc[5 * j + 2], yz = loc[5 * j + 3];
+        sums[10] += r; sums[11] += fabs(r); sums[9] += r * r;
+        sums[7] += yr; sums[8] += fabs(yr); sums[6] += yr * yr;
+        sums[4] += z; sums[5] += fabs(z); sums[3] += z * z;
+        sums[1] += yz; sums[2] += fabs(yz); sums[0] += yz * yz;
+        sums[18] += loc[5 * j + 4];
+    }
+    if (rows) memcpy(rows, loc, sizeof(double) * 5 * (size_t)nsamples);
     free(loc);
     return 0;
 }

@@ -100,6 +100,14 @@ int po_mlmc_level(po_problem *p, int level, int nlevels, int nsamples, uint64_t 
                   double mu, double sigma, double *sums, double *rows, int nthreads,
                   int64_t *total_iters);
 
+/* BayesianInverseProblem (/root/reference/src/BayesianInverseProblem.cpp:26-218): m pressure functionals g [m][Ne]
+ * (un-normalised), observed data, noise variance; and one level of ML_BayesRatio_Manager::InitRun
+ * (/root/reference/src/ML_BayesRatio_Manager.hpp:313-424): sums[20] in the manager's enum layout is ACCUMULATED into,
+ * rows (nsamples x 5: R, Y_R, Z, Y_Z, c) may be NULL. */
+int po_set_observations(po_problem *p, int level, int m, const double *g, const double *G_obs, double noise);
+int po_bayes_level(po_problem *p, int level, int nlevels, int nsamples, uint64_t pos0, double mu, double sigma,
+                   double *sums, double *rows, int nthreads);
+
 /* ----------------------------------------------------------------------------------------------
  * Manager statistics
  * -------------------------------------------------------------------------------------------- */

@@ -24,7 +24,8 @@ SYMBOLS = [
     "pmc_create", "pmc_destroy", "pmc_last_error", "pmc_host_alloc", "pmc_host_free", "pmc_set_stream", "pmc_synchronize", "pmc_set_tolerances",
     "pmc_set_preconditioner", "pmc_set_option", "pmc_set_batch", "pmc_upload_sampler_level", "pmc_upload_darcy_level", "pmc_upload_field_transfer", "pmc_clone", "pmc_prepare",
     "pmc_rng_init", "pmc_rng_fill_int", "pmc_rng_fill", "pmc_sampler_sample_batch", "pmc_sampler_eval_batch",
-    "pmc_darcy_solve_batch", "pmc_darcy_apply_batch", "pmc_mlmc_level_batch", "pmc_mc_level_batch", "pmc_profile",
+    "pmc_darcy_solve_batch", "pmc_darcy_apply_batch", "pmc_mlmc_level_batch", "pmc_mc_level_batch",
+    "pmc_upload_observations", "pmc_bayes_level_batch", "pmc_profile",
     "pmc_reset_stats", "pmc_kernel_stats",
 ]
 
@@ -100,6 +101,8 @@ def load():
     L.pmc_darcy_apply_batch.argtypes = [vp, C.c_int, C.c_int, _dp, _dp, _dp]
     L.pmc_mlmc_level_batch.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_uint64, _dp, _dp, C.POINTER(C.c_int64)]
     L.pmc_mc_level_batch.argtypes = [vp, C.c_int, C.c_int, C.c_uint64, _dp, _dp, C.POINTER(C.c_int64)]
+    L.pmc_upload_observations.argtypes = [vp, C.c_int, C.c_int, _dp, _dp, C.c_double]
+    L.pmc_bayes_level_batch.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_uint64, _dp, _dp, C.POINTER(C.c_int64)]
     L.pmc_profile.argtypes = [vp, C.c_uint]
     L.pmc_reset_stats.argtypes = [vp]
     L.pmc_kernel_stats.argtypes = [vp, C.POINTER(KernelStats)]
@@ -338,6 +341,23 @@ class Context:
         its = C.c_int64(0)
         self._ck(self._L.pmc_mc_level_batch(self._h, level, nsamples, C.c_uint64(pos0), _d(sums), _d(rows),
                                             C.byref(its)))
+        return sums, rows, its.value
+
+    # -- Bayesian inverse problem ------------------------------------------------------------------
+    def upload_observations(self, level: int, g: np.ndarray, G_obs: np.ndarray, noise: float):
+        g = np.ascontiguousarray(g, dtype=np.float64).reshape(-1, self.dNe[level])
+        G_obs = np.ascontiguousarray(G_obs, dtype=np.float64)
+        assert g.shape[0] == G_obs.shape[0]
+        self._ck(self._L.pmc_upload_observations(self._h, level, g.shape[0], _d(g), _d(G_obs), float(noise)))
+
+    def bayes_level_batch(self, level: int, nsamples: int, pos0: int, nlevels: Optional[int] = None,
+                          want_rows: bool = False, sums: Optional[np.ndarray] = None):
+        """Returns (sums[20] (accumulated, ML_BayesRatio_Manager enum layout), rows [n,5] | None, total_iters)."""
+        sums = np.zeros(20) if sums is None else sums
+        rows = np.zeros((nsamples, 5)) if want_rows else None
+        its = C.c_int64(0)
+        self._ck(self._L.pmc_bayes_level_batch(self._h, level, nlevels or self.nlevels, nsamples, C.c_uint64(pos0),
+                                               _d(sums), _d(rows), C.byref(its)))
         return sums, rows, its.value
 
     # -- instrumentation ---------------------------------------------------------------------------

@@ -144,6 +144,11 @@ struct DarcyLevel {
     std::vector<double> elem_mat, ess_data, rhs, obs;
     HCsr B, Pp;
     double *d_rhs_bc = nullptr, *d_obs = nullptr, *d_ess_u_data = nullptr;
+    // Bayesian inverse problem: m normalised pressure functionals [m][Ne], observed data and noise variance
+    int n_obs = 0;
+    double noise = 0.0;
+    std::vector<double> h_gobs_func, h_Gobs;
+    double *d_gobs_func = nullptr, *d_Gobs = nullptr;
     DevCsr Mbc;  // weighted coupling of non-essential rows to essential columns (rhs fix-up)
     SaddleSys sys;
 };
@@ -1453,6 +1458,13 @@ int pmc_clone(pmc_handle src, pmc_handle *out)
                                         D.rhs.data(), D.obs.data(), D.hasP ? D.Pp.cols : 0, D.hasP ? D.Pp.rowptr.data() : nullptr,
                                         D.hasP ? D.Pp.col.data() : nullptr, D.hasP ? D.Pp.val.data() : nullptr);
     }
+    for (int l = 0; l < src->nlevels && !rc; ++l) {
+        const DarcyLevel &D = src->d[l];
+        if (D.set && D.n_obs > 0) {
+            // the stored functionals are already normalised; normalising again divides by 1
+            rc = pmc_upload_observations(c, l, D.n_obs, D.h_gobs_func.data(), D.h_Gobs.data(), D.noise);
+        }
+    }
     if (!rc && src->rng_ready) rc = pmc_rng_init(c, src->mu, src->sigma, src->rng_nparts, src->rng_mypart);
     if (!rc) rc = pmc_prepare(c);
     if (rc) {
@@ -1734,6 +1746,7 @@ static int level_batch(Ctx *c, int level, int nlevels, int nsamples, uint64_t po
         o.y = vr(rhs_f, Ne);
         o.fixed = SF.w_sqrt;
         o.ca = -SF.g;
+        o.a0 = 1;
     }
     const int rng_op = 0;
     if (!coarsest) {
@@ -1837,6 +1850,153 @@ int pmc_mc_level_batch(pmc_handle c, int level, int nsamples, uint64_t pos0, dou
                        int64_t *total_iters)
 {
     return level_batch(c, level, c ? c->nlevels : 1, nsamples, pos0, sums, rows, total_iters, true);
+}
+
+// ---- Bayesian inverse problem ----------------------------------------------------------------------
+int pmc_upload_observations(pmc_handle c, int level, int m, const double *g, const double *G_obs, double noise)
+{
+    if (!c) return PMC_ERR_ARG;
+    if (level < 0 || level >= c->nlevels || m < 1 || !g || !G_obs || !(noise > 0.0))
+        return fail(c, PMC_ERR_ARG, "pmc_upload_observations: bad arguments");
+    DarcyLevel &L = c->d[level];
+    if (!L.set) return fail(c, PMC_ERR_STATE, "pmc_upload_observations: Darcy level %d not uploaded", level);
+    CK(cudaSetDevice(c->device));
+    L.h_gobs_func.assign((size_t)m * L.Ne, 0.0);
+    for (int i = 0; i < m; ++i) {
+        double sum = 0.0;  // ComputeG divides by sum(g_obs_func[i]) (/root/reference/src/BayesianInverseProblem.cpp:186-187)
+        for (int e = 0; e < L.Ne; ++e) sum += g[(size_t)i * L.Ne + e];
+        if (sum == 0.0) return fail(c, PMC_ERR_ARG, "observation functional %d sums to zero on level %d", i, level);
+        for (int e = 0; e < L.Ne; ++e) L.h_gobs_func[(size_t)i * L.Ne + e] = g[(size_t)i * L.Ne + e] / sum;
+    }
+    L.h_Gobs.assign(G_obs, G_obs + m);
+    L.n_obs = m;
+    L.noise = noise;
+    int rc;
+    if ((rc = to_device(c, L.h_gobs_func, &L.d_gobs_func))) return rc;
+    if ((rc = to_device(c, L.h_Gobs, &L.d_Gobs))) return rc;
+    return PMC_OK;
+}
+
+// noise draw -> SPDE solve (from zero) -> [transfer] -> exp -> Darcy solve -> likelihood (and R = Q * likelihood)
+static void emit_bayes_eval(Program &pg, Ctx *c, Rows &ar, Off mark, int level, Off rhs, Off k_ext, Off tbuf, Off Grow, Off Qrow,
+                            Off out_row, bool with_q)
+{
+    SamplerLevel &S = c->s[level];
+    DarcyLevel &D = c->d[level];
+    const int Nk = S.out_size();
+    {
+        ar.top = mark;
+        SolveWs ws;
+        carve_solve(ar, S.sys, ws);
+        emit_sampler_solve(pg, c, level, rhs, -1, ws, false);
+        VecRef fsrc = vr(ws.x, S.sys.N, S.sys.Nf);
+        if (S.hasT) {
+            emit_spmm(pg, KC_TRANSFER, EP_AX, S.dT, VNULL, fsrc, vr(tbuf), VNULL, VNULL, nullptr, VNULL, 0, 0, -1, false, false,
+                      (double)S.Ne + Nk);
+            fsrc = vr(tbuf);
+        }
+        if (S.lognormal) { Op &o = pg.add(OP_MAP_EXP, KC_MISC, Nk, 2.0 * Nk); o.x = fsrc; o.y = vr(k_ext); }
+        else emit_copy(pg, fsrc, vr(k_ext), Nk);
+        emit_fill(pg, vr(k_ext, 0, Nk), 1, 1.0);
+    }
+    {
+        ar.top = mark;
+        SolveWs ws;
+        carve_solve(ar, D.sys, ws);
+        emit_darcy_solve(pg, c, level, k_ext, ws, with_q ? Qrow : (Off)-1, false);
+        // G_i = g_i . p / sum(g_i)  (BayesianInverseProblem::ComputeG, /root/reference/src/BayesianInverseProblem.cpp:178-190)
+        for (int i = 0; i < D.n_obs; ++i) {
+            Op &o = pg.add(OP_DOT_FIXED, KC_MISC, D.Ne, D.Ne);
+            o.fixed = D.d_gobs_func + (size_t)i * D.Ne;
+            o.x = vr(ws.x, D.sys.N, D.sys.Nf);
+            o.y = vr(Grow, 0, i);
+        }
+        Op &o = pg.add(OP_LIKELIHOOD, KC_MISC, D.n_obs, D.n_obs);
+        o.x = vr(Grow);
+        o.fixed = D.d_Gobs;
+        o.ca = 1.0 / (2.0 * D.noise);  // exp((-1/(2 noise)) |G - G_obs|^2)  (:196-199)
+        o.r = with_q ? vr(Qrow) : VNULL;
+        o.y = vr(out_row);
+    }
+}
+
+int pmc_bayes_level_batch(pmc_handle c, int level, int nlevels, int nsamples, uint64_t pos0, double *sums, double *rows,
+                          int64_t *total_iters)
+{
+    if (!c) return PMC_ERR_ARG;
+    if (!sums || nsamples < 0) return fail(c, PMC_ERR_ARG, "pmc_bayes_level_batch: bad arguments");
+    if (nlevels < 1 || nlevels > c->nlevels || level < 0 || level >= nlevels)
+        return fail(c, PMC_ERR_ARG, "level %d / nlevels %d out of range", level, nlevels);
+    const bool coarsest = (level == nlevels - 1);
+    int rc = check_level(c, level, true, true);
+    if (rc) return rc;
+    if (!coarsest) {
+        if ((rc = check_level(c, level + 1, true, true))) return rc;
+        if (!c->s[level].hasP) return fail(c, PMC_ERR_STATE, "sampler level %d has no prolongator", level);
+    }
+    for (int l = level; l <= (coarsest ? level : level + 1); ++l) {
+        if (c->d[l].n_obs < 1) return fail(c, PMC_ERR_STATE, "no observations uploaded for level %d", l);
+        if (c->s[l].out_size() != c->d[l].Ne) return fail(c, PMC_ERR_STATE, "sampler output / Darcy size mismatch on level %d", l);
+    }
+    if (!c->rng_ready) return fail(c, PMC_ERR_STATE, "pmc_rng_init has not been called");
+    if (nsamples == 0) return PMC_OK;
+    SamplerLevel &SF = c->s[level];
+    DarcyLevel &DF = c->d[level];
+    const int Ne = SF.Ne, Nec = coarsest ? 0 : c->s[level + 1].Ne;
+    const int Nkmax = std::max(SF.out_size(), coarsest ? 0 : c->s[level + 1].out_size());
+    const int mobs = std::max(DF.n_obs, coarsest ? 0 : c->d[level + 1].n_obs);
+    // cost: every ComputeLikelihood / ComputeR adds the dofs of its solve (src/ML_BayesRatio_Manager.hpp:334-396)
+    const double cost = 2.0 * DF.sys.N + (coarsest ? 0.0 : 2.0 * c->d[level + 1].sys.N);
+    Rows ar;
+    const Off rhs_f = ar.alloc(Ne), rhs_c = coarsest ? -1 : ar.alloc(Nec);
+    const Off k_ext = ar.alloc(Nkmax + 1), tbuf = ar.alloc(Nkmax), Grow = ar.alloc(mobs), Qrow = ar.alloc(1);
+    const Off o_z = ar.alloc(1), o_zc = ar.alloc(1), o_r = ar.alloc(1), o_rc = ar.alloc(1);
+    const Off mark = ar.top;
+    Program pg;
+    std::vector<int> rng_ops;
+    for (int draw = 0; draw < 2; ++draw) {  // draw 0: zxi -> Z (likelihood); draw 1: xi -> R = Q * likelihood
+        rng_ops.push_back(pg.pc());
+        {
+            Op &o = pg.add(OP_RNG, KC_RNG, Ne, Ne);  // SamplePrior(ilevel, .): two vectors per realisation
+            o.y = vr(rhs_f, Ne);
+            o.fixed = SF.w_sqrt;
+            o.ca = -SF.g;
+            o.a0 = 2;
+        }
+        emit_bayes_eval(pg, c, ar, mark, level, rhs_f, k_ext, tbuf, Grow, Qrow, draw == 0 ? o_z : o_r, draw == 1);
+        if (!coarsest) {
+            // EvalPrior(ilevel+1, xi, .): 3-argument Eval, the right-hand side restricted with Ps^T
+            emit_spmm(pg, KC_TRANSFER, EP_AX, SF.dPt, VNULL, vr(rhs_f, Ne), vr(rhs_c, Nec), VNULL, VNULL, nullptr, VNULL, 0, 0, -1,
+                      false, false, (double)Ne + Nec);
+            emit_bayes_eval(pg, c, ar, mark, level + 1, rhs_c, k_ext, tbuf, Grow, Qrow, draw == 0 ? o_zc : o_rc, draw == 1);
+        }
+    }
+    const Off chunk = ar.peak;
+    const size_t per_sample = (size_t)chunk * 8 / TW + 64 + 48;
+    const int B = pick_batch(c, per_sample, nsamples);
+    if ((rc = ensure_arena(c, per_sample * (size_t)pad_ld(B) + (size_t)B * 40 + (1 << 16)))) return rc;
+    if ((rc = ensure_pinned(c, 32 + (rows ? (size_t)B * 5 : 0)))) return rc;
+    const unsigned long long it0 = c->iters_seen;
+    for (int s0 = 0; s0 < nsamples; s0 += B) {
+        const int ns = std::min(B, nsamples - s0);
+        const int ld = pad_ld(ns);
+        double *out20 = (double *)c->arena.base + (size_t)(ld / TW) * (size_t)chunk;
+        double *rows_d = rows ? out20 + 32 : nullptr;
+        for (int draw = 0; draw < 2; ++draw) pg.ops[rng_ops[draw]].u0 = pos0 + (uint64_t)(2 * (uint64_t)s0 + draw) * (uint64_t)Ne;
+        if ((rc = run_program(c, pg, ns, chunk, DF.sys.N))) return rc;
+        CK(cudaMemsetAsync(out20, 0, 20 * sizeof(double), c->stream));
+        launch(c, PMC_K_MISC, (double)ns * 32.0, k_bayes_accumulate, dim3(1), dim3(256), ns, (const double *)c->arena.base, chunk,
+               o_r, coarsest ? (Off)-1 : o_rc, o_z, coarsest ? (Off)-1 : o_zc, cost, out20, rows_d);
+        CK(cudaMemcpyAsync(c->h_pinned, out20, 20 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaMemcpyAsync(c->h_pinned + 20, &c->d_pstats->iters_total, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+        if (rows) CK(cudaMemcpyAsync(c->h_pinned + 32, rows_d, (size_t)ns * 5 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        if ((rc = finish(c))) return rc;
+        memcpy(&c->iters_seen, c->h_pinned + 20, sizeof(unsigned long long));
+        for (int k = 0; k < 20; ++k) sums[k] += c->h_pinned[k];
+        if (rows) memcpy(rows + 5 * (size_t)s0, c->h_pinned + 32, (size_t)ns * 5 * sizeof(double));
+    }
+    if (total_iters) *total_iters = (int64_t)(c->iters_seen - it0);
+    return PMC_OK;
 }
 
 // ---- instrumentation ------------------------------------------------------------------------------

@@ -56,7 +56,8 @@ enum OpKind {
     OP_CHECK,         // if no sample of the tile is active: pc = a0
     OP_JUMP,          // pc = a0
     OP_STORE_ITERS,   // y[0][j] = iterations of sample j (as double) ; total += iterations
-    OP_RNG,           // y[row][j] = (-g * N(mu,sigma)) * w_sqrt[row]  at stream position u0 + sample * n + row
+    OP_RNG,           // y[row][j] = (-g * N(mu,sigma)) * w_sqrt[row]  at stream position u0 + sample * a0 * n + row
+    OP_LIKELIHOOD,    // y[0][j] = exp(-sum_i (x[i][j] - fixed[i])^2 * ca) [* r[0][j]]   (n = number of observations)
     OP_KIND_COUNT
 };
 
@@ -473,7 +474,7 @@ __device__ __forceinline__ void op_rng(const Op &o, int tile, double *chunk, con
     uint32_t r[5], co[5];
 #pragma unroll
     for (int k = 0; k < 5; ++k) { r[k] = P.tab->r0[k]; co[k] = P.tab->a[k]; }
-    yarn5_jump(r, o.u0 + (uint64_t)sample * (uint64_t)o.n + (uint64_t)i0, P.tab->jump);
+    yarn5_jump(r, o.u0 + (uint64_t)sample * (uint64_t)o.a0 * (uint64_t)o.n + (uint64_t)i0, P.tab->jump);
     for (int i = i0; i < i1; ++i) {
         yarn5_step(r, co);
         const uint32_t v = yarn5_output(r[0], P.tab->powtab);
@@ -584,6 +585,20 @@ __global__ void __launch_bounds__(NTt, MINB) k_run_program(const ProgParams P)
             }
             break;
         case OP_RNG: op_rng<NTt>(o, tile, chunk, P); break;
+        case OP_LIKELIHOOD:
+            // BayesianInverseProblem::ComputeLikelihood / ComputeR (/root/reference/src/BayesianInverseProblem.cpp:190-218)
+            if (threadIdx.x < TW) {
+                const double *G = tp(o.x, chunk);
+                double acc2 = 0.0;
+                for (int i = 0; i < o.n; ++i) {
+                    const double dlt = G[(size_t)i * TW + threadIdx.x] - __ldg(o.fixed + i);
+                    acc2 = fma(dlt, dlt, acc2);
+                }
+                double like = exp(-acc2 * o.ca);
+                if (o.r.off >= 0) like *= tp(o.r, chunk)[threadIdx.x];
+                tp(o.y, chunk)[threadIdx.x] = like;
+            }
+            break;
         default: break;
         }
         __syncthreads();
@@ -681,6 +696,41 @@ __global__ void __launch_bounds__(256)
         __syncthreads();
     }
     if (threadIdx.x < 9) out9[threadIdx.x] = red[threadIdx.x][0];
+}
+
+// Sums of ML_BayesRatio_Manager::InitRun (/root/reference/src/ML_BayesRatio_Manager.hpp:313-424) in the layout of its
+// enum (:67-70): {YZ2, YZ, ABS_YZ, Z2, Z, ABS_Z, YR2, YR, ABS_YR, R2, R, ABS_R, ..., C = 18}.  One CTA, fixed tree.
+__global__ void __launch_bounds__(256)
+    k_bayes_accumulate(int nsamples, const double *__restrict__ base, long long chunk, long long off_r, long long off_rc,
+                       long long off_z, long long off_zc, double cost, double *__restrict__ out20, double *__restrict__ rows)
+{
+    __shared__ double red[13][256];
+    double a[13] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    for (int j = threadIdx.x; j < nsamples; j += 256) {
+        const size_t to = (size_t)(j / TW) * (size_t)chunk + (size_t)(j % TW);
+        const double r = base[to + off_r], z = base[to + off_z];
+        const double yr = off_rc >= 0 ? r - base[to + off_rc] : r;
+        const double yz = off_zc >= 0 ? z - base[to + off_zc] : z;
+        a[0] += yz * yz; a[1] += yz; a[2] += fabs(yz); a[3] += z * z; a[4] += z; a[5] += fabs(z);
+        a[6] += yr * yr; a[7] += yr; a[8] += fabs(yr); a[9] += r * r; a[10] += r; a[11] += fabs(r);
+        a[12] += cost;
+        if (rows) {
+            rows[5 * (size_t)j + 0] = r;
+            rows[5 * (size_t)j + 1] = yr;
+            rows[5 * (size_t)j + 2] = z;
+            rows[5 * (size_t)j + 3] = yz;
+            rows[5 * (size_t)j + 4] = cost;
+        }
+    }
+    for (int k = 0; k < 13; ++k) red[k][threadIdx.x] = a[k];
+    __syncthreads();
+    for (int w = 128; w > 0; w >>= 1) {
+        if (threadIdx.x < w)
+            for (int k = 0; k < 13; ++k) red[k][threadIdx.x] += red[k][threadIdx.x + w];
+        __syncthreads();
+    }
+    if (threadIdx.x < 12) out20[threadIdx.x] = red[threadIdx.x][0];
+    if (threadIdx.x == 12) out20[18] = red[12][0];
 }
 
 }  // namespace pmc

@@ -474,6 +474,33 @@ def l2_projection_transfers(orig: List[LevelData], embed: List[LevelData]):
     return out
 
 
+# --------------------------------------------------------------------------------------
+# Bayesian inverse problem set-up
+# --------------------------------------------------------------------------------------
+def observation_functionals(levels: List[LevelData], coords: Sequence[Sequence[float]], eps: float) -> List[np.ndarray]:
+    """g_obs_func[i][level] of `BayesianInverseProblem` (`/root/reference/src/BayesianInverseProblem.cpp:46-104`): on
+    level 0 the domain integral of 1 over the elements whose centre lies within `eps` (max-norm) of observation point i
+    (what `ChangeMeshAttributes` marks + `DomainLFIntegrator`: the element volumes), on coarser levels P^T of the finer
+    one.  With no coordinates: one functional, the integral of p over the domain.  Returns [level] -> array [m, Ne]."""
+    lv = levels[0]
+    if len(coords) == 0:
+        g0 = lv.Wdiag[None, :].copy()
+    else:
+        idx = lv.grid.elem_grid()
+        ctr = [0.5 * (lv.grid.nodes[a][:-1] + lv.grid.nodes[a][1:])[idx[a]] for a in range(lv.dim)]
+        g0 = np.zeros((len(coords), lv.Ne))
+        for i, pt in enumerate(coords):
+            near = np.ones(lv.Ne, dtype=bool)
+            for a in range(lv.dim):
+                near &= np.abs(ctr[a] - pt[a]) <= eps
+            assert near.any(), f"observation point {pt} marks no element"
+            g0[i, near] = lv.Wdiag[near]
+    out = [g0]
+    for l in range(len(levels) - 1):
+        out.append((levels[l].P_s.T @ out[-1].T).T)
+    return out
+
+
 # The reference's default MLMC problem (`examples/example_helpers/CreateMLMCParameterList.hpp:27-41`)
 MLMC_DEFAULT_BC = dict(ess_attr=[0, 1, 1, 1, 1, 0], obs_attr=[1, 0, 0, 0, 0, 0], inflow_attr=[0, 0, 0, 0, 0, 1])
 # SPE10 XML (`examples/SPE10/spe10_3D_parameters.xml:45-49`)

@@ -398,3 +398,130 @@ class MC_Manager:
         row("Var[Q_l] ", self.varQ)
         os.write("=" * W + "\n")
         os.flush()
+
+
+# enum of /root/reference/src/ML_BayesRatio_Manager.hpp:67-70
+BR = dict(YZ2=0, YZ=1, ABS_YZ=2, Z2=3, Z=4, ABS_Z=5, YR2=6, YR=7, ABS_YR=8, R2=9, R=10, ABS_R=11, C=18, NVAR=20)
+
+
+class ML_BayesRatio_Manager:
+    """`parelagmc::ML_BayesRatio_Manager` (`/root/reference/src/ML_BayesRatio_Manager.hpp:35-130`): multilevel estimator
+    of the posterior expectation E[Q | data] = E[R] / E[Z], R = Q * likelihood, Z = likelihood, with independent prior
+    draws for R and Z.  With nlevels = 1 it is the single-level `SL_BayesRatio_Manager`.  The inner loop
+    (`InitRun`, hpp:313-424) is one batched device call per level (`pmc_bayes_level_batch`)."""
+
+    def __init__(self, comm: Optional[_Comm], nlevels: int, backend, params: Optional[dict] = None, out=sys.stdout,
+                 stream_pos: int = 0):
+        params = params or {}
+        self.wallTime = True
+        self.comm = comm or _Comm()
+        self.nlevels = nlevels
+        self.backend = backend
+        self.eps2 = float(params.get("Mean square error", 0.001))
+        self.auto_eps2 = self.eps2 < 0
+        self.ratio = float(params.get("MSE splitting ratio", 0.5))
+        self.init_nsamples = int(params.get("Number of samples", 10))
+        self.v_init_nsamples = list(params.get("Array number of samples", [])) or [self.init_nsamples] * nlevels
+        self.out = out
+        self.pid = self.comm.rank
+        dNe, dNf = getattr(backend, "dNe", backend.Ne), getattr(backend, "dNf", backend.Nf)
+        self.M = np.array([dNe[i] + dNf[i] for i in range(nlevels)], dtype=np.float64)
+        self.stream_pos = stream_pos    # draws consumed before the run (e.g. by GenerateObservationalData)
+        self._reset()
+
+    def _reset(self):
+        L = self.nlevels
+        self.sums = np.zeros((L, BR["NVAR"]))
+        self.level_nsamples = np.zeros(L, dtype=np.int64)
+        self.level_nsamples_missing = np.zeros(L, dtype=np.int64)
+        self.level_time = np.zeros(L)
+        self.ml_estimator_variance = math.inf
+
+    def InitRun(self, level_nsamples_init: Sequence[int]):
+        local = np.zeros((self.nlevels, BR["NVAR"]))
+        for ilevel in range(self.nlevels - 1, -1, -1):       # coarsest first (hpp:322,366)
+            n = int(level_nsamples_init[ilevel])
+            Ne = self.backend.Ne[ilevel]
+            first, count = split_samples(n, self.comm.rank, self.comm.size)
+            t0 = time.perf_counter()
+            if count > 0:                                    # two prior draws per realisation
+                self.backend.bayes_level_batch(ilevel, count, self.stream_pos + 2 * first * Ne, nlevels=self.nlevels,
+                                               sums=local[ilevel])
+            self.level_time[ilevel] += time.perf_counter() - t0
+            self.stream_pos += 2 * n * Ne
+            self.level_nsamples[ilevel] += n
+        self.sums += self.comm.allreduce_sum(local)
+        self.computeNSamplesMSE()
+
+    def Run(self):
+        self._reset()
+        self.InitRun(self.v_init_nsamples)
+        grain = [0] * self.nlevels
+        while self.ml_estimator_variance > self.ratio * self.eps2:
+            for i in range(self.nlevels):
+                grain[i] = min(int(self.level_nsamples_missing[i]),
+                               self.v_init_nsamples[i] + grain[i] + int(self.level_nsamples_missing[i]) // 10)
+            if sum(grain) == 0:
+                break
+            self.InitRun(grain)
+        self.ShowMe()
+
+    def computeNSamplesMSE(self):
+        """hpp:572-726."""
+        L, n = self.nlevels, self.level_nsamples.astype(np.float64)
+        e = self.sums / n[:, None]
+        g = lambda k: e[:, BR[k]].copy()
+        self.eR, self.eABS_R, self.eYR, self.eABS_YR = g("R"), g("ABS_R"), g("YR"), g("ABS_YR")
+        self.eZ, self.eABS_Z, self.eYZ, self.eABS_YZ, self.eC = g("Z"), g("ABS_Z"), g("YZ"), g("ABS_YZ"), g("C")
+        with np.errstate(divide="ignore", invalid="ignore"):
+            unb = n / (n - 1.0)
+            self.varR = (g("R2") - self.eR ** 2) * unb
+            self.varYR = (g("YR2") - self.eYR ** 2) * unb
+            self.varZ = (g("Z2") - self.eZ ** 2) * unb
+            self.varYZ = (g("YZ2") - self.eYZ ** 2) * unb
+        cost = (self.level_time / n) if self.wallTime else self.eC
+        self.cost = np.asarray(cost, dtype=np.float64)
+        M = self.M
+        self.alphaABS_R = expWRegression(self.eABS_YR, M, 1)
+        self.alphaABS_Z = expWRegression(self.eABS_YZ, M, 1)
+
+        def bias2(eABS, a):
+            if L == 1:
+                return 0.0
+            m = M[0] / M[1]
+            if L > 3:
+                return max(m ** (2.0 * a) * eABS[1] ** 2, eABS[0] ** 2) / ((m ** (-2.0 * a) - 1.0) ** 2)
+            if L == 3:
+                return eABS[0] ** 2 / ((m ** (-a) - 1.0) ** 2)
+            return eABS[0] ** 2
+
+        self.expected_discretization_error2 = max(bias2(self.eABS_YR, self.alphaABS_R), bias2(self.eABS_YZ, self.alphaABS_Z))
+        if self.auto_eps2:
+            self.eps2 = self.expected_discretization_error2 / (1.0 - self.ratio)
+        self.ml_estimator_variance_Z = float(np.sum(self.varYZ / n))
+        self.ml_estimator_variance_R = float(np.sum(self.varYR / n))
+        self.ml_estimator_variance = max(self.ml_estimator_variance_Z, self.ml_estimator_variance_R)
+        self.actualMSE = self.expected_discretization_error2 + self.ml_estimator_variance
+        prop_R = float(np.sum(np.sqrt(np.maximum(self.varYR, 0) * self.cost))) / (self.ratio * self.eps2)
+        prop_Z = float(np.sum(np.sqrt(np.maximum(self.varYZ, 0) * self.cost))) / (self.ratio * self.eps2)
+        for i in range(L):
+            mR = prop_R * math.sqrt(max(self.varYR[i], 0) / self.cost[i]) - n[i]
+            mZ = prop_Z * math.sqrt(max(self.varYZ[i], 0) / self.cost[i]) - n[i]
+            self.level_nsamples_missing[i] = max(int(math.ceil(mR)), int(math.ceil(mZ)), 0)
+
+    def estimate(self) -> float:
+        """Posterior expectation: sum_l E[Y_R,l] / sum_l E[Y_Z,l]."""
+        return float(np.sum(self.eYR) / np.sum(self.eYZ))
+
+    def ShowMe(self, os=None):
+        os = os or self.out
+        if self.pid != 0 or os is None:
+            return
+        os.write("=" * 79 + "\nML Bayes Ratio Manager: \n" + "-" * 79 + "\n")
+        for name, v in (("E[R]/E[Z]", self.estimate()), ("Target MSE", self.eps2), ("Actual MSE", self.actualMSE),
+                        ("ML Estimator Variance", self.ml_estimator_variance)):
+            os.write(name.ljust(42) + ("%.8g" % v) + "\n")
+        for name, v in (("NumSamples ", self.level_nsamples), ("E[Y_R] ", self.eYR), ("Var[Y_R] ", self.varYR),
+                        ("E[Y_Z] ", self.eYZ), ("Var[Y_Z] ", self.varYZ), ("C_l ", self.eC)):
+            os.write(name.ljust(42) + "  ".join("%.8g" % x for x in v) + "\n")
+        os.write("=" * 79 + "\n")

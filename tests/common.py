@@ -100,9 +100,40 @@ class OracleBackend:
         sums += s
         return sums, (rows if want_rows else None), its
 
+    def bayes_level_batch(self, level, nsamples, pos0, nlevels=None, want_rows=False, sums=None):
+        s, rows = self.o.bayes_level(level, nsamples, pos0, nthreads=self.threads, nlevels=nlevels)
+        if sums is None:
+            sums = np.zeros(20)
+        sums += s
+        return sums, (rows if want_rows else None), 0
+
     def mc_level_batch(self, level, nsamples, pos0, want_rows=False, sums=None):
         s, rows, its = self.o.mlmc_level(level, nsamples, pos0, nthreads=self.threads, nlevels=level + 1)
         if sums is None:
             sums = np.zeros(4)
         sums += np.array([s[3], s[4], s[5], s[6]])
         return sums, (rows[:, [1, 3]] if want_rows else None), its
+
+
+@functools.lru_cache(maxsize=None)
+def bayes_problem(n=8, nlevels=2, noise=0.05):
+    """RatioEstimator_MLMC-style set-up (BASELINE configs[3]) on the hex box: local-average-pressure observations at
+    three interior points, synthetic data G_obs = G(k(xi_0)) + eta generated by the oracle from stream position 0 (the
+    noise eta from a second, default-seeded stream, as in
+    /root/reference/src/BayesianInverseProblem.cpp:159-175)."""
+    from oracle.binding import Yarn5
+    p = dict(hex_problem(n, nlevels))
+    coords = [(0.5, 0.5, 0.5), (1.0, 1.25, 0.75), (1.5, 0.75, 1.5)]
+    p["gobs"] = H.observation_functionals(p["levels"], coords, eps=0.3)
+    o = make_oracle(p)
+    Ne0 = p["sampler"][0].Ne
+    xi0 = Yarn5().normals(Ne0)                           # prior.Sample(0, xi)
+    k0, _, _ = o.sampler_eval(0, xi0)
+    _, _, sol, _ = o.darcy_solve(0, k0, want_sol=True)
+    pr = sol[p["darcy"][0].Nf:]
+    G = np.array([g @ pr / g.sum() for g in p["gobs"][0]])
+    eta = Yarn5().normals(len(G), 0.0, np.sqrt(noise))   # NormalDistributionSampler noise_dist(0, noise)
+    p["G_obs"] = G + eta
+    p["noise"] = noise
+    p["pos_after_setup"] = Ne0                            # the prior draw of the set-up consumed Ne0 positions
+    return p

@@ -384,3 +384,31 @@ def test_enlarged_domain_samplers_match_oracle(kind):
             assert np.array_equal(rows[:, 3], orows[:, 3])
     finally:
         c.close()
+
+
+def test_bayes_level_batch_matches_oracle():
+    """SURVEY 8f-3: BayesianInverseProblem likelihood / R and the level loop of ML_BayesRatio_Manager::InitRun."""
+    from common import bayes_problem
+    p = bayes_problem()
+    c = make_context(p)
+    o = make_oracle(p)
+    try:
+        for lev in range(p["nlevels"]):
+            c.upload_observations(lev, p["gobs"][lev], p["G_obs"], p["noise"])
+            o.set_observations(lev, p["gobs"][lev], p["G_obs"], p["noise"])
+        pos0 = p["pos_after_setup"]
+        for lev, ns in [(1, 10), (0, 6)]:
+            sums, rows, its = c.bayes_level_batch(lev, ns, pos0, want_rows=True)
+            osums, orows = o.bayes_level(lev, ns, pos0, nthreads=4)
+            assert np.allclose(rows, orows, rtol=1e-7, atol=1e-10), (lev, np.abs(rows - orows).max())
+            assert np.allclose(sums, osums, rtol=1e-7, atol=1e-10)
+            assert its > 0
+        # the ratio estimate E[R]/E[Z] of the two paths agrees
+        est = sums[10] / sums[4]
+        assert est == pytest.approx(osums[10] / osums[4], rel=1e-6)
+        c2 = c.clone()                       # observations travel with pmc_clone
+        s2, r2, _ = c2.bayes_level_batch(0, 6, pos0, want_rows=True)
+        c2.close()
+        assert np.array_equal(r2, rows)
+    finally:
+        c.close()

@@ -185,3 +185,27 @@ def test_bench_stream_positions():
     pos1 = bench.stream_positions(p, [10, 20], 1, 2)
     assert pos0[1] == 0 and pos1[1] == 20 * Ne[1]
     assert pos0[0] == 2 * 20 * Ne[1] and pos1[0] == 2 * 20 * Ne[1] + 10 * Ne[0]
+
+
+def test_bayes_ratio_manager():
+    """ML_BayesRatio_Manager mirror: stream positions (two draws per realisation, coarsest level first), statistics
+    (hpp:572-726) and the ratio estimate."""
+    from common import bayes_problem
+    p = bayes_problem()
+    be = OracleBackend(p, threads=4)
+    for lev in range(p["nlevels"]):
+        be.o.set_observations(lev, p["gobs"][lev], p["G_obs"], p["noise"])
+    m = MG.ML_BayesRatio_Manager(None, 2, be, {"Array number of samples": [6, 12], "Mean square error": 1e6}, out=None,
+                                 stream_pos=p["pos_after_setup"])
+    m.wallTime = False
+    m.Run()
+    n = m.level_nsamples.astype(float)
+    assert list(m.level_nsamples) == [6, 12]
+    assert np.allclose(m.eYR, m.sums[:, 7] / n) and np.allclose(m.eYZ, m.sums[:, 1] / n)
+    assert np.allclose(m.varYZ, (m.sums[:, 0] / n - (m.sums[:, 1] / n) ** 2) * n / (n - 1))
+    assert m.ml_estimator_variance == pytest.approx(max(np.sum(m.varYZ / n), np.sum(m.varYR / n)))
+    assert m.eC[0] == 2 * p["darcy"][0].N + 2 * p["darcy"][1].N and m.eC[1] == 2 * p["darcy"][1].N
+    est = m.estimate()
+    assert 1.0 < est < 4.0            # a posterior mean of the effective permeability of the same order as the prior's
+    # stream bookkeeping: level 1 first (12 samples x 2 draws), then level 0
+    assert m.stream_pos == p["pos_after_setup"] + 2 * 12 * be.Ne[1] + 2 * 6 * be.Ne[0]

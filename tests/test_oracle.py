@@ -210,3 +210,36 @@ def test_enlarged_domain_sampler_oracle(kind):
         assert rel_l2(emb, x[s.Nf:]) < 1e-8
     sums, rows, _ = o.mlmc_level(0, 3, 0)
     assert np.all(np.isfinite(rows)) and np.all(rows[:, 1] > 0)
+
+
+def test_bayes_level_oracle():
+    """BayesianInverseProblem likelihood / R and one level of ML_BayesRatio_Manager::InitRun: the oracle's level loop
+    against a by-hand evaluation with the oracle's building blocks."""
+    from common import bayes_problem
+    from oracle.binding import Yarn5
+    p = bayes_problem()
+    o = make_oracle(p)
+    for lev in range(p["nlevels"]):
+        o.set_observations(lev, p["gobs"][lev], p["G_obs"], p["noise"])
+    pos0 = p["pos_after_setup"]
+    sums, rows = o.bayes_level(0, 3, pos0, nthreads=2)
+    Ne = p["sampler"][0].Ne
+    y = Yarn5().jump(pos0)
+    for j in range(3):
+        zxi, xi = y.normals(Ne), y.normals(Ne)
+        vals = {}
+        for name, noise_vec in (("z", zxi), ("r", xi)):
+            for lev in (0, 1):
+                k, _, _ = o.sampler_eval(lev, noise_vec, xi_level=0)
+                q, _, sol, _ = o.darcy_solve(lev, k, want_sol=True)
+                pr = sol[p["darcy"][lev].Nf:]
+                G = np.array([g @ pr / g.sum() for g in p["gobs"][lev]])
+                like = np.exp(-np.sum((G - p["G_obs"]) ** 2) / (2 * p["noise"]))
+                vals[(name, lev)] = like * (q if name == "r" else 1.0)
+        assert rows[j, 0] == pytest.approx(vals[("r", 0)], rel=1e-9)
+        assert rows[j, 1] == pytest.approx(vals[("r", 0)] - vals[("r", 1)], rel=1e-7, abs=1e-12)
+        assert rows[j, 2] == pytest.approx(vals[("z", 0)], rel=1e-9)
+        assert rows[j, 3] == pytest.approx(vals[("z", 0)] - vals[("z", 1)], rel=1e-7, abs=1e-12)
+        assert rows[j, 4] == 2 * p["darcy"][0].N + 2 * p["darcy"][1].N
+    assert sums[10] == pytest.approx(rows[:, 0].sum()) and sums[4] == pytest.approx(rows[:, 2].sum())
+    assert 0.0 < rows[:, 2].min() and rows[:, 2].max() <= 1.0
