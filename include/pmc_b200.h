@@ -75,7 +75,9 @@ int pmc_set_preconditioner(pmc_handle h, int mass_degree, int schur_degree, doub
 /* Fine-grained options, to be set before the first solve / pmc_prepare.  Keys "sampler.<k>" / "darcy.<k>" with
  * <k> in {mass_degree, schur_degree, schur_ratio, coarse_degree, coarse_ratio, omega (over-correction factor of the
  * coarse-grid correction), max_vlevels (depth of the Schur V-cycle; 0 = full hierarchy, -1 = decide from the mass
- * term, sampler only)}; and "max_batch", "check_every". */
+ * term, sampler only), amg (coarse spaces of the Schur V-cycle: 0 = the hierarchy's L2 prolongators, 1 = strength-aware
+ * pairwise aggregation built at set-up, -1 = aggregation only when the couplings are anisotropic)}; and "max_batch",
+ * "cta_threads". */
 int pmc_set_option(pmc_handle h, const char *key, double value);
 /* Largest number of realisations processed per kernel launch (0 = choose from free device memory), and
  * how many MINRES iterations are queued between convergence checks. */

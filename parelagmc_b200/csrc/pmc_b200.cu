@@ -106,6 +106,8 @@ struct PrecCfg {
     double coarse_ratio = 30.0;
     double omega = 1.0;        // over-correction factor of the piecewise-constant coarse-grid correction
     int max_vlevels = 0;       // 0: as deep as the hierarchy allows; -1 (sampler): decide from the mass term
+    int amg = -1;              // Schur V-cycle coarse spaces: 0 the hierarchy's own L2 prolongators, 1 strength-aware
+                               // pairwise aggregation built here, -1 choose (aggregation when the couplings are anisotropic)
 };
 
 struct SaddleSys {
@@ -118,6 +120,7 @@ struct SaddleSys {
     DevCsr Dm;                      // Darcy: diag M(k) = Dm * k_ext   (Nf x (Ne+1))
     double m_lo = 0.5, m_hi = 1.5;  // spectrum of diag(M)^-1 M
     std::vector<VLevel> v;
+    std::vector<HCsr> own_P;        // aggregation prolongators built here (cfg.amg)
 };
 
 struct SamplerLevel {
@@ -389,6 +392,72 @@ static HCsr symmetrize_pattern(const HCsr &S)
     return csr_from_coo(S.rows, S.rows, e);
 }
 
+// ---- strength-aware aggregation for the Schur complement (host, once) --------------------------------------
+// One pass of pairwise matching: every unmatched node is paired with its most strongly (negatively) coupled unmatched
+// neighbour if that coupling is at least theta times its strongest coupling; otherwise it stays alone.
+static HCsr pairwise_aggregate(const HCsr &S, double theta)
+{
+    const int n = S.rows;
+    std::vector<int> agg(n, -1);
+    int nc = 0;
+    for (int i = 0; i < n; ++i) {
+        if (agg[i] >= 0) continue;
+        double smax = 0.0, best = 0.0;
+        int jb = -1;
+        for (int p = S.rowptr[i]; p < S.rowptr[i + 1]; ++p) {
+            const int j = S.col[p];
+            if (j == i || S.val[p] >= 0.0) continue;
+            smax = std::max(smax, -S.val[p]);
+            if (agg[j] < 0 && -S.val[p] > best) { best = -S.val[p]; jb = j; }
+        }
+        agg[i] = nc;
+        if (jb >= 0 && best >= theta * smax) agg[jb] = nc;
+        ++nc;
+    }
+    HCsr P;
+    P.rows = n;
+    P.cols = nc;
+    P.rowptr.resize(n + 1);
+    P.col.resize(n);
+    P.val.assign(n, 1.0);
+    for (int i = 0; i <= n; ++i) P.rowptr[i] = i;
+    for (int i = 0; i < n; ++i) P.col[i] = agg[i];
+    return P;
+}
+
+// Aggregation chain: two pairwise passes per level (aggregates of up to four strongly coupled nodes: semi-coarsening
+// along the strong direction of anisotropic operators), Galerkin coarse operators, until the level is small.
+static std::vector<HCsr> aggregation_chain(HCsr S, int min_size, int max_levels)
+{
+    std::vector<HCsr> Ps;
+    while (S.rows > min_size && (int)Ps.size() < max_levels) {
+        HCsr P1 = pairwise_aggregate(S, 0.25);
+        HCsr S1 = csr_matmul(csr_transpose(P1), csr_matmul(S, P1));
+        HCsr P2 = pairwise_aggregate(S1, 0.25);
+        HCsr P = csr_matmul(P1, P2);
+        if (P.cols > 0.8 * S.rows) break;
+        S = csr_matmul(csr_transpose(P), csr_matmul(S, P));
+        Ps.push_back(std::move(P));
+    }
+    return Ps;
+}
+
+// More than half of the rows have off-diagonal couplings that differ by more than a factor 4.
+static bool couplings_anisotropic(const HCsr &S)
+{
+    int aniso = 0, counted = 0;
+    for (int i = 0; i < S.rows; ++i) {
+        double lo = 1e300, hi = 0.0;
+        for (int p = S.rowptr[i]; p < S.rowptr[i + 1]; ++p)
+            if (S.col[p] != i && S.val[p] != 0.0) {
+                lo = std::min(lo, std::fabs(S.val[p]));
+                hi = std::max(hi, std::fabs(S.val[p]));
+            }
+        if (hi > 0.0) { ++counted; if (hi > 4.0 * lo) ++aniso; }
+    }
+    return counted > 0 && 2 * aniso > counted;
+}
+
 // ---- sampler system (everything fixed across samples) ---------------------------------------------------
 static int prepare_sampler(Ctx *c, int level)
 {
@@ -455,6 +524,11 @@ static int prepare_sampler(Ctx *c, int level)
             sys.cfg.coarse_degree = sys.cfg.coarse_ratio <= 8.0 ? 3 : 4;
         } else
             sys.cfg.max_vlevels = 0;
+    }
+    if (sys.cfg.max_vlevels != 1 && (sys.cfg.amg == 1 || (sys.cfg.amg < 0 && couplings_anisotropic(S)))) {
+        sys.own_P = aggregation_chain(S, 64, 16);
+        Ps.clear();
+        for (const HCsr &P : sys.own_P) Ps.push_back(&P);
     }
     if (sys.cfg.max_vlevels > 0 && (int)Ps.size() > sys.cfg.max_vlevels - 1) Ps.resize(sys.cfg.max_vlevels - 1);
     sys.v.resize(Ps.size() + 1);
@@ -579,6 +653,28 @@ static int prepare_darcy(Ctx *c, int level)
     // Schur complement S(k) = Be diag(M(k))^-1 Be^T: pattern, unique-value map T_0 and the Galerkin chain
     std::vector<const HCsr *> Ps;
     for (int m = level; m < c->nlevels - 1 && c->d[m].set && c->d[m].hasP; ++m) Ps.push_back(&c->d[m].Pp);
+    if (sys.cfg.max_vlevels != 1 && sys.cfg.amg != 0) {
+        // S at k = 1 decides the aggregates (fixed for all realisations; the values stay per sample)
+        std::vector<double> Md(Nf, 0.0);
+        {
+            size_t off = 0;
+            for (int el = 0; el < Ne; ++el) {
+                const int n = L.elem_ptr[el + 1] - L.elem_ptr[el];
+                const int *dof = L.elem_dofs.data() + L.elem_ptr[el];
+                for (int a = 0; a < n; ++a) Md[dof[a]] += L.elem_mat[off + (size_t)a * n + a];
+                off += (size_t)n * n;
+            }
+        }
+        HCsr Bs = Be;
+        for (int i = 0; i < Ne; ++i)
+            for (int p = Bs.rowptr[i]; p < Bs.rowptr[i + 1]; ++p) Bs.val[p] /= (Md[Bs.col[p]] > 0 ? Md[Bs.col[p]] : 1.0);
+        HCsr S1 = csr_matmul(Bs, Bet);
+        if (sys.cfg.amg == 1 || couplings_anisotropic(S1)) {
+            sys.own_P = aggregation_chain(S1, 64, 16);
+            Ps.clear();
+            for (const HCsr &P : sys.own_P) Ps.push_back(&P);
+        }
+    }
     if (sys.cfg.max_vlevels > 0 && (int)Ps.size() > sys.cfg.max_vlevels - 1) Ps.resize(sys.cfg.max_vlevels - 1);
     sys.v.resize(Ps.size() + 1);
     HCsr Spat;
@@ -1311,6 +1407,7 @@ int pmc_set_option(pmc_handle c, const char *key, double value)
         else if (k == "coarse_ratio" && value > 1) g->coarse_ratio = value;
         else if (k == "omega" && value > 0) g->omega = value;
         else if (k == "max_vlevels") g->max_vlevels = (int)value;
+        else if (k == "amg") g->amg = (int)value;
         else return fail(c, PMC_ERR_ARG, "pmc_set_option: bad key or value '%s' = %g", key, value);
         return PMC_OK;
     }
