@@ -189,7 +189,7 @@ struct pmc_context_s {
     double rel = 1e-6, abs_ = 1e-12;
     int maxit = 300;
     PrecCfg cfg_sampler, cfg_darcy;
-    int max_batch = 0, force_nt = 0;
+    int max_batch = 0, force_nt = 0, force_cs = 0;
     std::vector<SamplerLevel> s;
     std::vector<DarcyLevel> d;
     // rng
@@ -1178,6 +1178,27 @@ static int finish(Ctx *c)
 }
 
 // Upload the program and run it: one CTA per tile, one launch.
+template <int NTt, int MINB, int CS>
+static cudaError_t launch_program(const ProgParams &P, int ntiles, cudaStream_t stream)
+{
+    if (CS == 1) {
+        k_run_program<NTt, MINB, 1><<<ntiles, NTt, 0, stream>>>(P);
+        return cudaPeekAtLastError();
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(ntiles * CS));
+    cfg.blockDim = dim3(NTt);
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CS;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, k_run_program<NTt, MINB, CS>, P);
+}
+
 static int run_program(Ctx *c, Program &pg, int nsamples, Off chunk, int max_rows)
 {
     const int ntiles = (nsamples + TW - 1) / TW;
@@ -1217,10 +1238,22 @@ static int run_program(Ctx *c, Program &pg, int nsamples, Off chunk, int max_row
     while (nt < 512 && max_rows / (nt / LPR) > 32) nt *= 2;
     while (nt < 512 && (long long)ntiles * nt * 2 <= 148LL * 1024) nt *= 2;
     if (c->force_nt == 64 || c->force_nt == 128 || c->force_nt == 256 || c->force_nt == 512) nt = c->force_nt;
-    if (nt == 512) k_run_program<512, 2><<<ntiles, 512, 0, c->stream>>>(P);
-    else if (nt == 256) k_run_program<256, 4><<<ntiles, 256, 0, c->stream>>>(P);
-    else if (nt == 128) k_run_program<128, 8><<<ntiles, 128, 0, c->stream>>>(P);
-    else k_run_program<64, 16><<<ntiles, 64, 0, c->stream>>>(P);
+    // cluster size: split a tile over several CTAs while the batch has too few tiles to fill the machine and every
+    // CTA keeps at least ~1000 rows of the largest operand
+    int cs = 1;
+    if (nt >= 256) {
+        const long long slots = 148LL * (1024 / nt);
+        while (cs < 8 && (long long)ntiles * cs * 2 <= slots && max_rows / (cs * 2) >= 1024) cs *= 2;
+    }
+    if (c->force_cs == 1 || ((c->force_cs == 2 || c->force_cs == 4 || c->force_cs == 8) && nt >= 256)) cs = c->force_cs;
+    cudaError_t le = cudaSuccess;
+#define PMC_LAUNCH(NT_, MINB_, CS_) le = launch_program<NT_, MINB_, CS_>(P, ntiles, c->stream)
+    if (nt == 512) { if (cs == 8) PMC_LAUNCH(512, 2, 8); else if (cs == 4) PMC_LAUNCH(512, 2, 4); else if (cs == 2) PMC_LAUNCH(512, 2, 2); else PMC_LAUNCH(512, 2, 1); }
+    else if (nt == 256) { if (cs == 8) PMC_LAUNCH(256, 4, 8); else if (cs == 4) PMC_LAUNCH(256, 4, 4); else if (cs == 2) PMC_LAUNCH(256, 4, 2); else PMC_LAUNCH(256, 4, 1); }
+    else if (nt == 128) PMC_LAUNCH(128, 8, 1);
+    else PMC_LAUNCH(64, 16, 1);
+#undef PMC_LAUNCH
+    if (le != cudaSuccess && c->cuda_status == cudaSuccess) c->cuda_status = le;
     cudaEventRecord(ep.b, c->stream);
     c->ev_pending.push_back(ep);
     c->kernel_launches++;
@@ -1413,6 +1446,7 @@ int pmc_set_option(pmc_handle c, const char *key, double value)
     }
     if (k == "max_batch" && value >= 0) c->max_batch = (int)value;
     else if (k == "cta_threads") c->force_nt = (int)value;
+    else if (k == "cluster_size") c->force_cs = (int)value;
     else return fail(c, PMC_ERR_ARG, "pmc_set_option: unknown key '%s'", key);
     return PMC_OK;
 }
@@ -1538,7 +1572,7 @@ int pmc_clone(pmc_handle src, pmc_handle *out)
     if (rc) return fail(src, rc, "pmc_clone: %s", pmc_last_error(nullptr));
     c->rel = src->rel; c->abs_ = src->abs_; c->maxit = src->maxit;
     c->cfg_sampler = src->cfg_sampler; c->cfg_darcy = src->cfg_darcy;
-    c->max_batch = src->max_batch; c->force_nt = src->force_nt;
+    c->max_batch = src->max_batch; c->force_nt = src->force_nt; c->force_cs = src->force_cs;
     for (int l = 0; l < src->nlevels && !rc; ++l) {
         const SamplerLevel &S = src->s[l];
         if (S.set)

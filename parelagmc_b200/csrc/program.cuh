@@ -18,12 +18,15 @@
 // kernel is bound by HBM bandwidth and, per CTA, by memory latency -- hence CTA sizes chosen per level so that about
 // 1024 threads per SM are resident.
 #pragma once
+#include <cooperative_groups.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
 #include "rng.cuh"
 
 namespace pmc {
+
+namespace cg = cooperative_groups;
 
 constexpr int TW = 4;     // samples per tile (32-byte rows)
 constexpr int LPR = 2;    // lanes per row: two adjacent threads share a row, 16 bytes (one double2) each
@@ -120,6 +123,7 @@ struct Smem {
     double st[ST_COUNT][TW];
     double dots[4][TW];
     double red[MAXWARP][TW];
+    double part[TW];   // this CTA's share of a dot product (read by the other CTAs of the cluster through DSMEM)
     int active[TW];
     int iters[TW];
     unsigned long long cyc[KC_COUNT];
@@ -133,10 +137,36 @@ __device__ __forceinline__ void st2(double *p, D2 v) { *reinterpret_cast<double2
 __device__ __forceinline__ double *tp(const VecRef &v, double *chunk) { return v.off >= 0 ? chunk + v.off : nullptr; }
 __device__ __forceinline__ double safe_inv(double x) { return x != 0.0 ? 1.0 / x : 0.0; }
 
-// Deterministic CTA reduction.  Every thread holds the partial sums of its PW samples (lane parity selects which
-// samples); xor-butterfly over lanes of equal parity, then the warp results are added in warp order.  Result lands
-// in sm.dots[slot] (= or +=).
-template <int NTt>
+// CLUSTER SPLIT.  When a batch has too few tiles to fill the machine (a fine level with a handful of realisations, or
+// very large levels where memory limits the number of tiles), a tile is owned by a thread-block CLUSTER of CS CTAs:
+// every operation's rows are split into CS contiguous ranges (multiples of a slice), the barrier between operations
+// becomes a cluster barrier, and dot products are combined through distributed shared memory in rank order, so every
+// CTA of the cluster holds the same scalars and takes the same branches.  CS = 1 compiles to plain CTA barriers.
+template <int CS>
+__device__ __forceinline__ int cluster_rank()
+{
+    if (CS == 1) return 0;
+    return (int)cg::this_cluster().block_rank();
+}
+template <int CS>
+__device__ __forceinline__ void my_rows(int n, int &r0, int &r1)
+{
+    if (CS == 1) { r0 = 0; r1 = n; return; }
+    const int per = (((n + CS - 1) / CS) + SLICE - 1) & ~(SLICE - 1);
+    r0 = min(n, cluster_rank<CS>() * per);
+    r1 = min(n, r0 + per);
+}
+template <int CS>
+__device__ __forceinline__ void op_barrier()
+{
+    if (CS == 1) __syncthreads();
+    else cg::this_cluster().sync();
+}
+
+// Deterministic reduction.  Every thread holds the partial sums of its PW samples (lane parity selects which
+// samples); xor-butterfly over lanes of equal parity, the warp results are added in warp order, and with a cluster the
+// CTA results in rank order.  Result lands in sm.dots[slot] (= or +=) of every CTA.
+template <int NTt, int CS>
 __device__ __forceinline__ void block_dot(D2 acc, Smem &sm, int slot, bool accumulate)
 {
 #pragma unroll
@@ -150,11 +180,28 @@ __device__ __forceinline__ void block_dot(D2 acc, Smem &sm, int slot, bool accum
         sm.red[warp][lane * PW + 1] = acc.y;
     }
     __syncthreads();
-    if (threadIdx.x < TW) {
-        double s = accumulate ? sm.dots[slot][threadIdx.x] : 0.0;
+    if (CS == 1) {
+        if (threadIdx.x < TW) {
+            double s = accumulate ? sm.dots[slot][threadIdx.x] : 0.0;
 #pragma unroll
-        for (int w = 0; w < NTt / 32; ++w) s += sm.red[w][threadIdx.x];
-        sm.dots[slot][threadIdx.x] = s;
+            for (int w = 0; w < NTt / 32; ++w) s += sm.red[w][threadIdx.x];
+            sm.dots[slot][threadIdx.x] = s;
+        }
+    } else {
+        if (threadIdx.x < TW) {
+            double s = 0.0;
+#pragma unroll
+            for (int w = 0; w < NTt / 32; ++w) s += sm.red[w][threadIdx.x];
+            sm.part[threadIdx.x] = s;
+        }
+        cg::cluster_group cl = cg::this_cluster();
+        cl.sync();
+        if (threadIdx.x < TW) {
+            double s = accumulate ? sm.dots[slot][threadIdx.x] : 0.0;
+            for (int r = 0; r < CS; ++r) s += *cl.map_shared_rank(&sm.part[threadIdx.x], r);
+            sm.dots[slot][threadIdx.x] = s;
+        }
+        // the barrier that ends the operation keeps `part` alive until every CTA has read it
     }
 }
 
@@ -164,7 +211,7 @@ __device__ __forceinline__ void block_dot(D2 acc, Smem &sm, int slot, bool accum
 //                        p in [rowptr[2i+1], rowptr[2i+2])          sum += val[p] * x[col[p]]
 //   V = per-sample weights: the permeability k_e for M(k) = sum_e k_e R_e^T M_e R_e (the element reassembly of
 //   DarcySolver::assemble, /root/reference/src/DarcySolver.cpp:479, never materialised) or the Schur values.
-template <int NTt, int EP, bool WEIGHTED, bool BDINV, bool DOT>
+template <int NTt, int CS, int EP, bool WEIGHTED, bool BDINV, bool DOT>
 __device__ __forceinline__ void op_spmm(const Op &o, double *chunk, Smem &sm)
 {
     const int sub = (threadIdx.x % LPR) * PW;  // first sample of this thread inside the row
@@ -184,8 +231,10 @@ __device__ __forceinline__ void op_spmm(const Op &o, double *chunk, Smem &sm)
     const int *__restrict__ foff = o.foff;
     const int *__restrict__ fcol = o.fcol;
     const double *__restrict__ fval = o.fval;
-    const int npad = (o.n + SLICE - 1) & ~(SLICE - 1);  // whole warps stay converged through the slice loops
-    for (int row = threadIdx.x / LPR; row < npad; row += NTt / LPR) {
+    int r0, r1;
+    my_rows<CS>(o.n, r0, r1);
+    const int npad = (r1 + SLICE - 1) & ~(SLICE - 1);  // whole warps stay converged through the slice loops
+    for (int row = r0 + threadIdx.x / LPR; row < npad; row += NTt / LPR) {
         const int sl = row / SLICE, rs = row % SLICE;
         D2 s = make_double2(0.0, 0.0);
         if (WEIGHTED) {
@@ -219,7 +268,7 @@ __device__ __forceinline__ void op_spmm(const Op &o, double *chunk, Smem &sm)
                 s.y = fma(c, xv.y, s.y);
             }
         }
-        if (row >= o.n) continue;
+        if (row >= r1) continue;
         const size_t ro = (size_t)row * TW;
         D2 out;
         if (EP == EP_AX) {
@@ -256,13 +305,15 @@ __device__ __forceinline__ void op_spmm(const Op &o, double *chunk, Smem &sm)
             acc.y = fma(out.y, wv.y, acc.y);
         }
     }
-    if (DOT) block_dot<NTt>(acc, sm, o.slot, (o.flags & F_DOT_ACC) != 0);
+    if (DOT) block_dot<NTt, CS>(acc, sm, o.slot, (o.flags & F_DOT_ACC) != 0);
 }
 
-template <int NTt, bool BDINV>
+template <int NTt, int CS, bool BDINV>
 __device__ __forceinline__ void op_cheb_first(const Op &o, double *chunk, Smem &sm)
 {
     const int sub = (threadIdx.x % LPR) * PW;
+    int r0, r1;
+    my_rows<CS>(o.n, r0, r1);
     const double *__restrict__ r = tp(o.r, chunk) + sub;
     double *__restrict__ d = tp(o.d, chunk) + sub;
     double *__restrict__ z = tp(o.y, chunk) + sub;
@@ -270,7 +321,7 @@ __device__ __forceinline__ void op_cheb_first(const Op &o, double *chunk, Smem &
     const bool dot = (o.flags & F_DOT) != 0;
     D2 acc = make_double2(0.0, 0.0);
 #pragma unroll 4
-    for (int row = threadIdx.x / LPR; row < o.n; row += NTt / LPR) {
+    for (int row = r0 + threadIdx.x / LPR; row < r1; row += NTt / LPR) {
         const size_t ro = (size_t)row * TW;
         const D2 rv = ld2c(r + ro);
         D2 di;
@@ -282,15 +333,17 @@ __device__ __forceinline__ void op_cheb_first(const Op &o, double *chunk, Smem &
         st2(d + ro, dn);
         st2(z + ro, dn);
     }
-    if (dot) block_dot<NTt>(acc, sm, o.slot, (o.flags & F_DOT_ACC) != 0);
+    if (dot) block_dot<NTt, CS>(acc, sm, o.slot, (o.flags & F_DOT_ACC) != 0);
 }
 
 // Lanczos update v0 = cq q + cv1 v1 + cv0 v0, optionally fused with the Jacobi preconditioner of the RT mass block
 // (rows < a0): z = cb * dinv * v0 written to o.d, and the partial dot v0 . z of those rows.
-template <int NTt, bool JACOBI, bool BDINV>
+template <int NTt, int CS, bool JACOBI, bool BDINV>
 __device__ __forceinline__ void op_lincomb3(const Op &o, double *chunk, Smem &sm)
 {
     const int sub = (threadIdx.x % LPR) * PW;
+    int r0, r1;
+    my_rows<CS>(o.n, r0, r1);
     const double *__restrict__ q = tp(o.x, chunk) + sub;
     const double *__restrict__ v1 = tp(o.r, chunk) + sub;
     double *__restrict__ v0 = tp(o.y, chunk) + sub;
@@ -304,7 +357,7 @@ __device__ __forceinline__ void op_lincomb3(const Op &o, double *chunk, Smem &sm
     const double cb = o.cb;
     D2 acc = make_double2(0.0, 0.0);
 #pragma unroll 4
-    for (int row = threadIdx.x / LPR; row < o.n; row += NTt / LPR) {
+    for (int row = r0 + threadIdx.x / LPR; row < r1; row += NTt / LPR) {
         const size_t ro = (size_t)row * TW;
         const D2 qv = ld2c(q + ro), vv = ld2c(v1 + ro);
         D2 cv = make_double2(0.0, 0.0);
@@ -321,13 +374,15 @@ __device__ __forceinline__ void op_lincomb3(const Op &o, double *chunk, Smem &sm
             acc.y = fma(zn.y, vn.y, acc.y);
         }
     }
-    if (JACOBI) block_dot<NTt>(acc, sm, o.slot, false);
+    if (JACOBI) block_dot<NTt, CS>(acc, sm, o.slot, false);
 }
 
-template <int NTt>
+template <int NTt, int CS>
 __device__ __forceinline__ void op_sol_update(const Op &o, double *chunk, Smem &sm)
 {
     const int sub = (threadIdx.x % LPR) * PW;
+    int r0, r1;
+    my_rows<CS>(o.n, r0, r1);
     double *__restrict__ w0 = tp(o.y, chunk) + sub;
     const double *__restrict__ w1 = tp(o.r, chunk) + sub;
     const double *__restrict__ u1 = tp(o.x, chunk) + sub;
@@ -337,7 +392,7 @@ __device__ __forceinline__ void op_sol_update(const Op &o, double *chunk, Smem &
     const D2 c = make_double2(sm.st[ST_CU][sub], sm.st[ST_CU][sub + 1]);
     const D2 e = make_double2(sm.st[ST_CX][sub], sm.st[ST_CX][sub + 1]);
 #pragma unroll 4
-    for (int row = threadIdx.x / LPR; row < o.n; row += NTt / LPR) {
+    for (int row = r0 + threadIdx.x / LPR; row < r1; row += NTt / LPR) {
         const size_t ro = (size_t)row * TW;
         const D2 w0v = ld2c(w0 + ro), w1v = ld2c(w1 + ro), uv = ld2c(u1 + ro);
         D2 xv = ld2c(xs + ro);
@@ -349,14 +404,16 @@ __device__ __forceinline__ void op_sol_update(const Op &o, double *chunk, Smem &
     }
 }
 
-template <int NTt>
+template <int NTt, int CS>
 __device__ __forceinline__ void op_setup_spmm(const Op &o, double *chunk)
 {
     const int sub = (threadIdx.x % LPR) * PW;
+    int r0, r1;
+    my_rows<CS>(o.n, r0, r1);
     const double *__restrict__ x = tp(o.x, chunk) + sub;
     double *__restrict__ y = tp(o.y, chunk) + sub;
     const bool absx = (o.flags & F_ABSX) != 0, recip = (o.flags & F_RECIP) != 0;
-    for (int row = threadIdx.x / LPR; row < o.n; row += NTt / LPR) {
+    for (int row = r0 + threadIdx.x / LPR; row < r1; row += NTt / LPR) {
         D2 s = make_double2(0.0, 0.0);
         const int p0 = __ldg(o.rowptr + row), p1 = __ldg(o.rowptr + row + 1);
 #pragma unroll 4
@@ -457,12 +514,12 @@ __device__ __forceinline__ void sc_beta(const Op &o, Smem &sm, const ProgParams 
 
 // Noise generation fused with the SPDE right-hand-side scaling: thread (chunk c, sample j) jumps to stream position
 // u0 + sample * n + c * T and steps T times (PDESampler::Sample + :352-358 of src/PDESampler.cpp).
-template <int NTt>
+template <int NTt, int CS>
 __device__ __forceinline__ void op_rng(const Op &o, int tile, double *chunk, const ProgParams &P)
 {
     double *__restrict__ y = tp(o.y, chunk);
-    const int j = threadIdx.x & (TW - 1), c = threadIdx.x / TW;
-    constexpr int NCH = NTt / TW;
+    const int j = threadIdx.x & (TW - 1), c = cluster_rank<CS>() * (NTt / TW) + threadIdx.x / TW;
+    constexpr int NCH = CS * NTt / TW;
     const int T = (o.n + NCH - 1) / NCH;
     const int i0 = c * T, i1 = min(o.n, i0 + T);
     const int sample = tile * TW + j;
@@ -484,12 +541,12 @@ __device__ __forceinline__ void op_rng(const Op &o, int tile, double *chunk, con
     }
 }
 
-template <int NTt, int MINB>
+template <int NTt, int MINB, int CS>
 __global__ void __launch_bounds__(NTt, MINB) k_run_program(const ProgParams P)
 {
     __shared__ Smem sm;
-    const int tile = blockIdx.x;
-    if (tile >= P.ntiles) return;
+    const int tile = blockIdx.x / CS;  // the CS CTAs of a cluster share a tile
+    const int crank = cluster_rank<CS>();
     double *const chunk = P.base + (size_t)tile * (size_t)P.chunk;
     if (threadIdx.x < KC_COUNT) { sm.cyc[threadIdx.x] = 0ull; sm.cbytes[threadIdx.x] = 0.0; sm.cops[threadIdx.x] = 0u; }
     if (threadIdx.x < TW) { sm.active[threadIdx.x] = 0; sm.iters[threadIdx.x] = 0; }
@@ -506,41 +563,47 @@ __global__ void __launch_bounds__(NTt, MINB) k_run_program(const ProgParams P)
             const int ep = (flags >> F_EP_SHIFT) & 3;
             const bool w = flags & F_WEIGHTED, dot = flags & F_DOT;
             if (ep == EP_AX) {
-                if (w) { if (dot) op_spmm<NTt, EP_AX, true, false, true>(o, chunk, sm); else op_spmm<NTt, EP_AX, true, false, false>(o, chunk, sm); }
-                else   { if (dot) op_spmm<NTt, EP_AX, false, false, true>(o, chunk, sm); else op_spmm<NTt, EP_AX, false, false, false>(o, chunk, sm); }
+                if (w) { if (dot) op_spmm<NTt, CS, EP_AX, true, false, true>(o, chunk, sm); else op_spmm<NTt, CS, EP_AX, true, false, false>(o, chunk, sm); }
+                else   { if (dot) op_spmm<NTt, CS, EP_AX, false, false, true>(o, chunk, sm); else op_spmm<NTt, CS, EP_AX, false, false, false>(o, chunk, sm); }
             } else if (ep == EP_RESID) {
-                if (w) op_spmm<NTt, EP_RESID, true, false, false>(o, chunk, sm); else op_spmm<NTt, EP_RESID, false, false, false>(o, chunk, sm);
+                if (w) op_spmm<NTt, CS, EP_RESID, true, false, false>(o, chunk, sm); else op_spmm<NTt, CS, EP_RESID, false, false, false>(o, chunk, sm);
             } else if (ep == EP_ADD) {
-                op_spmm<NTt, EP_ADD, false, false, false>(o, chunk, sm);
+                op_spmm<NTt, CS, EP_ADD, false, false, false>(o, chunk, sm);
             } else {
-                if (w) { if (dot) op_spmm<NTt, EP_CHEB, true, true, true>(o, chunk, sm); else op_spmm<NTt, EP_CHEB, true, true, false>(o, chunk, sm); }
-                else   { if (dot) op_spmm<NTt, EP_CHEB, false, false, true>(o, chunk, sm); else op_spmm<NTt, EP_CHEB, false, false, false>(o, chunk, sm); }
+                if (w) { if (dot) op_spmm<NTt, CS, EP_CHEB, true, true, true>(o, chunk, sm); else op_spmm<NTt, CS, EP_CHEB, true, true, false>(o, chunk, sm); }
+                else   { if (dot) op_spmm<NTt, CS, EP_CHEB, false, false, true>(o, chunk, sm); else op_spmm<NTt, CS, EP_CHEB, false, false, false>(o, chunk, sm); }
             }
         } break;
         case OP_CHEB_FIRST:
-            if (flags & F_BDINV) op_cheb_first<NTt, true>(o, chunk, sm); else op_cheb_first<NTt, false>(o, chunk, sm);
+            if (flags & F_BDINV) op_cheb_first<NTt, CS, true>(o, chunk, sm); else op_cheb_first<NTt, CS, false>(o, chunk, sm);
             break;
         case OP_LINCOMB3:
-            if (flags & F_DOT) { if (flags & F_BDINV) op_lincomb3<NTt, true, true>(o, chunk, sm); else op_lincomb3<NTt, true, false>(o, chunk, sm); }
-            else op_lincomb3<NTt, false, false>(o, chunk, sm);
+            if (flags & F_DOT) { if (flags & F_BDINV) op_lincomb3<NTt, CS, true, true>(o, chunk, sm); else op_lincomb3<NTt, CS, true, false>(o, chunk, sm); }
+            else op_lincomb3<NTt, CS, false, false>(o, chunk, sm);
             break;
-        case OP_SOL_UPDATE: op_sol_update<NTt>(o, chunk, sm); break;
-        case OP_SETUP_SPMM: op_setup_spmm<NTt>(o, chunk); break;
+        case OP_SOL_UPDATE: op_sol_update<NTt, CS>(o, chunk, sm); break;
+        case OP_SETUP_SPMM: op_setup_spmm<NTt, CS>(o, chunk); break;
         case OP_FILL: {
             double *y = tp(o.y, chunk);
             const double v = o.ca;
-            for (int i = threadIdx.x; i < o.n * (TW / 2); i += NTt) reinterpret_cast<double2 *>(y)[i] = make_double2(v, v);
+            int r0, r1;
+            my_rows<CS>(o.n, r0, r1);
+            for (int i = r0 * (TW / 2) + threadIdx.x; i < r1 * (TW / 2); i += NTt) reinterpret_cast<double2 *>(y)[i] = make_double2(v, v);
         } break;
         case OP_COPY: {
             const double2 *x = reinterpret_cast<const double2 *>(tp(o.x, chunk));
             double2 *y = reinterpret_cast<double2 *>(tp(o.y, chunk));
+            int r0, r1;
+            my_rows<CS>(o.n, r0, r1);
 #pragma unroll 4
-            for (int i = threadIdx.x; i < o.n * (TW / 2); i += NTt) y[i] = x[i];
+            for (int i = r0 * (TW / 2) + threadIdx.x; i < r1 * (TW / 2); i += NTt) y[i] = x[i];
         } break;
         case OP_BROADCAST: {
             double *y = tp(o.y, chunk);
             const int sub = (threadIdx.x % LPR) * PW;
-            for (int row = threadIdx.x / LPR; row < o.n; row += NTt / LPR) {
+            int r0, r1;
+            my_rows<CS>(o.n, r0, r1);
+            for (int row = r0 + threadIdx.x / LPR; row < r1; row += NTt / LPR) {
                 const double v = __ldg(o.fixed + row);
                 st2(y + (size_t)row * TW + sub, make_double2((tile * TW + sub < P.nsamples) ? v : 0.0,
                                                               (tile * TW + sub + 1 < P.nsamples) ? v : 0.0));
@@ -549,13 +612,17 @@ __global__ void __launch_bounds__(NTt, MINB) k_run_program(const ProgParams P)
         case OP_MAP_EXP: {
             const double *x = tp(o.x, chunk);
             double *y = tp(o.y, chunk);
-            for (int i = threadIdx.x; i < o.n * TW; i += NTt) y[i] = exp(x[i]);
+            int r0, r1;
+            my_rows<CS>(o.n, r0, r1);
+            for (int i = r0 * TW + threadIdx.x; i < r1 * TW; i += NTt) y[i] = exp(x[i]);
         } break;
         case OP_DOT_FIXED: {
             const int sub = (threadIdx.x % LPR) * PW;
             const double *x = tp(o.x, chunk) + sub;
             D2 acc = make_double2(0.0, 0.0);
-            for (int row = threadIdx.x / LPR; row < o.n; row += NTt / LPR) {
+            int r0, r1;
+            my_rows<CS>(o.n, r0, r1);
+            for (int row = r0 + threadIdx.x / LPR; row < r1; row += NTt / LPR) {
                 const double w = __ldg(o.fixed + row);
                 if (w != 0.0) {
                     const D2 xv = ld2c(x + (size_t)row * TW);
@@ -563,9 +630,9 @@ __global__ void __launch_bounds__(NTt, MINB) k_run_program(const ProgParams P)
                     acc.y = fma(w, xv.y, acc.y);
                 }
             }
-            block_dot<NTt>(acc, sm, 3, false);
+            block_dot<NTt, CS>(acc, sm, 3, false);
             __syncthreads();
-            if (threadIdx.x < TW) tp(o.y, chunk)[threadIdx.x] = sm.dots[3][threadIdx.x];
+            if (threadIdx.x < TW && crank == 0) tp(o.y, chunk)[threadIdx.x] = sm.dots[3][threadIdx.x];
         } break;
         case OP_SC_INIT: sc_init(o, tile, sm, P); break;
         case OP_SC_ALPHA: sc_alpha(o, sm); break;
@@ -578,16 +645,16 @@ __global__ void __launch_bounds__(NTt, MINB) k_run_program(const ProgParams P)
         } break;
         case OP_JUMP: next = o.a0; break;
         case OP_STORE_ITERS:
-            if (threadIdx.x < TW) {
+            if (threadIdx.x < TW && crank == 0) {
                 const int sample = tile * TW + threadIdx.x;
                 if (o.y.off >= 0) tp(o.y, chunk)[threadIdx.x] = (double)sm.iters[threadIdx.x];
                 if (sample < P.nsamples) atomicAdd(&P.stats->iters_total, (unsigned long long)sm.iters[threadIdx.x]);
             }
             break;
-        case OP_RNG: op_rng<NTt>(o, tile, chunk, P); break;
+        case OP_RNG: op_rng<NTt, CS>(o, tile, chunk, P); break;
         case OP_LIKELIHOOD:
             // BayesianInverseProblem::ComputeLikelihood / ComputeR (/root/reference/src/BayesianInverseProblem.cpp:190-218)
-            if (threadIdx.x < TW) {
+            if (threadIdx.x < TW && crank == 0) {
                 const double *G = tp(o.x, chunk);
                 double acc2 = 0.0;
                 for (int i = 0; i < o.n; ++i) {
@@ -601,17 +668,19 @@ __global__ void __launch_bounds__(NTt, MINB) k_run_program(const ProgParams P)
             break;
         default: break;
         }
-        __syncthreads();
+        op_barrier<CS>();
         if (threadIdx.x == 0) {
             sm.cyc[o.kclass] += (unsigned long long)(clock64() - t0);
-            sm.cbytes[o.kclass] += o.bytes;
-            sm.cops[o.kclass] += 1u;
+            if (crank == 0) {  // bytes and operation counts once per tile
+                sm.cbytes[o.kclass] += o.bytes;
+                sm.cops[o.kclass] += 1u;
+            }
         }
         pc = next;
     }
-    __syncthreads();
+    op_barrier<CS>();  // no CTA of a cluster exits while another may still read its shared memory
+    if (threadIdx.x < KC_COUNT && sm.cyc[threadIdx.x]) atomicAdd(&P.stats->class_cycles[threadIdx.x], sm.cyc[threadIdx.x]);
     if (threadIdx.x < KC_COUNT && sm.cops[threadIdx.x]) {
-        atomicAdd(&P.stats->class_cycles[threadIdx.x], sm.cyc[threadIdx.x]);
         atomicAdd(&P.stats->class_bytes[threadIdx.x], sm.cbytes[threadIdx.x]);
         atomicAdd(&P.stats->class_ops[threadIdx.x], (unsigned long long)sm.cops[threadIdx.x]);
         atomicAdd(&P.stats->bytes, sm.cbytes[threadIdx.x]);

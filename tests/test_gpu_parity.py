@@ -412,3 +412,35 @@ def test_bayes_level_batch_matches_oracle():
         assert np.array_equal(r2, rows)
     finally:
         c.close()
+
+
+@pytest.mark.parametrize("cs", [2, 4, 8])
+def test_cluster_split_matches_single_cta(prob, cs):
+    """A tile owned by a thread-block cluster (rows split over CS CTAs, cluster barriers, DSMEM dot products) gives the
+    results of the one-CTA-per-tile kernel to round-off, and matches the oracle."""
+    from parelagmc_b200.capi import Context
+    def ctx_with(csize):
+        c = Context(prob["nlevels"], 0)
+        c.set_option("cta_threads", 256)
+        c.set_option("cluster_size", csize)
+        for l, s in enumerate(prob["sampler"]):
+            c.upload_sampler_level(l, s, prob["alpha"], prob["g"], True)
+        for l, d in enumerate(prob["darcy"]):
+            c.upload_darcy_level(l, d)
+        c.set_tolerances(1e-12, 1e-30, 2000)
+        c.rng_init(0.0, 1.0, 1, 0)
+        return c
+    c1, ck = ctx_with(1), ctx_with(cs)
+    try:
+        for lev, ns in [(0, 10), (1, 7)]:
+            _, r1, _ = c1.mlmc_level_batch(lev, ns, 55, want_rows=True)
+            _, rk, _ = ck.mlmc_level_batch(lev, ns, 55, want_rows=True)
+            assert np.allclose(r1, rk, rtol=1e-9, atol=1e-12), (cs, lev, np.abs(r1 - rk).max())
+        d = prob["darcy"][0]
+        k = np.exp(np.random.default_rng(3).standard_normal((5, d.Ne)))
+        Q1, _, s1, _ = c1.darcy_solve_batch(0, k, want_sol=True)
+        Qk, _, sk, _ = ck.darcy_solve_batch(0, k, want_sol=True)
+        assert rel_l2(sk, s1) < 1e-9
+    finally:
+        c1.close()
+        ck.close()
