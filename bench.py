@@ -119,12 +119,14 @@ cpu_reference_run.oracle = None
 
 
 def bounded_sample(p, threads, target_s):
-    """A sample of the workload in the same 1:3:6 level proportions, sized for ~target_s of wall time."""
-    probe = [max(1, threads // 4), max(1, 3 * threads // 4), max(1, 6 * threads // 4)]
-    pos = stream_positions(p, probe, 0, 1)
-    t = cpu_reference_run(p, probe, threads, pos)
-    scale = max(1.0, target_s / max(t, 1e-3))
-    return [max(1, int(round(x * scale))) for x in probe]
+    """A sample of the workload in the same 1:3:6 level proportions, sized for ~target_s of wall time (two calibration
+    rounds: a tiny probe, then a ~2 s run, because the per-sample cost of the probe is dominated by set-up)."""
+    smp = [max(1, threads // 4), max(1, 3 * threads // 4), max(1, 6 * threads // 4)]
+    for goal in (1.0, 4.0, target_s):
+        t = cpu_reference_run(p, smp, threads, stream_positions(p, smp, 0, 1))
+        scale = max(1.0, goal / max(t, 1e-3))
+        smp = [max(1, int(round(x * scale))) for x in smp]
+    return smp
 
 
 def run_reference(args):
