@@ -444,3 +444,36 @@ def test_cluster_split_matches_single_cta(prob, cs):
     finally:
         c1.close()
         ck.close()
+
+
+def test_iteration_cap_and_options(prob):
+    """Iteration cap (the reference's 'Maximum iterations'): realisations stop after max_iter iterations with finite
+    output; options are validated and frozen once the preconditioner exists."""
+    from parelagmc_b200.capi import Context, PmcError
+    c = Context(prob["nlevels"], 0)
+    try:
+        with pytest.raises(PmcError):
+            c.set_option("darcy.no_such_key", 1)
+        with pytest.raises(PmcError):
+            c.set_option("sampler.schur_ratio", 0.5)
+        c.set_option("darcy.schur_degree", 3)
+        for l, s in enumerate(prob["sampler"]):
+            c.upload_sampler_level(l, s, prob["alpha"], prob["g"], True)
+        for l, d in enumerate(prob["darcy"]):
+            c.upload_darcy_level(l, d)
+        with pytest.raises(PmcError):
+            c.upload_darcy_level(0, prob["darcy"][0])          # uploaded twice
+        c.set_tolerances(1e-14, 1e-300, 5)
+        c.rng_init(0.0, 1.0, 1, 0)
+        with pytest.raises(PmcError):
+            c.rng_init(0.0, 1.0, 4, 7)                          # mypart out of range
+        k = np.exp(np.random.default_rng(0).standard_normal((6, prob["darcy"][0].Ne)))
+        Q, C, sol, it = c.darcy_solve_batch(0, k, want_sol=True)
+        assert np.all(it == 5) and np.all(np.isfinite(sol)) and np.all(np.isfinite(Q))
+        with pytest.raises(PmcError):
+            c.set_option("darcy.schur_degree", 2)               # preconditioner already built
+        c.set_tolerances(1e-10, 1e-300, 2000)
+        Q2, _, _, it2 = c.darcy_solve_batch(0, k)
+        assert it2.max() < 2000 and np.all(np.abs(Q2 - Q) < 0.5)
+    finally:
+        c.close()
