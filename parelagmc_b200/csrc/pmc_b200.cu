@@ -28,10 +28,11 @@ struct DevCsr {
     // plain CSR (plain operators only; used by the per-solve set-up maps)
     int *rowptr = nullptr, *col = nullptr;
     double *val = nullptr;
-    // sliced ELL (SLICE rows per slice, per-slice width, zero padding): the apply format.  Weighted operators keep
-    // their weighted entries in s* (with widx) and their fixed entries in f*.
-    int *soff = nullptr, *scol = nullptr, *swidx = nullptr, *foff = nullptr, *fcol = nullptr;
-    double *sval = nullptr, *fval = nullptr;
+    // packed sliced ELL (SLICE rows per slice, per-slice width, zero padding): the apply format (layout: program.cuh,
+    // op_spmm).  The sample-independent entries of a weighted operator carry the index of a weight row that holds 1.
+    int *soff = nullptr;
+    unsigned char *spk = nullptr;
+    int max_width = 0;  // widest slice
     double matrix_bytes() const
     {
         return (double)nnz * (weighted ? 16.0 : 12.0) + (double)((weighted ? 2 : 1) * rows + 1) * 4.0;
@@ -190,6 +191,7 @@ struct pmc_context_s {
     int maxit = 300;
     PrecCfg cfg_sampler, cfg_darcy;
     int max_batch = 0, force_nt = 0, force_cs = 0;
+    bool staging = true;  // stage operator entries through shared memory (option "stage_operators")
     std::vector<SamplerLevel> s;
     std::vector<DarcyLevel> d;
     // rng
@@ -268,36 +270,51 @@ static int to_device(Ctx *c, const std::vector<T> &h, T **out)
     return PMC_OK;
 }
 
-// Sliced-ELL conversion of rows given as [begin, end) ranges into (col, val, widx) arrays.
+// Packed sliced-ELL conversion of rows given as [begin, end) ranges into (col, val, widx) arrays.
 struct HSell {
-    std::vector<int> off, col, widx;
-    std::vector<double> val;
+    std::vector<int> off;
+    std::vector<unsigned char> pk;
+    int max_width = 0;
 };
 static HSell make_sell(int rows, const std::vector<int> &beg, const std::vector<int> &end, const std::vector<int> &col,
                        const std::vector<double> &val, const std::vector<int> *widx)
 {
     HSell S;
     const int nsl = (rows + SLICE - 1) / SLICE;
+    const size_t es = widx ? 16 : 12;
     S.off.assign(nsl + 1, 0);
     for (int sl = 0; sl < nsl; ++sl) {
         int w = 0;
         for (int r = sl * SLICE; r < std::min(rows, (sl + 1) * SLICE); ++r) w = std::max(w, end[r] - beg[r]);
         S.off[sl + 1] = S.off[sl] + w;
+        S.max_width = std::max(S.max_width, w);
     }
-    const size_t total = (size_t)S.off[nsl] * SLICE;
-    S.col.assign(total, 0);
-    S.val.assign(total, 0.0);
-    if (widx) S.widx.assign(total, 0);
-    for (int r = 0; r < rows; ++r) {
-        const int sl = r / SLICE, rs = r % SLICE;
-        for (int p = beg[r], k = 0; p < end[r]; ++p, ++k) {
-            const size_t idx = (size_t)(S.off[sl] + k) * SLICE + rs;
-            S.col[idx] = col[p];
-            S.val[idx] = val[p];
-            if (widx) S.widx[idx] = (*widx)[p];
+    S.pk.assign(std::max<size_t>((size_t)S.off[nsl] * SLICE * es, 16), 0);
+    for (int sl = 0; sl < nsl; ++sl) {
+        const size_t w = (size_t)(S.off[sl + 1] - S.off[sl]);
+        unsigned char *base = S.pk.data() + (size_t)S.off[sl] * SLICE * es;
+        double *pv = reinterpret_cast<double *>(base);
+        int *pc = reinterpret_cast<int *>(base + w * SLICE * 8);
+        int *pw = pc + w * SLICE;
+        for (int r = sl * SLICE; r < std::min(rows, (sl + 1) * SLICE); ++r) {
+            const int rs = r % SLICE;
+            for (int p = beg[r], k = 0; p < end[r]; ++p, ++k) {
+                pv[(size_t)k * SLICE + rs] = val[p];
+                pc[(size_t)k * SLICE + rs] = col[p];
+                if (widx) pw[(size_t)k * SLICE + rs] = (*widx)[p];
+            }
         }
     }
     return S;
+}
+
+static int upload_sell(Ctx *c, const HSell &S, DevCsr &D)
+{
+    int rc;
+    if ((rc = to_device(c, S.off, &D.soff))) return rc;
+    if ((rc = to_device(c, S.pk, &D.spk))) return rc;
+    D.max_width = S.max_width;
+    return PMC_OK;
 }
 
 static int upload_csr(Ctx *c, const HCsr &A, DevCsr &D)
@@ -311,36 +328,26 @@ static int upload_csr(Ctx *c, const HCsr &A, DevCsr &D)
     if ((rc = to_device(c, A.col, &D.col))) return rc;
     if ((rc = to_device(c, A.val, &D.val))) return rc;
     std::vector<int> beg(A.rowptr.begin(), A.rowptr.end() - 1), end(A.rowptr.begin() + 1, A.rowptr.end());
-    HSell S = make_sell(A.rows, beg, end, A.col, A.val, nullptr);
-    if ((rc = to_device(c, S.off, &D.soff))) return rc;
-    if ((rc = to_device(c, S.col, &D.scol))) return rc;
-    if ((rc = to_device(c, S.val, &D.sval))) return rc;
-    return PMC_OK;
+    return upload_sell(c, make_sell(A.rows, beg, end, A.col, A.val, nullptr), D);
 }
 
-static int upload_wcsr(Ctx *c, const HWCsr &A, DevCsr &D)
+// const_widx: the weight row that holds the constant 1 (for the operator's sample-independent entries)
+static int upload_wcsr(Ctx *c, const HWCsr &A, DevCsr &D, int const_widx)
 {
     D.rows = A.rows;
     D.cols = A.cols;
     D.nnz = (int)A.col.size();
     D.weighted = true;
-    int rc;
-    std::vector<int> wb(A.rows), we(A.rows), fb(A.rows), fe(A.rows);
+    std::vector<int> beg(A.rows), end(A.rows), widx(A.widx);
     for (int r = 0; r < A.rows; ++r) {
-        wb[r] = A.rowptr2[2 * r];
-        we[r] = fb[r] = A.rowptr2[2 * r + 1];
-        fe[r] = A.rowptr2[2 * r + 2];
+        beg[r] = A.rowptr2[2 * r];
+        end[r] = A.rowptr2[2 * r + 2];
+        for (int p = A.rowptr2[2 * r + 1]; p < A.rowptr2[2 * r + 2]; ++p) {
+            if (const_widx < 0) return fail(c, PMC_ERR_STATE, "weighted operator with fixed entries but no constant weight row");
+            widx[p] = const_widx;
+        }
     }
-    HSell W = make_sell(A.rows, wb, we, A.col, A.val, &A.widx);
-    HSell F = make_sell(A.rows, fb, fe, A.col, A.val, nullptr);
-    if ((rc = to_device(c, W.off, &D.soff))) return rc;
-    if ((rc = to_device(c, W.col, &D.scol))) return rc;
-    if ((rc = to_device(c, W.widx, &D.swidx))) return rc;
-    if ((rc = to_device(c, W.val, &D.sval))) return rc;
-    if ((rc = to_device(c, F.off, &D.foff))) return rc;
-    if ((rc = to_device(c, F.col, &D.fcol))) return rc;
-    if ((rc = to_device(c, F.val, &D.fval))) return rc;
-    return PMC_OK;
+    return upload_sell(c, make_sell(A.rows, beg, end, A.col, A.val, &widx), D);
 }
 
 // Unique-value numbering of a symmetric pattern: uid(i,j) = uid(j,i), diagonal included.
@@ -621,11 +628,11 @@ static int prepare_darcy(Ctx *c, int level)
     int rc;
     {
         HWCsr A = wcsr_from_entries(N, N, eA);
-        if ((rc = upload_wcsr(c, A, sys.A))) return rc;
+        if ((rc = upload_wcsr(c, A, sys.A, Ne))) return rc;
         HWCsr M = wcsr_from_entries(Nf, Nf, eM);
-        if ((rc = upload_wcsr(c, M, sys.Muu))) return rc;
+        if ((rc = upload_wcsr(c, M, sys.Muu, Ne))) return rc;
         HWCsr Mbc = wcsr_from_entries(Nf, Nf, eBc);
-        if ((rc = upload_wcsr(c, Mbc, L.Mbc))) return rc;
+        if ((rc = upload_wcsr(c, Mbc, L.Mbc, Ne))) return rc;
         HCsr Dm = csr_from_coo(Nf, Ne + 1, eDm);
         if ((rc = upload_csr(c, Dm, sys.Dm))) return rc;
     }
@@ -709,7 +716,7 @@ static int prepare_darcy(Ctx *c, int level)
                     el.push_back({i, sp.uid[p], 1.0});
                 }
             HWCsr Sw = wcsr_from_entries(sp.n, sp.n, e);
-            if ((rc = upload_wcsr(c, Sw, V.S))) return rc;
+            if ((rc = upload_wcsr(c, Sw, V.S, -1))) return rc;
             HCsr Lm = csr_from_coo(sp.n, sp.nU, el);
             if ((rc = upload_csr(c, Lm, V.L))) return rc;
         }
@@ -774,6 +781,7 @@ struct Rows {
 
 struct Program {
     std::vector<Op> ops;
+    bool staging = true;  // stage operator entries through shared memory where the slices fit (F_STAGED)
     int pc() const { return (int)ops.size(); }
     Op &add(int kind, int kclass, int n, double rows_moved, double matrix_bytes = 0.0)
     {
@@ -796,9 +804,9 @@ static void emit_spmm(Program &pg, int kclass, int ep, const DevCsr &A, VecRef V
 {
     Op &o = pg.add(OP_SPMM, kclass, A.rows, rows_moved, A.matrix_bytes());
     o.flags = (ep << F_EP_SHIFT) | (A.weighted ? F_WEIGHTED : 0) | ((ep == EP_CHEB && A.weighted) ? F_BDINV : 0) |
-              (dot_slot >= 0 ? F_DOT : 0) | (dot_acc ? F_DOT_ACC : 0) | (dot_with_r ? F_DOT_WITH_R : 0);
-    o.rowptr = A.soff; o.col = A.scol; o.widx = A.swidx; o.val = A.sval;
-    o.foff = A.foff; o.fcol = A.fcol; o.fval = A.fval;
+              (dot_slot >= 0 ? F_DOT : 0) | (dot_acc ? F_DOT_ACC : 0) | (dot_with_r ? F_DOT_WITH_R : 0) |
+              ((pg.staging && A.max_width <= STW) ? F_STAGED : 0);
+    o.rowptr = A.soff; o.pk = A.spk;
     o.fixed = dinv_fixed;
     o.x = x; o.y = y; o.r = r; o.d = d; o.w = dinv_b; o.v = V;
     o.ca = ca; o.cb = cb;
@@ -1181,13 +1189,26 @@ static int finish(Ctx *c)
 template <int NTt, int MINB, int CS>
 static cudaError_t launch_program(const ProgParams &P, int ntiles, cudaStream_t stream)
 {
+    // dynamic shared memory: the per-warp operator staging buffers (program.cuh)
+    const size_t dyn = (size_t)(NTt / 32) * NSTAGE * sizeof(WarpStage);
+    static bool attr_set = false;  // per instantiation; the attribute is per device, set again on every device seen
+    static int attr_dev = -1;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!attr_set || attr_dev != dev) {
+        cudaError_t e = cudaFuncSetAttribute(k_run_program<NTt, MINB, CS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+        attr_dev = dev;
+    }
     if (CS == 1) {
-        k_run_program<NTt, MINB, 1><<<ntiles, NTt, 0, stream>>>(P);
+        k_run_program<NTt, MINB, 1><<<ntiles, NTt, dyn, stream>>>(P);
         return cudaPeekAtLastError();
     }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(ntiles * CS));
     cfg.blockDim = dim3(NTt);
+    cfg.dynamicSmemBytes = dyn;
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -1447,6 +1468,7 @@ int pmc_set_option(pmc_handle c, const char *key, double value)
     if (k == "max_batch" && value >= 0) c->max_batch = (int)value;
     else if (k == "cta_threads") c->force_nt = (int)value;
     else if (k == "cluster_size") c->force_cs = (int)value;
+    else if (k == "stage_operators") c->staging = value != 0;
     else return fail(c, PMC_ERR_ARG, "pmc_set_option: unknown key '%s'", key);
     return PMC_OK;
 }
@@ -1572,7 +1594,7 @@ int pmc_clone(pmc_handle src, pmc_handle *out)
     if (rc) return fail(src, rc, "pmc_clone: %s", pmc_last_error(nullptr));
     c->rel = src->rel; c->abs_ = src->abs_; c->maxit = src->maxit;
     c->cfg_sampler = src->cfg_sampler; c->cfg_darcy = src->cfg_darcy;
-    c->max_batch = src->max_batch; c->force_nt = src->force_nt; c->force_cs = src->force_cs;
+    c->max_batch = src->max_batch; c->force_nt = src->force_nt; c->force_cs = src->force_cs; c->staging = src->staging;
     for (int l = 0; l < src->nlevels && !rc; ++l) {
         const SamplerLevel &S = src->s[l];
         if (S.set)
@@ -1723,6 +1745,7 @@ int pmc_sampler_eval_batch(pmc_handle c, int level, int xi_level, int nsamples, 
     carve_solve(ar, sys, ws);
     const Off bufA = ar.alloc(nmax), bufB = ar.alloc(nmax), bufC = ar.alloc(nmax);
     Program pg;
+    pg.staging = c->staging;
     const Off rhs = emit_restrict(pg, c, xi_level, level, bufA, bufB);
     const Off t1 = (rhs == bufA) ? bufB : bufA;
     Off x0 = -1;
@@ -1782,6 +1805,7 @@ static int darcy_host_batch(Ctx *c, int level, int nsamples, const double *k, co
     carve_solve(ar, sys, ws);
     const Off k_ext = ar.alloc(Ne + 1), Qrow = ar.alloc(1);
     Program pg;
+    pg.staging = c->staging;
     if (apply_only) {
         Solver sv{&sys, &ws, vr(k_ext, Ne + 1)};
         emit_fill(pg, vr(k_ext, Ne + 1, Ne), 1, 1.0);  // weight of the fixed entries
@@ -1871,6 +1895,7 @@ static int level_batch(Ctx *c, int level, int nlevels, int nsamples, uint64_t po
     const Off tbuf = (SF.hasT || (!coarsest && c->s[level + 1].hasT)) ? ar.alloc(std::max(Nk, Nkc)) : -1;
     const Off mark = ar.top;
     Program pg;
+    pg.staging = c->staging;
     // Sample(level, xi) fused with rhs_s = -g W^{1/2} xi  (/root/reference/src/PDESampler.cpp:336-340, :352-358)
     {
         Op &o = pg.add(OP_RNG, KC_RNG, Ne, Ne);
@@ -2084,6 +2109,7 @@ int pmc_bayes_level_batch(pmc_handle c, int level, int nlevels, int nsamples, ui
     const Off o_z = ar.alloc(1), o_zc = ar.alloc(1), o_r = ar.alloc(1), o_rc = ar.alloc(1);
     const Off mark = ar.top;
     Program pg;
+    pg.staging = c->staging;
     std::vector<int> rng_ops;
     for (int draw = 0; draw < 2; ++draw) {  // draw 0: zxi -> Z (likelihood); draw 1: xi -> R = Q * likelihood
         rng_ops.push_back(pg.pc());

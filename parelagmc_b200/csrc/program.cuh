@@ -33,6 +33,9 @@ constexpr int LPR = 2;    // lanes per row: two adjacent threads share a row, 16
 constexpr int PW = TW / LPR;
 constexpr int SLICE = 32 / LPR;  // rows per sliced-ELL slice = rows one warp covers per pass
 constexpr int MAXWARP = 16;  // largest CTA: 512 threads
+constexpr int STW = 8;              // widest slice (entries per row) a staging buffer holds
+constexpr int STCAP = STW * SLICE;  // entries per staging buffer
+constexpr int NSTAGE = 2;           // staging buffers per warp
 
 enum { EP_AX = 0, EP_RESID = 1, EP_CHEB = 2, EP_ADD = 3 };
 
@@ -66,7 +69,8 @@ enum OpKind {
 
 enum {
     F_WEIGHTED = 1, F_BDINV = 2, F_DOT = 4, F_DOT_ACC = 8, F_DOT_WITH_R = 16, F_ABSX = 32, F_RECIP = 64,
-    F_EP_SHIFT = 8  // ep stored in bits 8..9
+    F_EP_SHIFT = 8,  // ep stored in bits 8..9
+    F_STAGED = 1024  // no slice of the operator is wider than STW: its entries are staged through shared memory
 };
 
 // kernel classes for the in-kernel time/byte accounting (same meaning as PMC_K_* in include/pmc_b200.h)
@@ -84,15 +88,13 @@ struct Op {
     int kind, flags, n, slot;
     int a0, a1, kclass, pad;
     // OP_SPMM: sliced-ELL arrays (slice = 16 rows = one warp pass; entry k of slice s, row r: index (k * 16 + r) with
-    // k in [rowptr[s], rowptr[s+1])); for weighted operators these hold the WEIGHTED entries and f* the FIXED entries.
+    // k in [rowptr[s], rowptr[s+1])); weighted operators carry a weight index per entry (their sample-independent
+    // entries point at a weight row that holds the constant 1).
     // OP_SETUP_SPMM: plain CSR arrays.
     const int *rowptr;
     const int *col;
-    const int *widx;
     const double *val;
-    const int *foff;
-    const int *fcol;
-    const double *fval;
+    const unsigned char *pk;
     const double *fixed;  // fixed (sample-independent) vector: 1/diag, obs, rhs, w_sqrt
     VecRef x, y, r, d, w, v;
     double ca, cb, bytes;  // bytes: algorithmic bytes this op moves per tile
@@ -126,6 +128,7 @@ struct Smem {
     double part[TW];   // this CTA's share of a dot product (read by the other CTAs of the cluster through DSMEM)
     int active[TW];
     int iters[TW];
+    unsigned long long bars[MAXWARP][NSTAGE];  // per-warp mbarriers of the operator staging buffers
     unsigned long long cyc[KC_COUNT];
     double cbytes[KC_COUNT];
     unsigned int cops[KC_COUNT];
@@ -205,15 +208,75 @@ __device__ __forceinline__ void block_dot(D2 acc, Smem &sm, int slot, bool accum
     }
 }
 
-// ---- sparse operator apply with fused epilogue ------------------------------------------------------------
-//   plain CSR   : row i: p in [rowptr[i], rowptr[i+1])              sum += val[p] * x[col[p]]
-//   weighted CSR: row i: p in [rowptr[2i], rowptr[2i+1])            sum += val[p] * V[widx[p]] * x[col[p]]
-//                        p in [rowptr[2i+1], rowptr[2i+2])          sum += val[p] * x[col[p]]
-//   V = per-sample weights: the permeability k_e for M(k) = sum_e k_e R_e^T M_e R_e (the element reassembly of
-//   DarcySolver::assemble, /root/reference/src/DarcySolver.cpp:479, never materialised) or the Schur values.
-template <int NTt, int CS, int EP, bool WEIGHTED, bool BDINV, bool DOT>
-__device__ __forceinline__ void op_spmm(const Op &o, double *chunk, Smem &sm)
+// ---- operator staging ------------------------------------------------------------------------------------
+// A sparse apply walks the operator slice by slice (one slice = the 16 rows a warp covers per pass).  Read straight
+// from L2, every pass is a chain of dependent long-latency loads: slice offsets -> entries (value, column, weight
+// index) -> gathers of the batched vector -> fma.  The entries of a slice are contiguous in the packed sliced-ELL
+// array, so each warp keeps NSTAGE passes of entries in flight with TMA bulk copies (cp.async.bulk, completion on a
+// per-warp mbarrier) into its own shared-memory buffers: the chain seen by the gathers shrinks to shared-memory reads.
+// No CTA-wide synchronisation is involved; warps stay decoupled.
+struct WarpStage {
+    unsigned char bytes[STCAP * 16];  // [val: w*16 doubles][col: w*16 ints][widx: w*16 ints], w <= STW
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
 {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra WAIT_DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "WAIT_DONE:\n\t"
+        "}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+                 "r"(bytes), "r"(bar)
+                 : "memory");
+}
+
+// per-warp staging state (registers; the same buffers and barriers serve every staged operation of the program)
+struct StageCtx {
+    WarpStage *buf;   // this warp's NSTAGE buffers
+    uint32_t bar;     // shared address of this warp's NSTAGE mbarriers
+    uint32_t phase;   // bit s: parity the next wait on buffer s expects
+};
+
+template <int ES>
+__device__ __forceinline__ void stage_issue(const unsigned char *pk, WarpStage *dst, uint32_t bar, int k0, int k1)
+{
+    if ((threadIdx.x & 31) == 0) {
+        const uint32_t bytes = (uint32_t)(k1 - k0) * (SLICE * ES);
+        mbar_arrive_tx(bar, bytes);
+        if (bytes) bulk_g2s(smem_u32(dst), pk + (size_t)k0 * (SLICE * ES), bytes, bar);
+    }
+}
+
+// ---- sparse operator apply with fused epilogue ------------------------------------------------------------
+//   plain    : row i of slice s: entries k in [off[s], off[s+1])     sum += val * x[col]
+//   weighted :                                                        sum += val * V[widx] * x[col]
+//   V = per-sample weights: the permeability k_e for M(k) = sum_e k_e R_e^T M_e R_e (the element reassembly of
+//   DarcySolver::assemble, /root/reference/src/DarcySolver.cpp:479, never materialised) or the Schur values; entries
+//   that do not depend on the sample (B, B^T, identity rows) point at a weight row holding the constant 1.
+//   Packed sliced ELL: slice s occupies bytes [off[s], off[s+1]) * 16 * ES of `pk` (ES = 16 weighted, 12 plain) as
+//   [val: w*16 doubles][col: w*16 ints][widx: w*16 ints], entry k of row r at index k * 16 + r.
+template <int NTt, int CS, int EP, bool WEIGHTED, bool BDINV, bool DOT, bool STAGED>
+__device__ __forceinline__ void op_spmm(const Op &o, double *chunk, Smem &sm, StageCtx &sc)
+{
+    constexpr int ES = WEIGHTED ? 16 : 12;
+    constexpr int NW = NTt / 32;
     const int sub = (threadIdx.x % LPR) * PW;  // first sample of this thread inside the row
     const double *__restrict__ x = tp(o.x, chunk) + sub;
     double *__restrict__ y = tp(o.y, chunk) + sub;
@@ -221,88 +284,117 @@ __device__ __forceinline__ void op_spmm(const Op &o, double *chunk, Smem &sm)
     double *__restrict__ d = (EP == EP_CHEB) ? tp(o.d, chunk) + sub : nullptr;
     const double *__restrict__ V = WEIGHTED ? tp(o.v, chunk) + sub : nullptr;
     const double *__restrict__ dinvb = (EP == EP_CHEB && BDINV) ? tp(o.w, chunk) + sub : nullptr;
-    const int *__restrict__ rowptr = o.rowptr;
-    const int *__restrict__ col = o.col;
-    const int *__restrict__ widx = o.widx;
-    const double *__restrict__ val = o.val;
+    const int *__restrict__ off = o.rowptr;
+    const unsigned char *__restrict__ pk = o.pk;
     const double ca = o.ca, cb = o.cb;
     const bool dot_r = (o.flags & F_DOT_WITH_R) != 0;
     D2 acc = make_double2(0.0, 0.0);
-    const int *__restrict__ foff = o.foff;
-    const int *__restrict__ fcol = o.fcol;
-    const double *__restrict__ fval = o.fval;
     int r0, r1;
     my_rows<CS>(o.n, r0, r1);
-    const int npad = (r1 + SLICE - 1) & ~(SLICE - 1);  // whole warps stay converged through the slice loops
-    for (int row = r0 + threadIdx.x / LPR; row < npad; row += NTt / LPR) {
-        const int sl = row / SLICE, rs = row % SLICE;
+    // whole warps stay converged through the slice loops; an empty range (r0 = r1 = n need not be slice-aligned) has no slices
+    const int sl_end = r1 > r0 ? (r1 + SLICE - 1) / SLICE : 0;
+    const int rs = (threadIdx.x & 31) / LPR;
+    int sl = r0 / SLICE + (threadIdx.x >> 5);
+    int wcur = 0, wnext = 0, st = 0;
+    if (STAGED) {
+#pragma unroll
+        for (int j = 0; j < NSTAGE; ++j) {
+            const int slj = sl + j * NW;
+            int k0 = 0, k1 = 0;
+            if (slj < sl_end) {
+                k0 = __ldg(off + slj);
+                k1 = __ldg(off + slj + 1);
+                stage_issue<ES>(pk, sc.buf + j, sc.bar + 8 * j, k0, k1);
+            }
+            if (j == 0) wcur = k1 - k0;
+            else wnext = k1 - k0;
+        }
+    }
+    for (; sl < sl_end; sl += NW) {
+        const int row = sl * SLICE + rs;
+        const bool live = row < r1;
+        const size_t ro = (size_t)row * TW;
+        // slice offsets of the pass that will reuse this buffer, and the streamed operands of the epilogue: issued
+        // before the gathers so that their latency overlaps them
+        const int sl2 = sl + NSTAGE * NW;
+        int n0 = 0, n1 = 0;
+        if (STAGED && sl2 < sl_end) {
+            n0 = __ldg(off + sl2);
+            n1 = __ldg(off + sl2 + 1);
+        }
+        D2 rv = make_double2(0.0, 0.0), di = rv, dv = rv, xr = rv, yv = rv;
+        if (live) {
+            if (EP == EP_RESID || EP == EP_CHEB) rv = ld2c(r + ro);
+            if (EP == EP_ADD) yv = ld2c(y + ro);
+            if (EP == EP_CHEB) {
+                if (BDINV) di = ld2c(dinvb + ro);
+                else { const double t = __ldg(o.fixed + row); di = make_double2(t, t); }
+                if (ca != 0.0) dv = ld2c(d + ro);
+            }
+            if (EP == EP_CHEB || (DOT && !dot_r)) xr = ld2c(x + ro);
+        }
+        const unsigned char *base;
+        int w;
+        if (STAGED) {
+            mbar_wait(sc.bar + 8 * st, (sc.phase >> st) & 1u);
+            sc.phase ^= 1u << st;
+            base = sc.buf[st].bytes;
+            w = wcur;
+        } else {
+            const int k0 = __ldg(off + sl);
+            w = __ldg(off + sl + 1) - k0;
+            base = pk + (size_t)k0 * (SLICE * ES);
+        }
+        const double *__restrict__ eval = reinterpret_cast<const double *>(base) + rs;
+        const int *__restrict__ ecol = reinterpret_cast<const int *>(base + (size_t)w * (SLICE * 8)) + rs;
+        const int *__restrict__ ewid = ecol + w * SLICE;
         D2 s = make_double2(0.0, 0.0);
-        if (WEIGHTED) {
-            const int k0 = __ldg(rowptr + sl), k1 = __ldg(rowptr + sl + 1);
-            const int f0 = __ldg(foff + sl), f1 = __ldg(foff + sl + 1);
 #pragma unroll 4
-            for (int k = k0; k < k1; ++k) {
-                const int idx = k * SLICE + rs;
-                const double c = __ldg(val + idx);
-                const D2 wv = ld2c(V + (size_t)__ldg(widx + idx) * TW);
-                const D2 xv = ld2c(x + (size_t)__ldg(col + idx) * TW);
+        for (int k = 0; k < w; ++k) {
+            const double c = eval[k * SLICE];
+            const D2 xv = ld2c(x + (size_t)ecol[k * SLICE] * TW);
+            if (WEIGHTED) {
+                const D2 wv = ld2c(V + (size_t)ewid[k * SLICE] * TW);
                 s.x = fma(c * wv.x, xv.x, s.x);
                 s.y = fma(c * wv.y, xv.y, s.y);
-            }
-#pragma unroll 4
-            for (int k = f0; k < f1; ++k) {
-                const int idx = k * SLICE + rs;
-                const double c = __ldg(fval + idx);
-                const D2 xv = ld2c(x + (size_t)__ldg(fcol + idx) * TW);
-                s.x = fma(c, xv.x, s.x);
-                s.y = fma(c, xv.y, s.y);
-            }
-        } else {
-            const int k0 = __ldg(rowptr + sl), k1 = __ldg(rowptr + sl + 1);
-#pragma unroll 4
-            for (int k = k0; k < k1; ++k) {
-                const int idx = k * SLICE + rs;
-                const double c = __ldg(val + idx);
-                const D2 xv = ld2c(x + (size_t)__ldg(col + idx) * TW);
+            } else {
                 s.x = fma(c, xv.x, s.x);
                 s.y = fma(c, xv.y, s.y);
             }
         }
-        if (row >= r1) continue;
-        const size_t ro = (size_t)row * TW;
-        D2 out;
-        if (EP == EP_AX) {
-            out = s;
-        } else if (EP == EP_RESID) {
-            const D2 rv = ld2c(r + ro);
-            out = make_double2(rv.x - s.x, rv.y - s.y);
-        } else if (EP == EP_ADD) {
-            const D2 yv = ld2c(y + ro);
-            out = make_double2(fma(ca, s.x, yv.x), fma(ca, s.y, yv.y));
-        } else {  // EP_CHEB: d = ca d + cb dinv (r - A z);  z_out = z + d
-            const D2 rv = ld2c(r + ro);
-            D2 di;
-            if (BDINV) di = ld2c(dinvb + ro);
-            else { const double t = __ldg(o.fixed + row); di = make_double2(t, t); }
-            D2 dn = make_double2(cb * di.x * (rv.x - s.x), cb * di.y * (rv.y - s.y));
-            if (ca != 0.0) {
-                const D2 dv = ld2c(d + ro);
-                dn.x = fma(ca, dv.x, dn.x);
-                dn.y = fma(ca, dv.y, dn.y);
+        if (live) {
+            D2 out;
+            if (EP == EP_AX) {
+                out = s;
+            } else if (EP == EP_RESID) {
+                out = make_double2(rv.x - s.x, rv.y - s.y);
+            } else if (EP == EP_ADD) {
+                out = make_double2(fma(ca, s.x, yv.x), fma(ca, s.y, yv.y));
+            } else {  // EP_CHEB: d = ca d + cb dinv (r - A z);  z_out = z + d
+                D2 dn = make_double2(cb * di.x * (rv.x - s.x), cb * di.y * (rv.y - s.y));
+                if (ca != 0.0) {
+                    dn.x = fma(ca, dv.x, dn.x);
+                    dn.y = fma(ca, dv.y, dn.y);
+                }
+                st2(d + ro, dn);
+                out = make_double2(xr.x + dn.x, xr.y + dn.y);
+                if (DOT && dot_r) {
+                    acc.x = fma(out.x, rv.x, acc.x);
+                    acc.y = fma(out.y, rv.y, acc.y);
+                }
             }
-            st2(d + ro, dn);
-            const D2 zv = ld2c(x + ro);
-            out = make_double2(zv.x + dn.x, zv.y + dn.y);
-            if (DOT && dot_r) {
-                acc.x = fma(out.x, rv.x, acc.x);
-                acc.y = fma(out.y, rv.y, acc.y);
+            st2(y + ro, out);
+            if (DOT && !dot_r) {
+                acc.x = fma(out.x, xr.x, acc.x);
+                acc.y = fma(out.y, xr.y, acc.y);
             }
         }
-        st2(y + ro, out);
-        if (DOT && !dot_r) {
-            const D2 wv = ld2c(x + ro);
-            acc.x = fma(out.x, wv.x, acc.x);
-            acc.y = fma(out.y, wv.y, acc.y);
+        if (STAGED) {
+            __syncwarp();  // every lane is done with buffer st before it is refilled
+            if (sl2 < sl_end) stage_issue<ES>(pk, sc.buf + st, sc.bar + 8 * st, n0, n1);
+            wcur = wnext;
+            wnext = n1 - n0;
+            st ^= 1;
         }
     }
     if (DOT) block_dot<NTt, CS>(acc, sm, o.slot, (o.flags & F_DOT_ACC) != 0);
@@ -545,11 +637,21 @@ template <int NTt, int MINB, int CS>
 __global__ void __launch_bounds__(NTt, MINB) k_run_program(const ProgParams P)
 {
     __shared__ Smem sm;
+    extern __shared__ __align__(128) unsigned char dyn_smem[];  // NTt/32 warps x NSTAGE staging buffers
     const int tile = blockIdx.x / CS;  // the CS CTAs of a cluster share a tile
     const int crank = cluster_rank<CS>();
     double *const chunk = P.base + (size_t)tile * (size_t)P.chunk;
     if (threadIdx.x < KC_COUNT) { sm.cyc[threadIdx.x] = 0ull; sm.cbytes[threadIdx.x] = 0.0; sm.cops[threadIdx.x] = 0u; }
     if (threadIdx.x < TW) { sm.active[threadIdx.x] = 0; sm.iters[threadIdx.x] = 0; }
+    StageCtx sc;
+    sc.buf = reinterpret_cast<WarpStage *>(dyn_smem) + (threadIdx.x >> 5) * NSTAGE;
+    sc.bar = smem_u32(&sm.bars[threadIdx.x >> 5][0]);
+    sc.phase = 0u;
+    if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+        for (int j = 0; j < NSTAGE; ++j) mbar_init(sc.bar + 8 * j, 1u);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     __syncthreads();
     const long long t_begin = clock64();
     int pc = 0;
@@ -562,17 +664,23 @@ __global__ void __launch_bounds__(NTt, MINB) k_run_program(const ProgParams P)
         case OP_SPMM: {
             const int ep = (flags >> F_EP_SHIFT) & 3;
             const bool w = flags & F_WEIGHTED, dot = flags & F_DOT;
+#define PMC_SPMM(EP_, W_, BD_, DOT_)                                                          \
+    do {                                                                                      \
+        if (flags & F_STAGED) op_spmm<NTt, CS, EP_, W_, BD_, DOT_, true>(o, chunk, sm, sc);   \
+        else op_spmm<NTt, CS, EP_, W_, BD_, DOT_, false>(o, chunk, sm, sc);                   \
+    } while (0)
             if (ep == EP_AX) {
-                if (w) { if (dot) op_spmm<NTt, CS, EP_AX, true, false, true>(o, chunk, sm); else op_spmm<NTt, CS, EP_AX, true, false, false>(o, chunk, sm); }
-                else   { if (dot) op_spmm<NTt, CS, EP_AX, false, false, true>(o, chunk, sm); else op_spmm<NTt, CS, EP_AX, false, false, false>(o, chunk, sm); }
+                if (w) { if (dot) PMC_SPMM(EP_AX, true, false, true); else PMC_SPMM(EP_AX, true, false, false); }
+                else   { if (dot) PMC_SPMM(EP_AX, false, false, true); else PMC_SPMM(EP_AX, false, false, false); }
             } else if (ep == EP_RESID) {
-                if (w) op_spmm<NTt, CS, EP_RESID, true, false, false>(o, chunk, sm); else op_spmm<NTt, CS, EP_RESID, false, false, false>(o, chunk, sm);
+                if (w) PMC_SPMM(EP_RESID, true, false, false); else PMC_SPMM(EP_RESID, false, false, false);
             } else if (ep == EP_ADD) {
-                op_spmm<NTt, CS, EP_ADD, false, false, false>(o, chunk, sm);
+                PMC_SPMM(EP_ADD, false, false, false);
             } else {
-                if (w) { if (dot) op_spmm<NTt, CS, EP_CHEB, true, true, true>(o, chunk, sm); else op_spmm<NTt, CS, EP_CHEB, true, true, false>(o, chunk, sm); }
-                else   { if (dot) op_spmm<NTt, CS, EP_CHEB, false, false, true>(o, chunk, sm); else op_spmm<NTt, CS, EP_CHEB, false, false, false>(o, chunk, sm); }
+                if (w) { if (dot) PMC_SPMM(EP_CHEB, true, true, true); else PMC_SPMM(EP_CHEB, true, true, false); }
+                else   { if (dot) PMC_SPMM(EP_CHEB, false, false, true); else PMC_SPMM(EP_CHEB, false, false, false); }
             }
+#undef PMC_SPMM
         } break;
         case OP_CHEB_FIRST:
             if (flags & F_BDINV) op_cheb_first<NTt, CS, true>(o, chunk, sm); else op_cheb_first<NTt, CS, false>(o, chunk, sm);
