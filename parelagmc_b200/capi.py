@@ -13,7 +13,7 @@ from typing import Optional, Sequence
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libpmc_b200.so")
+LIB_PATH = os.environ.get("PMC_B200_LIB") or os.path.join(_HERE, "lib", "libpmc_b200.so")   # env: diagnostic builds
 CSRC = os.path.join(_HERE, "csrc")
 
 K_CLASSES = ["saddle_apply", "lanczos_update", "solution_update", "mass_smooth", "schur_smooth", "transfer",

@@ -1249,6 +1249,12 @@ static int run_program(Ctx *c, Program &pg, int nsamples, Off chunk, int max_row
     P.stats = c->d_pstats;
     P.base = (double *)c->arena.base;
     P.chunk = chunk;
+    P.op_cycles = nullptr;
+    const char *prof_path = getenv("PMC_OP_PROFILE");  // diagnostic: per-operation cycle table of every launch
+    if (prof_path && *prof_path) {
+        CK(cudaMalloc((void **)&P.op_cycles, pg.ops.size() * 16));
+        CK(cudaMemsetAsync(P.op_cycles, 0, pg.ops.size() * 16, c->stream));
+    }
     EventPair ep;
     if (!c->ev_free.empty()) { ep = c->ev_free.back(); c->ev_free.pop_back(); }
     else { cudaEventCreate(&ep.a); cudaEventCreate(&ep.b); }
@@ -1276,6 +1282,20 @@ static int run_program(Ctx *c, Program &pg, int nsamples, Off chunk, int max_row
 #undef PMC_LAUNCH
     if (le != cudaSuccess && c->cuda_status == cudaSuccess) c->cuda_status = le;
     cudaEventRecord(ep.b, c->stream);
+    if (P.op_cycles) {
+        std::vector<unsigned long long> h(pg.ops.size() * 2);
+        cudaStreamSynchronize(c->stream);
+        cudaMemcpy(h.data(), P.op_cycles, h.size() * 8, cudaMemcpyDeviceToHost);
+        cudaFree(P.op_cycles);
+        if (FILE *f = fopen(prof_path, "a")) {
+            fprintf(f, "# launch: %d tiles, %zu ops, nt %d cs %d\n# pc kind class n flags bytes_per_tile executions cycles_per_execution\n", ntiles, pg.ops.size(), nt, cs);
+            for (size_t i = 0; i < pg.ops.size(); ++i)
+                if (h[2 * i + 1])
+                    fprintf(f, "%zu %d %d %d %d %.0f %llu %.0f\n", i, pg.ops[i].kind, pg.ops[i].kclass, pg.ops[i].n, pg.ops[i].flags,
+                            pg.ops[i].bytes, h[2 * i + 1], (double)h[2 * i] / (double)h[2 * i + 1]);
+            fclose(f);
+        }
+    }
     c->ev_pending.push_back(ep);
     c->kernel_launches++;
     cudaError_t e = cudaPeekAtLastError();

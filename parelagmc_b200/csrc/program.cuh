@@ -119,6 +119,7 @@ struct ProgParams {
     ProgStats *stats;
     double *base;      // tile chunks
     long long chunk;   // doubles per tile chunk
+    unsigned long long *op_cycles;  // diagnostic (PMC_OP_PROFILE): per-operation {cycles, executions} summed over CTAs, or null
 };
 
 struct Smem {
@@ -778,6 +779,10 @@ __global__ void __launch_bounds__(NTt, MINB) k_run_program(const ProgParams P)
         }
         op_barrier<CS>();
         if (threadIdx.x == 0) {
+            if (P.op_cycles) {
+                atomicAdd(&P.op_cycles[2 * pc], (unsigned long long)(clock64() - t0));
+                atomicAdd(&P.op_cycles[2 * pc + 1], 1ull);
+            }
             sm.cyc[o.kclass] += (unsigned long long)(clock64() - t0);
             if (crank == 0) {  // bytes and operation counts once per tile
                 sm.cbytes[o.kclass] += o.bytes;

@@ -58,9 +58,16 @@ def make_oracle(p, lognormal=True, rel=1e-12, abs_=1e-30, maxit=2000):
     return op
 
 
-def make_context(p, lognormal=True, rel=1e-12, abs_=1e-30, maxit=2000, device=0):
+def make_context(p, lognormal=True, rel=1e-12, abs_=1e-30, maxit=2000, device=0, options=None):
+    import os
     from parelagmc_b200.capi import Context
     ctx = Context(p["nlevels"], device)
+    options = dict(options or {})
+    for kv in filter(None, os.environ.get("PMC_OPTS", "").split(",")):    # diagnostic: PMC_OPTS="key=value,..."
+        k, v = kv.split("=")
+        options[k] = float(v)
+    for k, v in options.items():
+        ctx.set_option(k, v)
     for l, s in enumerate(p["sampler"]):
         ctx.upload_sampler_level(l, s, p["alpha"], p["g"], lognormal)
     if p["darcy"] is not None:
