@@ -191,6 +191,10 @@ struct pmc_context_s {
     int maxit = 300;
     PrecCfg cfg_sampler, cfg_darcy;
     int max_batch = 0, force_nt = 0, force_cs = 0;
+    int force_group = 0;  // grid-group size G (option "group_size"; 0: choose, -1: never)
+    int solo_rows = 512;  // grid-group mode: operations with at most this many rows run on the group's first CTA alone
+    void *d_grp = nullptr;   // grid-group barrier words and dot-product shares
+    size_t grp_cap = 0;
     bool staging = true;  // stage operator entries through shared memory (option "stage_operators")
     std::vector<SamplerLevel> s;
     std::vector<DarcyLevel> d;
@@ -781,6 +785,10 @@ struct Rows {
 
 struct Program {
     std::vector<Op> ops;
+    int force_group = 0;  // grid-group size G (option "group_size"; 0: choose, -1: never)
+    int solo_rows = 512;  // grid-group mode: operations with at most this many rows run on the group's first CTA alone
+    void *d_grp = nullptr;   // grid-group barrier words and dot-product shares
+    size_t grp_cap = 0;
     bool staging = true;  // stage operator entries through shared memory where the slices fit (F_STAGED)
     int pc() const { return (int)ops.size(); }
     Op &add(int kind, int kclass, int n, double rows_moved, double matrix_bytes = 0.0)
@@ -1205,6 +1213,19 @@ static cudaError_t launch_program(const ProgParams &P, int ntiles, cudaStream_t 
         k_run_program<NTt, MINB, 1><<<ntiles, NTt, dyn, stream>>>(P);
         return cudaPeekAtLastError();
     }
+    if (CS == 0) {  // grid groups: cooperative launch, P.group CTAs per tile, all co-resident
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)(ntiles * P.group));
+        cfg.blockDim = dim3(NTt);
+        cfg.dynamicSmemBytes = dyn;
+        cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeCooperative;
+        attr[0].val.cooperative = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        return cudaLaunchKernelEx(&cfg, k_run_program<NTt, MINB, 0>, P);
+    }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(ntiles * CS));
     cfg.blockDim = dim3(NTt);
@@ -1233,8 +1254,6 @@ static int run_program(Ctx *c, Program &pg, int nsamples, Off chunk, int max_row
     } else {
         CK(cudaStreamSynchronize(c->stream));  // the pinned staging buffer may still be in use by the previous copy
     }
-    memcpy(c->h_ops, pg.ops.data(), bytes);
-    CK(cudaMemcpyAsync(c->d_ops, c->h_ops, bytes, cudaMemcpyHostToDevice, c->stream));
     ProgParams P;
     P.ops = c->d_ops;
     P.nops = (int)pg.ops.size();
@@ -1273,9 +1292,61 @@ static int run_program(Ctx *c, Program &pg, int nsamples, Off chunk, int max_row
         while (cs < 8 && (long long)ntiles * cs * 2 <= slots && max_rows / (cs * 2) >= 1024) cs *= 2;
     }
     if (c->force_cs == 1 || ((c->force_cs == 2 || c->force_cs == 4 || c->force_cs == 8) && nt >= 256)) cs = c->force_cs;
+    // grid groups: when even clusters of 8 would leave most of the machine idle (one or two tiles of a very large
+    // level), a tile is split over G co-resident CTAs of a cooperative launch, every CTA keeping >= ~2000 rows
+    int group = 0;
+    {
+        const long long slots = 148LL * 2;  // 512-thread CTAs, two per SM
+        if (c->force_group > 1) group = c->force_group;
+        else if (c->force_group == 0 && c->force_cs == 0 && nt == 512 && (long long)ntiles * 8 * 3 <= slots) {
+            long long g = std::min<long long>(slots / ntiles, max_rows / 2048);
+            if (g > 8) group = (int)g;
+        }
+        if (group > 1 && (long long)ntiles * group > slots) group = (int)(slots / ntiles);
+        if (group <= 1) group = 0;
+    }
+    P.group = group;
+    P.grp_bar = nullptr;
+    P.grp_part = nullptr;
+    if (group) {
+        nt = 512;
+        cs = 0;
+        const size_t bar_bytes = (((size_t)ntiles * 2 * sizeof(unsigned int)) + 255) & ~(size_t)255;
+        const size_t need = bar_bytes + (size_t)ntiles * group * TW * sizeof(double);
+        if (need > c->grp_cap) {
+            if (c->d_grp) { cudaStreamSynchronize(c->stream); cudaFree(c->d_grp); }
+            c->d_grp = nullptr;
+            c->grp_cap = 0;
+            CK(cudaMalloc(&c->d_grp, need));
+            c->grp_cap = need;
+        }
+        CK(cudaMemsetAsync(c->d_grp, 0, bar_bytes, c->stream));
+        P.grp_bar = (unsigned int *)c->d_grp;
+        P.grp_part = (double *)((char *)c->d_grp + bar_bytes);
+        // operations that stay on the group's first CTA, and the barriers that can stay CTA-local
+        std::vector<Op> &ops = pg.ops;
+        auto solo_kind = [](int k) {
+            return k == OP_SPMM || k == OP_CHEB_FIRST || k == OP_LINCOMB3 || k == OP_SOL_UPDATE || k == OP_SETUP_SPMM || k == OP_FILL ||
+                   k == OP_COPY || k == OP_BROADCAST || k == OP_MAP_EXP;
+        };
+        auto scalar_kind = [](int k) {
+            return k == OP_SC_INIT || k == OP_SC_ALPHA || k == OP_SC_BETA || k == OP_CHECK || k == OP_JUMP || k == OP_STORE_ITERS ||
+                   k == OP_LIKELIHOOD;
+        };
+        for (Op &o : ops) {
+            o.flags &= ~(F_SOLO | F_LOCAL_SYNC);
+            if (solo_kind(o.kind) && o.n <= c->solo_rows && !(o.flags & F_DOT)) o.flags |= F_SOLO;
+            if (scalar_kind(o.kind)) o.flags |= F_LOCAL_SYNC;
+        }
+        for (size_t i = 0; i + 1 < ops.size(); ++i)
+            if ((ops[i].flags & F_SOLO) && (ops[i + 1].flags & F_SOLO)) ops[i].flags |= F_LOCAL_SYNC;
+    }
+    memcpy(c->h_ops, pg.ops.data(), bytes);
+    CK(cudaMemcpyAsync(c->d_ops, c->h_ops, bytes, cudaMemcpyHostToDevice, c->stream));
     cudaError_t le = cudaSuccess;
 #define PMC_LAUNCH(NT_, MINB_, CS_) le = launch_program<NT_, MINB_, CS_>(P, ntiles, c->stream)
-    if (nt == 512) { if (cs == 8) PMC_LAUNCH(512, 2, 8); else if (cs == 4) PMC_LAUNCH(512, 2, 4); else if (cs == 2) PMC_LAUNCH(512, 2, 2); else PMC_LAUNCH(512, 2, 1); }
+    if (group) PMC_LAUNCH(512, 2, 0);
+    else if (nt == 512) { if (cs == 8) PMC_LAUNCH(512, 2, 8); else if (cs == 4) PMC_LAUNCH(512, 2, 4); else if (cs == 2) PMC_LAUNCH(512, 2, 2); else PMC_LAUNCH(512, 2, 1); }
     else if (nt == 256) { if (cs == 8) PMC_LAUNCH(256, 4, 8); else if (cs == 4) PMC_LAUNCH(256, 4, 4); else if (cs == 2) PMC_LAUNCH(256, 4, 2); else PMC_LAUNCH(256, 4, 1); }
     else if (nt == 128) PMC_LAUNCH(128, 8, 1);
     else PMC_LAUNCH(64, 16, 1);
@@ -1411,6 +1482,7 @@ void pmc_destroy(pmc_handle c)
     cudaFree(c->d_pstats);
     cudaFree(c->d_tab);
     if (c->d_ops) cudaFree(c->d_ops);
+    if (c->d_grp) cudaFree(c->d_grp);
     if (c->h_ops) cudaFreeHost(c->h_ops);
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
     for (auto &ep : c->ev_pending) { cudaEventDestroy(ep.a); cudaEventDestroy(ep.b); }
@@ -1489,6 +1561,8 @@ int pmc_set_option(pmc_handle c, const char *key, double value)
     else if (k == "cta_threads") c->force_nt = (int)value;
     else if (k == "cluster_size") c->force_cs = (int)value;
     else if (k == "stage_operators") c->staging = value != 0;
+    else if (k == "group_size") c->force_group = (int)value;
+    else if (k == "solo_rows" && value >= 0) c->solo_rows = (int)value;
     else return fail(c, PMC_ERR_ARG, "pmc_set_option: unknown key '%s'", key);
     return PMC_OK;
 }
@@ -1614,7 +1688,7 @@ int pmc_clone(pmc_handle src, pmc_handle *out)
     if (rc) return fail(src, rc, "pmc_clone: %s", pmc_last_error(nullptr));
     c->rel = src->rel; c->abs_ = src->abs_; c->maxit = src->maxit;
     c->cfg_sampler = src->cfg_sampler; c->cfg_darcy = src->cfg_darcy;
-    c->max_batch = src->max_batch; c->force_nt = src->force_nt; c->force_cs = src->force_cs; c->staging = src->staging;
+    c->max_batch = src->max_batch; c->force_nt = src->force_nt; c->force_cs = src->force_cs; c->staging = src->staging; c->force_group = src->force_group; c->solo_rows = src->solo_rows;
     for (int l = 0; l < src->nlevels && !rc; ++l) {
         const SamplerLevel &S = src->s[l];
         if (S.set)

@@ -70,7 +70,10 @@ enum OpKind {
 enum {
     F_WEIGHTED = 1, F_BDINV = 2, F_DOT = 4, F_DOT_ACC = 8, F_DOT_WITH_R = 16, F_ABSX = 32, F_RECIP = 64,
     F_EP_SHIFT = 8,  // ep stored in bits 8..9
-    F_STAGED = 1024  // no slice of the operator is wider than STW: its entries are staged through shared memory
+    F_STAGED = 1024,  // no slice of the operator is wider than STW: its entries are staged through shared memory
+    // grid-group mode only (a tile owned by G CTAs of a cooperative launch):
+    F_SOLO = 2048,       // small operation: executed by the group's first CTA alone
+    F_LOCAL_SYNC = 4096  // nothing this operation writes is read by another CTA before the next group barrier
 };
 
 // kernel classes for the in-kernel time/byte accounting (same meaning as PMC_K_* in include/pmc_b200.h)
@@ -119,6 +122,9 @@ struct ProgParams {
     ProgStats *stats;
     double *base;      // tile chunks
     long long chunk;   // doubles per tile chunk
+    int group;                 // grid-group mode (CS = 0): CTAs per tile
+    unsigned int *grp_bar;     //   [ntiles][2] barrier words, zeroed before the launch
+    double *grp_part;          //   [ntiles][group][TW]
     unsigned long long *op_cycles;  // diagnostic (PMC_OP_PROFILE): per-operation {cycles, executions} summed over CTAs, or null
 };
 
@@ -130,6 +136,9 @@ struct Smem {
     int active[TW];
     int iters[TW];
     unsigned long long bars[MAXWARP][NSTAGE];  // per-warp mbarriers of the operator staging buffers
+    int grp_size, grp_rank;                    // grid-group mode: CTAs per tile and this CTA's rank among them
+    unsigned int *grp_bar;                     //   {count, generation} of the tile's barrier (global memory)
+    double *grp_part;                          //   [grp_size][TW] dot-product shares of the tile (global memory)
     unsigned long long cyc[KC_COUNT];
     double cbytes[KC_COUNT];
     unsigned int cops[KC_COUNT];
@@ -146,25 +155,60 @@ __device__ __forceinline__ double safe_inv(double x) { return x != 0.0 ? 1.0 / x
 // every operation's rows are split into CS contiguous ranges (multiples of a slice), the barrier between operations
 // becomes a cluster barrier, and dot products are combined through distributed shared memory in rank order, so every
 // CTA of the cluster holds the same scalars and takes the same branches.  CS = 1 compiles to plain CTA barriers.
+//
+// GRID GROUPS (CS = 0).  A cluster is at most 8 CTAs, so a batch of one or two tiles of a very large level (SPE10's
+// 4.5 M-row fine level holds 2 GB per tile) would still leave most of the machine idle.  In this mode a tile is owned
+// by a GROUP of G CTAs of a cooperative launch (all co-resident): rows are split G ways, the barrier between
+// operations is a sense-reversing barrier on a word in global memory (release/acquire fences at GPU scope, which also
+// invalidate the SM's L1), dot-product shares travel through global memory and are added in rank order by every CTA.
+// Operations too small to be worth a group barrier (the coarse levels of the V-cycle) are executed by the group's
+// first CTA alone (F_SOLO) and chained with CTA-local barriers (F_LOCAL_SYNC); scalar operations only touch shared
+// memory and never need the group barrier.
 template <int CS>
-__device__ __forceinline__ int cluster_rank()
+__device__ __forceinline__ int cluster_rank(const Smem &sm)
 {
     if (CS == 1) return 0;
+    if (CS == 0) return sm.grp_rank;
     return (int)cg::this_cluster().block_rank();
 }
 template <int CS>
-__device__ __forceinline__ void my_rows(int n, int &r0, int &r1)
+__device__ __forceinline__ void my_rows(const Op &o, const Smem &sm, int &r0, int &r1)
 {
+    const int n = o.n;
     if (CS == 1) { r0 = 0; r1 = n; return; }
-    const int per = (((n + CS - 1) / CS) + SLICE - 1) & ~(SLICE - 1);
-    r0 = min(n, cluster_rank<CS>() * per);
+    if (CS == 0 && (o.flags & F_SOLO)) { r0 = 0; r1 = sm.grp_rank == 0 ? n : 0; return; }
+    const int parts = CS == 0 ? sm.grp_size : CS;
+    const int per = (((n + parts - 1) / parts) + SLICE - 1) & ~(SLICE - 1);
+    r0 = min(n, cluster_rank<CS>(sm) * per);
     r1 = min(n, r0 + per);
 }
+// barrier of the tile's grid group: every thread of every CTA of the group calls it
+__device__ __forceinline__ void group_barrier(const Smem &sm)
+{
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        volatile unsigned int *gen_p = sm.grp_bar + 1;
+        const unsigned int gen = *gen_p;  // cannot advance before this CTA has arrived
+        __threadfence();
+        if (atomicAdd(sm.grp_bar, 1u) == (unsigned int)sm.grp_size - 1u) {
+            *(volatile unsigned int *)sm.grp_bar = 0u;
+            __threadfence();
+            atomicAdd(sm.grp_bar + 1, 1u);
+        } else {
+            while (*gen_p == gen) __nanosleep(32);
+        }
+        __threadfence();
+    }
+    __syncthreads();
+}
 template <int CS>
-__device__ __forceinline__ void op_barrier()
+__device__ __forceinline__ void op_barrier(const Smem &sm, int flags)
 {
     if (CS == 1) __syncthreads();
-    else cg::this_cluster().sync();
+    else if (CS == 0) {
+        if (flags & F_LOCAL_SYNC) __syncthreads();
+        else group_barrier(sm);
+    } else cg::this_cluster().sync();
 }
 
 // Deterministic reduction.  Every thread holds the partial sums of its PW samples (lane parity selects which
@@ -191,6 +235,20 @@ __device__ __forceinline__ void block_dot(D2 acc, Smem &sm, int slot, bool accum
             for (int w = 0; w < NTt / 32; ++w) s += sm.red[w][threadIdx.x];
             sm.dots[slot][threadIdx.x] = s;
         }
+    } else if (CS == 0) {
+        if (threadIdx.x < TW) {
+            double s = 0.0;
+#pragma unroll
+            for (int w = 0; w < NTt / 32; ++w) s += sm.red[w][threadIdx.x];
+            sm.grp_part[sm.grp_rank * TW + threadIdx.x] = s;
+        }
+        group_barrier(sm);
+        if (threadIdx.x < TW) {
+            double s = accumulate ? sm.dots[slot][threadIdx.x] : 0.0;
+            for (int r = 0; r < sm.grp_size; ++r) s += __ldcg(sm.grp_part + r * TW + threadIdx.x);
+            sm.dots[slot][threadIdx.x] = s;
+        }
+        // the group barrier that ends the operation keeps the shares alive until every CTA has read them
     } else {
         if (threadIdx.x < TW) {
             double s = 0.0;
@@ -291,7 +349,7 @@ __device__ __forceinline__ void op_spmm(const Op &o, double *chunk, Smem &sm, St
     const bool dot_r = (o.flags & F_DOT_WITH_R) != 0;
     D2 acc = make_double2(0.0, 0.0);
     int r0, r1;
-    my_rows<CS>(o.n, r0, r1);
+    my_rows<CS>(o, sm, r0, r1);
     // whole warps stay converged through the slice loops; an empty range (r0 = r1 = n need not be slice-aligned) has no slices
     const int sl_end = r1 > r0 ? (r1 + SLICE - 1) / SLICE : 0;
     const int rs = (threadIdx.x & 31) / LPR;
@@ -406,7 +464,7 @@ __device__ __forceinline__ void op_cheb_first(const Op &o, double *chunk, Smem &
 {
     const int sub = (threadIdx.x % LPR) * PW;
     int r0, r1;
-    my_rows<CS>(o.n, r0, r1);
+    my_rows<CS>(o, sm, r0, r1);
     const double *__restrict__ r = tp(o.r, chunk) + sub;
     double *__restrict__ d = tp(o.d, chunk) + sub;
     double *__restrict__ z = tp(o.y, chunk) + sub;
@@ -436,7 +494,7 @@ __device__ __forceinline__ void op_lincomb3(const Op &o, double *chunk, Smem &sm
 {
     const int sub = (threadIdx.x % LPR) * PW;
     int r0, r1;
-    my_rows<CS>(o.n, r0, r1);
+    my_rows<CS>(o, sm, r0, r1);
     const double *__restrict__ q = tp(o.x, chunk) + sub;
     const double *__restrict__ v1 = tp(o.r, chunk) + sub;
     double *__restrict__ v0 = tp(o.y, chunk) + sub;
@@ -475,7 +533,7 @@ __device__ __forceinline__ void op_sol_update(const Op &o, double *chunk, Smem &
 {
     const int sub = (threadIdx.x % LPR) * PW;
     int r0, r1;
-    my_rows<CS>(o.n, r0, r1);
+    my_rows<CS>(o, sm, r0, r1);
     double *__restrict__ w0 = tp(o.y, chunk) + sub;
     const double *__restrict__ w1 = tp(o.r, chunk) + sub;
     const double *__restrict__ u1 = tp(o.x, chunk) + sub;
@@ -498,11 +556,11 @@ __device__ __forceinline__ void op_sol_update(const Op &o, double *chunk, Smem &
 }
 
 template <int NTt, int CS>
-__device__ __forceinline__ void op_setup_spmm(const Op &o, double *chunk)
+__device__ __forceinline__ void op_setup_spmm(const Op &o, double *chunk, const Smem &sm)
 {
     const int sub = (threadIdx.x % LPR) * PW;
     int r0, r1;
-    my_rows<CS>(o.n, r0, r1);
+    my_rows<CS>(o, sm, r0, r1);
     const double *__restrict__ x = tp(o.x, chunk) + sub;
     double *__restrict__ y = tp(o.y, chunk) + sub;
     const bool absx = (o.flags & F_ABSX) != 0, recip = (o.flags & F_RECIP) != 0;
@@ -608,11 +666,11 @@ __device__ __forceinline__ void sc_beta(const Op &o, Smem &sm, const ProgParams 
 // Noise generation fused with the SPDE right-hand-side scaling: thread (chunk c, sample j) jumps to stream position
 // u0 + sample * n + c * T and steps T times (PDESampler::Sample + :352-358 of src/PDESampler.cpp).
 template <int NTt, int CS>
-__device__ __forceinline__ void op_rng(const Op &o, int tile, double *chunk, const ProgParams &P)
+__device__ __forceinline__ void op_rng(const Op &o, int tile, double *chunk, const ProgParams &P, const Smem &sm)
 {
     double *__restrict__ y = tp(o.y, chunk);
-    const int j = threadIdx.x & (TW - 1), c = cluster_rank<CS>() * (NTt / TW) + threadIdx.x / TW;
-    constexpr int NCH = CS * NTt / TW;
+    const int j = threadIdx.x & (TW - 1), c = cluster_rank<CS>(sm) * (NTt / TW) + threadIdx.x / TW;
+    const int NCH = (CS == 0 ? sm.grp_size : CS) * NTt / TW;
     const int T = (o.n + NCH - 1) / NCH;
     const int i0 = c * T, i1 = min(o.n, i0 + T);
     const int sample = tile * TW + j;
@@ -639,8 +697,14 @@ __global__ void __launch_bounds__(NTt, MINB) k_run_program(const ProgParams P)
 {
     __shared__ Smem sm;
     extern __shared__ __align__(128) unsigned char dyn_smem[];  // NTt/32 warps x NSTAGE staging buffers
-    const int tile = blockIdx.x / CS;  // the CS CTAs of a cluster share a tile
-    const int crank = cluster_rank<CS>();
+    const int gsz = CS == 0 ? P.group : CS;
+    const int tile = blockIdx.x / gsz;  // the CTAs of a cluster / grid group share a tile
+    if (CS == 0 && threadIdx.x == 0) {
+        sm.grp_size = gsz;
+        sm.grp_rank = blockIdx.x % gsz;
+        sm.grp_bar = P.grp_bar + 2 * (size_t)tile;
+        sm.grp_part = P.grp_part + (size_t)tile * gsz * TW;
+    }
     double *const chunk = P.base + (size_t)tile * (size_t)P.chunk;
     if (threadIdx.x < KC_COUNT) { sm.cyc[threadIdx.x] = 0ull; sm.cbytes[threadIdx.x] = 0.0; sm.cops[threadIdx.x] = 0u; }
     if (threadIdx.x < TW) { sm.active[threadIdx.x] = 0; sm.iters[threadIdx.x] = 0; }
@@ -654,6 +718,7 @@ __global__ void __launch_bounds__(NTt, MINB) k_run_program(const ProgParams P)
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
+    const int crank = cluster_rank<CS>(sm);
     const long long t_begin = clock64();
     int pc = 0;
     while (pc < P.nops) {
@@ -691,19 +756,19 @@ __global__ void __launch_bounds__(NTt, MINB) k_run_program(const ProgParams P)
             else op_lincomb3<NTt, CS, false, false>(o, chunk, sm);
             break;
         case OP_SOL_UPDATE: op_sol_update<NTt, CS>(o, chunk, sm); break;
-        case OP_SETUP_SPMM: op_setup_spmm<NTt, CS>(o, chunk); break;
+        case OP_SETUP_SPMM: op_setup_spmm<NTt, CS>(o, chunk, sm); break;
         case OP_FILL: {
             double *y = tp(o.y, chunk);
             const double v = o.ca;
             int r0, r1;
-            my_rows<CS>(o.n, r0, r1);
+            my_rows<CS>(o, sm, r0, r1);
             for (int i = r0 * (TW / 2) + threadIdx.x; i < r1 * (TW / 2); i += NTt) reinterpret_cast<double2 *>(y)[i] = make_double2(v, v);
         } break;
         case OP_COPY: {
             const double2 *x = reinterpret_cast<const double2 *>(tp(o.x, chunk));
             double2 *y = reinterpret_cast<double2 *>(tp(o.y, chunk));
             int r0, r1;
-            my_rows<CS>(o.n, r0, r1);
+            my_rows<CS>(o, sm, r0, r1);
 #pragma unroll 4
             for (int i = r0 * (TW / 2) + threadIdx.x; i < r1 * (TW / 2); i += NTt) y[i] = x[i];
         } break;
@@ -711,7 +776,7 @@ __global__ void __launch_bounds__(NTt, MINB) k_run_program(const ProgParams P)
             double *y = tp(o.y, chunk);
             const int sub = (threadIdx.x % LPR) * PW;
             int r0, r1;
-            my_rows<CS>(o.n, r0, r1);
+            my_rows<CS>(o, sm, r0, r1);
             for (int row = r0 + threadIdx.x / LPR; row < r1; row += NTt / LPR) {
                 const double v = __ldg(o.fixed + row);
                 st2(y + (size_t)row * TW + sub, make_double2((tile * TW + sub < P.nsamples) ? v : 0.0,
@@ -722,7 +787,7 @@ __global__ void __launch_bounds__(NTt, MINB) k_run_program(const ProgParams P)
             const double *x = tp(o.x, chunk);
             double *y = tp(o.y, chunk);
             int r0, r1;
-            my_rows<CS>(o.n, r0, r1);
+            my_rows<CS>(o, sm, r0, r1);
             for (int i = r0 * TW + threadIdx.x; i < r1 * TW; i += NTt) y[i] = exp(x[i]);
         } break;
         case OP_DOT_FIXED: {
@@ -730,7 +795,7 @@ __global__ void __launch_bounds__(NTt, MINB) k_run_program(const ProgParams P)
             const double *x = tp(o.x, chunk) + sub;
             D2 acc = make_double2(0.0, 0.0);
             int r0, r1;
-            my_rows<CS>(o.n, r0, r1);
+            my_rows<CS>(o, sm, r0, r1);
             for (int row = r0 + threadIdx.x / LPR; row < r1; row += NTt / LPR) {
                 const double w = __ldg(o.fixed + row);
                 if (w != 0.0) {
@@ -760,7 +825,7 @@ __global__ void __launch_bounds__(NTt, MINB) k_run_program(const ProgParams P)
                 if (sample < P.nsamples) atomicAdd(&P.stats->iters_total, (unsigned long long)sm.iters[threadIdx.x]);
             }
             break;
-        case OP_RNG: op_rng<NTt, CS>(o, tile, chunk, P); break;
+        case OP_RNG: op_rng<NTt, CS>(o, tile, chunk, P, sm); break;
         case OP_LIKELIHOOD:
             // BayesianInverseProblem::ComputeLikelihood / ComputeR (/root/reference/src/BayesianInverseProblem.cpp:190-218)
             if (threadIdx.x < TW && crank == 0) {
@@ -777,7 +842,7 @@ __global__ void __launch_bounds__(NTt, MINB) k_run_program(const ProgParams P)
             break;
         default: break;
         }
-        op_barrier<CS>();
+        op_barrier<CS>(sm, flags);
         if (threadIdx.x == 0) {
             if (P.op_cycles) {
                 atomicAdd(&P.op_cycles[2 * pc], (unsigned long long)(clock64() - t0));
@@ -791,7 +856,7 @@ __global__ void __launch_bounds__(NTt, MINB) k_run_program(const ProgParams P)
         }
         pc = next;
     }
-    op_barrier<CS>();  // no CTA of a cluster exits while another may still read its shared memory
+    op_barrier<CS>(sm, 0);  // no CTA of a cluster exits while another may still read its shared memory
     if (threadIdx.x < KC_COUNT && sm.cyc[threadIdx.x]) atomicAdd(&P.stats->class_cycles[threadIdx.x], sm.cyc[threadIdx.x]);
     if (threadIdx.x < KC_COUNT && sm.cops[threadIdx.x]) {
         atomicAdd(&P.stats->class_bytes[threadIdx.x], sm.cbytes[threadIdx.x]);

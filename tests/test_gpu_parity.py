@@ -446,6 +446,44 @@ def test_cluster_split_matches_single_cta(prob, cs):
         ck.close()
 
 
+@pytest.mark.parametrize("group,solo", [(3, 0), (5, 64), (16, 4096), (37, 100)])
+def test_grid_group_matches_single_cta(prob, group, solo):
+    """A tile owned by a group of G CTAs of a cooperative launch (rows split G ways, barrier and dot-product shares
+    through global memory, small operations on the group's first CTA alone) gives the results of the
+    one-CTA-per-tile kernel to round-off."""
+    from parelagmc_b200.capi import Context
+    def ctx_with(g):
+        c = Context(prob["nlevels"], 0)
+        if g:
+            c.set_option("group_size", g)
+            c.set_option("solo_rows", solo)
+        else:
+            c.set_option("group_size", -1)
+            c.set_option("cluster_size", 1)
+        for l, s in enumerate(prob["sampler"]):
+            c.upload_sampler_level(l, s, prob["alpha"], prob["g"], True)
+        for l, d in enumerate(prob["darcy"]):
+            c.upload_darcy_level(l, d)
+        c.set_tolerances(1e-12, 1e-30, 2000)
+        c.rng_init(0.0, 1.0, 1, 0)
+        return c
+    c1, cg = ctx_with(0), ctx_with(group)
+    try:
+        for lev, ns in [(0, 6), (1, 7), (2, 3)]:
+            _, r1, _ = c1.mlmc_level_batch(lev, ns, 55, want_rows=True)
+            for rep in range(2):                                  # the barrier words are reused launch after launch
+                _, rg, _ = cg.mlmc_level_batch(lev, ns, 55, want_rows=True)
+                assert np.allclose(r1, rg, rtol=1e-9, atol=1e-12), (group, lev, rep, np.abs(r1 - rg).max())
+        d = prob["darcy"][0]
+        k = np.exp(np.random.default_rng(3).standard_normal((5, d.Ne)))
+        Q1, _, s1, it1 = c1.darcy_solve_batch(0, k, want_sol=True)
+        Qg, _, sg, itg = cg.darcy_solve_batch(0, k, want_sol=True)
+        assert rel_l2(sg, s1) < 1e-9 and np.array_equal(it1, itg)
+    finally:
+        c1.close()
+        cg.close()
+
+
 def test_iteration_cap_and_options(prob):
     """Iteration cap (the reference's 'Maximum iterations'): realisations stop after max_iter iterations with finite
     output; options are validated and frozen once the preconditioner exists."""

@@ -18,6 +18,8 @@ ap.add_argument("--check", action="store_true", help="compare the coarsest level
 ap.add_argument("--rel", type=float, default=1e-6)
 ap.add_argument("--opt", action="append", default=[], help="key=value for pmc_set_option")
 ap.add_argument("--min-level", type=int, default=0)
+ap.add_argument("--max-level", type=int, default=-1, help="coarsest level to run (default: all)")
+ap.add_argument("--repeat", type=int, default=1)
 a = ap.parse_args()
 n = [max(8, int(round(x * a.scale))) for x in (60, 220, 85)]
 t0 = time.time()
@@ -40,7 +42,8 @@ c.set_tolerances(a.rel, 1e-14, 3000)
 c.rng_init(0.0, 1.0, 1, 0)
 c.prepare()
 print(f"upload + device set-up {time.time()-t0:.1f} s", flush=True)
-for lev in range(a.levels - 1, a.min_level - 1, -1):
+for lev in range(a.levels - 1 if a.max_level < 0 else a.max_level, a.min_level - 1, -1):
+  for rep in range(a.repeat):
     ns = a.samples * (4 ** min(lev, 2))
     c.reset_stats()
     t0 = time.time()
