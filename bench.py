@@ -267,10 +267,19 @@ def run_product(args):
     st = solo[dom]
     kst = st["kernel"]
     classes = [n for n in st if n != "kernel"]
+    traffic, traffic_note = None, None
+    try:   # DRAM bytes of the dominant launch from the committed ncu capture (per launch, like algo_bytes of the solo pass)
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r1g_traffic.json")))
+        traffic = float(tj["dram_bytes_read"] + tj["dram_bytes_write"])
+        traffic_note = (f"dram__bytes_read.sum + dram__bytes_write.sum of one level-0 launch, {tj['source']}; algorithmic "
+                        f"bytes of that launch {tj['algo_bytes'] / 1e9:.2f} GB")
+    except Exception:
+        pass
     roofline = {"bound": "hbm",
                 "kernel": "k_run_program (tile-persistent solver: a whole level batch per launch; the 3 level batches of a "
                           "step run as 3 concurrent launches)",
-                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                "traffic_note": traffic_note,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
                 "launches": n_launch, "algo_bytes_per_launch": total_bytes / max(1, n_launch),
                 "avg_launch_us": 1e3 * sum(x["kernel"]["ms"] for x in stats) / max(1, n_launch),
