@@ -76,8 +76,12 @@ int pmc_set_preconditioner(pmc_handle h, int mass_degree, int schur_degree, doub
  * <k> in {mass_degree, schur_degree, schur_ratio, coarse_degree, coarse_ratio, omega (over-correction factor of the
  * coarse-grid correction), max_vlevels (depth of the Schur V-cycle; 0 = full hierarchy, -1 = decide from the mass
  * term, sampler only), amg (coarse spaces of the Schur V-cycle: 0 = the hierarchy's L2 prolongators, 1 = strength-aware
- * pairwise aggregation built at set-up, -1 = aggregation only when the couplings are anisotropic)}; and "max_batch",
- * "cta_threads". */
+ * pairwise aggregation built at set-up, -1 = aggregation only when the couplings are anisotropic)}; and the launch
+ * shape of the solver kernel (all optional, the library chooses): "max_batch", "cta_threads" (64/128/256/512),
+ * "cluster_size" (1/2/4/8 CTAs of a thread-block cluster per tile of 4 realisations), "group_size" (G > 1: G co-resident
+ * CTAs of a cooperative launch per tile, for one or two tiles of very large levels; -1 = never), "solo_rows" (in a group,
+ * operations with at most this many rows run on its first CTA), "stage_operators" (0 = read operator entries from L2
+ * instead of staging them through shared memory with TMA bulk copies). */
 int pmc_set_option(pmc_handle h, const char *key, double value);
 /* Largest number of realisations processed per kernel launch (0 = choose from free device memory), and
  * how many MINRES iterations are queued between convergence checks. */
