@@ -321,6 +321,143 @@ def build_box_hierarchy(n_fine: Sequence[int], lengths: Sequence[float], nlevels
 
 
 # --------------------------------------------------------------------------------------
+# tetrahedral meshes (BASELINE configs[2] is a tet mesh): Kuhn triangulation of a cube grid, nested under refinement
+# --------------------------------------------------------------------------------------
+_KUHN = [(0, 1, 2), (0, 2, 1), (1, 0, 2), (1, 2, 0), (2, 0, 1), (2, 1, 0)]
+
+
+def _kuhn_locate(x: np.ndarray, n: int, h: float) -> np.ndarray:
+    """Index of a Kuhn simplex (cell * 6 + permutation) whose closure contains each point of x [m, 3]."""
+    c = np.clip(np.floor(x / h + 1e-12).astype(np.int64), 0, n - 1)
+    loc = x / h - c
+    order = np.argsort(-loc, axis=1, kind="stable")          # a_{pi0} >= a_{pi1} >= a_{pi2}
+    code = order[:, 0] * 9 + order[:, 1] * 3 + order[:, 2]
+    lut = np.full(27, -1, dtype=np.int64)
+    for i, pm in enumerate(_KUHN):
+        lut[pm[0] * 9 + pm[1] * 3 + pm[2]] = i
+    cell = (c[:, 2] * n + c[:, 1]) * n + c[:, 0]
+    return cell * 6 + lut[code]
+
+
+@dataclass
+class _TetMesh:
+    n: int
+    h: float
+    verts: np.ndarray      # [nv, 3]
+    tets: np.ndarray       # [Ne, 4] vertex ids; local face a is opposite vertex a
+    tet_face: np.ndarray   # [Ne, 4] global face ids
+    tet_sign: np.ndarray   # [Ne, 4] +1 if the tet's outward normal agrees with the face's global orientation
+    face_verts: np.ndarray  # [Nf, 3] sorted vertex ids (global orientation = (b-a) x (c-a))
+    vol: np.ndarray        # [Ne]
+
+
+def _kuhn_mesh(n: int, length: float) -> _TetMesh:
+    h = length / n
+    g = np.arange(n + 1) * h
+    X, Y, Z = np.meshgrid(g, g, g, indexing="ij")
+    vid = lambda i, j, k: (k * (n + 1) + j) * (n + 1) + i
+    verts = np.empty(((n + 1) ** 3, 3))
+    I, J, K = np.meshgrid(np.arange(n + 1), np.arange(n + 1), np.arange(n + 1), indexing="ij")
+    verts[vid(I, J, K).ravel()] = np.stack([X.ravel(), Y.ravel(), Z.ravel()], axis=1)
+    ci, cj, ck = np.meshgrid(np.arange(n), np.arange(n), np.arange(n), indexing="ij")
+    order = np.argsort(((ck * n + cj) * n + ci).ravel(), kind="stable")
+    ci, cj, ck = ci.ravel()[order], cj.ravel()[order], ck.ravel()[order]
+    tets = np.empty((n ** 3, 6, 4), dtype=np.int64)
+    for t, pm in enumerate(_KUHN):
+        off = np.zeros((4, 3), dtype=np.int64)
+        for s_ in range(3):
+            off[s_ + 1] = off[s_]
+            off[s_ + 1, pm[s_]] += 1
+        for v in range(4):
+            tets[:, t, v] = vid(ci + off[v, 0], cj + off[v, 1], ck + off[v, 2])
+    tets = tets.reshape(-1, 4)
+    Ne = tets.shape[0]
+    # faces: local face a = the three vertices other than a; numbered in order of first appearance (locality)
+    loc = np.stack([np.sort(np.delete(tets, a, axis=1), axis=1) for a in range(4)], axis=1).reshape(-1, 3)   # [Ne*4, 3]
+    key = (loc[:, 0] * verts.shape[0] + loc[:, 1]) * verts.shape[0] + loc[:, 2]
+    uniq, first, inv = np.unique(key, return_index=True, return_inverse=True)
+    rank = np.empty_like(first)
+    rank[np.argsort(first, kind="stable")] = np.arange(first.size)
+    tet_face = rank[inv].reshape(Ne, 4)
+    face_verts = np.empty((first.size, 3), dtype=np.int64)
+    face_verts[rank] = loc[first]
+    Pv = verts[tets]                                                  # [Ne, 4, 3]
+    vol = np.abs(np.einsum("ex,ex->e", np.cross(Pv[:, 1] - Pv[:, 0], Pv[:, 2] - Pv[:, 0]), Pv[:, 3] - Pv[:, 0])) / 6.0
+    fa, fb, fc = (verts[face_verts[:, i]] for i in range(3))
+    area_vec = 0.5 * np.cross(fb - fa, fc - fa)                       # global orientation
+    cen = (fa + fb + fc) / 3.0
+    sign = np.empty((Ne, 4))
+    for a in range(4):
+        f = tet_face[:, a]
+        sign[:, a] = np.sign(np.einsum("ex,ex->e", area_vec[f], cen[f] - Pv[:, a]))
+    return _TetMesh(n=n, h=h, verts=verts, tets=tets, tet_face=tet_face, tet_sign=sign, face_verts=face_verts, vol=vol)
+
+
+def _tet_level(m: _TetMesh, length: float) -> LevelData:
+    """RT0 / P0 on tetrahedra with flux dofs: phi_a = sigma_a (x - p_a) / (3 |T|), so that the flux of phi_a through
+    face a in the face's global orientation is 1 (the dofs ParELAG's finest level inherits from MFEM's RT0)."""
+    Ne, Nf = m.tets.shape[0], m.face_verts.shape[0]
+    Pv = m.verts[m.tets]
+    A = Pv[:, None, :, :] - Pv[:, :, None, :]                          # A[e, a, c] = p_c - p_a
+    G = np.einsum("eacx,ebdx->eabcd", A, A)
+    I = (G.sum(axis=(3, 4)) + np.einsum("eabcc->eab", G)) * (m.vol / 20.0)[:, None, None]
+    mats = m.tet_sign[:, :, None] * m.tet_sign[:, None, :] * I / (9.0 * m.vol * m.vol)[:, None, None]
+    rows = np.repeat(np.arange(Ne, dtype=np.int64), 4)
+    Binc = _csr(sp.coo_matrix((m.tet_sign.ravel(), (rows, m.tet_face.ravel())), shape=(Ne, Nf)))
+    D = _csr(sp.diags(1.0 / m.vol) @ Binc)
+    B = _csr(sp.diags(m.vol) @ D)
+    # boundary faces: exactly one adjacent tet; attribute from the cube side (same numbering as the hex meshes)
+    cnt = np.bincount(m.tet_face.ravel(), minlength=Nf)
+    bf = np.nonzero(cnt == 1)[0]
+    fv = m.verts[m.face_verts[bf]]                                    # [nb, 3, 3]
+    attr_of = {(2, 0): 1, (1, 0): 2, (0, 1): 3, (1, 1): 4, (0, 0): 5, (2, 1): 6}
+    ba = np.zeros(bf.size, dtype=np.int32)
+    for (axis, side), at in attr_of.items():
+        on = np.all(np.abs(fv[:, :, axis] - (0.0 if side == 0 else length)) < 1e-9 * max(length, 1.0), axis=1)
+        ba[on] = at
+    assert np.all(ba > 0)
+    sgn_of_face = np.zeros(Nf)
+    sgn_of_face[m.tet_face.ravel()] = m.tet_sign.ravel()              # boundary faces have one contributor
+    return LevelData(dim=3, Ne=Ne, Nf=Nf, elem_ptr=(np.arange(Ne + 1, dtype=np.int64) * 4).astype(np.int32),
+                     elem_dofs=m.tet_face.ravel().astype(np.int32), elem_mat_ptr=np.arange(Ne + 1, dtype=np.int64) * 16,
+                     elem_mat=mats.ravel(), Wdiag=m.vol.copy(), D=D, B=B, bdr_face=bf.astype(np.int32), bdr_attr=ba,
+                     bdr_sign=sgn_of_face[bf].copy())
+
+
+def _tet_prolongators(fine: _TetMesh, coarse: _TetMesh):
+    """Nested Kuhn meshes: P_s = injection of piecewise constants; P_u = RT0 interpolation, i.e. the flux of every
+    coarse basis function through every fine face."""
+    cen_t = fine.verts[fine.tets].mean(axis=1)
+    parent = _kuhn_locate(cen_t, coarse.n, coarse.h)
+    P_s = _csr(sp.coo_matrix((np.ones(parent.size), (np.arange(parent.size), parent)),
+                             shape=(fine.tets.shape[0], coarse.tets.shape[0])))
+    fa, fb, fc = (fine.verts[fine.face_verts[:, i]] for i in range(3))
+    S = 0.5 * np.cross(fb - fa, fc - fa)
+    xc = (fa + fb + fc) / 3.0
+    T = _kuhn_locate(xc, coarse.n, coarse.h)
+    Pv = coarse.verts[coarse.tets[T]]                                  # [Nf_f, 4, 3]
+    val = coarse.tet_sign[T] * np.einsum("fax,fx->fa", xc[:, None, :] - Pv, S) / (3.0 * coarse.vol[T])[:, None]
+    rows = np.repeat(np.arange(xc.shape[0]), 4)
+    cols = coarse.tet_face[T].ravel()
+    v = val.ravel()
+    keep = np.abs(v) > 1e-12
+    P_u = _csr(sp.coo_matrix((v[keep], (rows[keep], cols[keep])), shape=(xc.shape[0], coarse.face_verts.shape[0])))
+    return P_u, P_s
+
+
+def build_tet_hierarchy(n_fine: int, length: float, nlevels: int) -> List[LevelData]:
+    """Levels 0 (finest) .. nlevels-1 of the Kuhn triangulation (6 tetrahedra per cube) of an n_fine^3 grid on
+    [0, length]^3, coarsened by halving the grid; the coarse spaces are RT0 / P0 on the coarse tetrahedra, which the
+    nested refinement makes subspaces of the fine ones."""
+    assert n_fine % (2 ** (nlevels - 1)) == 0
+    meshes = [_kuhn_mesh(n_fine >> l, length) for l in range(nlevels)]
+    levels = [_tet_level(m, length) for m in meshes]
+    for l in range(nlevels - 1):
+        levels[l].P_u, levels[l].P_s = _tet_prolongators(meshes[l], meshes[l + 1])
+    return levels
+
+
+# --------------------------------------------------------------------------------------
 # host-once setup that the reference performs in BuildHierarchy / Build*Functional
 # --------------------------------------------------------------------------------------
 @dataclass
@@ -445,6 +582,24 @@ def embedded_selection(orig: List[LevelData], embed: List[LevelData], pad_cells:
         idx = lo.grid.elem_grid()
         j = le.grid.elem_index([i + pad for i in idx])
         out.append(_csr(sp.coo_matrix((np.ones(lo.Ne), (np.arange(lo.Ne), j)), shape=(lo.Ne, le.Ne))))
+    return out
+
+
+def tet_embedded_selection(n_orig: int, pad_cells: int, nlevels: int) -> List[sp.csr_matrix]:
+    """meshP for the tetrahedral pair of `MLMC_EmbeddedPDESampler` (BASELINE configs[2]): the Kuhn mesh of the n^3 box
+    sits `pad_cells` fine cells inside the Kuhn mesh of the (n + 2 pad)^3 box; tetrahedron (cell, permutation) of the
+    original mesh coincides with (shifted cell, same permutation) of the enlarged one on every level."""
+    out = []
+    for l in range(nlevels):
+        n, pad = n_orig >> l, pad_cells >> l
+        assert pad << l == pad_cells and n << l == n_orig
+        ne = n + 2 * pad
+        i, j, k = np.meshgrid(np.arange(n), np.arange(n), np.arange(n), indexing="ij")
+        co = ((k * n + j) * n + i).ravel()
+        ce = (((k + pad) * ne + (j + pad)) * ne + (i + pad)).ravel()
+        rows = (co[:, None] * 6 + np.arange(6)[None, :]).ravel()
+        cols = (ce[:, None] * 6 + np.arange(6)[None, :]).ravel()
+        out.append(_csr(sp.coo_matrix((np.ones(rows.size), (rows, cols)), shape=(6 * n ** 3, 6 * ne ** 3))))
     return out
 
 

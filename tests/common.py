@@ -21,6 +21,17 @@ def hex_problem(n=16, nlevels=3, corlen=0.1, length=2.0, bc="mlmc"):
 
 
 @functools.lru_cache(maxsize=None)
+def tet_problem(n=4, nlevels=2, corlen=0.3, length=2.0):
+    """Tetrahedral meshes (BASELINE configs[2] runs on a tet mesh): Kuhn triangulation of an n^3 grid on [0,2]^3,
+    nested coarsening, RT0 / P0 on every level, the MLMC drivers' boundary conditions."""
+    L = H.build_tet_hierarchy(n, length, nlevels)
+    SL = H.build_sampler_levels(L)
+    DL = H.build_darcy_levels(L, **H.MLMC_DEFAULT_BC)
+    return dict(levels=L, sampler=SL, darcy=DL, alpha=H.spde_alpha(corlen),
+                g=H.matern_scaling_coefficient(corlen, 3), nlevels=nlevels)
+
+
+@functools.lru_cache(maxsize=None)
 def quad_problem(n=4, nlevels=2, corlen=0.1):
     """PDESamplerTest on inline_quad.mesh: unit square, 2x2 quads refined to n x n."""
     L = H.build_box_hierarchy([n] * 2, [1.0] * 2, nlevels)
@@ -37,6 +48,16 @@ def enlarged_problem(kind="embedded", n=8, nlevels=2, corlen=0.3):
     (L2ProjectionPDESampler)."""
     import dataclasses
     h = 2.0 / n
+    if kind == "embedded_tet":      # BASELINE configs[2]: tetrahedral forward mesh inside a tetrahedral enlarged mesh
+        n, pad = 4, 2
+        h = 2.0 / n
+        orig = H.build_tet_hierarchy(n, 2.0, nlevels)
+        emb = H.build_tet_hierarchy(n + 2 * pad, 2.0 + 2 * pad * h, nlevels)
+        T = [(m, None) for m in H.tet_embedded_selection(n, pad, nlevels)]
+        SL = [dataclasses.replace(s, T=t[0], Tscale=t[1]) for s, t in zip(H.build_sampler_levels(emb), T)]
+        DL = H.build_darcy_levels(orig, **H.MLMC_DEFAULT_BC)
+        return dict(levels=orig, embed_levels=emb, sampler=SL, darcy=DL, alpha=H.spde_alpha(corlen),
+                    g=H.matern_scaling_coefficient(corlen, 3), nlevels=nlevels)
     orig = H.build_box_hierarchy([n] * 3, [2.0] * 3, nlevels)
     if kind == "embedded":
         pad = 2

@@ -343,6 +343,38 @@ def test_other_problems_match_oracle(case):
         c.close()
 
 
+def test_tetrahedral_hierarchy_matches_oracle():
+    """Unstructured-style input (RT0 on tetrahedra: 4 dofs per element, 7-entry mass rows, 4-entry prolongator rows):
+    Darcy solutions, sampler fields and MLMC rows against the oracle, and Q = 2 for k == 1."""
+    from common import tet_problem
+    p = tet_problem(4, 2)
+    c = make_context(p)
+    o = make_oracle(p)
+    try:
+        rng = np.random.default_rng(11)
+        for lev in range(2):
+            d, s = p["darcy"][lev], p["sampler"][lev]
+            Q, C, _, _ = c.darcy_solve_batch(lev, np.ones((3, d.Ne)))
+            assert np.allclose(Q, 2.0, atol=1e-9) and np.all(C == d.N)
+            k = np.exp(0.8 * rng.standard_normal((5, d.Ne)))
+            Q, C, sol, it = c.darcy_solve_batch(lev, k, want_sol=True)
+            for j in range(5):
+                q, _, so, _ = o.darcy_solve(lev, k[j], want_sol=True)
+                assert rel_l2(sol[j], so) < FIELD_TOL, (lev, j, rel_l2(sol[j], so))
+                assert abs(Q[j] - q) <= 1e-8 * max(abs(q), 1e-3)
+            xi = rng.standard_normal((4, s.Ne))
+            kk, emb, _ = c.sampler_eval_batch(lev, xi)
+            for j in range(4):
+                ko, eo, _ = o.sampler_eval(lev, xi[j])
+                assert rel_l2(emb[j], eo) < FIELD_TOL and rel_l2(kk[j], ko) < FIELD_TOL
+        sums, rows, _ = c.mlmc_level_batch(0, 7, 31, want_rows=True)
+        osums, orows, _ = o.mlmc_level(0, 7, 31, nthreads=4)
+        assert np.allclose(rows[:, :3], orows[:, :3], rtol=1e-7, atol=1e-9)
+        assert np.allclose(sums, osums, rtol=1e-6, atol=1e-9)
+    finally:
+        c.close()
+
+
 def test_clone_runs_levels_concurrently_with_identical_results(ctx, prob):
     """pmc_clone: same hierarchy and stream of random numbers, own CUDA stream; results are bitwise those of the
     original handle, also when the level batches run from concurrent host threads."""
@@ -359,7 +391,7 @@ def test_clone_runs_levels_concurrently_with_identical_results(ctx, prob):
         c2.close()
 
 
-@pytest.mark.parametrize("kind", ["embedded", "l2proj"])
+@pytest.mark.parametrize("kind", ["embedded", "l2proj", "embedded_tet"])
 def test_enlarged_domain_samplers_match_oracle(kind):
     """SURVEY 8f-1 (EmbeddedPDESampler, matching enlarged mesh + meshP selection) and 8f-2 (L2ProjectionPDESampler apply,
     non-matching enlarged mesh + W^-1 G^T): sampler outputs on the forward mesh, and the fused MLMC level loop."""

@@ -41,6 +41,38 @@ def test_quad_level_sizes():
     assert [(s.Ne, s.Nf) for s in p["sampler"]] == [(16, 40), (4, 12)]
 
 
+def test_tet_hierarchy_known_answers():
+    """Tetrahedral levels: the transfer operators commute with the divergence, the coarse spaces are nested (Galerkin
+    mass = coarse mass), and with k == 1 the exact solution (pressure linear in z, constant flux) lies in RT0 x P0, so
+    Q = 2 on every level as on the hex meshes."""
+    from common import tet_problem
+    p = tet_problem(4, 2)
+    f, c = p["levels"]
+    assert (f.Ne, f.Nf, c.Ne, c.Nf) == (384, 864, 48, 120)
+    assert abs(f.D @ f.P_u - f.P_s @ c.D).max() < 1e-12
+    assert abs(f.P_u.T @ f.assemble_M() @ f.P_u - c.assemble_M()).max() < 1e-12
+    assert np.diff(f.assemble_M().indptr).max() == 7        # 2 tetrahedra x 4 faces, one shared
+    o = make_oracle(p)
+    for lev in range(2):
+        d = p["darcy"][lev]
+        q, cdofs, sol, _ = o.darcy_solve(lev, np.ones(d.Ne), want_sol=True)
+        assert cdofs == d.N and q == pytest.approx(2.0, abs=1e-9)
+    rng = np.random.default_rng(4)
+    for lev in range(2):                                    # variable k and the SPDE sampler against direct solves
+        d, lv, s = p["darcy"][lev], p["levels"][lev], p["sampler"][lev]
+        k = np.exp(rng.standard_normal(d.Ne))
+        keep = sp.diags((d.ess_u == 0).astype(float))
+        A = sp.bmat([[keep @ lv.assemble_M(k) @ keep + sp.diags((d.ess_u != 0).astype(float)), (d.B @ keep).T],
+                     [d.B @ keep, None]], format="csc")
+        rhs = d.rhs.copy()
+        rhs[:d.Nf][d.ess_u != 0] = 0.0
+        assert rel_l2(o.darcy_solve(lev, k, want_sol=True)[2], spla.spsolve(A, rhs)) < 1e-8
+        xi = rng.standard_normal(s.Ne)
+        As = sp.bmat([[s.M, s.B.T], [s.B, -p["alpha"] * sp.diags(s.Wdiag)]], format="csc")
+        x = spla.spsolve(As, np.concatenate([np.zeros(s.Nf), -p["g"] * xi * s.w_sqrt]))
+        assert rel_l2(o.sampler_eval(lev, xi)[1], x[s.Nf:]) < 1e-9
+
+
 def test_sampler_against_direct_solve():
     p = hex_problem(8, 3)
     o = make_oracle(p, lognormal=False)
@@ -183,7 +215,7 @@ def test_exp_w_regression_and_statistics():
     assert r1["missing"] == max(int(math.ceil(v / (0.5 * 1e-3) - 50)), 0)
 
 
-@pytest.mark.parametrize("kind", ["embedded", "l2proj"])
+@pytest.mark.parametrize("kind", ["embedded", "l2proj", "embedded_tet"])
 def test_enlarged_domain_sampler_oracle(kind):
     """EmbeddedPDESampler / L2ProjectionPDESampler apply step: oracle against a direct solve on the
     enlarged mesh followed by the transfer, and basic properties of the transfer matrices."""
@@ -194,7 +226,7 @@ def test_enlarged_domain_sampler_oracle(kind):
     for lev in range(p["nlevels"]):
         s = p["sampler"][lev]
         assert s.T.shape == (p["darcy"][lev].Ne, s.Ne)
-        if kind == "embedded":
+        if kind in ("embedded", "embedded_tet"):
             assert np.all(s.T.data == 1.0) and np.all(np.diff(s.T.indptr) == 1)   # 0/1 selection
         else:
             assert np.allclose(s.Tscale * np.asarray(s.T.sum(axis=1)).ravel(), 1.0)   # averages: constants preserved
