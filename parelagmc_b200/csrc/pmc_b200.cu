@@ -196,6 +196,7 @@ struct pmc_context_s {
     void *d_grp = nullptr;   // grid-group barrier words and dot-product shares
     size_t grp_cap = 0;
     bool staging = true;  // stage operator entries through shared memory (option "stage_operators")
+    bool defer_x = true;  // option "defer_x"
     std::vector<SamplerLevel> s;
     std::vector<DarcyLevel> d;
     // rng
@@ -790,6 +791,7 @@ struct Program {
     void *d_grp = nullptr;   // grid-group barrier words and dot-product shares
     size_t grp_cap = 0;
     bool staging = true;  // stage operator entries through shared memory where the slices fit (F_STAGED)
+    bool defer_x = true;  // MINRES: apply the solution updates of an iteration pair in one pass (option "defer_x")
     int pc() const { return (int)ops.size(); }
     Op &add(int kind, int kclass, int n, double rows_moved, double matrix_bytes = 0.0)
     {
@@ -1056,8 +1058,9 @@ static void emit_minres(Program &pg, Solver &sv, bool x_nonzero, bool store_iter
     emit_fill(pg, vr(ws.w1, N), N, 0.0);
     emit_prec(pg, sv, ws.v1, ws.u1, 1);
     { Op &o = pg.add(OP_SC_INIT, KC_SCALAR, 0, 0); o.slot = 1; }
-    std::vector<int> exits;
-    exits.push_back(pg.pc());
+    std::vector<int> exits_a, exits_b;
+    const bool defer_x = pg.defer_x;
+    exits_b.push_back(pg.pc());
     pg.add(OP_CHECK, KC_SCALAR, 0, 0);
     const int loop_start = pg.pc();
     Off v0 = ws.v0, v1 = ws.v1, w0 = ws.w0, w1 = ws.w1, u1 = ws.u1, q = ws.q;
@@ -1081,17 +1084,29 @@ static void emit_minres(Program &pg, Solver &sv, bool x_nonzero, bool store_iter
             }
         }
         emit_prec(pg, sv, v0, q, 1, fuse_jacobi);
-        { Op &o = pg.add(OP_SC_BETA, KC_SCALAR, 0, 0); o.slot = 1; }
-        { Op &o = pg.add(OP_SOL_UPDATE, KC_SOLUPD, N, 6.0 * N); o.y = vr(w0, N); o.r = vr(w1, N); o.x = vr(u1, N); o.d = vr(ws.x, N); }
-        exits.push_back(pg.pc());
+        // The solution update x += cx w of the first iteration of a pair is deferred and applied together with the
+        // second one's (which reads that direction vector anyway): one read and one write of x less per pair, the same
+        // floating-point operations in the same order.
+        { Op &o = pg.add(OP_SC_BETA, KC_SCALAR, 0, 0); o.slot = 1; o.a0 = defer_x && parity == 0 ? 1 : 0; }
+        {
+            const int mode = !defer_x ? 0 : (parity == 0 ? 1 : 2);
+            Op &o = pg.add(OP_SOL_UPDATE, KC_SOLUPD, N, mode == 1 ? 4.0 * N : 6.0 * N);
+            o.y = vr(w0, N); o.r = vr(w1, N); o.x = vr(u1, N); o.d = vr(ws.x, N);
+            o.a0 = mode;
+        }
+        (parity == 0 ? exits_a : exits_b).push_back(pg.pc());
         pg.add(OP_CHECK, KC_SCALAR, 0, 0);
         std::swap(u1, q);
         std::swap(v0, v1);
         std::swap(w0, w1);
     }
     { Op &o = pg.add(OP_JUMP, KC_SCALAR, 0, 0); o.a0 = loop_start; }
-    const int exit_pc = pg.pc();
-    for (int e : exits) pg.ops[e].a0 = exit_pc;
+    // leaving after the first iteration of a pair: apply its deferred update (w0 of that iteration = ws.w0)
+    const int exit_a = pg.pc();
+    if (defer_x) { Op &o = pg.add(OP_SOL_UPDATE, KC_SOLUPD, N, 3.0 * N); o.y = vr(ws.w0, N); o.d = vr(ws.x, N); o.a0 = 3; }
+    const int exit_b = pg.pc();
+    for (int e : exits_a) pg.ops[e].a0 = exit_a;
+    for (int e : exits_b) pg.ops[e].a0 = exit_b;
     { Op &o = pg.add(OP_STORE_ITERS, KC_SCALAR, 0, 0); o.y = store_iters ? vr(ws.iters) : VNULL; }
 }
 
@@ -1561,6 +1576,7 @@ int pmc_set_option(pmc_handle c, const char *key, double value)
     else if (k == "cta_threads") c->force_nt = (int)value;
     else if (k == "cluster_size") c->force_cs = (int)value;
     else if (k == "stage_operators") c->staging = value != 0;
+    else if (k == "defer_x") c->defer_x = value != 0;
     else if (k == "group_size") c->force_group = (int)value;
     else if (k == "solo_rows" && value >= 0) c->solo_rows = (int)value;
     else return fail(c, PMC_ERR_ARG, "pmc_set_option: unknown key '%s'", key);
@@ -1688,7 +1704,7 @@ int pmc_clone(pmc_handle src, pmc_handle *out)
     if (rc) return fail(src, rc, "pmc_clone: %s", pmc_last_error(nullptr));
     c->rel = src->rel; c->abs_ = src->abs_; c->maxit = src->maxit;
     c->cfg_sampler = src->cfg_sampler; c->cfg_darcy = src->cfg_darcy;
-    c->max_batch = src->max_batch; c->force_nt = src->force_nt; c->force_cs = src->force_cs; c->staging = src->staging; c->force_group = src->force_group; c->solo_rows = src->solo_rows;
+    c->max_batch = src->max_batch; c->force_nt = src->force_nt; c->force_cs = src->force_cs; c->staging = src->staging; c->defer_x = src->defer_x; c->force_group = src->force_group; c->solo_rows = src->solo_rows;
     for (int l = 0; l < src->nlevels && !rc; ++l) {
         const SamplerLevel &S = src->s[l];
         if (S.set)
@@ -1840,6 +1856,7 @@ int pmc_sampler_eval_batch(pmc_handle c, int level, int xi_level, int nsamples, 
     const Off bufA = ar.alloc(nmax), bufB = ar.alloc(nmax), bufC = ar.alloc(nmax);
     Program pg;
     pg.staging = c->staging;
+    pg.defer_x = c->defer_x;
     const Off rhs = emit_restrict(pg, c, xi_level, level, bufA, bufB);
     const Off t1 = (rhs == bufA) ? bufB : bufA;
     Off x0 = -1;
@@ -1900,6 +1917,7 @@ static int darcy_host_batch(Ctx *c, int level, int nsamples, const double *k, co
     const Off k_ext = ar.alloc(Ne + 1), Qrow = ar.alloc(1);
     Program pg;
     pg.staging = c->staging;
+    pg.defer_x = c->defer_x;
     if (apply_only) {
         Solver sv{&sys, &ws, vr(k_ext, Ne + 1)};
         emit_fill(pg, vr(k_ext, Ne + 1, Ne), 1, 1.0);  // weight of the fixed entries
@@ -1990,6 +2008,7 @@ static int level_batch(Ctx *c, int level, int nlevels, int nsamples, uint64_t po
     const Off mark = ar.top;
     Program pg;
     pg.staging = c->staging;
+    pg.defer_x = c->defer_x;
     // Sample(level, xi) fused with rhs_s = -g W^{1/2} xi  (/root/reference/src/PDESampler.cpp:336-340, :352-358)
     {
         Op &o = pg.add(OP_RNG, KC_RNG, Ne, Ne);
@@ -2204,6 +2223,7 @@ int pmc_bayes_level_batch(pmc_handle c, int level, int nlevels, int nsamples, ui
     const Off mark = ar.top;
     Program pg;
     pg.staging = c->staging;
+    pg.defer_x = c->defer_x;
     std::vector<int> rng_ops;
     for (int draw = 0; draw < 2; ++draw) {  // draw 0: zxi -> Z (likelihood); draw 1: xi -> R = Q * likelihood
         rng_ops.push_back(pg.pc());

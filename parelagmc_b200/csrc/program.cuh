@@ -41,7 +41,7 @@ enum { EP_AX = 0, EP_RESID = 1, EP_CHEB = 2, EP_ADD = 3 };
 
 enum {
     ST_BETA = 0, ST_IB, ST_IBPREV, ST_G0, ST_G1, ST_S0, ST_S1, ST_ETA, ST_GOAL, ST_ALPHA,
-    ST_CQ, ST_CV1, ST_CV0, ST_CW0, ST_CW1, ST_CU, ST_CX, ST_COUNT
+    ST_CQ, ST_CV1, ST_CV0, ST_CW0, ST_CW1, ST_CU, ST_CX, ST_CXP, ST_COUNT
 };
 
 enum OpKind {
@@ -50,6 +50,9 @@ enum OpKind {
     OP_LINCOMB3,      // y = cq x + cv1 r + cv0 y  (per-sample coefficients); with F_DOT: fused mass-block Jacobi
                       //   d[row < a0] = cb * dinv * y, dots[slot] = y . d over those rows
     OP_SOL_UPDATE,    // y = cw0 y + cw1 r + cu x ; d += cx y   (y = w0, r = w1, x = u1, d = solution)
+                      //   a0 = 1: the solution update is deferred (its coefficient is kept in ST_CXP)
+                      //   a0 = 2: d += cxp r + cx y  (the deferred update of the previous iteration, then this one)
+                      //   a0 = 3: d += cxp y only    (flush of a deferred update when the loop is left)
     OP_SETUP_SPMM,    // y = f(A g(x))           flags: absx | recip
     OP_FILL,          // y = ca
     OP_COPY,          // y = x
@@ -535,19 +538,48 @@ __device__ __forceinline__ void op_sol_update(const Op &o, double *chunk, Smem &
     int r0, r1;
     my_rows<CS>(o, sm, r0, r1);
     double *__restrict__ w0 = tp(o.y, chunk) + sub;
+    const int mode = o.a0;
+    const D2 ep = make_double2(sm.st[ST_CXP][sub], sm.st[ST_CXP][sub + 1]);
+    if (mode == 3) {  // x += cxp w0
+        double *__restrict__ xs = tp(o.d, chunk) + sub;
+        if (ep.x == 0.0 && ep.y == 0.0) return;
+#pragma unroll 4
+        for (int row = r0 + threadIdx.x / LPR; row < r1; row += NTt / LPR) {
+            const size_t ro = (size_t)row * TW;
+            const D2 wv = ld2c(w0 + ro);
+            D2 xv = ld2c(xs + ro);
+            if (ep.x != 0.0) xv.x = fma(ep.x, wv.x, xv.x);
+            if (ep.y != 0.0) xv.y = fma(ep.y, wv.y, xv.y);
+            st2(xs + ro, xv);
+        }
+        return;
+    }
     const double *__restrict__ w1 = tp(o.r, chunk) + sub;
     const double *__restrict__ u1 = tp(o.x, chunk) + sub;
-    double *__restrict__ xs = tp(o.d, chunk) + sub;
+    double *__restrict__ xs = mode == 1 ? nullptr : tp(o.d, chunk) + sub;
     const D2 a = make_double2(sm.st[ST_CW0][sub], sm.st[ST_CW0][sub + 1]);
     const D2 b = make_double2(sm.st[ST_CW1][sub], sm.st[ST_CW1][sub + 1]);
     const D2 c = make_double2(sm.st[ST_CU][sub], sm.st[ST_CU][sub + 1]);
     const D2 e = make_double2(sm.st[ST_CX][sub], sm.st[ST_CX][sub + 1]);
+    if (mode == 1) {  // directions only; the solution is updated together with the next iteration's
+#pragma unroll 4
+        for (int row = r0 + threadIdx.x / LPR; row < r1; row += NTt / LPR) {
+            const size_t ro = (size_t)row * TW;
+            const D2 w0v = ld2c(w0 + ro), w1v = ld2c(w1 + ro), uv = ld2c(u1 + ro);
+            st2(w0 + ro, make_double2(fma(a.x, w0v.x, fma(b.x, w1v.x, c.x * uv.x)), fma(a.y, w0v.y, fma(b.y, w1v.y, c.y * uv.y))));
+        }
+        return;
+    }
 #pragma unroll 4
     for (int row = r0 + threadIdx.x / LPR; row < r1; row += NTt / LPR) {
         const size_t ro = (size_t)row * TW;
         const D2 w0v = ld2c(w0 + ro), w1v = ld2c(w1 + ro), uv = ld2c(u1 + ro);
         D2 xv = ld2c(xs + ro);
         const D2 wn = make_double2(fma(a.x, w0v.x, fma(b.x, w1v.x, c.x * uv.x)), fma(a.y, w0v.y, fma(b.y, w1v.y, c.y * uv.y)));
+        if (mode == 2) {  // the previous iteration's update first: same operations in the same order as undeferred
+            if (ep.x != 0.0) xv.x = fma(ep.x, w1v.x, xv.x);
+            if (ep.y != 0.0) xv.y = fma(ep.y, w1v.y, xv.y);
+        }
         if (e.x != 0.0) xv.x = fma(e.x, wn.x, xv.x);
         if (e.y != 0.0) xv.y = fma(e.y, wn.y, xv.y);
         st2(w0 + ro, wn);
@@ -599,6 +631,7 @@ __device__ __forceinline__ void sc_init(const Op &o, int tile, Smem &sm, const P
     sm.st[ST_S1][j] = 0.0;
     sm.st[ST_ETA][j] = eta;
     sm.st[ST_GOAL][j] = goal;
+    sm.st[ST_CXP][j] = 0.0;
     sm.active[j] = (sample < P.nsamples) && (eta > goal);
     sm.iters[j] = 0;
 }
@@ -661,6 +694,7 @@ __device__ __forceinline__ void sc_beta(const Op &o, Smem &sm, const ProgParams 
     sm.st[ST_CW1][j] = cw1;
     sm.st[ST_CU][j] = cu;
     sm.st[ST_CX][j] = cx;
+    if (o.a0) sm.st[ST_CXP][j] = cx;  // this iteration's solution update is deferred to the next one
 }
 
 // Noise generation fused with the SPDE right-hand-side scaling: thread (chunk c, sample j) jumps to stream position
