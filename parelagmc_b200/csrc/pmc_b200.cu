@@ -787,10 +787,6 @@ struct Rows {
 
 struct Program {
     std::vector<Op> ops;
-    int force_group = 0;  // grid-group size G (option "group_size"; 0: choose, -1: never)
-    int solo_rows = 512;  // grid-group mode: operations with at most this many rows run on the group's first CTA alone
-    void *d_grp = nullptr;   // grid-group barrier words and dot-product shares
-    size_t grp_cap = 0;
     bool staging = true;  // stage operator entries through shared memory where the slices fit (F_STAGED)
     bool defer_x = true;  // MINRES: apply the solution updates of an iteration pair in one pass (option "defer_x")
     int pc() const { return (int)ops.size(); }
@@ -1225,11 +1221,10 @@ static cudaError_t launch_program(const ProgParams &P, int ntiles, cudaStream_t 
         attr_set = true;
         attr_dev = dev;
     }
-    if (CS == 1) {
+    if constexpr (CS == 1) {
         k_run_program<NTt, MINB, 1><<<ntiles, NTt, dyn, stream>>>(P);
         return cudaPeekAtLastError();
-    }
-    if (CS == 0) {  // grid groups: cooperative launch, P.group CTAs per tile, all co-resident
+    } else if constexpr (CS == 0) {  // grid groups: cooperative launch, P.group CTAs per tile, all co-resident
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3((unsigned)(ntiles * P.group));
         cfg.blockDim = dim3(NTt);
@@ -1241,7 +1236,7 @@ static cudaError_t launch_program(const ProgParams &P, int ntiles, cudaStream_t 
         cfg.attrs = attr;
         cfg.numAttrs = 1;
         return cudaLaunchKernelEx(&cfg, k_run_program<NTt, MINB, 0>, P);
-    }
+    } else {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(ntiles * CS));
     cfg.blockDim = dim3(NTt);
@@ -1255,6 +1250,7 @@ static cudaError_t launch_program(const ProgParams &P, int ntiles, cudaStream_t 
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     return cudaLaunchKernelEx(&cfg, k_run_program<NTt, MINB, CS>, P);
+    }
 }
 
 static int run_program(Ctx *c, Program &pg, int nsamples, Off chunk, int max_rows)
@@ -1365,12 +1361,24 @@ static int run_program(Ctx *c, Program &pg, int nsamples, Off chunk, int max_row
     memcpy(c->h_ops, pg.ops.data(), bytes);
     CK(cudaMemcpyAsync(c->d_ops, c->h_ops, bytes, cudaMemcpyHostToDevice, c->stream));
     cudaError_t le = cudaSuccess;
+    // Kernel variants.  The nominal CTA sizes 512 / 256 / 128 / 64 of the selection above run as 448 / 224 / 128 / 64
+    // threads with at most 896 threads resident per SM, which leaves 72 registers per thread: the interpreter with its
+    // inlined sparse applies wants more than the 64 registers that 1024 resident threads would allow, and the better
+    // schedule of the gather loops outweighs the lost eighth of the threads (level-0 batch of the bench: 54.2 -> 47.9 ms).
+#ifndef PMC_NT_L
+#define PMC_NT_L 448
+#define PMC_NT_M 224
+#define PMC_MINB_L 2
+#define PMC_MINB_M 4
+#define PMC_MINB_S 7
+#define PMC_MINB_XS 14
+#endif
 #define PMC_LAUNCH(NT_, MINB_, CS_) le = launch_program<NT_, MINB_, CS_>(P, ntiles, c->stream)
-    if (group) PMC_LAUNCH(512, 2, 0);
-    else if (nt == 512) { if (cs == 8) PMC_LAUNCH(512, 2, 8); else if (cs == 4) PMC_LAUNCH(512, 2, 4); else if (cs == 2) PMC_LAUNCH(512, 2, 2); else PMC_LAUNCH(512, 2, 1); }
-    else if (nt == 256) { if (cs == 8) PMC_LAUNCH(256, 4, 8); else if (cs == 4) PMC_LAUNCH(256, 4, 4); else if (cs == 2) PMC_LAUNCH(256, 4, 2); else PMC_LAUNCH(256, 4, 1); }
-    else if (nt == 128) PMC_LAUNCH(128, 8, 1);
-    else PMC_LAUNCH(64, 16, 1);
+    if (group) PMC_LAUNCH(PMC_NT_L, PMC_MINB_L, 0);
+    else if (nt == 512) { if (cs == 8) PMC_LAUNCH(PMC_NT_L, PMC_MINB_L, 8); else if (cs == 4) PMC_LAUNCH(PMC_NT_L, PMC_MINB_L, 4); else if (cs == 2) PMC_LAUNCH(PMC_NT_L, PMC_MINB_L, 2); else PMC_LAUNCH(PMC_NT_L, PMC_MINB_L, 1); }
+    else if (nt == 256) { if (cs == 8) PMC_LAUNCH(PMC_NT_M, PMC_MINB_M, 8); else if (cs == 4) PMC_LAUNCH(PMC_NT_M, PMC_MINB_M, 4); else if (cs == 2) PMC_LAUNCH(PMC_NT_M, PMC_MINB_M, 2); else PMC_LAUNCH(PMC_NT_M, PMC_MINB_M, 1); }
+    else if (nt == 128) PMC_LAUNCH(128, PMC_MINB_S, 1);
+    else PMC_LAUNCH(64, PMC_MINB_XS, 1);
 #undef PMC_LAUNCH
     if (le != cudaSuccess && c->cuda_status == cudaSuccess) c->cuda_status = le;
     cudaEventRecord(ep.b, c->stream);
@@ -1584,6 +1592,8 @@ int pmc_set_option(pmc_handle c, const char *key, double value)
     else if (k == "stage_operators") c->staging = value != 0;
     else if (k == "defer_x") c->defer_x = value != 0;
     else if (k == "single_wave") c->single_wave = value != 0;
+    else if (k == "group_size") c->force_group = (int)value;
+    else if (k == "solo_rows" && value >= 0) c->solo_rows = (int)value;
     else return fail(c, PMC_ERR_ARG, "pmc_set_option: unknown key '%s'", key);
     return PMC_OK;
 }

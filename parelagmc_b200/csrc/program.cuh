@@ -326,6 +326,28 @@ __device__ __forceinline__ void stage_issue(const unsigned char *pk, WarpStage *
     }
 }
 
+// One row's entries, compile-time width: sum_k val_k [V[widx_k]] x[col_k] in entry order.
+template <bool WEIGHTED, int WF>
+__device__ __forceinline__ D2 gather_fixed(const double *__restrict__ eval, const int *__restrict__ ecol, const int *__restrict__ ewid,
+                                           const double *__restrict__ x, const double *__restrict__ V)
+{
+    D2 s = make_double2(0.0, 0.0);
+#pragma unroll
+    for (int k = 0; k < WF; ++k) {
+        const double c = eval[k * SLICE];
+        const D2 xv = ld2c(x + (size_t)ecol[k * SLICE] * TW);
+        if (WEIGHTED) {
+            const D2 wv = ld2c(V + (size_t)ewid[k * SLICE] * TW);
+            s.x = fma(c * wv.x, xv.x, s.x);
+            s.y = fma(c * wv.y, xv.y, s.y);
+        } else {
+            s.x = fma(c, xv.x, s.x);
+            s.y = fma(c, xv.y, s.y);
+        }
+    }
+    return s;
+}
+
 // ---- sparse operator apply with fused epilogue ------------------------------------------------------------
 //   plain    : row i of slice s: entries k in [off[s], off[s+1])     sum += val * x[col]
 //   weighted :                                                        sum += val * V[widx] * x[col]
@@ -410,18 +432,27 @@ __device__ __forceinline__ void op_spmm(const Op &o, double *chunk, Smem &sm, St
         const double *__restrict__ eval = reinterpret_cast<const double *>(base) + rs;
         const int *__restrict__ ecol = reinterpret_cast<const int *>(base + (size_t)w * (SLICE * 8)) + rs;
         const int *__restrict__ ewid = ecol + w * SLICE;
-        D2 s = make_double2(0.0, 0.0);
+        D2 s;
+#ifndef PMC_NO_FIXED_WIDTHS
+        // the widths of the structured hot operators get fully unrolled bodies
+        if (w == 7) s = gather_fixed<WEIGHTED, 7>(eval, ecol, ewid, x, V);
+        else if (w == 6) s = gather_fixed<WEIGHTED, 6>(eval, ecol, ewid, x, V);
+        else
+#endif
+        {
+            s = make_double2(0.0, 0.0);
 #pragma unroll 4
-        for (int k = 0; k < w; ++k) {
-            const double c = eval[k * SLICE];
-            const D2 xv = ld2c(x + (size_t)ecol[k * SLICE] * TW);
-            if (WEIGHTED) {
-                const D2 wv = ld2c(V + (size_t)ewid[k * SLICE] * TW);
-                s.x = fma(c * wv.x, xv.x, s.x);
-                s.y = fma(c * wv.y, xv.y, s.y);
-            } else {
-                s.x = fma(c, xv.x, s.x);
-                s.y = fma(c, xv.y, s.y);
+            for (int k = 0; k < w; ++k) {
+                const double c = eval[k * SLICE];
+                const D2 xv = ld2c(x + (size_t)ecol[k * SLICE] * TW);
+                if (WEIGHTED) {
+                    const D2 wv = ld2c(V + (size_t)ewid[k * SLICE] * TW);
+                    s.x = fma(c * wv.x, xv.x, s.x);
+                    s.y = fma(c * wv.y, xv.y, s.y);
+                } else {
+                    s.x = fma(c, xv.x, s.x);
+                    s.y = fma(c, xv.y, s.y);
+                }
             }
         }
         if (live) {

@@ -7,11 +7,13 @@
 #include <vector>
 #include <algorithm>
 #include <cuda_runtime.h>
+#include <cstring>
+#include "../../parelagmc_b200/csrc/program.cuh"
 
-constexpr int TW = 4;
-typedef double2 D2;
+using pmc::TW;
+using pmc::D2;
 __device__ __forceinline__ D2 ld2(const double *p) { return *reinterpret_cast<const double2 *>(p); }
-__device__ __forceinline__ void st2(double *p, D2 v) { *reinterpret_cast<double2 *>(p) = v; }
+using pmc::st2;
 
 struct Mat {            // ELL, width W, column-major within slices of S rows: idx = (slice * W + k) * S + r
     int n, W;
@@ -21,11 +23,18 @@ struct Mat {            // ELL, width W, column-major within slices of S rows: i
 struct Chunk { long long x, y, r, d, dinv, V, stride; };
 
 // V0: two lanes per row (16 B each), entries one after the other (the compiler's order), indices straight from global
+__device__ int g_desync = 0;   // > 0: every CTA first waits a pseudo-random time up to g_desync microseconds
 template <int W>
 __global__ void __launch_bounds__(512, 2) k_v0(Mat A, double *base, Chunk c, int reps)
 {
     double *ch = base + (size_t)blockIdx.x * c.stride;
     const int sub = (threadIdx.x & 1) * 2;
+    if (g_desync > 0) {
+        const unsigned h = (blockIdx.x * 2654435761u) >> 8;
+        const long long wait = (long long)(h % 1000) * g_desync * 2;   // ~2 cycles per ns
+        const long long t0 = clock64();
+        while (clock64() - t0 < wait) { }
+    }
     for (int rep = 0; rep < reps; ++rep) {
         const double *x = ch + ((rep & 1) ? c.y : c.x) + sub;
         double *y = ch + ((rep & 1) ? c.x : c.y) + sub;
@@ -203,6 +212,126 @@ __global__ void __launch_bounds__(512, 2) k_mix(Mat A, double *base, Chunk c, in
     }
 }
 
+// the product's own sparse apply (program.cuh, op_spmm: weighted, Chebyshev epilogue) on the same data, outside the
+// interpreter kernel
+template <bool STAGED>
+__global__ void __launch_bounds__(512, 2) k_product_op(pmc::Op o0, double *base, long long stride, long long xoff, long long yoff, int reps)
+{
+    using namespace pmc;
+    __shared__ Smem sm;
+    extern __shared__ __align__(128) unsigned char dyn_smem[];
+    StageCtx sc;
+    sc.buf = reinterpret_cast<WarpStage *>(dyn_smem) + (threadIdx.x >> 5) * NSTAGE;
+    sc.bar = smem_u32(&sm.bars[threadIdx.x >> 5][0]);
+    sc.phase = 0u;
+    if ((threadIdx.x & 31) == 0) {
+        for (int j = 0; j < NSTAGE; ++j) mbar_init(sc.bar + 8 * j, 1u);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    double *chunk = base + (size_t)blockIdx.x * stride;
+    for (int rep = 0; rep < reps; ++rep) {
+        Op o = o0;
+        o.x.off = (rep & 1) ? yoff : xoff;
+        o.y.off = (rep & 1) ? xoff : yoff;
+        op_spmm<512, 1, EP_CHEB, true, true, false, STAGED>(o, chunk, sm, sc);
+        __syncthreads();
+    }
+}
+
+// experimental copy of the staged apply: HOIST (epilogue operands before the gathers), WFIX (compile-time width, 0 = runtime),
+// USEVAL (multiply by the stored coefficient)
+template <bool HOIST, int WFIX, bool USEVAL>
+__global__ void __launch_bounds__(512, 2) k_exp(pmc::Op o0, double *base, long long stride, long long xoff, long long yoff, int reps)
+{
+    using namespace pmc;
+    __shared__ Smem sm;
+    extern __shared__ __align__(128) unsigned char dyn_smem[];
+    StageCtx sc;
+    sc.buf = reinterpret_cast<WarpStage *>(dyn_smem) + (threadIdx.x >> 5) * NSTAGE;
+    sc.bar = smem_u32(&sm.bars[threadIdx.x >> 5][0]);
+    sc.phase = 0u;
+    if ((threadIdx.x & 31) == 0) {
+        for (int j = 0; j < NSTAGE; ++j) mbar_init(sc.bar + 8 * j, 1u);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    double *chunk = base + (size_t)blockIdx.x * stride;
+    constexpr int ES = 16, NW = 16;
+    const int sub = (threadIdx.x % LPR) * PW;
+    for (int rep = 0; rep < reps; ++rep) {
+        const Op &o = o0;
+        const double *__restrict__ x = chunk + ((rep & 1) ? yoff : xoff) + sub;
+        double *__restrict__ y = chunk + ((rep & 1) ? xoff : yoff) + sub;
+        const double *__restrict__ r = chunk + o.r.off + sub;
+        double *__restrict__ d = chunk + o.d.off + sub;
+        const double *__restrict__ V = chunk + o.v.off + sub;
+        const double *__restrict__ dinvb = chunk + o.w.off + sub;
+        const int *__restrict__ off = o.rowptr;
+        const unsigned char *__restrict__ pk = o.pk;
+        const double ca = o.ca, cb = o.cb;
+        const int r1 = o.n, sl_end = (r1 + SLICE - 1) / SLICE;
+        const int rs = (threadIdx.x & 31) / LPR;
+        int sl = threadIdx.x >> 5;
+        int wcur = 0, wnext = 0, st = 0;
+        for (int j = 0; j < NSTAGE; ++j) {
+            const int slj = sl + j * NW;
+            int k0 = 0, k1 = 0;
+            if (slj < sl_end) { k0 = __ldg(off + slj); k1 = __ldg(off + slj + 1); stage_issue<ES>(pk, sc.buf + j, sc.bar + 8 * j, k0, k1); }
+            if (j == 0) wcur = k1 - k0; else wnext = k1 - k0;
+        }
+        for (; sl < sl_end; sl += NW) {
+            const int row = sl * SLICE + rs;
+            const bool live = row < r1;
+            const size_t ro = (size_t)row * TW;
+            const int sl2 = sl + NSTAGE * NW;
+            int n0 = 0, n1 = 0;
+            if (sl2 < sl_end) { n0 = __ldg(off + sl2); n1 = __ldg(off + sl2 + 1); }
+            D2 rv = make_double2(0, 0), di = rv, dv = rv, xr = rv;
+            if (HOIST && live) { rv = ld2c(r + ro); di = ld2c(dinvb + ro); dv = ld2c(d + ro); xr = ld2c(x + ro); }
+            mbar_wait(sc.bar + 8 * st, (sc.phase >> st) & 1u);
+            sc.phase ^= 1u << st;
+            const unsigned char *bse = sc.buf[st].bytes;
+            const int w = WFIX ? WFIX : wcur;
+            const double *__restrict__ eval = reinterpret_cast<const double *>(bse) + rs;
+            const int *__restrict__ ecol = reinterpret_cast<const int *>(bse + (size_t)w * (SLICE * 8)) + rs;
+            const int *__restrict__ ewid = ecol + w * SLICE;
+            D2 s = make_double2(0, 0);
+            if (WFIX) {
+#pragma unroll
+                for (int k = 0; k < (WFIX ? WFIX : 1); ++k) {
+                    const D2 xv = ld2c(x + (size_t)ecol[k * SLICE] * TW), wv = ld2c(V + (size_t)ewid[k * SLICE] * TW);
+                    const double cc = USEVAL ? eval[k * SLICE] : 1.0;
+                    s.x = fma(cc * wv.x, xv.x, s.x);
+                    s.y = fma(cc * wv.y, xv.y, s.y);
+                }
+            } else {
+#pragma unroll 4
+                for (int k = 0; k < w; ++k) {
+                    const D2 xv = ld2c(x + (size_t)ecol[k * SLICE] * TW), wv = ld2c(V + (size_t)ewid[k * SLICE] * TW);
+                    const double cc = USEVAL ? eval[k * SLICE] : 1.0;
+                    s.x = fma(cc * wv.x, xv.x, s.x);
+                    s.y = fma(cc * wv.y, xv.y, s.y);
+                }
+            }
+            if (live) {
+                if (!HOIST) { rv = ld2c(r + ro); di = ld2c(dinvb + ro); dv = ld2c(d + ro); xr = ld2c(x + ro); }
+                D2 dn = make_double2(cb * di.x * (rv.x - s.x), cb * di.y * (rv.y - s.y));
+                dn.x = fma(ca, dv.x, dn.x);
+                dn.y = fma(ca, dv.y, dn.y);
+                st2(d + ro, dn);
+                st2(y + ro, make_double2(xr.x + dn.x, xr.y + dn.y));
+            }
+            __syncwarp();
+            if (sl2 < sl_end) stage_issue<ES>(pk, sc.buf + st, sc.bar + 8 * st, n0, n1);
+            wcur = wnext;
+            wnext = n1 - n0;
+            st ^= 1;
+        }
+        __syncthreads();
+    }
+}
+
 int main(int argc, char **argv)
 {
     const int g = argc > 1 ? atoi(argv[1]) : 16;
@@ -310,6 +439,57 @@ int main(int argc, char **argv)
                 printf("mix apply/stream %s ctas %4d: %8.2f us/op  %7.0f GB/s  (%s)\n", pm ? "out of phase" : "in phase    ", ctas,
                        ms * 1e3 / reps, mixbytes * ctas * reps / ms / 1e6, cudaGetErrorString(cudaGetLastError()));
             }
+    }
+    for (int us : {30, 100}) {
+        cudaMemcpyToSymbol(g_desync, &us, sizeof(int));
+        timeit(us == 30 ? "v0, CTAs desynchronised up to 30 us" : "v0, CTAs desynchronised up to 100 us", 296,
+               [&](int n_, int r_) { k_v0<7><<<n_, 512>>>(A, base, c, r_); });
+    }
+    { int z = 0; cudaMemcpyToSymbol(g_desync, &z, sizeof(int)); }
+    {   // packed sliced ELL of the product (slice: [val w*16][col w*16][widx w*16]), width 7 everywhere
+        const int nsl = (n + 15) / 16;
+        std::vector<int> off(nsl + 1);
+        for (int i = 0; i <= nsl; ++i) off[i] = i * W;
+        std::vector<unsigned char> pk((size_t)nsl * W * 16 * 16, 0);
+        for (int sl = 0; sl < nsl; ++sl) {
+            unsigned char *b = pk.data() + (size_t)sl * W * 16 * 16;
+            double *pv = (double *)b;
+            int *pc = (int *)(b + W * 16 * 8), *pw = pc + W * 16;
+            for (int k = 0; k < W; ++k)
+                for (int r = 0; r < 16; ++r) {
+                    const int e = sl * 16 + r;
+                    if (e >= n) continue;
+                    const bool on = k < (int)cols[e].size();
+                    pv[k * 16 + r] = on ? 1.0 : 0.0;
+                    pc[k * 16 + r] = on ? cols[e][k] : e;
+                    pw[k * 16 + r] = on ? uid[e][k] : 0;
+                }
+        }
+        int *doff; unsigned char *dpk;
+        cudaMalloc(&doff, off.size() * 4); cudaMalloc(&dpk, pk.size());
+        cudaMemcpy(doff, off.data(), off.size() * 4, cudaMemcpyHostToDevice); cudaMemcpy(dpk, pk.data(), pk.size(), cudaMemcpyHostToDevice);
+        pmc::Op o;
+        memset(&o, 0, sizeof o);
+        o.kind = pmc::OP_SPMM; o.n = n; o.flags = 0;
+        o.rowptr = doff; o.pk = dpk;
+        o.x.off = c.x; o.y.off = c.y; o.r.off = c.r; o.d.off = c.d; o.w.off = c.dinv; o.v.off = c.V;
+        o.ca = 0.3; o.cb = 0.7;
+        const size_t dyn = 16 * pmc::NSTAGE * sizeof(pmc::WarpStage);
+        cudaFuncSetAttribute(k_product_op<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+        cudaFuncSetAttribute(k_product_op<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+#define EXPRUN(NAME, ...)                                                                                      \
+    cudaFuncSetAttribute(k_exp<__VA_ARGS__>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);                 \
+    timeit(NAME, 296, [&](int n_, int r_) { k_exp<__VA_ARGS__><<<n_, 512, dyn>>>(o, base, c.stride, c.x, c.y, r_); });
+        EXPRUN("exp: hoist, runtime w, val", true, 0, true)
+        EXPRUN("exp: no hoist, runtime w, val", false, 0, true)
+        EXPRUN("exp: hoist, W=7, val", true, 7, true)
+        EXPRUN("exp: no hoist, W=7, val", false, 7, true)
+        EXPRUN("exp: no hoist, W=7, no val", false, 7, false)
+        EXPRUN("exp: hoist, W=7, no val", true, 7, false)
+        for (int ctas : {148, 296}) {
+            timeit("product op_spmm, staged (TMA)", ctas, [&](int n_, int r_) { k_product_op<true><<<n_, 512, dyn>>>(o, base, c.stride, c.x, c.y, r_); });
+            timeit("product op_spmm, entries from L2", ctas, [&](int n_, int r_) { k_product_op<false><<<n_, 512, dyn>>>(o, base, c.stride, c.x, c.y, r_); });
+        }
     }
     timeit("v1 2 lanes/row, batched, 128 regs", 148, [&](int n_, int r_) { k_v1<7, 1><<<n_, 512>>>(A, base, c, r_); });
     timeit("v2 4 lanes/row, batched, 128 regs", 148, [&](int n_, int r_) { k_v2<7, 1><<<n_, 512>>>(A, base, c, r_); });
