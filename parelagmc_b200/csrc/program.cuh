@@ -407,7 +407,11 @@ __device__ __forceinline__ void op_spmm(const Op &o, double *chunk, Smem &sm, St
             n1 = __ldg(off + sl2 + 1);
         }
         D2 rv = make_double2(0.0, 0.0), di = rv, dv = rv, xr = rv, yv = rv;
+#ifdef PMC_HOIST_EPILOGUE   // measured: loading the epilogue operands after the gathers is 1 % faster (registers)
         if (live) {
+#else
+        if (false) {
+#endif
             if (EP == EP_RESID || EP == EP_CHEB) rv = ld2c(r + ro);
             if (EP == EP_ADD) yv = ld2c(y + ro);
             if (EP == EP_CHEB) {
@@ -437,6 +441,7 @@ __device__ __forceinline__ void op_spmm(const Op &o, double *chunk, Smem &sm, St
         // the widths of the structured hot operators get fully unrolled bodies
         if (w == 7) s = gather_fixed<WEIGHTED, 7>(eval, ecol, ewid, x, V);
         else if (w == 6) s = gather_fixed<WEIGHTED, 6>(eval, ecol, ewid, x, V);
+        else if (w == 5) s = gather_fixed<WEIGHTED, 5>(eval, ecol, ewid, x, V);
         else
 #endif
         {
@@ -456,6 +461,16 @@ __device__ __forceinline__ void op_spmm(const Op &o, double *chunk, Smem &sm, St
             }
         }
         if (live) {
+#ifndef PMC_HOIST_EPILOGUE
+            if (EP == EP_RESID || EP == EP_CHEB) rv = ld2c(r + ro);
+            if (EP == EP_ADD) yv = ld2c(y + ro);
+            if (EP == EP_CHEB) {
+                if (BDINV) di = ld2c(dinvb + ro);
+                else { const double t = __ldg(o.fixed + row); di = make_double2(t, t); }
+                if (ca != 0.0) dv = ld2c(d + ro);
+            }
+            if (EP == EP_CHEB || (DOT && !dot_r)) xr = ld2c(x + ro);
+#endif
             D2 out;
             if (EP == EP_AX) {
                 out = s;
