@@ -148,6 +148,7 @@ struct DarcyLevel {
     std::vector<double> elem_mat, ess_data, rhs, obs;
     HCsr B, Pp;
     double *d_rhs_bc = nullptr, *d_obs = nullptr, *d_ess_u_data = nullptr;
+    int *d_rowmap = nullptr;  // caller's numbering of the N unknowns -> the library's (RT dofs renumbered for locality)
     // Bayesian inverse problem: m normalised pressure functionals [m][Ne], observed data and noise variance
     int n_obs = 0;
     double noise = 0.0;
@@ -197,6 +198,7 @@ struct pmc_context_s {
     size_t grp_cap = 0;
     bool staging = true;  // stage operator entries through shared memory (option "stage_operators")
     bool defer_x = true;  // option "defer_x"
+    bool renumber = true;  // option "renumber": first-touch renumbering of the RT dofs inside the library
     bool single_wave = false;  // option "single_wave": prefer one wave of smaller CTAs over a mostly empty second wave
     std::vector<SamplerLevel> s;
     std::vector<DarcyLevel> d;
@@ -263,6 +265,38 @@ static void launch(Ctx *c, int kclass, double bytes, void (*kernel)(KArgs...), d
 // --------------------------------------------------------------------------------------------------
 // uploads
 // --------------------------------------------------------------------------------------------------
+// The RT (face) dofs are renumbered inside the library in order of first appearance when the elements are walked in
+// their own order, so that the faces of an element, its pressure dof and its neighbours' sit at proportional positions
+// of the u and p blocks: the gathers of the saddle apply then stay in a band that lives in L1, whatever numbering the
+// mesh generator chose (direction-blocked Cartesian numberings stream the p block three times per apply).  The block
+// structure [u; p] is kept; solutions and operands cross the ABI in the caller's numbering (k_to_tiles / k_from_tiles).
+static std::vector<int> first_touch_order(int Nf, int Ne, const int *ptr, const int *dofs)
+{
+    std::vector<int> perm(Nf, -1);
+    int next = 0;
+    for (int e = 0; e < Ne; ++e)
+        for (int t = ptr[e]; t < ptr[e + 1]; ++t)
+            if (perm[dofs[t]] < 0) perm[dofs[t]] = next++;
+    for (int f = 0; f < Nf; ++f)
+        if (perm[f] < 0) perm[f] = next++;
+    return perm;
+}
+static HCsr csr_permuted(const HCsr &A, const int *rowperm, const int *colperm)
+{
+    std::vector<Coo> e;
+    e.reserve(A.col.size());
+    for (int i = 0; i < A.rows; ++i)
+        for (int p = A.rowptr[i]; p < A.rowptr[i + 1]; ++p)
+            e.push_back({rowperm ? rowperm[i] : i, colperm ? colperm[A.col[p]] : A.col[p], A.val[p]});
+    return csr_from_coo(A.rows, A.cols, e);
+}
+template <typename T>
+static void permute_head(std::vector<T> &v, const std::vector<int> &perm)
+{
+    std::vector<T> t(v.begin(), v.begin() + perm.size());
+    for (size_t i = 0; i < perm.size(); ++i) v[perm[i]] = t[i];
+}
+
 template <typename T>
 static int to_device(Ctx *c, const std::vector<T> &h, T **out)
 {
@@ -1437,24 +1471,25 @@ static dim3 grid1d(size_t n) { return dim3((unsigned)std::min<size_t>((n + 255) 
 
 // host [ns][n] -> tile-major batched (via the staging buffer `stage`)
 static int upload_rows(Ctx *c, const double *host, int ns, int n, double *stage, Off dst, Off chunk, int mode, double neg_g,
-                       const double *w_sqrt)
+                       const double *w_sqrt, const int *rowmap = nullptr)
 {
     const int ntiles = (ns + TW - 1) / TW;
     double *d = (double *)c->arena.base + dst;
     CK(cudaMemcpyAsync(stage, host, (size_t)ns * n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
     const size_t total = (size_t)ntiles * n * TW;
-    if (mode == 1) launch(c, PMC_K_MISC, (double)total * 16.0, k_to_tiles<1>, grid1d(total), dim3(256), n, chunk, ntiles, ns, (const double *)stage, d, neg_g, w_sqrt);
-    else launch(c, PMC_K_MISC, (double)total * 16.0, k_to_tiles<0>, grid1d(total), dim3(256), n, chunk, ntiles, ns, (const double *)stage, d, neg_g, w_sqrt);
+    if (mode == 1) launch(c, PMC_K_MISC, (double)total * 16.0, k_to_tiles<1>, grid1d(total), dim3(256), n, chunk, ntiles, ns, (const double *)stage, d, neg_g, w_sqrt, rowmap);
+    else launch(c, PMC_K_MISC, (double)total * 16.0, k_to_tiles<0>, grid1d(total), dim3(256), n, chunk, ntiles, ns, (const double *)stage, d, neg_g, w_sqrt, rowmap);
     return PMC_OK;
 }
 
 // tile-major batched view -> host [ns][n]
-static int download_rows(Ctx *c, Off src_off, Off chunk, int ns, int n, double *stage, double *host, bool do_exp)
+static int download_rows(Ctx *c, Off src_off, Off chunk, int ns, int n, double *stage, double *host, bool do_exp,
+                         const int *rowmap = nullptr)
 {
     const size_t total = (size_t)ns * n;
     const double *src = (const double *)c->arena.base + src_off;
-    if (do_exp) launch(c, PMC_K_MISC, (double)total * 16.0, k_from_tiles<1>, grid1d(total), dim3(256), n, chunk, ns, src, stage);
-    else launch(c, PMC_K_MISC, (double)total * 16.0, k_from_tiles<0>, grid1d(total), dim3(256), n, chunk, ns, src, stage);
+    if (do_exp) launch(c, PMC_K_MISC, (double)total * 16.0, k_from_tiles<1>, grid1d(total), dim3(256), n, chunk, ns, src, stage, rowmap);
+    else launch(c, PMC_K_MISC, (double)total * 16.0, k_from_tiles<0>, grid1d(total), dim3(256), n, chunk, ns, src, stage, rowmap);
     CK(cudaMemcpyAsync(host, stage, total * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     return PMC_OK;
 }
@@ -1592,6 +1627,11 @@ int pmc_set_option(pmc_handle c, const char *key, double value)
     else if (k == "stage_operators") c->staging = value != 0;
     else if (k == "defer_x") c->defer_x = value != 0;
     else if (k == "single_wave") c->single_wave = value != 0;
+    else if (k == "renumber") {
+        for (int l = 0; l < c->nlevels; ++l)
+            if (c->s[l].set || c->d[l].set) return fail(c, PMC_ERR_STATE, "pmc_set_option(renumber): set it before the uploads");
+        c->renumber = value != 0;
+    }
     else if (k == "group_size") c->force_group = (int)value;
     else if (k == "solo_rows" && value >= 0) c->solo_rows = (int)value;
     else return fail(c, PMC_ERR_ARG, "pmc_set_option: unknown key '%s'", key);
@@ -1620,6 +1660,11 @@ int pmc_upload_sampler_level(pmc_handle c, int level, int Ne, int Nf, const int 
     L.Ne = Ne; L.Nf = Nf; L.alpha = alpha; L.g = matern_coeff; L.lognormal = lognormal;
     L.M = csr_copy(Nf, Nf, M_rowptr, M_col, M_val);
     L.B = csr_copy(Ne, Nf, B_rowptr, B_col, B_val);
+    if (c->renumber) {  // the u block never crosses the ABI for the sampler: renumber and forget
+        const std::vector<int> perm = first_touch_order(Nf, Ne, L.B.rowptr.data(), L.B.col.data());
+        L.M = csr_permuted(L.M, perm.data(), perm.data());
+        L.B = csr_permuted(L.B, nullptr, perm.data());
+    }
     L.Wdiag.assign(Wdiag, Wdiag + Ne);
     std::vector<double> ws(Ne);
     for (int i = 0; i < Ne; ++i) ws[i] = std::sqrt(Wdiag[i]);  // /root/reference/src/PDESampler.cpp:248-254
@@ -1666,6 +1711,20 @@ int pmc_upload_darcy_level(pmc_handle c, int level, int Ne, int Nf, const int *e
     L.obs.assign(obs, obs + Nf + Ne);
     L.hasP = Pp_rowptr != nullptr;
     if (L.hasP) L.Pp = csr_copy(Ne, Pp_cols, Pp_rowptr, Pp_col, Pp_val);
+    if (c->renumber) {
+        const std::vector<int> perm = first_touch_order(Nf, Ne, L.elem_ptr.data(), L.elem_dofs.data());
+        for (int &d : L.elem_dofs) d = perm[d];
+        L.B = csr_permuted(L.B, nullptr, perm.data());
+        permute_head(L.ess_u, perm);
+        permute_head(L.ess_data, perm);
+        permute_head(L.rhs, perm);
+        permute_head(L.obs, perm);
+        std::vector<int> rowmap(Nf + Ne);
+        for (int f = 0; f < Nf; ++f) rowmap[f] = perm[f];
+        for (int e = 0; e < Ne; ++e) rowmap[Nf + e] = Nf + e;
+        int rc = to_device(c, rowmap, &L.d_rowmap);
+        if (rc) return rc;
+    }
     L.set = true;
     return PMC_OK;
 }
@@ -1719,7 +1778,7 @@ int pmc_clone(pmc_handle src, pmc_handle *out)
     if (rc) return fail(src, rc, "pmc_clone: %s", pmc_last_error(nullptr));
     c->rel = src->rel; c->abs_ = src->abs_; c->maxit = src->maxit;
     c->cfg_sampler = src->cfg_sampler; c->cfg_darcy = src->cfg_darcy;
-    c->max_batch = src->max_batch; c->force_nt = src->force_nt; c->force_cs = src->force_cs; c->staging = src->staging; c->defer_x = src->defer_x; c->single_wave = src->single_wave; c->force_group = src->force_group; c->solo_rows = src->solo_rows;
+    c->max_batch = src->max_batch; c->force_nt = src->force_nt; c->force_cs = src->force_cs; c->staging = src->staging; c->defer_x = src->defer_x; c->single_wave = src->single_wave; c->renumber = src->renumber; c->force_group = src->force_group; c->solo_rows = src->solo_rows;
     for (int l = 0; l < src->nlevels && !rc; ++l) {
         const SamplerLevel &S = src->s[l];
         if (S.set)
@@ -1952,9 +2011,9 @@ static int darcy_host_batch(Ctx *c, int level, int nsamples, const double *k, co
         double *stage = (double *)c->arena.base + (size_t)(ld / TW) * (size_t)chunk;
         if ((rc = upload_rows(c, k + (size_t)s0 * Ne, ns, Ne, stage, k_ext, chunk, 0, 0.0, nullptr))) return rc;
         if (apply_only) {
-            if ((rc = upload_rows(c, xin + (size_t)s0 * N, ns, N, stage, ws.x, chunk, 0, 0.0, nullptr))) return rc;
+            if ((rc = upload_rows(c, xin + (size_t)s0 * N, ns, N, stage, ws.x, chunk, 0, 0.0, nullptr, L.d_rowmap))) return rc;
             if ((rc = run_program(c, pg, ns, chunk, N))) return rc;
-            if ((rc = download_rows(c, ws.q, chunk, ns, N, stage, sol_out + (size_t)s0 * N, false))) return rc;
+            if ((rc = download_rows(c, ws.q, chunk, ns, N, stage, sol_out + (size_t)s0 * N, false, L.d_rowmap))) return rc;
             if ((rc = finish(c))) return rc;
             continue;
         }
@@ -1962,7 +2021,7 @@ static int darcy_host_batch(Ctx *c, int level, int nsamples, const double *k, co
         if (Q_out && (rc = download_rows(c, Qrow, chunk, ns, 1, stage, Q_out + s0, false))) return rc;
         if (C_out)
             for (int j = 0; j < ns; ++j) C_out[s0 + j] = (double)N;  // /root/reference/src/DarcySolver.cpp:429
-        if (sol_out && (rc = download_rows(c, ws.x, chunk, ns, N, stage, sol_out + (size_t)s0 * N, false))) return rc;
+        if (sol_out && (rc = download_rows(c, ws.x, chunk, ns, N, stage, sol_out + (size_t)s0 * N, false, L.d_rowmap))) return rc;
         if (iters_out) {
             itbuf.resize(ns);
             if ((rc = download_rows(c, ws.iters, chunk, ns, 1, stage, itbuf.data(), false))) return rc;

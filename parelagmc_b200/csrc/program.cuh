@@ -952,7 +952,8 @@ __global__ void __launch_bounds__(NTt, MINB) k_run_program(const ProgParams P)
 // out = (-g * xi) * w_sqrt[row] (/root/reference/src/PDESampler.cpp:352-358).
 template <int MODE>
 __global__ void k_to_tiles(int n, long long chunk, int ntiles, int nsamples, const double *__restrict__ src,
-                           double *__restrict__ dst, double neg_g, const double *__restrict__ w_sqrt)
+                           double *__restrict__ dst, double neg_g, const double *__restrict__ w_sqrt,
+                           const int *__restrict__ rowmap)
 {
     const size_t total = (size_t)ntiles * n * TW;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -962,19 +963,22 @@ __global__ void k_to_tiles(int n, long long chunk, int ntiles, int nsamples, con
         const int s = tile * TW + j;
         double v = s < nsamples ? src[(size_t)s * n + row] : 0.0;
         if (MODE == 1) v = __dmul_rn(__dmul_rn(neg_g, v), __ldg(w_sqrt + row));
-        dst[(size_t)tile * (size_t)chunk + (size_t)row * TW + j] = v;
+        const int irow = rowmap ? __ldg(rowmap + row) : row;  // the library's internal numbering of the row
+        dst[(size_t)tile * (size_t)chunk + (size_t)irow * TW + j] = v;
     }
 }
 
 // rows of the tile chunks (src = base + operand offset) -> host layout [nsamples][n];  MODE 1 applies exp.
 template <int MODE>
-__global__ void k_from_tiles(int n, long long chunk, int nsamples, const double *__restrict__ src, double *__restrict__ dst)
+__global__ void k_from_tiles(int n, long long chunk, int nsamples, const double *__restrict__ src, double *__restrict__ dst,
+                             const int *__restrict__ rowmap)
 {
     const size_t total = (size_t)nsamples * n;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
         const int row = (int)(i % n), s = (int)(i / n);
         const int tile = s / TW, j = s % TW;
-        double v = src[(size_t)tile * (size_t)chunk + (size_t)row * TW + j];
+        const int irow = rowmap ? __ldg(rowmap + row) : row;
+        double v = src[(size_t)tile * (size_t)chunk + (size_t)irow * TW + j];
         if (MODE == 1) v = exp(v);
         dst[i] = v;
     }
