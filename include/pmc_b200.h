@@ -81,7 +81,9 @@ int pmc_set_preconditioner(pmc_handle h, int mass_degree, int schur_degree, doub
  * "cluster_size" (1/2/4/8 CTAs of a thread-block cluster per tile of 4 realisations), "group_size" (G > 1: G co-resident
  * CTAs of a cooperative launch per tile, for one or two tiles of very large levels; -1 = never), "solo_rows" (in a group,
  * operations with at most this many rows run on its first CTA), "stage_operators" (0 = read operator entries from L2
- * instead of staging them through shared memory with TMA bulk copies). */
+ * instead of staging them through shared memory with TMA bulk copies), "defer_x" (0 = update the MINRES solution
+ * every iteration instead of once per iteration pair), "single_wave" (1 = prefer one wave of smaller CTAs), and
+ * "renumber" (0 = keep the caller's numbering of the RT dofs inside the library; to be set before the uploads). */
 int pmc_set_option(pmc_handle h, const char *key, double value);
 /* Largest number of realisations processed per kernel launch (0 = choose from free device memory), and
  * how many MINRES iterations are queued between convergence checks. */
