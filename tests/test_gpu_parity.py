@@ -516,6 +516,40 @@ def test_grid_group_matches_single_cta(prob, group, solo):
         cg.close()
 
 
+@pytest.mark.parametrize("opt", ["stage_operators", "defer_x", "renumber", "single_wave"])
+def test_kernel_variants_agree(prob, opt):
+    """The performance switches do not change what is computed: operator entries staged by TMA or read from L2, the
+    MINRES solution update deferred within an iteration pair or not (both bitwise), the library's internal renumbering
+    of the RT dofs on or off (round-off: rows are summed in a different order; solutions cross the ABI in the caller's
+    numbering either way), one wave of smaller CTAs."""
+    from parelagmc_b200.capi import Context
+    def run(value):
+        c = Context(prob["nlevels"], 0)
+        c.set_option(opt, value)
+        for l, s in enumerate(prob["sampler"]):
+            c.upload_sampler_level(l, s, prob["alpha"], prob["g"], True)
+        for l, d in enumerate(prob["darcy"]):
+            c.upload_darcy_level(l, d)
+        c.set_tolerances(1e-12, 1e-30, 2000)
+        c.rng_init(0.0, 1.0, 1, 0)
+        try:
+            _, rows, its = c.mlmc_level_batch(0, 9, 77, want_rows=True)
+            d = prob["darcy"][0]
+            k = np.exp(np.random.default_rng(8).standard_normal((5, d.Ne)))
+            Q, _, sol, it = c.darcy_solve_batch(0, k, want_sol=True)
+            y = c.darcy_apply_batch(0, k, sol)
+            return rows, its, Q, sol, it, y
+        finally:
+            c.close()
+    a, b = run(0), run(1)
+    if opt in ("stage_operators", "defer_x", "single_wave"):
+        assert np.array_equal(a[0], b[0]) and a[1] == b[1]
+        assert np.array_equal(a[3], b[3]) and np.array_equal(a[4], b[4]) and np.array_equal(a[5], b[5])
+    else:
+        assert np.allclose(a[0][:, :3], b[0][:, :3], rtol=1e-9, atol=1e-12)
+        assert rel_l2(a[3], b[3]) < 1e-9 and rel_l2(a[5], b[5]) < 1e-9 and np.allclose(a[2], b[2], rtol=1e-9)
+
+
 def test_iteration_cap_and_options(prob):
     """Iteration cap (the reference's 'Maximum iterations'): realisations stop after max_iter iterations with finite
     output; options are validated and frozen once the preconditioner exists."""
