@@ -270,13 +270,29 @@ static void launch(Ctx *c, int kclass, double bytes, void (*kernel)(KArgs...), d
 // of the u and p blocks: the gathers of the saddle apply then stay in a band that lives in L1, whatever numbering the
 // mesh generator chose (direction-blocked Cartesian numberings stream the p block three times per apply).  The block
 // structure [u; p] is kept; solutions and operands cross the ABI in the caller's numbering (k_to_tiles / k_from_tiles).
+static int renumber_block()
+{
+    const char *e = getenv("PMC_RENUMBER_BLOCK");  // diagnostic override
+    const int b = e ? atoi(e) : 4 * SLICE;  // measured on the bench hierarchy: 1 / 16 / 64 / 256 / all = 46.5 / 46.5 / 46.2 / 46.2 / 47.2 ms
+    return b > 0 ? b : 1;
+}
 static std::vector<int> first_touch_order(int Nf, int Ne, const int *ptr, const int *dofs)
 {
+    // Elements are walked in blocks of 64; inside a block the dofs are taken local slot by local slot (all first
+    // faces of the block's elements, then all second faces, ...).  A slice of 16 consecutive rows then mostly holds
+    // the same kind of face of 16 consecutive elements, so the k-th gathers of its rows fall into a few contiguous
+    // lines (coalesced), while the block keeps everything within a band (local).
     std::vector<int> perm(Nf, -1);
     int next = 0;
-    for (int e = 0; e < Ne; ++e)
-        for (int t = ptr[e]; t < ptr[e + 1]; ++t)
-            if (perm[dofs[t]] < 0) perm[dofs[t]] = next++;
+    const int blk = renumber_block();
+    for (int e0 = 0; e0 < Ne; e0 += blk) {
+        const int e1 = std::min(Ne, e0 + blk);
+        int slots = 0;
+        for (int e = e0; e < e1; ++e) slots = std::max(slots, ptr[e + 1] - ptr[e]);
+        for (int sl = 0; sl < slots; ++sl)
+            for (int e = e0; e < e1; ++e)
+                if (ptr[e] + sl < ptr[e + 1] && perm[dofs[ptr[e] + sl]] < 0) perm[dofs[ptr[e] + sl]] = next++;
+    }
     for (int f = 0; f < Nf; ++f)
         if (perm[f] < 0) perm[f] = next++;
     return perm;
@@ -350,6 +366,20 @@ static HSell make_sell(int rows, const std::vector<int> &beg, const std::vector<
 
 static int upload_sell(Ctx *c, const HSell &S, DevCsr &D)
 {
+    if (const char *pre = getenv("PMC_DUMP_SELL")) {  // diagnostic: packed operators for the stand-alone micro-benchmarks
+        static int seq = 0;
+        char name[512];
+        snprintf(name, sizeof name, "%s_%03d_r%d_c%d_%s.bin", pre, seq++, D.rows, D.cols, D.weighted ? "w" : "p");
+        if (FILE *f = fopen(name, "wb")) {
+            const int hdr[4] = {D.rows, D.cols, D.weighted ? 1 : 0, (int)S.off.size()};
+            const long long nb = (long long)S.pk.size();
+            fwrite(hdr, sizeof hdr, 1, f);
+            fwrite(&nb, sizeof nb, 1, f);
+            fwrite(S.off.data(), sizeof(int), S.off.size(), f);
+            fwrite(S.pk.data(), 1, S.pk.size(), f);
+            fclose(f);
+        }
+    }
     int rc;
     if ((rc = to_device(c, S.off, &D.soff))) return rc;
     if ((rc = to_device(c, S.pk, &D.spk))) return rc;
