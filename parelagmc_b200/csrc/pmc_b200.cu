@@ -122,6 +122,7 @@ struct SaddleSys {
     double m_lo = 0.5, m_hi = 1.5;  // spectrum of diag(M)^-1 M
     std::vector<VLevel> v;
     std::vector<HCsr> own_P;        // aggregation prolongators built here (cfg.amg)
+    double *d_coarse_coef = nullptr;  // {ca_j, cb_j} of the coarsest level's Chebyshev iteration (OP_CHEB_SMALL)
 };
 
 struct SamplerLevel {
@@ -149,6 +150,7 @@ struct DarcyLevel {
     HCsr B, Pp;
     double *d_rhs_bc = nullptr, *d_obs = nullptr, *d_ess_u_data = nullptr;
     int *d_rowmap = nullptr;  // caller's numbering of the N unknowns -> the library's (RT dofs renumbered for locality)
+    std::vector<int> h_rowmap;
     // Bayesian inverse problem: m normalised pressure functionals [m][Ne], observed data and noise variance
     int n_obs = 0;
     double noise = 0.0;
@@ -198,6 +200,7 @@ struct pmc_context_s {
     size_t grp_cap = 0;
     bool staging = true;  // stage operator entries through shared memory (option "stage_operators")
     bool defer_x = true;  // option "defer_x"
+    bool fuse_coarse = true;  // option "fuse_coarse"
     bool renumber = true;  // option "renumber": first-touch renumbering of the RT dofs inside the library
     bool single_wave = false;  // option "single_wave": prefer one wave of smaller CTAs over a mostly empty second wave
     std::vector<SamplerLevel> s;
@@ -228,6 +231,7 @@ struct pmc_context_s {
 typedef pmc_context_s Ctx;
 
 static std::string g_create_error;
+static std::vector<double> cheb_coefficients(double lo, double hi, int deg);
 
 static int fail(Ctx *c, int code, const char *fmt, ...)
 {
@@ -628,6 +632,10 @@ static int prepare_sampler(Ctx *c, int level)
             S = csr_matmul(Pt, csr_matmul(S, P));
         }
     }
+    {
+        std::vector<double> cc = cheb_coefficients(1.0 / sys.cfg.coarse_ratio, 1.0, sys.cfg.coarse_degree);
+        if ((rc = to_device(c, cc, &sys.d_coarse_coef))) return rc;
+    }
     sys.ready = true;
     return PMC_OK;
 }
@@ -821,6 +829,10 @@ static int prepare_darcy(Ctx *c, int level)
             sp = std::move(spc);
         }
     }
+    {
+        std::vector<double> cc = cheb_coefficients(1.0 / sys.cfg.coarse_ratio, 1.0, sys.cfg.coarse_degree);
+        if ((rc = to_device(c, cc, &sys.d_coarse_coef))) return rc;
+    }
     sys.ready = true;
     return PMC_OK;
 }
@@ -853,6 +865,7 @@ struct Program {
     std::vector<Op> ops;
     bool staging = true;  // stage operator entries through shared memory where the slices fit (F_STAGED)
     bool defer_x = true;  // MINRES: apply the solution updates of an iteration pair in one pass (option "defer_x")
+    bool fuse_coarse = true;  // coarsest Chebyshev iteration as one shared-memory operation (option "fuse_coarse")
     int pc() const { return (int)ops.size(); }
     Op &add(int kind, int kclass, int n, double rows_moved, double matrix_bytes = 0.0)
     {
@@ -949,6 +962,24 @@ static VecRef emit_cheb(Program &pg, const ChebOp &op, VecRef r, VecRef d, int d
 // --------------------------------------------------------------------------------------------------
 // solve workspace (tile-major batched vectors: n rows -> n * ld doubles, ld = ntiles * TW)
 // --------------------------------------------------------------------------------------------------
+// {ca_j, cb_j}, j = 0..deg-1, of emit_cheb's recurrence (from_zero) on [lo, hi]
+static std::vector<double> cheb_coefficients(double lo, double hi, int deg)
+{
+    const double theta = 0.5 * (hi + lo), delta = 0.5 * (hi - lo), sigma = theta / delta;
+    double rho = 1.0 / sigma;
+    std::vector<double> c(2 * (size_t)deg);
+    for (int j = 0; j < deg; ++j) {
+        if (j == 0) { c[0] = 0.0; c[1] = 1.0 / theta; }
+        else {
+            const double rho_new = 1.0 / (2.0 * sigma - rho);
+            c[2 * j] = rho_new * rho;
+            c[2 * j + 1] = 2.0 * rho_new / delta;
+            rho = rho_new;
+        }
+    }
+    return c;
+}
+
 struct SolveWs {
     Off v0, v1, w0, w1, u1, q, x, b;  // MINRES, N rows each
     Off mu_d, mu_z;                   // mass-block Chebyshev scratch, Nf rows
@@ -1024,6 +1055,17 @@ static void emit_vcycle(Program &pg, Solver &sv, int m, VecRef r, VecRef zout, V
     const bool last = (m + 1 == (int)sys.v.size());
     if (last) {
         op.lo = 1.0 / cfg.coarse_ratio;
+        if (pg.fuse_coarse && sys.d_coarse_coef && L.n <= SMALLN && L.S.max_width > 0) {
+            // one operation for the whole iteration; the result always lands in zout
+            Op &o = pg.add(OP_CHEB_SMALL, KC_SCHUR, L.n,
+                           cfg.coarse_degree * (L.n * (5.0 + (sys.weighted ? 1 : 0)) + op.vrows) - 2.0 * L.n - op.vrows);
+            o.flags = (sys.weighted ? F_WEIGHTED : 0) | (dot_slot >= 0 ? (F_DOT | F_DOT_ACC) : 0);
+            o.rowptr = L.S.soff; o.pk = L.S.spk; o.val = sys.d_coarse_coef; o.fixed = op.dinv_f;
+            o.r = r; o.y = zout; o.v = op.V; o.w = op.dinv_b;
+            o.a0 = cfg.coarse_degree;
+            o.slot = dot_slot < 0 ? 0 : dot_slot;
+            return;
+        }
         emit_cheb(pg, op, r, d, cfg.coarse_degree, true, zout, ztmp, dot_slot, dot_slot >= 0);
         return;
     }
@@ -1656,6 +1698,7 @@ int pmc_set_option(pmc_handle c, const char *key, double value)
     else if (k == "cluster_size") c->force_cs = (int)value;
     else if (k == "stage_operators") c->staging = value != 0;
     else if (k == "defer_x") c->defer_x = value != 0;
+    else if (k == "fuse_coarse") c->fuse_coarse = value != 0;
     else if (k == "single_wave") c->single_wave = value != 0;
     else if (k == "renumber") {
         for (int l = 0; l < c->nlevels; ++l)
@@ -1754,6 +1797,7 @@ int pmc_upload_darcy_level(pmc_handle c, int level, int Ne, int Nf, const int *e
         for (int e = 0; e < Ne; ++e) rowmap[Nf + e] = Nf + e;
         int rc = to_device(c, rowmap, &L.d_rowmap);
         if (rc) return rc;
+        L.h_rowmap = std::move(rowmap);
     }
     L.set = true;
     return PMC_OK;
@@ -1808,7 +1852,8 @@ int pmc_clone(pmc_handle src, pmc_handle *out)
     if (rc) return fail(src, rc, "pmc_clone: %s", pmc_last_error(nullptr));
     c->rel = src->rel; c->abs_ = src->abs_; c->maxit = src->maxit;
     c->cfg_sampler = src->cfg_sampler; c->cfg_darcy = src->cfg_darcy;
-    c->max_batch = src->max_batch; c->force_nt = src->force_nt; c->force_cs = src->force_cs; c->staging = src->staging; c->defer_x = src->defer_x; c->single_wave = src->single_wave; c->renumber = src->renumber; c->force_group = src->force_group; c->solo_rows = src->solo_rows;
+    c->max_batch = src->max_batch; c->force_nt = src->force_nt; c->force_cs = src->force_cs; c->staging = src->staging; c->defer_x = src->defer_x; c->fuse_coarse = src->fuse_coarse; c->single_wave = src->single_wave; c->renumber = src->renumber; c->force_group = src->force_group; c->solo_rows = src->solo_rows;
+    c->renumber = false;  // the source's stored operators are already in the library's numbering
     for (int l = 0; l < src->nlevels && !rc; ++l) {
         const SamplerLevel &S = src->s[l];
         if (S.set)
@@ -1824,7 +1869,12 @@ int pmc_clone(pmc_handle src, pmc_handle *out)
                                         D.B.rowptr.data(), D.B.col.data(), D.B.val.data(), D.ess_u.data(), D.ess_data.data(),
                                         D.rhs.data(), D.obs.data(), D.hasP ? D.Pp.cols : 0, D.hasP ? D.Pp.rowptr.data() : nullptr,
                                         D.hasP ? D.Pp.col.data() : nullptr, D.hasP ? D.Pp.val.data() : nullptr);
+        if (!rc && D.set && !D.h_rowmap.empty()) {  // ... and the clone maps the caller's numbering the same way
+            c->d[l].h_rowmap = D.h_rowmap;
+            rc = to_device(c, c->d[l].h_rowmap, &c->d[l].d_rowmap);
+        }
     }
+    c->renumber = src->renumber;
     for (int l = 0; l < src->nlevels && !rc; ++l) {
         const DarcyLevel &D = src->d[l];
         if (D.set && D.n_obs > 0) {
@@ -1961,6 +2011,7 @@ int pmc_sampler_eval_batch(pmc_handle c, int level, int xi_level, int nsamples, 
     Program pg;
     pg.staging = c->staging;
     pg.defer_x = c->defer_x;
+    pg.fuse_coarse = c->fuse_coarse;
     const Off rhs = emit_restrict(pg, c, xi_level, level, bufA, bufB);
     const Off t1 = (rhs == bufA) ? bufB : bufA;
     Off x0 = -1;
@@ -2022,6 +2073,7 @@ static int darcy_host_batch(Ctx *c, int level, int nsamples, const double *k, co
     Program pg;
     pg.staging = c->staging;
     pg.defer_x = c->defer_x;
+    pg.fuse_coarse = c->fuse_coarse;
     if (apply_only) {
         Solver sv{&sys, &ws, vr(k_ext, Ne + 1)};
         emit_fill(pg, vr(k_ext, Ne + 1, Ne), 1, 1.0);  // weight of the fixed entries
@@ -2113,6 +2165,7 @@ static int level_batch(Ctx *c, int level, int nlevels, int nsamples, uint64_t po
     Program pg;
     pg.staging = c->staging;
     pg.defer_x = c->defer_x;
+    pg.fuse_coarse = c->fuse_coarse;
     // Sample(level, xi) fused with rhs_s = -g W^{1/2} xi  (/root/reference/src/PDESampler.cpp:336-340, :352-358)
     {
         Op &o = pg.add(OP_RNG, KC_RNG, Ne, Ne);
@@ -2328,6 +2381,7 @@ int pmc_bayes_level_batch(pmc_handle c, int level, int nlevels, int nsamples, ui
     Program pg;
     pg.staging = c->staging;
     pg.defer_x = c->defer_x;
+    pg.fuse_coarse = c->fuse_coarse;
     std::vector<int> rng_ops;
     for (int draw = 0; draw < 2; ++draw) {  // draw 0: zxi -> Z (likelihood); draw 1: xi -> R = Q * likelihood
         rng_ops.push_back(pg.pc());

@@ -33,6 +33,7 @@ constexpr int LPR = 2;    // lanes per row: two adjacent threads share a row, 16
 constexpr int PW = TW / LPR;
 constexpr int SLICE = 32 / LPR;  // rows per sliced-ELL slice = rows one warp covers per pass
 constexpr int MAXWARP = 16;  // largest CTA: 512 threads
+constexpr int SMALLN = 64;   // OP_CHEB_SMALL: largest level whose iterates fit the staging buffers of the smallest CTA
 constexpr int STW = 8;              // widest slice (entries per row) a staging buffer holds
 constexpr int STCAP = STW * SLICE;  // entries per staging buffer
 constexpr int NSTAGE = 2;           // staging buffers per warp
@@ -66,6 +67,7 @@ enum OpKind {
     OP_JUMP,          // pc = a0
     OP_STORE_ITERS,   // y[0][j] = iterations of sample j (as double) ; total += iterations
     OP_RNG,           // y[row][j] = (-g * N(mu,sigma)) * w_sqrt[row]  at stream position u0 + sample * a0 * n + row
+    OP_CHEB_SMALL,    // whole Chebyshev iteration z = p(A) r on a level of at most SMALLN rows, iterates in shared memory
     OP_LIKELIHOOD,    // y[0][j] = exp(-sum_i (x[i][j] - fixed[i])^2 * ca) [* r[0][j]]   (n = number of observations)
     OP_KIND_COUNT
 };
@@ -633,6 +635,85 @@ __device__ __forceinline__ void op_sol_update(const Op &o, double *chunk, Smem &
     }
 }
 
+// The coarsest level of the Schur V-cycle (and the whole Schur preconditioner of the coarsest mesh level) is a
+// Chebyshev iteration of degree a0 on a few dozen rows.  As separate operations every step costs the fixed latency of
+// an operation (operation fetch, first memory round trip, barrier: 4-14 k cycles for 2 KB of data).  Here the whole
+// iteration is ONE operation: the iterates z, d live in shared memory (the staging buffers, idle meanwhile), the steps
+// are separated by CTA barriers, r and 1/l1 are re-read from L1.  The arithmetic per row is the one of OP_CHEB_FIRST
+// followed by OP_SPMM/EP_CHEB steps with the same host-computed coefficients (o.val = {ca_j, cb_j}), so the results
+// are bitwise those of the unfused sequence.  With clusters / grid groups the first CTA of the tile does the work.
+template <int NTt, int CS, bool WEIGHTED>
+__device__ __forceinline__ void op_cheb_small(const Op &o, double *chunk, Smem &sm, unsigned char *scratch)
+{
+    const int sub = (threadIdx.x % LPR) * PW;
+    const int n = o.n, deg = o.a0;
+    const bool mine = cluster_rank<CS>(sm) == 0;
+    const double *__restrict__ r = tp(o.r, chunk) + sub;
+    double *__restrict__ zg = tp(o.y, chunk) + sub;
+    const double *__restrict__ V = WEIGHTED ? tp(o.v, chunk) + sub : nullptr;
+    const double *__restrict__ dinvb = WEIGHTED ? tp(o.w, chunk) + sub : nullptr;
+    const double *__restrict__ coef = o.val;
+    double *zs0 = reinterpret_cast<double *>(scratch) + sub, *zs1 = zs0 + SMALLN * TW, *ds = zs1 + SMALLN * TW;
+    constexpr int ES = WEIGHTED ? 16 : 12;
+    D2 acc = make_double2(0.0, 0.0);
+    if (mine) {
+        double *zin = zs0, *zout = zs1;
+        for (int j = 0; j < deg; ++j) {
+            const double ca = __ldg(coef + 2 * j), cb = __ldg(coef + 2 * j + 1);
+            for (int row = threadIdx.x / LPR; row < n; row += NTt / LPR) {
+                const size_t ro = (size_t)row * TW;
+                const D2 rv = ld2c(r + ro);
+                D2 di;
+                if (WEIGHTED) di = ld2c(dinvb + ro);
+                else { const double t = __ldg(o.fixed + row); di = make_double2(t, t); }
+                D2 dn, zn;
+                if (j == 0) {  // OP_CHEB_FIRST: d = z = cb dinv r
+                    dn = make_double2(cb * di.x * rv.x, cb * di.y * rv.y);
+                    zn = dn;
+                } else {       // EP_CHEB: d = ca d + cb dinv (r - A z);  z' = z + d
+                    const int sl = row / SLICE, rs = row % SLICE;
+                    const int k0 = __ldg(o.rowptr + sl), w = __ldg(o.rowptr + sl + 1) - k0;
+                    const unsigned char *base = o.pk + (size_t)k0 * (SLICE * ES);
+                    const double *__restrict__ eval = reinterpret_cast<const double *>(base) + rs;
+                    const int *__restrict__ ecol = reinterpret_cast<const int *>(base + (size_t)w * (SLICE * 8)) + rs;
+                    const int *__restrict__ ewid = ecol + w * SLICE;
+                    D2 s = make_double2(0.0, 0.0);
+                    for (int k = 0; k < w; ++k) {
+                        const double c = __ldg(eval + k * SLICE);
+                        const D2 xv = ld2c(zin + (size_t)__ldg(ecol + k * SLICE) * TW);
+                        if (WEIGHTED) {
+                            const D2 wv = ld2c(V + (size_t)__ldg(ewid + k * SLICE) * TW);
+                            s.x = fma(c * wv.x, xv.x, s.x);
+                            s.y = fma(c * wv.y, xv.y, s.y);
+                        } else {
+                            s.x = fma(c, xv.x, s.x);
+                            s.y = fma(c, xv.y, s.y);
+                        }
+                    }
+                    dn = make_double2(cb * di.x * (rv.x - s.x), cb * di.y * (rv.y - s.y));
+                    if (ca != 0.0) {
+                        const D2 dv = ld2c(ds + ro);
+                        dn.x = fma(ca, dv.x, dn.x);
+                        dn.y = fma(ca, dv.y, dn.y);
+                    }
+                    const D2 zv = ld2c(zin + ro);
+                    zn = make_double2(zv.x + dn.x, zv.y + dn.y);
+                }
+                st2(ds + ro, dn);
+                st2(zout + ro, zn);
+                if (j == deg - 1) {
+                    st2(zg + ro, zn);
+                    acc.x = fma(zn.x, rv.x, acc.x);
+                    acc.y = fma(zn.y, rv.y, acc.y);
+                }
+            }
+            __syncthreads();
+            double *t = zin; zin = zout; zout = t;
+        }
+    }
+    if (o.flags & F_DOT) block_dot<NTt, CS>(acc, sm, o.slot, (o.flags & F_DOT_ACC) != 0);
+}
+
 template <int NTt, int CS>
 __device__ __forceinline__ void op_setup_spmm(const Op &o, double *chunk, const Smem &sm)
 {
@@ -906,6 +987,10 @@ __global__ void __launch_bounds__(NTt, MINB) k_run_program(const ProgParams P)
             }
             break;
         case OP_RNG: op_rng<NTt, CS>(o, tile, chunk, P, sm); break;
+        case OP_CHEB_SMALL:
+            if (flags & F_WEIGHTED) op_cheb_small<NTt, CS, true>(o, chunk, sm, dyn_smem);
+            else op_cheb_small<NTt, CS, false>(o, chunk, sm, dyn_smem);
+            break;
         case OP_LIKELIHOOD:
             // BayesianInverseProblem::ComputeLikelihood / ComputeR (/root/reference/src/BayesianInverseProblem.cpp:190-218)
             if (threadIdx.x < TW && crank == 0) {
