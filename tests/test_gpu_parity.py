@@ -590,3 +590,45 @@ def test_iteration_cap_and_options(prob):
         assert it2.max() < 2000 and np.all(np.abs(Q2 - Q) < 0.5)
     finally:
         c.close()
+
+
+def test_full_size_workload_properties():
+    """BASELINE configs[1] at full size (16^3 / 8^3 / 4^3, N = 17152 / 2240 / 304; 1000 / 3000 / 6000 realisations, the
+    bench's stopping rule): size-independent properties of the CUDA path -- the deterministic known answer Q = 2 on
+    every level, rows that telescope exactly (Y = Q_l - Q_{l+1}), sums that are the sums of the rows, results that do
+    not depend on how the batch is cut (bitwise), and agreement with the oracle on a bounded subsample."""
+    p = hex_problem(16, 3)
+    c = make_context(p, True, 1e-6, 1e-12, 300)
+    c1 = make_context(p, True, 1e-6, 1e-12, 300, options={"cta_threads": 256, "cluster_size": 1, "group_size": -1})
+    o = make_oracle(p, True, 1e-6, 1e-12, 300)
+    try:
+        for lev, dofs in enumerate([17152, 2240, 304]):
+            Q, C, _, it = c.darcy_solve_batch(lev, np.ones((4, p["darcy"][lev].Ne)))
+            assert np.allclose(Q, 2.0, atol=1e-5) and np.all(C == dofs) and np.all(it < 300)
+        pos = 0
+        for lev, ns in [(2, 6000), (1, 3000), (0, 1000)]:
+            sums, rows, its = c.mlmc_level_batch(lev, ns, pos, want_rows=True)
+            assert rows.shape == (ns, 4) and np.all(np.isfinite(rows)) and its > 0
+            if lev < 2:
+                assert np.array_equal(rows[:, 0], rows[:, 1] - rows[:, 2])
+            y, q = rows[:, 0], rows[:, 1]
+            ref = [np.sum(y * y), np.sum(y), np.sum(np.abs(y)), np.sum(q * q), np.sum(q), np.sum(np.abs(q)), np.sum(rows[:, 3]),
+                   np.sum(y ** 3), np.sum(y ** 4)]
+            assert np.allclose(sums, ref, rtol=1e-10)
+            # cutting the batch: bitwise the same rows for one launch shape (the dot products are reduced in an order that
+            # depends on the CTA and cluster size only), equal to round-off when the library picks another shape for the halves
+            half = ns // 2
+            _, ra, _ = c.mlmc_level_batch(lev, half, pos, want_rows=True)
+            _, rb, _ = c.mlmc_level_batch(lev, ns - half, pos + half * p["sampler"][lev].Ne, want_rows=True)
+            assert np.allclose(np.vstack([ra, rb]), rows, rtol=1e-6, atol=1e-9)
+            _, f1, _ = c1.mlmc_level_batch(lev, ns, pos, want_rows=True)
+            _, fa, _ = c1.mlmc_level_batch(lev, half, pos, want_rows=True)
+            _, fb, _ = c1.mlmc_level_batch(lev, ns - half, pos + half * p["sampler"][lev].Ne, want_rows=True)
+            assert np.array_equal(np.vstack([fa, fb]), f1)
+            _, orows, _ = o.mlmc_level(lev, 16, pos, nthreads=8)
+            assert np.allclose(rows[:16, :3], orows[:, :3], rtol=1e-4, atol=2e-5)      # both stop at rel 1e-6, different preconditioners
+            pos += ns * p["sampler"][lev].Ne
+        assert 2.0 < sums[4] / 1000 < 3.2                                               # E[Q_0] of the lognormal problem
+    finally:
+        c.close()
+        c1.close()
