@@ -1397,7 +1397,7 @@ static int run_program(Ctx *c, Program &pg, int nsamples, Off chunk, int max_row
     else { cudaEventCreate(&ep.a); cudaEventCreate(&ep.b); }
     cudaEventRecord(ep.a, c->stream);
     // CTA size: at most ~32 rows per row lane on the largest operand, enlarged while the tiles of the batch would not fill the
-    // machine; every variant keeps 1024 threads per SM resident (64 registers per thread)
+    // machine (nominal sizes; the kernel variants launched for them are listed below)
     int nt = 64;
     while (nt < 512 && max_rows / (nt / LPR) > 32) nt *= 2;
     while (nt < 512 && (long long)ntiles * nt * 2 <= 148LL * 1024) nt *= 2;

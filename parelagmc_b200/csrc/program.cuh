@@ -16,7 +16,7 @@
 // that lives in the SM's L1.  The sparse operators (CSR, weighted CSR) are shared by all tiles and stay in L2.  All
 // traffic of the batched vectors goes to HBM once per operation (ncu: dram bytes = 1.03 x algorithmic bytes): the
 // kernel is bound by HBM bandwidth and, per CTA, by memory latency -- hence CTA sizes chosen per level so that about
-// 1024 threads per SM are resident.
+// 900 threads per SM are resident (72 registers per thread).
 #pragma once
 #include <cooperative_groups.h>
 #include <cuda_runtime.h>
@@ -32,7 +32,7 @@ constexpr int TW = 4;     // samples per tile (32-byte rows)
 constexpr int LPR = 2;    // lanes per row: two adjacent threads share a row, 16 bytes (one double2) each
 constexpr int PW = TW / LPR;
 constexpr int SLICE = 32 / LPR;  // rows per sliced-ELL slice = rows one warp covers per pass
-constexpr int MAXWARP = 16;  // largest CTA: 512 threads
+constexpr int MAXWARP = 16;  // largest CTA: 512 threads (the variants in use run at most 448)
 constexpr int SMALLN = 64;   // OP_CHEB_SMALL: largest level whose iterates fit the staging buffers of the smallest CTA
 constexpr int STW = 8;              // widest slice (entries per row) a staging buffer holds
 constexpr int STCAP = STW * SLICE;  // entries per staging buffer
