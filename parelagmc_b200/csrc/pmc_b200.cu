@@ -1468,7 +1468,8 @@ static int run_program(Ctx *c, Program &pg, int nsamples, Off chunk, int max_row
     CK(cudaMemcpyAsync(c->d_ops, c->h_ops, bytes, cudaMemcpyHostToDevice, c->stream));
     cudaError_t le = cudaSuccess;
     // Kernel variants.  The nominal CTA sizes 512 / 256 / 128 / 64 of the selection above run as 448 / 224 / 128 / 64
-    // threads with at most 896 threads resident per SM, which leaves 72 registers per thread: the interpreter with its
+    // threads with at most 896 (128 / 64: 768, measured 9 % faster on the coarsest level) threads resident per SM, which
+    // leaves 72 (80) registers per thread: the interpreter with its
     // inlined sparse applies wants more than the 64 registers that 1024 resident threads would allow, and the better
     // schedule of the gather loops outweighs the lost eighth of the threads (level-0 batch of the bench: 54.2 -> 47.9 ms).
 #ifndef PMC_NT_L
@@ -1476,8 +1477,8 @@ static int run_program(Ctx *c, Program &pg, int nsamples, Off chunk, int max_row
 #define PMC_NT_M 224
 #define PMC_MINB_L 2
 #define PMC_MINB_M 4
-#define PMC_MINB_S 7
-#define PMC_MINB_XS 14
+#define PMC_MINB_S 6
+#define PMC_MINB_XS 12
 #endif
 #define PMC_LAUNCH(NT_, MINB_, CS_) le = launch_program<NT_, MINB_, CS_>(P, ntiles, c->stream)
     if (group) PMC_LAUNCH(PMC_NT_L, PMC_MINB_L, 0);
