@@ -280,7 +280,7 @@ def run_product(args):
     classes = [n for n in st if n != "kernel"]
     traffic, traffic_note = None, None
     try:   # DRAM bytes of the dominant launch from the committed ncu capture (per launch, like algo_bytes of the solo pass)
-        tj = json.load(open(os.path.join(ROOT, "profiles", "r1h_traffic.json")))
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r1i_traffic.json")))
         traffic = float(tj["dram_bytes_read"] + tj["dram_bytes_write"])
         traffic_note = (f"dram__bytes_read.sum + dram__bytes_write.sum of one level-0 launch, {tj['source']}; algorithmic "
                         f"bytes of that launch {tj['algo_bytes'] / 1e9:.2f} GB")
