@@ -569,6 +569,99 @@ def build_darcy_levels(levels: List[LevelData], ess_attr: Sequence[int], obs_att
 
 
 # --------------------------------------------------------------------------------------
+# element numbering of the reference's meshes (what maps stream position -> element)
+# --------------------------------------------------------------------------------------
+# offsets of the children of a quad / hex in the order of the parent's local vertices (MFEM's reference elements)
+_CHILD_OFFSETS = {2: [(0, 0), (1, 0), (1, 1), (0, 1)],
+                  3: [(0, 0, 0), (1, 0, 0), (1, 1, 0), (0, 1, 0), (0, 0, 1), (1, 0, 1), (1, 1, 1), (0, 1, 1)]}
+
+
+def mfem_refined_box_numbering(n_coarse: Sequence[int], nref: int) -> List[np.ndarray]:
+    """Element numbering of an MFEM Cartesian mesh (`mfem::Mesh(nx, ny[, nz], ...)`, elements x fastest: what
+    `/root/reference/examples/example_helpers/Build3DMesh.hpp:23-27` and the inline meshes under `/root/reference/meshes`
+    produce) after `nref` calls of `UniformRefinement()` as the drivers make them
+    (`/root/reference/examples/PDESamplerTest.cpp:151-156`): the child at the parent's local vertex 0 keeps the parent's
+    index i, the children at local vertices 1 .. 2^d - 1 are appended at `NE + (2^d - 1) i + (j - 1)`.  This is the
+    numbering ParELAG's `MFEMRefinedMeshPartitioner` relies on (`/root/reference/src/Utilities.cpp:28-38`: the first
+    `level_nElements[l+1]` elements are the children 0, the rest come in groups of 2^d - 1), so the agglomerate of fine
+    element i is `i` if `i < NE_coarse` else `(i - NE_coarse) / (2^d - 1)`, and level l's elements are numbered like the
+    mesh refined `nref - l` times.
+
+    Returns, for levels 0 (finest) .. nref (the unrefined mesh), `to_cart[l][e]` = x-fastest Cartesian index of element e
+    in this numbering.  Pinned by the reference's own ctest goldens (`tests/test_reference_goldens.py`): the noise vector
+    is consumed in this order (`/root/reference/src/NormalDistributionSampler.cpp:31-37`)."""
+    dim = len(n_coarse)
+    off = np.array(_CHILD_OFFSETS[dim], dtype=np.int64)
+    nch = 1 << dim
+    n = np.array(n_coarse, dtype=np.int64)
+    grids = np.meshgrid(*[np.arange(int(m)) for m in n], indexing="ij")
+    ijk = np.stack([g.ravel(order="F") for g in grids], axis=1)          # x fastest
+    out = []
+    for r in range(nref + 1):
+        stride = np.concatenate([[1], np.cumprod(n[:-1])])
+        out.append((ijk * stride[None, :]).sum(axis=1))
+        if r == nref:
+            break
+        ne = ijk.shape[0]
+        new = np.empty((nch * ne, dim), dtype=np.int64)
+        new[:ne] = 2 * ijk + off[0][None, :]
+        rest = (2 * ijk[:, None, :] + off[None, 1:, :]).reshape(-1, dim)     # parent-major, children 1..2^d-1
+        new[ne:] = rest
+        ijk = new
+        n = 2 * n
+    return out[::-1]
+
+
+def _perm_rows(m, p):
+    return None if m is None else _csr(sp.csr_matrix(m)[p, :])
+
+
+def _perm_cols(m, p):
+    return None if m is None else _csr(sp.csr_matrix(m)[:, p])
+
+
+def renumber_sampler_levels(sampler: List["SamplerLevel"], to_old: Sequence[np.ndarray],
+                            out_to_old: Optional[Sequence[np.ndarray]] = None) -> List["SamplerLevel"]:
+    """The same sampler hierarchy with element (L2 dof) e of level l being the old element `to_old[l][e]`; RT dofs keep
+    their numbers.  `out_to_old` renumbers the rows of the field transfer T (the forward mesh's elements)."""
+    import dataclasses
+    out = []
+    for l, s in enumerate(sampler):
+        p = np.asarray(to_old[l])
+        pc = np.asarray(to_old[l + 1]) if s.P is not None else None
+        T, Ts = s.T, s.Tscale
+        if T is not None:
+            T = _perm_cols(T, p)
+            if out_to_old is not None:
+                T = _perm_rows(T, np.asarray(out_to_old[l]))
+                Ts = None if Ts is None else Ts[np.asarray(out_to_old[l])]
+        out.append(dataclasses.replace(
+            s, B=_perm_rows(s.B, p), Wdiag=s.Wdiag[p].copy(), w_sqrt=s.w_sqrt[p].copy(),
+            P=None if s.P is None else _perm_cols(_perm_rows(s.P, p), pc), T=T, Tscale=Ts))
+    return out
+
+
+def renumber_darcy_levels(darcy: List["DarcyLevel"], to_old: Sequence[np.ndarray]) -> List["DarcyLevel"]:
+    """The same Darcy hierarchy with element e of level l being the old element `to_old[l][e]`."""
+    import dataclasses
+    out = []
+    for l, d in enumerate(darcy):
+        p = np.asarray(to_old[l])
+        pc = np.asarray(to_old[l + 1]) if d.P_p is not None else None
+        ne = np.diff(d.elem_ptr)
+        ptr = np.concatenate([[0], np.cumsum(ne[p])]).astype(np.int32)
+        dofs = np.concatenate([d.elem_dofs[d.elem_ptr[e]:d.elem_ptr[e + 1]] for e in p]).astype(np.int32)
+        mptr = np.concatenate([[0], np.cumsum((ne[p].astype(np.int64)) ** 2)])
+        mats = np.concatenate([d.elem_mat[d.elem_mat_ptr[e]:d.elem_mat_ptr[e + 1]] for e in p])
+        perm_all = np.concatenate([np.arange(d.Nf), d.Nf + p])
+        out.append(dataclasses.replace(
+            d, elem_ptr=ptr, elem_dofs=dofs, elem_mat_ptr=mptr, elem_mat=mats, B=_perm_rows(d.B, p),
+            ess_data=d.ess_data[perm_all].copy(), rhs=d.rhs[perm_all].copy(), obs=d.obs[perm_all].copy(),
+            P_p=None if d.P_p is None else _perm_cols(_perm_rows(d.P_p, p), pc)))
+    return out
+
+
+# --------------------------------------------------------------------------------------
 # enlarged-domain samplers (SURVEY section 8f-1, 8f-2)
 # --------------------------------------------------------------------------------------
 def embedded_selection(orig: List[LevelData], embed: List[LevelData], pad_cells: int) -> List[sp.csr_matrix]:
@@ -632,11 +725,15 @@ def l2_projection_transfers(orig: List[LevelData], embed: List[LevelData]):
 # --------------------------------------------------------------------------------------
 # Bayesian inverse problem set-up
 # --------------------------------------------------------------------------------------
-def observation_functionals(levels: List[LevelData], coords: Sequence[Sequence[float]], eps: float) -> List[np.ndarray]:
+def observation_functionals(levels: List[LevelData], coords: Sequence[Sequence[float]], eps: float,
+                            rule: str = "center") -> List[np.ndarray]:
     """g_obs_func[i][level] of `BayesianInverseProblem` (`/root/reference/src/BayesianInverseProblem.cpp:46-104`): on
-    level 0 the domain integral of 1 over the elements whose centre lies within `eps` (max-norm) of observation point i
-    (what `ChangeMeshAttributes` marks + `DomainLFIntegrator`: the element volumes), on coarser levels P^T of the finer
-    one.  With no coordinates: one functional, the integral of p over the domain.  Returns [level] -> array [m, Ne]."""
+    level 0 the domain integral of 1 (`DomainLFIntegrator`: the element volumes) over the elements marked for observation
+    point i, on coarser levels P^T of the finer one.  rule = "bbox" marks exactly what `ChangeMeshAttributes` does
+    (`/root/reference/src/MeshUtilities.cpp:268-335`, default eps 0.01 at `MeshUtilities.hpp:61-62`): the elements whose
+    bounding box, enlarged by eps, contains the point (`min - eps <= x < max + eps` per axis); rule = "center" marks the
+    elements whose centre lies within `eps` (max-norm) of the point.  With no coordinates: one functional, the integral
+    of p over the domain.  Returns [level] -> array [m, Ne]."""
     lv = levels[0]
     if len(coords) == 0:
         g0 = lv.Wdiag[None, :].copy()
@@ -647,7 +744,11 @@ def observation_functionals(levels: List[LevelData], coords: Sequence[Sequence[f
         for i, pt in enumerate(coords):
             near = np.ones(lv.Ne, dtype=bool)
             for a in range(lv.dim):
-                near &= np.abs(ctr[a] - pt[a]) <= eps
+                if rule == "bbox":
+                    lo, hi = lv.grid.nodes[a][:-1][idx[a]], lv.grid.nodes[a][1:][idx[a]]
+                    near &= (lo - eps <= pt[a]) & (pt[a] < hi + eps)
+                else:
+                    near &= np.abs(ctr[a] - pt[a]) <= eps
             assert near.any(), f"observation point {pt} marks no element"
             g0[i, near] = lv.Wdiag[near]
     out = [g0]

@@ -165,3 +165,44 @@ def bayes_problem(n=8, nlevels=2, noise=0.05):
     p["noise"] = noise
     p["pos_after_setup"] = Ne0                            # the prior draw of the set-up consumed Ne0 positions
     return p
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# The reference's own ctest problems (examples/CMakeLists.txt:55-118), in the reference's element numbering
+# ------------------------------------------------------------------------------------------------------------------
+@functools.lru_cache(maxsize=None)
+def reference_sampler_problem():
+    """PDESamplerTest.exe defaults (`/root/reference/examples/example_helpers/CreateSamplerParameterList.hpp:26-33`):
+    Build3DHexMesh 4^3 on [0,2]^3, 2 parallel refinements (16^3 / 8^3 / 4^3), Gaussian, variance 1, corlen 0.1, elements
+    numbered as MFEM numbers them under UniformRefinement."""
+    p = dict(hex_problem(16, 3, 0.1))
+    num = H.mfem_refined_box_numbering([4] * 3, 2)
+    p["sampler"] = H.renumber_sampler_levels(p["sampler"], num)
+    p["darcy"] = H.renumber_darcy_levels(p["darcy"], num)
+    p["numbering"] = num
+    return p
+
+
+@functools.lru_cache(maxsize=None)
+def reference_enlarged_problem(with_transfer=True):
+    """The matching enlarged-mesh pair of EmbeddedPDESamplerTest / DarcyTest_RandomInput / LikelihoodExample /
+    RatioEstimator_MC (`/root/reference/examples/example_helpers/Build3DMesh.hpp:23-40`): forward mesh 4^3 on [0,2]^3,
+    enlarged mesh 6^3 on [-0.5,2.5]^3, both refined twice (16^3 in 24^3, 4 fine cells of padding), MFEM numbering on
+    both.  On matching meshes the L2 projection W^-1 G^T of L2ProjectionPDESampler is the 0/1 selection meshP."""
+    import dataclasses
+    orig = H.build_box_hierarchy([16] * 3, [2.0] * 3, 3)
+    emb = H.build_box_hierarchy([24] * 3, [3.0] * 3, 3)
+    num_o = H.mfem_refined_box_numbering([4] * 3, 2)
+    num_e = H.mfem_refined_box_numbering([6] * 3, 2)
+    SL = H.build_sampler_levels(emb)
+    T = H.embedded_selection(orig, emb, 4)
+    inside = [np.asarray(t.sum(axis=0)).ravel()[n] > 0 for t, n in zip(T, num_e)]   # enlarged elements inside [0,2]^3
+    if with_transfer:
+        SL = [dataclasses.replace(s, T=t, Tscale=None) for s, t in zip(SL, T)]
+    SL = H.renumber_sampler_levels(SL, num_e, num_o)
+    DL = H.renumber_darcy_levels(H.build_darcy_levels(orig, **H.MLMC_DEFAULT_BC), num_o)
+    # BayesianInverseProblem defaults (CreateBayesianParameterList.hpp:48-51): one point (1,1,1), noise 0.1
+    gobs = [g[:, n] for g, n in zip(H.observation_functionals(orig, [(1.0, 1.0, 1.0)], 0.01, rule="bbox"), num_o)]
+    return dict(levels=orig, embed_levels=emb, sampler=SL, darcy=DL if with_transfer else None,
+                alpha=H.spde_alpha(0.1), g=H.matern_scaling_coefficient(0.1, 3), nlevels=3, inside=inside, gobs=gobs,
+                noise=0.1)
