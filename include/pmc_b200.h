@@ -142,6 +142,10 @@ int pmc_rng_fill_int(pmc_handle h, uint64_t pos, int64_t n, int32_t *out);
 /* operator()(mfem::Vector&) (src/NormalDistributionSampler.cpp:31-37): out[i] = mu + sigma *
  * inv_Phi(uniformoo(engine draw pos+i)); host out. */
 int pmc_rng_fill(pmc_handle h, uint64_t pos, int64_t n, double *out);
+/* The map of trng::normal_dist<double> alone (src/NormalDistributionSampler.hpp:64): out[i] = mu + sigma *
+ * inv_Phi(uniformoo(engine[i])) for caller-chosen engine outputs in [0, 2^31 - 2] (both extreme tails are reachable
+ * this way; the stream visits them once in 2^31 draws); host in, host out. */
+int pmc_rng_map(pmc_handle h, int64_t n, const int32_t *engine, double *out);
 
 /* ---- PDESampler (src/PDESampler.hpp:68-206) ----------------------------------------------------- */
 /* Sample(level, xi) (src/PDESampler.cpp:336-340) for nsamples consecutive realisations: xi_out is

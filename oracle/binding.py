@@ -66,6 +66,8 @@ def lib():
         L.po_yarn5_split.argtypes = [C.POINTER(_Yarn5), C.c_uint, C.c_uint]
         L.po_yarn5_fill_int.argtypes = [C.POINTER(_Yarn5), C.c_int64, C.POINTER(C.c_int32)]
         L.po_normal_fill.argtypes = [C.POINTER(_Yarn5), C.c_double, C.c_double, C.c_int64, _dp]
+        L.po_normal_map.argtypes = [C.c_int64, C.POINTER(C.c_int32), C.c_double, C.c_double, _dp]
+        L.po_det_eval.argtypes = [C.c_int, C.c_int64, _dp, _dp]
         L.po_set_sampler_level.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, _ip, _ip, _dp, _ip, _ip, _dp,
                                            _dp, C.c_int, _ip, _ip, _dp, C.c_double, C.c_double, C.c_int]
         L.po_set_darcy_level.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, _ip, _ip, _dp, _ip, _ip, _dp,
@@ -115,6 +117,26 @@ class Yarn5:
     @property
     def state(self):
         return list(self.g.r), list(self.g.a)
+
+
+def normal_map(engine, mu: float = 0.0, sigma: float = 1.0) -> np.ndarray:
+    """Normal deviates of given engine outputs: inv_Phi(uniformoo(x)) * sigma + mu (`po_normal_map`)."""
+    engine = np.ascontiguousarray(engine, dtype=np.int32)
+    out = np.empty(engine.shape[0], dtype=np.float64)
+    lib().po_normal_map(engine.shape[0], engine.ctypes.data_as(C.POINTER(C.c_int32)), mu, sigma, _d(out))
+    return out
+
+
+DET_FUNCS = {"exp": 0, "log": 1, "erf": 2, "erfc": 3, "inv_Phi": 4, "inv_Phi_libm": 5}
+
+
+def det_eval(which: str, x) -> np.ndarray:
+    """The deterministic elementary functions of parelagmc_b200/csrc/detmath.h as compiled into the oracle, and inv_Phi
+    over them ("inv_Phi") or over glibc's libm ("inv_Phi_libm")."""
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    y = np.empty_like(x)
+    lib().po_det_eval(DET_FUNCS[which], x.shape[0], _d(x), _d(y))
+    return y
 
 
 def _csr_args(m):

@@ -16,6 +16,9 @@
  * At tolerance 1e-12 the solution does not depend on the preconditioner.
  */
 #include "pmc_oracle.h"
+/* One operation sequence for exp/log/erf/erfc shared with the CUDA build, so that the deviates are bit-identical on
+ * both sides (libm's and CUDA's own implementations differ in the last place); see the header for accuracy. */
+#include "../parelagmc_b200/csrc/detmath.h"
 
 #include <math.h>
 #include <stdio.h>
@@ -164,16 +167,19 @@ void po_yarn5_fill_int(po_yarn5 *g, int64_t n, int32_t *out)
 /* utility::uniformoo<double>: (x - min + 1) / (max - min + 2) with min = 0, max = 2^31 - 2 */
 double po_uniformoo(int32_t x) { return ((double)x + 1.0) * (1.0 / 2147483648.0); }
 
-static double po_Phi(double x)
+/* trng::math::Phi / inv_Phi (TRNG 4.19 special_functions.hpp; restated, source absent): Acklam's rational approximation
+ * followed by one step of Halley's rational method.  `libm` selects glibc's erf/erfc/exp/log (what a TRNG build on this
+ * host would call) instead of the deterministic ones of detmath.h; the product and the parity tests use libm = 0. */
+static double po_Phi_impl(double x, int libm)
 {
     const double one_over_sqrt_2 = 0.70710678118654752440;
     x *= one_over_sqrt_2;
-    if (x < -0.6744897501960817 * one_over_sqrt_2) return 0.5 * erfc(-x);
-    if (x > +0.6744897501960817 * one_over_sqrt_2) return 1.0 - 0.5 * erfc(x);
-    return 0.5 + 0.5 * erf(x);
+    if (x < -0.6744897501960817 * one_over_sqrt_2) return 0.5 * (libm ? erfc(-x) : pmc_erfc(-x));
+    if (x > +0.6744897501960817 * one_over_sqrt_2) return 1.0 - 0.5 * (libm ? erfc(x) : pmc_erfc(x));
+    return 0.5 + 0.5 * (libm ? erf(x) : pmc_erf(x));
 }
 
-static double po_inv_Phi_approx(double x)
+static double po_inv_Phi_approx(double x, int libm)
 {
     /* P. J. Acklam's rational approximation */
     static const double a[6] = {-3.969683028665376e+01, 2.209460984245205e+02, -2.759285104469687e+02,
@@ -190,7 +196,7 @@ static double po_inv_Phi_approx(double x)
     if (x == 1.0) return INFINITY;
     double t, q;
     if (x < x_low) {
-        q = sqrt(-2.0 * log(x));
+        q = sqrt(-2.0 * (libm ? log(x) : pmc_log(x)));
         t = (((((c[0] * q + c[1]) * q + c[2]) * q + c[3]) * q + c[4]) * q + c[5]) /
             ((((d[0] * q + d[1]) * q + d[2]) * q + d[3]) * q + 1.0);
     } else if (x < x_high) {
@@ -199,28 +205,49 @@ static double po_inv_Phi_approx(double x)
         t = (((((a[0] * r + a[1]) * r + a[2]) * r + a[3]) * r + a[4]) * r + a[5]) * q /
             (((((b[0] * r + b[1]) * r + b[2]) * r + b[3]) * r + b[4]) * r + 1.0);
     } else {
-        q = sqrt(-2.0 * log(1.0 - x));
+        q = sqrt(-2.0 * (libm ? log(1.0 - x) : pmc_log(1.0 - x)));
         t = -(((((c[0] * q + c[1]) * q + c[2]) * q + c[3]) * q + c[4]) * q + c[5]) /
             ((((d[0] * q + d[1]) * q + d[2]) * q + d[3]) * q + 1.0);
     }
     return t;
 }
 
-double po_inv_Phi(double x)
+static double po_inv_Phi_impl(double x, int libm)
 {
-    double y = po_inv_Phi_approx(x);
+    double y = po_inv_Phi_approx(x, libm);
     if (isfinite(y)) { /* one step of Halley's rational method */
         const double sqrt_2pi = 2.50662827463100050242;
-        double e = po_Phi(y) - x;
-        double u = e * sqrt_2pi * exp(y * y / 2.0);
+        double e = po_Phi_impl(y, libm) - x;
+        double u = e * sqrt_2pi * (libm ? exp(y * y / 2.0) : pmc_exp(y * y / 2.0));
         y -= u / (1.0 + y * u / 2.0);
     }
     return y;
 }
 
+double po_inv_Phi(double x) { return po_inv_Phi_impl(x, 0); }
+double po_inv_Phi_libm(double x) { return po_inv_Phi_impl(x, 1); }
+
+/* the deterministic elementary functions on their own (accuracy tests against mpmath / libm) */
+double po_det_exp(double x) { return pmc_exp(x); }
+double po_det_log(double x) { return pmc_log(x); }
+double po_det_erf(double x) { return pmc_erf(x); }
+double po_det_erfc(double x) { return pmc_erfc(x); }
+void po_det_eval(int which, int64_t n, const double *x, double *y)
+{
+    for (int64_t i = 0; i < n; ++i)
+        y[i] = which == 0 ? pmc_exp(x[i]) : which == 1 ? pmc_log(x[i]) : which == 2 ? pmc_erf(x[i])
+             : which == 3 ? pmc_erfc(x[i]) : which == 4 ? po_inv_Phi_impl(x[i], 0) : po_inv_Phi_impl(x[i], 1);
+}
+
 void po_normal_fill(po_yarn5 *g, double mu, double sigma, int64_t n, double *out)
 {
     for (int64_t i = 0; i < n; ++i) out[i] = po_inv_Phi(po_uniformoo(po_yarn5_next(g))) * sigma + mu;
+}
+
+/* the map of trng::normal_dist<double> on caller-chosen engine outputs (reaches both extreme tails) */
+void po_normal_map(int64_t n, const int32_t *engine, double mu, double sigma, double *out)
+{
+    for (int64_t i = 0; i < n; ++i) out[i] = po_inv_Phi(po_uniformoo(engine[i])) * sigma + mu;
 }
 
 /* ============================================================================================ */

@@ -43,6 +43,10 @@ void po_yarn5_split(po_yarn5 *g, unsigned s, unsigned n);    /* split(s, n): lea
 void po_yarn5_fill_int(po_yarn5 *g, int64_t n, int32_t *out);
 double po_uniformoo(int32_t x);                              /* utility::uniformoo<double>           */
 double po_inv_Phi(double u);                                 /* math::inv_Phi (Acklam + Halley)      */
+double po_inv_Phi_libm(double u);                            /* same, with glibc's erf/erfc/exp/log   */
+/* which: 0 exp, 1 log, 2 erf, 3 erfc (parelagmc_b200/csrc/detmath.h), 4 inv_Phi, 5 inv_Phi over libm */
+void po_det_eval(int which, int64_t n, const double *x, double *y);
+void po_normal_map(int64_t n, const int32_t *engine, double mu, double sigma, double *out);
 /* NormalDistributionSampler::operator()(Vector&): out[i] = mu + sigma * inv_Phi(uniformoo(rng())) */
 void po_normal_fill(po_yarn5 *g, double mu, double sigma, int64_t n, double *out);
 

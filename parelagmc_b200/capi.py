@@ -23,7 +23,7 @@ K_CLASSES = ["saddle_apply", "lanczos_update", "solution_update", "mass_smooth",
 SYMBOLS = [
     "pmc_create", "pmc_destroy", "pmc_last_error", "pmc_host_alloc", "pmc_host_free", "pmc_set_stream", "pmc_synchronize", "pmc_set_tolerances",
     "pmc_set_preconditioner", "pmc_set_option", "pmc_set_batch", "pmc_upload_sampler_level", "pmc_upload_darcy_level", "pmc_upload_field_transfer", "pmc_clone", "pmc_prepare",
-    "pmc_rng_init", "pmc_rng_fill_int", "pmc_rng_fill", "pmc_sampler_sample_batch", "pmc_sampler_eval_batch",
+    "pmc_rng_init", "pmc_rng_fill_int", "pmc_rng_fill", "pmc_rng_map", "pmc_sampler_sample_batch", "pmc_sampler_eval_batch",
     "pmc_darcy_solve_batch", "pmc_darcy_apply_batch", "pmc_mlmc_level_batch", "pmc_mc_level_batch",
     "pmc_upload_observations", "pmc_bayes_level_batch", "pmc_profile",
     "pmc_reset_stats", "pmc_kernel_stats",
@@ -95,6 +95,7 @@ def load():
     L.pmc_rng_init.argtypes = [vp, C.c_double, C.c_double, C.c_int, C.c_int]
     L.pmc_rng_fill_int.argtypes = [vp, C.c_uint64, C.c_int64, C.POINTER(C.c_int32)]
     L.pmc_rng_fill.argtypes = [vp, C.c_uint64, C.c_int64, _dp]
+    L.pmc_rng_map.argtypes = [vp, C.c_int64, C.POINTER(C.c_int32), _dp]
     L.pmc_sampler_sample_batch.argtypes = [vp, C.c_int, C.c_int, C.c_uint64, _dp]
     L.pmc_sampler_eval_batch.argtypes = [vp, C.c_int, C.c_int, C.c_int, _dp, _dp, C.c_int, C.c_int, _dp, _dp, _ip]
     L.pmc_darcy_solve_batch.argtypes = [vp, C.c_int, C.c_int, _dp, _dp, _dp, _dp, _ip]
@@ -269,6 +270,13 @@ class Context:
     def rng_fill(self, pos: int, n: int) -> np.ndarray:
         out = np.empty(n, dtype=np.float64)
         self._ck(self._L.pmc_rng_fill(self._h, C.c_uint64(pos), n, _d(out)))
+        return out
+
+    def rng_map(self, engine: np.ndarray) -> np.ndarray:
+        """Normal deviates of caller-chosen engine outputs (`pmc_rng_map`)."""
+        engine = np.ascontiguousarray(engine, dtype=np.int32)
+        out = np.empty(engine.shape[0], dtype=np.float64)
+        self._ck(self._L.pmc_rng_map(self._h, engine.shape[0], engine.ctypes.data_as(C.POINTER(C.c_int32)), _d(out)))
         return out
 
     # -- sampler -----------------------------------------------------------------------------------

@@ -1946,6 +1946,23 @@ static int rng_fill_common(Ctx *c, int mode, uint64_t pos, int64_t n, void *out)
 int pmc_rng_fill_int(pmc_handle c, uint64_t pos, int64_t n, int32_t *out) { return rng_fill_common(c, 0, pos, n, out); }
 int pmc_rng_fill(pmc_handle c, uint64_t pos, int64_t n, double *out) { return rng_fill_common(c, 1, pos, n, out); }
 
+int pmc_rng_map(pmc_handle c, int64_t n, const int32_t *engine, double *out)
+{
+    if (!c || n < 0 || (n > 0 && (!out || !engine))) return PMC_ERR_ARG;
+    if (!c->rng_ready) return fail(c, PMC_ERR_STATE, "pmc_rng_init has not been called");
+    if (n == 0) return PMC_OK;
+    CK(cudaSetDevice(c->device));
+    const size_t off = ((size_t)n * 8 + 255) & ~(size_t)255;
+    int rc = ensure_arena(c, off + (size_t)n * 4 + 4096);
+    if (rc) return rc;
+    double *d_out = (double *)c->arena.base;
+    int32_t *d_in = (int32_t *)((char *)c->arena.base + off);
+    CK(cudaMemcpyAsync(d_in, engine, (size_t)n * 4, cudaMemcpyHostToDevice, c->stream));
+    launch(c, PMC_K_RNG, (double)n * 12.0, k_rng_map, grid1d((size_t)n), dim3(256), n, (const int32_t *)d_in, d_out, c->mu, c->sigma);
+    CK(cudaMemcpyAsync(out, d_out, (size_t)n * 8, cudaMemcpyDeviceToHost, c->stream));
+    return finish(c);
+}
+
 int pmc_sampler_sample_batch(pmc_handle c, int level, int nsamples, uint64_t pos0, double *xi_out)
 {
     if (!c) return PMC_ERR_ARG;

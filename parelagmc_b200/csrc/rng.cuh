@@ -11,6 +11,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "detmath.h"
+
 namespace pmc {
 
 constexpr uint32_t YARN_M = 2147483647u;
@@ -72,8 +74,9 @@ __device__ __forceinline__ void yarn5_jump(uint32_t r[5], uint64_t n, const uint
 }
 
 // trng::math::inv_Phi: Acklam's rational approximation + one Halley step (restated; TRNG source absent).
-// The polynomial parts use explicit round-to-nearest multiplies/adds (no FMA contraction) so that they follow
-// the same operation sequence as a host build without contraction; erf/erfc/exp/log are CUDA's.
+// Every operation is an explicit round-to-nearest multiply/add/divide (no FMA contraction) and erf/erfc/exp/log are the
+// deterministic ones of detmath.h, so a host build of the same sequence (the CPU oracle) produces bit-identical
+// deviates (tests/test_gpu_parity.py::test_normal_deviates_bit_exact).
 __device__ __forceinline__ double dm(double a, double b) { return __dmul_rn(a, b); }
 __device__ __forceinline__ double da(double a, double b) { return __dadd_rn(a, b); }
 
@@ -81,9 +84,9 @@ __device__ __forceinline__ double dev_Phi(double x)
 {
     const double one_over_sqrt_2 = 0.70710678118654752440;
     x = dm(x, one_over_sqrt_2);
-    if (x < dm(-0.6744897501960817, one_over_sqrt_2)) return dm(0.5, erfc(-x));
-    if (x > dm(+0.6744897501960817, one_over_sqrt_2)) return da(1.0, -dm(0.5, erfc(x)));
-    return da(0.5, dm(0.5, erf(x)));
+    if (x < dm(-0.6744897501960817, one_over_sqrt_2)) return dm(0.5, pmc_erfc(-x));
+    if (x > dm(+0.6744897501960817, one_over_sqrt_2)) return da(1.0, -dm(0.5, pmc_erfc(x)));
+    return da(0.5, dm(0.5, pmc_erf(x)));
 }
 
 __device__ __forceinline__ double dev_inv_Phi(double x)
@@ -99,7 +102,7 @@ __device__ __forceinline__ double dev_inv_Phi(double x)
     const double x_low = 0.02425, x_high = 1.0 - 0.02425;
     double t, q;
     if (x < x_low) {
-        q = sqrt(dm(-2.0, log(x)));
+        q = __dsqrt_rn(dm(-2.0, pmc_log(x)));
         const double num = da(dm(da(dm(da(dm(da(dm(da(dm(c0, q), c1), q), c2), q), c3), q), c4), q), c5);
         const double den = da(dm(da(dm(da(dm(da(dm(d0, q), d1), q), d2), q), d3), q), 1.0);
         t = __ddiv_rn(num, den);
@@ -110,7 +113,7 @@ __device__ __forceinline__ double dev_inv_Phi(double x)
         const double den = da(dm(da(dm(da(dm(da(dm(da(dm(b0, r), b1), r), b2), r), b3), r), b4), r), 1.0);
         t = __ddiv_rn(num, den);
     } else {
-        q = sqrt(dm(-2.0, log(da(1.0, -x))));
+        q = __dsqrt_rn(dm(-2.0, pmc_log(da(1.0, -x))));
         const double num = da(dm(da(dm(da(dm(da(dm(da(dm(c0, q), c1), q), c2), q), c3), q), c4), q), c5);
         const double den = da(dm(da(dm(da(dm(da(dm(d0, q), d1), q), d2), q), d3), q), 1.0);
         t = -__ddiv_rn(num, den);
@@ -118,9 +121,25 @@ __device__ __forceinline__ double dev_inv_Phi(double x)
     // one step of Halley's rational method
     const double sqrt_2pi = 2.50662827463100050242;
     const double e = da(dev_Phi(t), -x);
-    const double u = dm(dm(e, sqrt_2pi), exp(__ddiv_rn(dm(t, t), 2.0)));
+    const double u = dm(dm(e, sqrt_2pi), pmc_exp(__ddiv_rn(dm(t, t), 2.0)));
     t = da(t, -__ddiv_rn(u, da(1.0, __ddiv_rn(dm(t, u), 2.0))));
     return t;
+}
+
+// trng::normal_dist<double>::operator()(R&): icdf(uniformoo(r)) = inv_Phi(u) * sigma + mu with u = (x + 1) / 2^31 for the
+// engine output x in [0, 2^31 - 2] (utility::uniformoo<double>: the open interval (0,1)).
+__device__ __forceinline__ double dev_normal_from_engine(uint32_t v, double mu, double sigma)
+{
+    const double u = dm((double)v + 1.0, 1.0 / 2147483648.0);
+    return da(dm(dev_inv_Phi(u), sigma), mu);
+}
+
+// out[i] = normal deviate of the engine output in[i] (the map alone, for caller-chosen engine values)
+__global__ void __launch_bounds__(256) k_rng_map(int64_t n, const int32_t *__restrict__ in, double *__restrict__ out, double mu,
+                                                 double sigma)
+{
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        out[i] = dev_normal_from_engine((uint32_t)in[i], mu, sigma);
 }
 
 // Work decomposition: thread (j, c) produces values i in [c*T, min(ni, (c+1)*T)) of sequence j, i.e. stream
@@ -163,9 +182,7 @@ __global__ void __launch_bounds__(128) k_rng(const RngArgs a, const RngTables *_
         if (MODE == 0) {
             a.out_i[o] = (int32_t)v;
         } else {
-            // trng::utility::uniformoo<double>: (x + 1) / (max - min + 2), open interval (0,1)
-            const double u = dm((double)v + 1.0, 1.0 / 2147483648.0);
-            double z = da(dm(dev_inv_Phi(u), a.sigma), a.mu);
+            double z = dev_normal_from_engine(v, a.mu, a.sigma);
             if (MODE == 2) z = dm(dm(a.neg_g, z), __ldg(a.w_sqrt + i));
             a.out[o] = z;
         }

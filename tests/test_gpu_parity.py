@@ -54,26 +54,34 @@ def test_yarn5_split_streams_bit_exact(prob):
         c.close()
 
 
-def test_normal_deviates_match_oracle(ctx):
-    """Doubles: the integer draw is bit-exact; inv_Phi goes through CUDA's erf/erfc/exp/log instead of glibc's,
-    so equality is asserted to a few ulp and the bit-exact fraction is reported."""
-    from oracle.binding import Yarn5
-    n = 200000
+def test_normal_deviates_bit_exact(ctx):
+    """Doubles, bit for bit (north_star: "white-noise vectors ... bit-exact"): the integer draw is exact, and uniformoo,
+    Acklam's approximation, the Halley step and erf/erfc/exp/log (csrc/detmath.h) are one IEEE operation sequence on
+    both sides.  1.2 M consecutive draws of the stream, both extreme tails and the branch points of inv_Phi through
+    `pmc_rng_map`, and a non-trivial (mu, sigma)."""
+    from oracle.binding import Yarn5, normal_map
+    n = 1200000
     ref = Yarn5().jump(1000).normals(n, 0.0, 1.0)
     got = ctx.rng_fill(1000, n)
-    # Both sides run the same Acklam + Halley sequence on the same integer draw; only erf/erfc/exp/log differ
-    # (CUDA's vs glibc's, each within a few ulp).  The Halley step divides the CDF residual by the density phi(y),
-    # so a 1-ulp difference in Phi(y) (ulp(1) = 2.2e-16 in the upper tail, where Phi -> 1) moves y by ulp(1)/phi(y):
-    # the bound is a few ulp(1) scaled by max(1, 1/phi(y)).
-    phi = np.exp(-0.5 * ref * ref) / np.sqrt(2.0 * np.pi)
-    tol = 4.0 * np.spacing(1.0) * np.maximum(1.0, 1.0 / phi)
-    err = np.abs(got - ref)
-    exact = float(np.mean(got == ref))
-    print(f"normal deviates: bit-exact fraction {exact:.4f}, max abs error {err.max():.3e}, "
-          f"max error/bound {np.max(err / tol):.3f}")
-    assert np.all(err <= tol)
-    assert exact > 0.8
+    assert np.array_equal(got, ref)
     assert abs(got.mean()) < 0.01 and abs(got.std() - 1.0) < 0.01
+    m = 2 ** 31 - 1                                            # engine outputs lie in [0, m - 1]
+    lo, hi = int(0.02425 * 2 ** 31), int((1.0 - 0.02425) * 2 ** 31)      # inv_Phi's branch points x_low, x_high
+    q1, q3 = int(0.25 * 2 ** 31), int(0.75 * 2 ** 31)                    # Phi's |x| = 0.6745 branch points
+    eng = np.concatenate([np.arange(0, 60000), np.arange(m - 60000, m), np.arange(lo - 3000, lo + 3000),
+                          np.arange(hi - 3000, hi + 3000), np.arange(q1 - 3000, q1 + 3000), np.arange(q3 - 3000, q3 + 3000),
+                          np.arange(2 ** 30 - 3000, 2 ** 30 + 3000),
+                          np.random.default_rng(5).integers(0, m, 400000)]).astype(np.int32)
+    ref_t = normal_map(eng)
+    got_t = ctx.rng_map(eng)
+    assert np.array_equal(got_t, ref_t)
+    assert ref_t.min() < -6.1 and ref_t.max() > 6.1 and np.all(np.isfinite(ref_t))   # u = 2^-31 and 1 - 2^-31
+    ctx.rng_init(3.0, 2.0, 1, 0)
+    try:
+        assert np.array_equal(ctx.rng_fill(5, 50000), Yarn5().jump(5).normals(50000, 3.0, 2.0))
+        assert np.array_equal(ctx.rng_map(eng[:70000]), normal_map(eng[:70000], 3.0, 2.0))
+    finally:
+        ctx.rng_init(0.0, 1.0, 1, 0)
 
 
 def test_sample_batch_is_stream_in_order(ctx, prob):
@@ -81,7 +89,7 @@ def test_sample_batch_is_stream_in_order(ctx, prob):
     Ne = prob["sampler"][1].Ne
     xi = ctx.sampler_sample_batch(1, 5, 777)
     ref = Yarn5().jump(777).normals(5 * Ne).reshape(5, Ne)
-    assert np.allclose(xi, ref, rtol=0, atol=1e-14)
+    assert np.array_equal(xi, ref)
 
 
 def test_darcy_operator_apply_matches_assembled(ctx, prob):

@@ -144,6 +144,47 @@ def test_normal_deviates_statistics():
     assert lib().po_inv_Phi(0.5) == 0.0
 
 
+def test_detmath_accuracy():
+    """parelagmc_b200/csrc/detmath.h (the exp/log/erf/erfc both the CUDA build and the oracle evaluate inv_Phi with)
+    against mpmath, in ulp of the exact value, on the domain the sampler reaches."""
+    import mpmath as mp
+    from oracle.binding import det_eval
+    mp.mp.dps = 40
+    rng = np.random.default_rng(3)
+
+    def max_ulp(which, x, f):
+        y = det_eval(which, x)
+        worst = 0.0
+        for a, b in zip(y, x):
+            t = f(mp.mpf(float(b)))
+            worst = max(worst, float(abs(mp.mpf(float(a)) - t) / np.spacing(abs(float(t)))))
+        return worst
+
+    assert max_ulp("exp", rng.uniform(-30, 30, 3000), mp.exp) < 1.0
+    assert max_ulp("log", np.exp(rng.uniform(-25, 3, 3000)), mp.log) < 2.0
+    assert max_ulp("erf", rng.uniform(-0.5, 0.5, 3000), mp.erf) < 1.0
+    assert max_ulp("erfc", rng.uniform(0.5, 6.8, 6000), mp.erfc) < 4.0
+    assert max_ulp("erfc", rng.uniform(6.8, 26.0, 1500), mp.erfc) < 4.0
+    assert max_ulp("erfc", rng.uniform(-6.0, 0.5, 1500), mp.erfc) < 1.5
+    # special values
+    assert det_eval("exp", [0.0, -800.0, 800.0]).tolist() == [1.0, 0.0, np.inf]
+    assert det_eval("log", [1.0])[0] == 0.0 and det_eval("erf", [0.0])[0] == 0.0 and det_eval("erfc", [30.0])[0] == 0.0
+
+
+def test_normals_vs_libm():
+    """The deviates computed over detmath.h agree with the same Acklam + Halley sequence over glibc's erf/erfc/exp/log (what
+    a TRNG build on this host would call) to a few ulp(1) / phi(y): the Halley step divides the difference of the two
+    Phi values (each within a few ulp) by the density.  Most are bit-identical."""
+    from oracle.binding import det_eval
+    m = 2 ** 31 - 1
+    v = np.concatenate([np.arange(0, 20000), np.arange(m - 20000, m), np.random.default_rng(7).integers(0, m, 400000)])
+    u = (v.astype(np.float64) + 1.0) / 2147483648.0
+    a, b = det_eval("inv_Phi", u), det_eval("inv_Phi_libm", u)
+    phi = np.exp(-0.5 * b * b) / np.sqrt(2.0 * np.pi)
+    assert np.all(np.abs(a - b) <= 6.0 * np.spacing(1.0) * np.maximum(1.0, 1.0 / phi) * np.maximum(1.0, np.abs(b)))
+    assert np.mean(a == b) > 0.85
+
+
 def test_golden_fixtures():
     """tests/golden/oracle_golden.json (tools/make_golden.py) pins the oracle's stream, fields and QoIs."""
     from oracle.binding import Yarn5
