@@ -124,11 +124,28 @@ int pmc_upload_darcy_level(pmc_handle h, int level, int Ne, int Nf,
 int pmc_upload_field_transfer(pmc_handle h, int level, int n_out, const int *T_rowptr, const int *T_col,
                               const double *T_val, const double *row_scale);
 
-/* A second handle on the same device with the same uploaded levels, options, tolerances and random stream but its own
- * CUDA stream and workspace.  The level loops of one InitRun are independent of one another, so a manager keeps one
- * handle per level and issues the level batches from one host thread each: their kernels then share the GPU (a single
- * fine-level batch of ~1000 realisations does not fill it). */
+/* A second handle on the same device with the same levels, options, tolerances and random stream but its own CUDA
+ * stream and workspace.  The uploaded operators are SHARED with the source (one copy per device, freed with the last
+ * handle that uses them); pmc_clone prepares the source first.  The level loops of one InitRun are independent of one
+ * another, so a manager keeps one handle per level and issues the level batches from one host thread each: their
+ * kernels then share the GPU (a single fine-level batch of ~1000 realisations does not fill it).  Create the clones
+ * before the threads that use them start. */
 int pmc_clone(pmc_handle src, pmc_handle *out);
+
+/* ---- ranks that share one sample budget (replaces the communicator of MLMC_Manager / MC_Manager,
+ * src/MLMC_Manager.hpp:34, src/MC_Manager.hpp:32) -------------------------------------------------------------------
+ * Every rank (one handle per GPU: processes under MPI / torchrun, or host threads of one process) owns a slice of every
+ * level's realisations and the per-level sums are combined once per InitRun with ncclAllReduce(ncclDouble, ncclSum)
+ * over NVLink.  Rank 0 obtains PMC_COMM_ID_BYTES opaque bytes from pmc_comm_unique_id and ships them to the other
+ * ranks by whatever the host program uses (MPI_Bcast in the reference's drivers); every rank then calls pmc_comm_init
+ * (collective).  pmc_allreduce_sums reduces `count` doubles in place (host array) on the handle's stream and returns
+ * when the result is in `sums`; with one rank both calls are no-ops.  libnccl.so.2 is loaded on first use (dlopen;
+ * PMC_NCCL_LIB overrides the name), so the library has no link-time dependency on NCCL. */
+#define PMC_COMM_ID_BYTES 128
+int pmc_comm_unique_id(void *id_out);
+int pmc_comm_init(pmc_handle h, int nranks, int rank, const void *id);
+int pmc_allreduce_sums(pmc_handle h, double *sums, int count);
+int pmc_comm_destroy(pmc_handle h);
 
 /* Build every derived device structure now (Schur-complement hierarchies, block operators) instead of on
  * first use, so that set-up time stays out of timed regions. */
@@ -203,7 +220,7 @@ int pmc_bayes_level_batch(pmc_handle h, int level, int nlevels, int nsamples, ui
                           double *rows, int64_t *total_iters);
 
 /* ---- instrumentation ---------------------------------------------------------------------------- */
-/* Kernel classes for pmc_profile / pmc_kernel_stats. */
+/* Kernel classes of pmc_kernel_stats. */
 enum {
     PMC_K_SADDLE_APPLY = 0, /* block operator apply  q = A u (+ fused u.q)                          */
     PMC_K_LANCZOS_UPDATE,   /* v0 = cq q + cv1 v1 + cv0 v0                                           */
@@ -230,8 +247,6 @@ typedef struct {
     int64_t ops_executed;                 /* operations executed inside them, summed over tiles                         */
     int64_t minres_iterations;            /* MINRES iterations, summed over realisations and solves                     */
 } pmc_kernel_stats_t;
-/* Kept for ABI stability: the persistent kernel always accounts time and bytes per operation class. */
-int pmc_profile(pmc_handle h, unsigned mask);
 int pmc_reset_stats(pmc_handle h);
 int pmc_kernel_stats(pmc_handle h, pmc_kernel_stats_t *out);
 

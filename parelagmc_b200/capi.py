@@ -25,8 +25,8 @@ SYMBOLS = [
     "pmc_set_preconditioner", "pmc_set_option", "pmc_set_batch", "pmc_upload_sampler_level", "pmc_upload_darcy_level", "pmc_upload_field_transfer", "pmc_clone", "pmc_prepare",
     "pmc_rng_init", "pmc_rng_fill_int", "pmc_rng_fill", "pmc_rng_map", "pmc_sampler_sample_batch", "pmc_sampler_eval_batch",
     "pmc_darcy_solve_batch", "pmc_darcy_apply_batch", "pmc_mlmc_level_batch", "pmc_mc_level_batch",
-    "pmc_upload_observations", "pmc_bayes_level_batch", "pmc_profile",
-    "pmc_reset_stats", "pmc_kernel_stats",
+    "pmc_upload_observations", "pmc_bayes_level_batch", "pmc_comm_unique_id", "pmc_comm_init", "pmc_allreduce_sums",
+    "pmc_comm_destroy", "pmc_reset_stats", "pmc_kernel_stats",
 ]
 
 
@@ -104,7 +104,10 @@ def load():
     L.pmc_mc_level_batch.argtypes = [vp, C.c_int, C.c_int, C.c_uint64, _dp, _dp, C.POINTER(C.c_int64)]
     L.pmc_upload_observations.argtypes = [vp, C.c_int, C.c_int, _dp, _dp, C.c_double]
     L.pmc_bayes_level_batch.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_uint64, _dp, _dp, C.POINTER(C.c_int64)]
-    L.pmc_profile.argtypes = [vp, C.c_uint]
+    L.pmc_comm_unique_id.argtypes = [C.c_char_p]
+    L.pmc_comm_init.argtypes = [vp, C.c_int, C.c_int, C.c_char_p]
+    L.pmc_allreduce_sums.argtypes = [vp, _dp, C.c_int]
+    L.pmc_comm_destroy.argtypes = [vp]
     L.pmc_reset_stats.argtypes = [vp]
     L.pmc_kernel_stats.argtypes = [vp, C.POINTER(KernelStats)]
     for name in SYMBOLS:
@@ -154,6 +157,19 @@ def pinned_empty(shape, dtype=np.float64) -> np.ndarray:
     buf = (C.c_char * max(n, 1)).from_address(p.value)
     buf._owner = _PinnedBlock(p, L)
     return np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+
+
+COMM_ID_BYTES = 128
+
+
+def comm_unique_id() -> bytes:
+    """`pmc_comm_unique_id`: the opaque NCCL id rank 0 creates and ships to the other ranks."""
+    L = load()
+    buf = C.create_string_buffer(COMM_ID_BYTES)
+    rc = L.pmc_comm_unique_id(buf)
+    if rc != 0:
+        raise PmcError(rc, (L.pmc_last_error(None) or b"").decode())
+    return buf.raw
 
 
 class Context:
@@ -369,11 +385,25 @@ class Context:
         return sums, rows, its.value
 
     # -- instrumentation ---------------------------------------------------------------------------
-    def profile(self, classes: Sequence[str] = ()):
-        mask = 0
-        for n in classes:
-            mask |= 1 << K_CLASSES.index(n)
-        self._ck(self._L.pmc_profile(self._h, mask))
+    # -- ranks sharing a sample budget (NCCL behind the C ABI) --------------------------------------
+    def comm_init(self, nranks: int, rank: int, unique_id: Optional[bytes]):
+        """`pmc_comm_init` (collective over the ranks).  `unique_id`: the bytes `comm_unique_id()` returned on rank 0."""
+        self._ck(self._L.pmc_comm_init(self._h, nranks, rank, unique_id))
+
+    def allreduce_sums(self, sums: np.ndarray) -> np.ndarray:
+        """`pmc_allreduce_sums`: in-place sum over the ranks of a contiguous float64 array."""
+        assert sums.dtype == np.float64 and sums.flags.c_contiguous
+        self._ck(self._L.pmc_allreduce_sums(self._h, _d(sums), int(sums.size)))
+        return sums
+
+    def comm_destroy(self):
+        self._ck(self._L.pmc_comm_destroy(self._h))
+
+    def kernel_ms(self) -> float:
+        """CUDA-event time (ms) of all persistent-kernel launches of this handle since the last `reset_stats`."""
+        st = KernelStats()
+        self._ck(self._L.pmc_kernel_stats(self._h, C.byref(st)))
+        return float(st.kernel_ms)
 
     def reset_stats(self):
         self._ck(self._L.pmc_reset_stats(self._h))

@@ -6,11 +6,16 @@
 #include "../../include/pmc_b200.h"
 
 #include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>   // types and enums only: the symbols are resolved with dlopen at the first pmc_comm_* call
 
+#include <atomic>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
 #include <map>
+#include <memory>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -181,6 +186,19 @@ struct EventPair {
     cudaEvent_t a, b;
 };
 
+// Device buffers of the uploaded (immutable) operators.  A handle and its clones (pmc_clone) share one store: the
+// operators of a hierarchy exist once per device however many handles (one per level in the managers) run on it.
+struct DevStore {
+    int device = 0;
+    std::mutex mu;
+    std::vector<void *> owned;
+    ~DevStore()
+    {
+        cudaSetDevice(device);
+        for (void *p : owned) cudaFree(p);
+    }
+};
+
 }  // namespace pmc
 
 using namespace pmc;
@@ -212,7 +230,13 @@ struct pmc_context_s {
     RngTables *d_tab = nullptr;
     // memory
     Arena arena;
-    std::vector<void *> owned;
+    std::shared_ptr<DevStore> store;
+    int num_sms = 148;   // multiProcessorCount of the handle's device
+    // NCCL communicator over the ranks that share the sample budget (pmc_comm_init); null for a single rank
+    void *nccl_comm = nullptr;
+    int comm_ranks = 1, comm_rank = 0;
+    double *d_comm_buf = nullptr;
+    size_t comm_buf_count = 0;
     Op *d_ops = nullptr, *h_ops = nullptr;  // program buffer (device / pinned staging)
     size_t ops_cap = 0;
     ProgStats *d_pstats = nullptr;
@@ -230,7 +254,7 @@ struct pmc_context_s {
 
 typedef pmc_context_s Ctx;
 
-static std::string g_create_error;
+static thread_local std::string g_create_error;   // message of the last failed call that has no handle
 static std::vector<double> cheb_coefficients(double lo, double hi, int deg);
 
 static int fail(Ctx *c, int code, const char *fmt, ...)
@@ -324,7 +348,10 @@ static int to_device(Ctx *c, const std::vector<T> &h, T **out)
     const size_t bytes = std::max<size_t>(h.size(), 1) * sizeof(T);
     void *p = nullptr;
     CK(cudaMalloc(&p, bytes));
-    c->owned.push_back(p);
+    {
+        std::lock_guard<std::mutex> lk(c->store->mu);
+        c->store->owned.push_back(p);
+    }
     if (!h.empty()) CK(cudaMemcpy(p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
     *out = reinterpret_cast<T *>(p);
     return PMC_OK;
@@ -1272,6 +1299,24 @@ static int pick_batch(Ctx *c, size_t bytes_per_sample, int nsamples)
     return std::min(b, std::max(nsamples, 1));
 }
 
+// Size the batch and its workspace in one step.  The managers run one handle per level from concurrent host threads on
+// the same device: the free-memory reading and the allocation it leads to are made under one process-wide lock, so two
+// handles never size their batches against the same free bytes, and an allocation that still fails (another process on
+// the device) is retried with half the batch.  `per_sample` bytes per realisation, `extra` bytes per realisation of
+// per-sample results, both for padded batches.
+static std::mutex g_arena_mutex;
+static int size_batch(Ctx *c, size_t per_sample, size_t extra, int nsamples, int *B_out)
+{
+    std::lock_guard<std::mutex> lk(g_arena_mutex);
+    int B = pick_batch(c, per_sample, nsamples);
+    for (;;) {
+        int rc = ensure_arena(c, per_sample * (size_t)pad_ld(B) + (size_t)B * extra + (1 << 16));
+        if (rc == PMC_OK) { *B_out = B; return PMC_OK; }
+        if (rc != PMC_ERR_NOMEM || B <= TW) return rc;
+        B = std::max(TW, ((B / 2) / TW) * TW);
+    }
+}
+
 static int check_level(Ctx *c, int level, bool sampler, bool darcy)
 {
     if (!c) return PMC_ERR_ARG;
@@ -1317,15 +1362,16 @@ static cudaError_t launch_program(const ProgParams &P, int ntiles, cudaStream_t 
 {
     // dynamic shared memory: the per-warp operator staging buffers (program.cuh)
     const size_t dyn = (size_t)(NTt / 32) * NSTAGE * sizeof(WarpStage);
-    static bool attr_set = false;  // per instantiation; the attribute is per device, set again on every device seen
-    static int attr_dev = -1;
+    // the attribute is per (instantiation, device); level batches are launched from concurrent host threads, so the
+    // "already set" cache is an atomic bit mask over devices (setting the attribute twice is harmless)
+    static std::atomic<unsigned long long> attr_mask{0ull};
     int dev = 0;
     cudaGetDevice(&dev);
-    if (!attr_set || attr_dev != dev) {
+    const unsigned long long bit = 1ull << (dev & 63);
+    if (!(attr_mask.load(std::memory_order_acquire) & bit)) {
         cudaError_t e = cudaFuncSetAttribute(k_run_program<NTt, MINB, CS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
         if (e != cudaSuccess) return e;
-        attr_set = true;
-        attr_dev = dev;
+        attr_mask.fetch_or(bit, std::memory_order_release);
     }
     if constexpr (CS == 1) {
         k_run_program<NTt, MINB, 1><<<ntiles, NTt, dyn, stream>>>(P);
@@ -1400,18 +1446,18 @@ static int run_program(Ctx *c, Program &pg, int nsamples, Off chunk, int max_row
     // machine (nominal sizes; the kernel variants launched for them are listed below)
     int nt = 64;
     while (nt < 512 && max_rows / (nt / LPR) > 32) nt *= 2;
-    while (nt < 512 && (long long)ntiles * nt * 2 <= 148LL * 1024) nt *= 2;
+    while (nt < 512 && (long long)ntiles * nt * 2 <= (long long)c->num_sms * 1024) nt *= 2;
     // a batch that needs a second, mostly empty wave of CTAs runs better as one wave of smaller CTAs, as long as those
     // still fill at least half of the machine's threads (level 1 of the bench: 750 tiles, 20.5 -> 18.4 ms)
-    while (c->single_wave && nt > 64 && (long long)ntiles * nt > 148LL * 1024 && (long long)ntiles * (nt / 2) <= 148LL * 1024 &&
-           (long long)ntiles * (nt / 2) * 2 >= 148LL * 1024)
+    while (c->single_wave && nt > 64 && (long long)ntiles * nt > (long long)c->num_sms * 1024 && (long long)ntiles * (nt / 2) <= (long long)c->num_sms * 1024 &&
+           (long long)ntiles * (nt / 2) * 2 >= (long long)c->num_sms * 1024)
         nt /= 2;
     if (c->force_nt == 64 || c->force_nt == 128 || c->force_nt == 256 || c->force_nt == 512) nt = c->force_nt;
     // cluster size: split a tile over several CTAs while the batch has too few tiles to fill the machine and every
     // CTA keeps at least ~1000 rows of the largest operand
     int cs = 1;
     if (nt >= 256) {
-        const long long slots = 148LL * (1024 / nt);
+        const long long slots = (long long)c->num_sms * (1024 / nt);
         while (cs < 8 && (long long)ntiles * cs * 2 <= slots && max_rows / (cs * 2) >= 1024) cs *= 2;
     }
     if (c->force_cs == 1 || ((c->force_cs == 2 || c->force_cs == 4 || c->force_cs == 8) && nt >= 256)) cs = c->force_cs;
@@ -1419,7 +1465,7 @@ static int run_program(Ctx *c, Program &pg, int nsamples, Off chunk, int max_row
     // level), a tile is split over G co-resident CTAs of a cooperative launch, every CTA keeping >= ~2000 rows
     int group = 0;
     {
-        const long long slots = 148LL * 2;  // 512-thread CTAs, two per SM
+        const long long slots = (long long)c->num_sms * 2;  // 512-thread CTAs, two per SM
         if (c->force_group > 1) group = c->force_group;
         else if (c->force_group == 0 && c->force_cs == 0 && nt == 512 && (long long)ntiles * 8 * 3 <= slots) {
             long long g = std::min<long long>(slots / ntiles, max_rows / 2048);
@@ -1591,6 +1637,9 @@ int pmc_create(int device, int nlevels, pmc_handle *out)
     Ctx *c = new Ctx();
     c->device = device;
     c->nlevels = nlevels;
+    c->num_sms = prop.multiProcessorCount;
+    c->store = std::make_shared<DevStore>();
+    c->store->device = device;
     c->cfg_sampler.max_vlevels = -1;  // single-level Schur smoother when alpha*W dominates (short correlation length)
     c->cfg_darcy.omega = 2.5;         // aggregation-type coarse spaces under-correct the pressure Laplacian
     c->cfg_darcy.mass_degree = 1;     // plain Jacobi on the RT mass block: fewest bytes per unit of convergence
@@ -1614,7 +1663,9 @@ void pmc_destroy(pmc_handle c)
     if (!c) return;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    for (void *p : c->owned) cudaFree(p);
+    if (c->nccl_comm) pmc_comm_destroy(c);
+    if (c->d_comm_buf) cudaFree(c->d_comm_buf);
+    c->store.reset();   // frees the operators with the last handle that shares them
     if (c->arena.base) cudaFree(c->arena.base);
     cudaFree(c->d_pstats);
     cudaFree(c->d_tab);
@@ -1848,49 +1899,152 @@ int pmc_clone(pmc_handle src, pmc_handle *out)
 {
     if (!src || !out) return PMC_ERR_ARG;
     *out = nullptr;
+    // The clone shares the source's device operators (DevStore): build every derived structure of the source first, so
+    // that the copied level descriptors are complete and the clone never has to prepare anything itself.
+    int rc = pmc_prepare(src);
+    if (rc) return rc;
     pmc_handle c = nullptr;
-    int rc = pmc_create(src->device, src->nlevels, &c);
+    rc = pmc_create(src->device, src->nlevels, &c);
     if (rc) return fail(src, rc, "pmc_clone: %s", pmc_last_error(nullptr));
     c->rel = src->rel; c->abs_ = src->abs_; c->maxit = src->maxit;
     c->cfg_sampler = src->cfg_sampler; c->cfg_darcy = src->cfg_darcy;
-    c->max_batch = src->max_batch; c->force_nt = src->force_nt; c->force_cs = src->force_cs; c->staging = src->staging; c->defer_x = src->defer_x; c->fuse_coarse = src->fuse_coarse; c->single_wave = src->single_wave; c->renumber = src->renumber; c->force_group = src->force_group; c->solo_rows = src->solo_rows;
-    c->renumber = false;  // the source's stored operators are already in the library's numbering
-    for (int l = 0; l < src->nlevels && !rc; ++l) {
-        const SamplerLevel &S = src->s[l];
-        if (S.set)
-            rc = pmc_upload_sampler_level(c, l, S.Ne, S.Nf, S.M.rowptr.data(), S.M.col.data(), S.M.val.data(), S.B.rowptr.data(),
-                                          S.B.col.data(), S.B.val.data(), S.Wdiag.data(), S.hasP ? S.P.cols : 0,
-                                          S.hasP ? S.P.rowptr.data() : nullptr, S.hasP ? S.P.col.data() : nullptr,
-                                          S.hasP ? S.P.val.data() : nullptr, S.alpha, S.g, S.lognormal);
-        if (!rc && S.set && S.hasT)
-            rc = pmc_upload_field_transfer(c, l, S.n_out, S.T.rowptr.data(), S.T.col.data(), S.T.val.data(), nullptr);
-        const DarcyLevel &D = src->d[l];
-        if (!rc && D.set)
-            rc = pmc_upload_darcy_level(c, l, D.Ne, D.Nf, D.elem_ptr.data(), D.elem_dofs.data(), D.elem_mat.data(),
-                                        D.B.rowptr.data(), D.B.col.data(), D.B.val.data(), D.ess_u.data(), D.ess_data.data(),
-                                        D.rhs.data(), D.obs.data(), D.hasP ? D.Pp.cols : 0, D.hasP ? D.Pp.rowptr.data() : nullptr,
-                                        D.hasP ? D.Pp.col.data() : nullptr, D.hasP ? D.Pp.val.data() : nullptr);
-        if (!rc && D.set && !D.h_rowmap.empty()) {  // ... and the clone maps the caller's numbering the same way
-            c->d[l].h_rowmap = D.h_rowmap;
-            rc = to_device(c, c->d[l].h_rowmap, &c->d[l].d_rowmap);
-        }
-    }
-    c->renumber = src->renumber;
-    for (int l = 0; l < src->nlevels && !rc; ++l) {
-        const DarcyLevel &D = src->d[l];
-        if (D.set && D.n_obs > 0) {
-            // the stored functionals are already normalised; normalising again divides by 1
-            rc = pmc_upload_observations(c, l, D.n_obs, D.h_gobs_func.data(), D.h_Gobs.data(), D.noise);
-        }
-    }
-    if (!rc && src->rng_ready) rc = pmc_rng_init(c, src->mu, src->sigma, src->rng_nparts, src->rng_mypart);
-    if (!rc) rc = pmc_prepare(c);
+    c->max_batch = src->max_batch; c->force_nt = src->force_nt; c->force_cs = src->force_cs; c->staging = src->staging;
+    c->defer_x = src->defer_x; c->fuse_coarse = src->fuse_coarse; c->single_wave = src->single_wave; c->renumber = src->renumber;
+    c->force_group = src->force_group; c->solo_rows = src->solo_rows;
+    c->store = src->store;   // one copy of the operators per device, freed with the last handle that uses them
+    c->s = src->s;           // level descriptors: host arrays by value, device pointers into the shared store
+    c->d = src->d;
+    if (src->rng_ready) rc = pmc_rng_init(c, src->mu, src->sigma, src->rng_nparts, src->rng_mypart);
     if (rc) {
         fail(src, rc, "pmc_clone: %s", pmc_last_error(c));
         pmc_destroy(c);
         return rc;
     }
     *out = c;
+    return PMC_OK;
+}
+
+// ---- ranks that share a sample budget: NCCL all-reduce of the per-level sums ------------------------------------------
+// (/root/reference/src/MLMC_Manager.cpp computes every rank's samples redundantly and needs no reduction; here the
+// ranks own disjoint slices of every level's budget, SURVEY section 8e, so InitRun ends with one all-reduce.)
+// libnccl is loaded at the first use (dlopen), so the library itself links only the CUDA runtime and loads on hosts
+// without NCCL; a process that already holds libnccl.so.2 (torch) shares that copy.
+namespace {
+struct NcclApi {
+    void *lib = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    const char *(*GetErrorString)(ncclResult_t) = nullptr;
+    std::string err;
+};
+NcclApi *nccl_api()
+{
+    static NcclApi api;
+    static std::once_flag once;
+    std::call_once(once, []() {
+        const char *names[] = {getenv("PMC_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+        for (const char *n : names) {
+            if (!n || !*n) continue;
+            api.lib = dlopen(n, RTLD_NOW | RTLD_LOCAL);
+            if (api.lib) break;
+            api.err = dlerror();
+        }
+        if (!api.lib) return;
+        api.GetUniqueId = (decltype(api.GetUniqueId))dlsym(api.lib, "ncclGetUniqueId");
+        api.CommInitRank = (decltype(api.CommInitRank))dlsym(api.lib, "ncclCommInitRank");
+        api.AllReduce = (decltype(api.AllReduce))dlsym(api.lib, "ncclAllReduce");
+        api.CommDestroy = (decltype(api.CommDestroy))dlsym(api.lib, "ncclCommDestroy");
+        api.GetErrorString = (decltype(api.GetErrorString))dlsym(api.lib, "ncclGetErrorString");
+        if (!api.GetUniqueId || !api.CommInitRank || !api.AllReduce || !api.CommDestroy || !api.GetErrorString) {
+            api.err = "libnccl lacks a required symbol";
+            api.lib = nullptr;
+        }
+    });
+    return api.lib ? &api : nullptr;
+}
+const char *nccl_load_error()
+{
+    static NcclApi *probe = nccl_api();
+    (void)probe;
+    return "libnccl.so.2 could not be loaded (set PMC_NCCL_LIB)";
+}
+}  // namespace
+
+static_assert(PMC_COMM_ID_BYTES == sizeof(ncclUniqueId), "PMC_COMM_ID_BYTES must be the size of ncclUniqueId");
+
+int pmc_comm_unique_id(void *id_out)
+{
+    if (!id_out) return fail(nullptr, PMC_ERR_ARG, "pmc_comm_unique_id: null argument");
+    NcclApi *n = nccl_api();
+    if (!n) return fail(nullptr, PMC_ERR_STATE, "pmc_comm_unique_id: %s", nccl_load_error());
+    ncclUniqueId id;
+    ncclResult_t r = n->GetUniqueId(&id);
+    if (r != ncclSuccess) return fail(nullptr, PMC_ERR_CUDA, "ncclGetUniqueId: %s", n->GetErrorString(r));
+    memcpy(id_out, &id, sizeof id);
+    return PMC_OK;
+}
+
+int pmc_comm_init(pmc_handle c, int nranks, int rank, const void *id)
+{
+    if (!c) return PMC_ERR_ARG;
+    if (nranks < 1 || rank < 0 || rank >= nranks) return fail(c, PMC_ERR_ARG, "pmc_comm_init: rank %d of %d", rank, nranks);
+    if (c->nccl_comm) pmc_comm_destroy(c);
+    c->comm_ranks = nranks;
+    c->comm_rank = rank;
+    if (nranks == 1) return PMC_OK;
+    if (!id) return fail(c, PMC_ERR_ARG, "pmc_comm_init: the unique id is required for more than one rank");
+    NcclApi *n = nccl_api();
+    if (!n) return fail(c, PMC_ERR_STATE, "pmc_comm_init: %s", nccl_load_error());
+    CK(cudaSetDevice(c->device));
+    ncclUniqueId uid;
+    memcpy(&uid, id, sizeof uid);
+    ncclComm_t comm = nullptr;
+    ncclResult_t r = n->CommInitRank(&comm, nranks, uid, rank);
+    if (r != ncclSuccess) return fail(c, PMC_ERR_CUDA, "ncclCommInitRank: %s", n->GetErrorString(r));
+    c->nccl_comm = comm;
+    return PMC_OK;
+}
+
+int pmc_comm_destroy(pmc_handle c)
+{
+    if (!c) return PMC_ERR_ARG;
+    if (c->nccl_comm) {
+        NcclApi *n = nccl_api();
+        cudaSetDevice(c->device);
+        cudaStreamSynchronize(c->stream);
+        if (n) n->CommDestroy((ncclComm_t)c->nccl_comm);
+        c->nccl_comm = nullptr;
+    }
+    c->comm_ranks = 1;
+    c->comm_rank = 0;
+    return PMC_OK;
+}
+
+int pmc_allreduce_sums(pmc_handle c, double *sums, int count)
+{
+    if (!c || count < 0 || (count > 0 && !sums)) return PMC_ERR_ARG;
+    if (c->comm_ranks == 1 || count == 0) return PMC_OK;
+    if (!c->nccl_comm) return fail(c, PMC_ERR_STATE, "pmc_allreduce_sums: pmc_comm_init has not been called");
+    NcclApi *n = nccl_api();
+    CK(cudaSetDevice(c->device));
+    if (c->comm_buf_count < (size_t)count) {
+        if (c->d_comm_buf) cudaFree(c->d_comm_buf);
+        c->d_comm_buf = nullptr;
+        c->comm_buf_count = 0;
+        CK(cudaMalloc((void **)&c->d_comm_buf, (size_t)count * sizeof(double)));
+        c->comm_buf_count = (size_t)count;
+    }
+    int rc = ensure_pinned(c, (size_t)count);
+    if (rc) return rc;
+    memcpy(c->h_pinned, sums, (size_t)count * sizeof(double));
+    CK(cudaMemcpyAsync(c->d_comm_buf, c->h_pinned, (size_t)count * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    ncclResult_t r = n->AllReduce(c->d_comm_buf, c->d_comm_buf, (size_t)count, ncclDouble, ncclSum, (ncclComm_t)c->nccl_comm, c->stream);
+    if (r != ncclSuccess) return fail(c, PMC_ERR_CUDA, "ncclAllReduce: %s", n->GetErrorString(r));
+    CK(cudaMemcpyAsync(c->h_pinned, c->d_comm_buf, (size_t)count * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    memcpy(sums, c->h_pinned, (size_t)count * sizeof(double));
     return PMC_OK;
 }
 
@@ -2047,8 +2201,8 @@ int pmc_sampler_eval_batch(pmc_handle c, int level, int xi_level, int nsamples, 
     }
     const Off chunk = ar.peak;
     const size_t per_sample = (size_t)chunk * 8 / TW + (size_t)std::max(nmax, Nout) * 8 + 64;
-    const int B = pick_batch(c, per_sample, nsamples);
-    if ((rc = ensure_arena(c, per_sample * (size_t)pad_ld(B) + (1 << 16)))) return rc;
+    int B = 0;
+    if ((rc = size_batch(c, per_sample, 0, nsamples, &B))) return rc;
     std::vector<double> itbuf;
     for (int s0 = 0; s0 < nsamples; s0 += B) {
         const int ns = std::min(B, nsamples - s0);
@@ -2102,8 +2256,8 @@ static int darcy_host_batch(Ctx *c, int level, int nsamples, const double *k, co
     }
     const Off chunk = ar.peak;
     const size_t per_sample = (size_t)chunk * 8 / TW + (size_t)N * 8 + 64;
-    const int B = pick_batch(c, per_sample, nsamples);
-    if ((rc = ensure_arena(c, per_sample * (size_t)pad_ld(B) + (1 << 16)))) return rc;
+    int B = 0;
+    if ((rc = size_batch(c, per_sample, 0, nsamples, &B))) return rc;
     std::vector<double> itbuf;
     for (int s0 = 0; s0 < nsamples; s0 += B) {
         const int ns = std::min(B, nsamples - s0);
@@ -2248,8 +2402,8 @@ static int level_batch(Ctx *c, int level, int nlevels, int nsamples, uint64_t po
     }
     const Off chunk = ar.peak;
     const size_t per_sample = (size_t)chunk * 8 / TW + 64 + 40;
-    const int B = pick_batch(c, per_sample, nsamples);
-    if ((rc = ensure_arena(c, per_sample * (size_t)pad_ld(B) + (size_t)B * 32 + (1 << 16)))) return rc;
+    int B = 0;
+    if ((rc = size_batch(c, per_sample, 32, nsamples, &B))) return rc;
     if ((rc = ensure_pinned(c, 16 + (rows ? (size_t)B * 4 : 0)))) return rc;
     const unsigned long long it0 = c->iters_seen;
     for (int s0 = 0; s0 < nsamples; s0 += B) {
@@ -2420,8 +2574,8 @@ int pmc_bayes_level_batch(pmc_handle c, int level, int nlevels, int nsamples, ui
     }
     const Off chunk = ar.peak;
     const size_t per_sample = (size_t)chunk * 8 / TW + 64 + 48;
-    const int B = pick_batch(c, per_sample, nsamples);
-    if ((rc = ensure_arena(c, per_sample * (size_t)pad_ld(B) + (size_t)B * 40 + (1 << 16)))) return rc;
+    int B = 0;
+    if ((rc = size_batch(c, per_sample, 40, nsamples, &B))) return rc;
     if ((rc = ensure_pinned(c, 32 + (rows ? (size_t)B * 5 : 0)))) return rc;
     const unsigned long long it0 = c->iters_seen;
     for (int s0 = 0; s0 < nsamples; s0 += B) {
@@ -2447,13 +2601,6 @@ int pmc_bayes_level_batch(pmc_handle c, int level, int nlevels, int nsamples, ui
 }
 
 // ---- instrumentation ------------------------------------------------------------------------------
-int pmc_profile(pmc_handle c, unsigned mask)
-{
-    if (!c) return PMC_ERR_ARG;
-    (void)mask;  // the persistent kernel always accounts time and bytes per operation class; nothing to switch on
-    return PMC_OK;
-}
-
 int pmc_reset_stats(pmc_handle c)
 {
     if (!c) return PMC_ERR_ARG;

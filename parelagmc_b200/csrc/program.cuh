@@ -847,8 +847,7 @@ __device__ __forceinline__ void op_rng(const Op &o, int tile, double *chunk, con
     for (int i = i0; i < i1; ++i) {
         yarn5_step(r, co);
         const uint32_t v = yarn5_output(r[0], P.tab->powtab);
-        const double u = dm((double)v + 1.0, 1.0 / 2147483648.0);
-        const double z = da(dm(dev_inv_Phi(u), P.sigma), P.mu);
+        const double z = dev_normal_from_engine(v, P.mu, P.sigma);
         y[(size_t)i * TW + j] = dm(dm(o.ca, z), __ldg(o.fixed + i));
     }
 }

@@ -1,5 +1,7 @@
 #include "MC_Manager.hpp"
 
+#include <stdexcept>
+
 #include <algorithm>
 #include <chrono>
 #include <cmath>
@@ -9,6 +11,7 @@
 
 #include "DarcySolver.hpp"
 #include "PDESampler.hpp"
+#include "RankComm.hpp"
 
 namespace parelagmc {
 
@@ -25,10 +28,8 @@ MC_Manager::MC_Manager(MPI_Comm comm_, PhysicalMLSolver &pSolver_, MLSampler &sa
       actualMSE(std::numeric_limits<double>::infinity()), eQ(0), eABSQ(0), eC(0), varQ(0),
       M(pSolver_.GetGlobalNumberOfDofs(0)), time_(0), level_nsamples(0), level_nsamples_missing(0)
 {
-#ifdef PARELAGMC_B200_WITH_PARELAG
-    MPI_Comm_size(comm, &rank);
+    MPI_Comm_size(comm, &rank);  // the communicator size, as in the reference (src/MC_Manager.cpp:44)
     MPI_Comm_rank(comm, &pid);
-#endif
     std::fill(sums, sums + NVAR, 0.);
     if (pid == 0 && !file_name.empty()) logger.open(file_name);
     if (!pid)
@@ -47,13 +48,27 @@ void MC_Manager::InitRun(int nsamples)
     const bool batched = bs && bd && bs->Device().get() == bd->Device().get();
     const auto t0 = std::chrono::steady_clock::now();
     if (batched && nsamples > 0) {
-        const uint64_t pos0 = bs->Distribution().Advance((uint64_t)nsamples * (uint64_t)bs->NoiseSize(0));
-        std::vector<double> rows(logger.is_open() ? (size_t)nsamples * 2 : 0);
-        bs->Device()->check(pmc_mc_level_batch(bs->Device()->handle(), 0, nsamples, pos0, sums,
-                                               rows.empty() ? nullptr : rows.data(), nullptr),
-                            "pmc_mc_level_batch");
+        // the ranks own disjoint slices of the realisations; one all-reduce of {sums, time} per InitRun (RankComm.hpp)
+        pmc_handle h = bs->Device()->handle();
+        if (rank > 1 && !comm_ready) {
+            InitDeviceComm(comm, h);
+            comm_ready = true;
+        }
+        int first = 0, mine = 0;
+        SplitSamples(nsamples, pid, rank, first, mine);
+        const uint64_t pos0 = bs->Distribution().Advance((uint64_t)nsamples * (uint64_t)bs->NoiseSize(0)) +
+                              (uint64_t)first * (uint64_t)bs->NoiseSize(0);
+        std::vector<double> rows(logger.is_open() ? (size_t)mine * 2 : 0);
+        double round[NVAR + 1] = {0.};
+        if (mine > 0)
+            bs->Device()->check(pmc_mc_level_batch(h, 0, mine, pos0, round, rows.empty() ? nullptr : rows.data(), nullptr),
+                                "pmc_mc_level_batch");
+        round[NVAR] = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        if (rank > 1) bs->Device()->check(pmc_allreduce_sums(h, round, NVAR + 1), "pmc_allreduce_sums");
+        for (int i = 0; i < NVAR; ++i) sums[i] += round[i];
+        time_ += round[NVAR];
         if (!pid && logger.is_open())
-            for (int j = 0; j < nsamples; ++j)
+            for (int j = 0; j < mine; ++j)
                 logger << std::setw(14) << rows[2 * j] << std::setw(14) << rows[2 * j + 1] << "\n";
     } else {
         // reference loop (src/MC_Manager.cpp:91-109)
@@ -70,7 +85,7 @@ void MC_Manager::InitRun(int nsamples)
             if (!pid && logger.is_open()) logger << std::setw(14) << q << std::setw(14) << c << "\n";
         }
     }
-    time_ += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    if (!(batched && nsamples > 0)) time_ += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     level_nsamples += nsamples;
     if (pid == 0 && logger.is_open()) logger << std::flush;
     computeNSamplesMSE();
@@ -121,6 +136,7 @@ void MC_Manager::ShowMe(std::ostream &os)
 void MC_Manager::computeNSamplesMSE()
 {
     // src/MC_Manager.cpp:194-239
+    if (level_nsamples < 2) throw std::runtime_error("MC_Manager: at least 2 samples are needed for the variance estimate");
     const double nl = static_cast<double>(level_nsamples);
     eQ = sums[Q] / nl;
     eABSQ = sums[ABSQ] / nl;

@@ -41,5 +41,6 @@ private:
     double eQ, eABSQ, eC, varQ, M, time_;
     int level_nsamples, level_nsamples_missing;
     std::ofstream logger;
+    bool comm_ready = false;   // NCCL communicator of the ranks (RankComm.hpp) created
 };
 }  // namespace parelagmc

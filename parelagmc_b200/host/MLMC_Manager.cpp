@@ -10,6 +10,7 @@
 
 #include "DarcySolver.hpp"
 #include "PDESampler.hpp"
+#include "RankComm.hpp"
 
 namespace parelagmc {
 
@@ -46,10 +47,8 @@ MLMC_Manager::MLMC_Manager(MPI_Comm comm_, const int nlevels_, PhysicalMLSolver 
       level_time(nlevels_, 0.), sampler_nnz(nlevels_), physical_nnz(nlevels_), alpha(0.), alphaABS(0.), beta(0.),
       gamma(0.), level_nsamples(nlevels_, 0), level_nsamples_missing(nlevels_, 0)
 {
-#ifdef PARELAGMC_B200_WITH_PARELAG
     MPI_Comm_size(comm, &rank);  // sic: the reference keeps the communicator size in `rank` (src/MLMC_Manager.cpp:62)
     MPI_Comm_rank(comm, &pid);
-#endif
     for (int i = 0; i < nlevels; ++i) M[i] = pSolver.GetGlobalNumberOfDofs(i);
     if (pid == 0 && !file_name.empty()) logger.open(file_name);
     if (use_array_samples && static_cast<int>(v_init_nsamples.size()) != nlevels) use_array_samples = false;
@@ -99,6 +98,10 @@ void MLMC_Manager::InitRun(std::vector<int> &level_nsamples_init)
         // stream positions are the ones the reference's sequential Sample() calls would have consumed: coarsest level
         // first, then nlevels-2 .. 0 (src/MLMC_Manager.cpp:110,140).
         pmc_handle main_h = bs->Device()->handle();
+        if (rank > 1 && !comm_ready) {   // the ranks own disjoint slices of every level's realisations (RankComm.hpp)
+            InitDeviceComm(comm, main_h);
+            comm_ready = true;
+        }
         while ((int)clones.size() < nlevels - 1) {
             pmc_handle h = nullptr;
             bs->Device()->check(pmc_clone(main_h, &h), "pmc_clone");
@@ -108,30 +111,39 @@ void MLMC_Manager::InitRun(std::vector<int> &level_nsamples_init)
         for (int ilevel = nlevels - 1; ilevel >= 0; --ilevel)
             pos0[ilevel] = bs->Distribution().Advance((uint64_t)level_nsamples_init[ilevel] * (uint64_t)bs->NoiseSize(ilevel));
         std::vector<std::vector<double>> rows(nlevels);
-        std::vector<int> rcs(nlevels, 0);
-        std::vector<double> secs(nlevels, 0.0);
+        std::vector<int> rcs(nlevels, 0), mine(nlevels, 0);
+        // this round's contribution of this rank: [nlevels x NVAR sums | nlevels times]; reduced over the ranks in ONE
+        // collective, so that the sample allocation below sees identical inputs on every rank
+        std::vector<double> round(nlevels * (NVAR + 1), 0.0);
+        double *secs = &round[nlevels * NVAR];
         std::vector<std::thread> workers;
         for (int ilevel = 0; ilevel < nlevels; ++ilevel) {
-            const int nsamples = level_nsamples_init[ilevel];
+            int first = 0;
+            SplitSamples(level_nsamples_init[ilevel], pid, rank, first, mine[ilevel]);
+            const int nsamples = mine[ilevel];
             if (nsamples <= 0) continue;
             if (logger.is_open()) rows[ilevel].resize((size_t)nsamples * 4);
             pmc_handle h = ilevel == 0 ? main_h : clones[ilevel - 1];
-            workers.emplace_back([&, ilevel, nsamples, h]() {
+            const uint64_t pos = pos0[ilevel] + (uint64_t)first * (uint64_t)bs->NoiseSize(ilevel);
+            workers.emplace_back([&, ilevel, nsamples, h, pos]() {
                 const auto t0 = std::chrono::steady_clock::now();
-                rcs[ilevel] = pmc_mlmc_level_batch(h, ilevel, nlevels, nsamples, pos0[ilevel], &sums[ilevel * NVAR],
+                rcs[ilevel] = pmc_mlmc_level_batch(h, ilevel, nlevels, nsamples, pos, &round[ilevel * NVAR],
                                                    rows[ilevel].empty() ? nullptr : rows[ilevel].data(), nullptr);
                 secs[ilevel] = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
             });
         }
         for (auto &w : workers) w.join();
-        for (int ilevel = nlevels - 1; ilevel >= 0; --ilevel) {
-            const int nsamples = level_nsamples_init[ilevel];
+        for (int ilevel = 0; ilevel < nlevels; ++ilevel)
             if (rcs[ilevel] != 0)
                 throw std::runtime_error(std::string("pmc_mlmc_level_batch: ") +
                                          pmc_last_error(ilevel == 0 ? main_h : clones[ilevel - 1]));
+        if (rank > 1) bs->Device()->check(pmc_allreduce_sums(main_h, round.data(), (int)round.size()), "pmc_allreduce_sums");
+        for (int i = 0; i < nlevels * NVAR; ++i) sums[i] += round[i];
+        for (int ilevel = nlevels - 1; ilevel >= 0; --ilevel) {
+            const int nsamples = level_nsamples_init[ilevel];
             const bool coarsest = (ilevel == nlevels - 1);
-            if (!pid && logger.is_open())
-                for (int j = 0; j < nsamples; ++j) {
+            if (!pid && logger.is_open())   // with several ranks the log holds rank 0's slice
+                for (int j = 0; j < mine[ilevel]; ++j) {
                     const double *r = &rows[ilevel][4 * (size_t)j];
                     logger << std::setw(width) << ilevel << std::setw(width) << r[0] << std::setw(width) << r[1]
                            << std::setw(width);
@@ -263,6 +275,10 @@ void MLMC_Manager::ShowMe(std::ostream &os)
 
 void MLMC_Manager::computeNSamplesMSE()
 {
+    for (int l = 0; l < nlevels; ++l)   // the reference would go on with inf/NaN (src/MLMC_Manager.cpp:319-321)
+        if (level_nsamples[l] < 2)
+            throw std::runtime_error("MLMC_Manager: at least 2 samples per level are needed for the variance estimate (level " +
+                                     std::to_string(l) + " has " + std::to_string(level_nsamples[l]) + ")");
     for (int l = 0; l < nlevels; ++l) {
         const double n = static_cast<double>(level_nsamples[l]);
         const double *s = &sums[l * NVAR];

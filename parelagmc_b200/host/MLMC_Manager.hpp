@@ -62,6 +62,7 @@ private:
     std::vector<int> level_nsamples, level_nsamples_missing;
     std::ofstream logger;
     std::vector<pmc_context_s *> clones;  // one extra device handle per level > 0 (concurrent level loops)
+    bool comm_ready = false;              // NCCL communicator of the ranks (RankComm.hpp) created
 };
 
 /// expWRegression (/root/reference/src/Utilities.cpp:257-283)

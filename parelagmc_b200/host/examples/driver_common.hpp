@@ -16,6 +16,9 @@ struct DriverArgs {
     static DriverArgs Parse(int argc, char **argv)
     {
         DriverArgs a;
+        // one rank per GPU: the launcher's LOCAL_RANK (torchrun) or PMC_RANK picks the device unless --device is given
+        if (const char *lr = getenv("LOCAL_RANK")) a.device = atoi(lr);
+        else if (const char *r = getenv("PMC_RANK")) a.device = atoi(r);
         for (int i = 1; i < argc; ++i) {
             auto next = [&]() -> const char * { return i + 1 < argc ? argv[++i] : ""; };
             if (!strcmp(argv[i], "--hierarchy")) a.hierarchy = next();

@@ -13,10 +13,22 @@
 #include <string>
 #include <vector>
 
+#include <cstdlib>
+
 typedef int MPI_Comm;
 #ifndef MPI_COMM_WORLD
 #define MPI_COMM_WORLD 0
 #endif
+// Without MPI the ranks of a multi-GPU run are plain processes started by a launcher that sets PMC_WORLD_SIZE / PMC_RANK
+// (or torchrun's WORLD_SIZE / RANK): the two calls of MPI the managers make read those (RankComm.hpp).
+inline int pmc_shim_env_int(const char *a, const char *b, int def)
+{
+    const char *v = std::getenv(a);
+    if (!v || !*v) v = std::getenv(b);
+    return v && *v ? std::atoi(v) : def;
+}
+inline int MPI_Comm_size(MPI_Comm, int *n) { *n = pmc_shim_env_int("PMC_WORLD_SIZE", "WORLD_SIZE", 1); return 0; }
+inline int MPI_Comm_rank(MPI_Comm, int *r) { *r = pmc_shim_env_int("PMC_RANK", "RANK", 0); return 0; }
 
 namespace mfem {
 class Vector {

@@ -47,12 +47,15 @@ def split_samples(n: int, rank: int, world: int):
 
 
 class _Comm:
-    """Thin wrapper: torch.distributed group (any backend) or single process."""
+    """The ranks that share a sample budget: a single process, a `torch.distributed` group (any backend; gloo in the CPU
+    tests), or -- `_Comm.over_capi` -- the NCCL communicator behind the C ABI (`pmc_comm_init` / `pmc_allreduce_sums`),
+    which is what a C/C++ host program uses."""
 
     def __init__(self, group=None, use_dist: bool = False, device=None):
         self.use_dist = use_dist
         self.group = group
         self.device = device
+        self.ctx = None
         if use_dist:
             import torch.distributed as dist
             self.dist = dist
@@ -61,15 +64,44 @@ class _Comm:
         else:
             self.rank, self.size = 0, 1
 
+    @classmethod
+    def over_capi(cls, ctx, nranks: int, rank: int, unique_id):
+        """All-reduce through the library's own NCCL communicator (collective: every rank calls it)."""
+        c = cls()
+        ctx.comm_init(nranks, rank, unique_id)
+        c.ctx, c.rank, c.size = ctx, rank, nranks
+        return c
+
     def allreduce_sum(self, a: np.ndarray) -> np.ndarray:
-        if not self.use_dist or self.size == 1:
+        if self.size == 1:
             return a
+        if self.ctx is not None:
+            return self.ctx.allreduce_sums(np.ascontiguousarray(a, dtype=np.float64).copy())
         import torch
         t = torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64))
         if self.device is not None:
             t = t.to(self.device)
         self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, group=self.group)
         return t.cpu().numpy()
+
+    def reduce_sums_and_times(self, local: np.ndarray, times: np.ndarray):
+        """One collective for the per-level sums AND the per-level timings of this round: the sample allocation
+        (`computeNSamplesMSE`) must see identical inputs on every rank, otherwise the ranks request different sample
+        counts, their slices overlap or leave gaps and one of them can leave the adaptive loop alone.  Returns the summed
+        sums and the rank-MEAN of the times."""
+        if self.size == 1:
+            return local, times
+        buf = np.concatenate([np.ravel(local), np.ravel(times)]).astype(np.float64)
+        buf = self.allreduce_sum(buf)
+        return buf[:local.size].reshape(local.shape), buf[local.size:].reshape(times.shape) / self.size
+
+
+def _check_two_samples(level_nsamples):
+    """The unbiased variance n/(n-1) needs two realisations per level; the reference would go on with inf/NaN
+    (`/root/reference/src/MLMC_Manager.cpp:319-321`) and report a converged run."""
+    bad = [int(i) for i, n in enumerate(np.atleast_1d(level_nsamples)) if n < 2]
+    if bad:
+        raise ValueError(f"at least 2 samples per level are needed for the variance estimate (levels {bad} have fewer)")
 
 
 class MLMC_Manager:
@@ -154,15 +186,21 @@ class MLMC_Manager:
             self.stream_pos += n * Ne
             self.level_nsamples[ilevel] += n
 
+        # handles are created here, on the calling thread, before any worker uses them (pmc_clone prepares its source)
+        backends = {ilevel: self._level_backend(ilevel) for ilevel, count, _ in jobs if count > 0}
+
         def run(job):
             ilevel, count, pos = job
             t0 = time.perf_counter()
-            rows, its = None, 0
+            rows, its, dt = None, 0, None
             if count > 0:
-                be = self._level_backend(ilevel)
+                be = backends[ilevel]
+                dev0 = be.kernel_ms() if hasattr(be, "kernel_ms") else None
                 _, rows, its = be.mlmc_level_batch(ilevel, count, pos, nlevels=self.nlevels, want_rows=want_rows,
                                                    sums=local[ilevel])
-            return ilevel, rows, its, time.perf_counter() - t0
+                if dev0 is not None:      # device time of this level's launches: free of the host-side queueing behind
+                    dt = 1e-3 * (be.kernel_ms() - dev0)     # the other levels' threads (they still share the GPU)
+            return ilevel, rows, its, (time.perf_counter() - t0) if dt is None else dt
 
         if self.concurrent_levels and self.nlevels > 1 and hasattr(self.backend, "clone"):
             # the level loops are independent: one handle (own stream and workspace) and one host thread per level
@@ -172,13 +210,16 @@ class MLMC_Manager:
             results = list(self._pool.map(run, jobs))
         else:
             results = [run(j) for j in jobs]
+        round_time = np.zeros(self.nlevels)
         for ilevel, rows, its, dt in results:
             self.total_iters += its
-            self.level_time[ilevel] += dt
+            round_time[ilevel] += dt
             if want_rows and rows is not None:
                 for r in rows:
                     self.logger.write(f"{ilevel:14d}{r[0]:14.6g}{r[1]:14.6g}{r[2]:14.6g}{r[3]:14.6g}\n")
-        self.sums += self.comm.allreduce_sum(local)
+        gsums, gtime = self.comm.reduce_sums_and_times(local, round_time)
+        self.sums += gsums
+        self.level_time += gtime * self.comm.size    # total time of the round over the ranks (n counts all ranks' samples)
         if self.logger:
             self.logger.flush()
         self.computeNSamplesMSE()
@@ -203,6 +244,7 @@ class MLMC_Manager:
     def computeNSamplesMSE(self):
         """`MLMC_Manager.cpp:300-401`."""
         L = self.nlevels
+        _check_two_samples(self.level_nsamples)
         n = self.level_nsamples.astype(np.float64)
         e = self.sums / n[:, None]
         self.eY, self.eABSY, self.eQ, self.eABSQ, self.eC = (e[:, Y].copy(), e[:, ABSY].copy(), e[:, Q].copy(),
@@ -334,10 +376,11 @@ class MC_Manager:
             if want_rows:
                 for r in rows:
                     self.logger.write(f"{r[0]:14.6g}{r[1]:14.6g}\n")
-        self.time += time.perf_counter() - t0
         self.stream_pos += int(nsamples) * Ne
         self.level_nsamples += int(nsamples)
-        self.sums += self.comm.allreduce_sum(local)
+        gsums, gtime = self.comm.reduce_sums_and_times(local, np.array([time.perf_counter() - t0]))
+        self.sums += gsums
+        self.time += float(gtime[0]) * self.comm.size
         self.computeNSamplesMSE()
 
     def Run(self):
@@ -357,6 +400,7 @@ class MC_Manager:
 
     def computeNSamplesMSE(self):
         """`MC_Manager.cpp:194-239`."""
+        _check_two_samples(self.level_nsamples)
         nl = float(self.level_nsamples)
         self.eQ = self.sums[SL_Q] / nl
         self.eABSQ = self.sums[SL_ABSQ] / nl
@@ -439,6 +483,7 @@ class ML_BayesRatio_Manager:
 
     def InitRun(self, level_nsamples_init: Sequence[int]):
         local = np.zeros((self.nlevels, BR["NVAR"]))
+        round_time = np.zeros(self.nlevels)
         for ilevel in range(self.nlevels - 1, -1, -1):       # coarsest first (hpp:322,366)
             n = int(level_nsamples_init[ilevel])
             Ne = self.backend.Ne[ilevel]
@@ -447,10 +492,12 @@ class ML_BayesRatio_Manager:
             if count > 0:                                    # two prior draws per realisation
                 self.backend.bayes_level_batch(ilevel, count, self.stream_pos + 2 * first * Ne, nlevels=self.nlevels,
                                                sums=local[ilevel])
-            self.level_time[ilevel] += time.perf_counter() - t0
+            round_time[ilevel] += time.perf_counter() - t0
             self.stream_pos += 2 * n * Ne
             self.level_nsamples[ilevel] += n
-        self.sums += self.comm.allreduce_sum(local)
+        gsums, gtime = self.comm.reduce_sums_and_times(local, round_time)
+        self.sums += gsums
+        self.level_time += gtime * self.comm.size
         self.computeNSamplesMSE()
 
     def Run(self):
@@ -468,6 +515,7 @@ class ML_BayesRatio_Manager:
 
     def computeNSamplesMSE(self):
         """hpp:572-726."""
+        _check_two_samples(self.level_nsamples)
         L, n = self.nlevels, self.level_nsamples.astype(np.float64)
         e = self.sums / n[:, None]
         g = lambda k: e[:, BR[k]].copy()

@@ -176,6 +176,74 @@ def test_sharded_run_world2_gloo():
     assert c0[1] == (0, 3, 9 * Ne[1]) and c1[1] == (0, 2, 9 * Ne[1] + 3 * Ne[0])
 
 
+def _gloo_adaptive_worker(rank, world, port, q):
+    import time
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from common import hex_problem, OracleBackend
+    from parelagmc_b200 import managers as MG
+
+    class Skewed(OracleBackend):          # rank 1 is a 4x slower machine: its local timings differ wildly from rank 0's
+        def mlmc_level_batch(self, *a, **k):
+            t0 = time.perf_counter()
+            r = super().mlmc_level_batch(*a, **k)
+            if rank == 1:
+                time.sleep(3.0 * (time.perf_counter() - t0))
+            return r
+
+    p = hex_problem(4, 2)
+    be = Skewed(p, threads=1)
+    m = MG.MLMC_Manager(MG._Comm(None, True), 2, be, {"Number of samples": 6, "Mean square error": 4e-3,
+                                                      "Output filename for MC managers": ""}, out=None)
+    assert m.wallTime            # the default: cost from timers, which differ per rank
+    m.concurrent_levels = False
+    m.Run()
+    q.put((rank, m.sums.copy(), m.level_nsamples.copy(), m.level_nsamples_missing.copy(), m.stream_pos,
+           m.ml_estimator_variance, m.eps2, list(be.calls)))
+    dist.destroy_process_group()
+
+
+def test_adaptive_run_world2_wall_time_costs_agree():
+    """Run() with a finite MSE target and wallTime = True on two ranks whose timers disagree: the timings are reduced in
+    the same collective as the sums, so both ranks request the same sample counts every round, their slices tile the
+    stream without gaps or overlap, and both leave the loop together."""
+    import socket
+    import torch.multiprocessing as mp
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_gloo_adaptive_worker, args=(r, 2, port, q)) for r in range(2)]
+    for pr in procs:
+        pr.start()
+    res = sorted([q.get(timeout=600) for _ in range(2)], key=lambda t: t[0])
+    for pr in procs:
+        pr.join(timeout=60)
+        assert pr.exitcode == 0
+    (_, s0, n0, miss0, pos0, var0, eps0, calls0), (_, s1, n1, miss1, pos1, var1, eps1, calls1) = res
+    assert np.array_equal(n0, n1) and np.array_equal(miss0, miss1) and pos0 == pos1
+    assert np.allclose(s0, s1, rtol=0, atol=0)
+    assert var0 == var1 and var0 <= 0.5 * eps0 and n0.sum() > 12
+    assert len(calls0) == len(calls1)
+    Ne = hex_problem(4, 2)["sampler"]
+    for (l0, c0, p0), (l1, c1, p1) in zip(calls0, calls1):       # same level, adjacent slices of the stream
+        assert l0 == l1 and p1 == p0 + c0 * Ne[l0].Ne
+
+
+def test_managers_refuse_single_sample_levels():
+    p = hex_problem(4, 2)
+    be = OracleBackend(p)
+    m = MG.MLMC_Manager(None, 2, be, {"Use array samples": True, "Array number of samples": [1, 5],
+                                      "Mean square error": 1e6, "Output filename for MC managers": ""}, out=None)
+    with pytest.raises(ValueError, match="at least 2 samples"):
+        m.Run()
+
+
 def test_bench_stream_positions():
     sys.path.insert(0, ROOT)
     import bench
