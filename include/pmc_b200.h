@@ -74,7 +74,10 @@ int pmc_set_preconditioner(pmc_handle h, int mass_degree, int schur_degree, doub
                            int coarse_degree, double coarse_ratio);
 /* Fine-grained options, to be set before the first solve / pmc_prepare.  Keys "sampler.<k>" / "darcy.<k>" with
  * <k> in {mass_degree, schur_degree, schur_ratio, coarse_degree, coarse_ratio, omega (over-correction factor of the
- * coarse-grid correction), max_vlevels (depth of the Schur V-cycle; 0 = full hierarchy, -1 = decide from the mass
+ * coarse-grid correction), method (sampler only: 0 = MINRES on the saddle system [M B^T; B -alpha W], 1 = Jacobi-preconditioned CG
+ * on its SPD form (M + alpha^-1 B^T W^-1 B) u = alpha^-1 B^T W^-1 f, s = (B u - f) / (alpha W) -- the elimination of
+ * src/PDESampler_Legacy.cpp:172-176 -- , -1 = CG when alpha W dominates the Schur complement, i.e. for short correlation
+ * lengths), max_vlevels (depth of the Schur V-cycle; 0 = full hierarchy, -1 = decide from the mass
  * term, sampler only), amg (coarse spaces of the Schur V-cycle: 0 = the hierarchy's L2 prolongators, 1 = strength-aware
  * pairwise aggregation built at set-up, -1 = aggregation only when the couplings are anisotropic)}; and the launch
  * shape of the solver kernel (all optional, the library chooses): "max_batch", "cta_threads" (64/128/256/512),

@@ -112,6 +112,8 @@ struct PrecCfg {
     double coarse_ratio = 30.0;
     double omega = 1.0;        // over-correction factor of the piecewise-constant coarse-grid correction
     int max_vlevels = 0;       // 0: as deep as the hierarchy allows; -1 (sampler): decide from the mass term
+    int method = -1;           // sampler only: 0 = MINRES on the saddle system, 1 = Jacobi-PCG on its SPD form (u eliminated
+                               // system (M + alpha^-1 B^T W^-1 B) u = alpha^-1 B^T W^-1 f), -1 = PCG when alpha W dominates
     int amg = -1;              // Schur V-cycle coarse spaces: 0 the hierarchy's own L2 prolongators, 1 strength-aware
                                // pairwise aggregation built here, -1 choose (aggregation when the couplings are anisotropic)
 };
@@ -128,6 +130,11 @@ struct SaddleSys {
     std::vector<VLevel> v;
     std::vector<HCsr> own_P;        // aggregation prolongators built here (cfg.amg)
     double *d_coarse_coef = nullptr;  // {ca_j, cb_j} of the coarsest level's Chebyshev iteration (OP_CHEB_SMALL)
+    // sampler, SPD form (emit_sampler_pcg): Bs = diag(1/(alpha W)) B (Ne x Nf), MBt = [M | B^T] (Nf x N),
+    // dinvH = 1/diag(M + alpha^-1 B^T W^-1 B), inv_aw = 1/(alpha W)
+    bool pcg = false;
+    DevCsr Bs, MBt;
+    double *dinvH = nullptr, *inv_aw = nullptr;
 };
 
 struct SamplerLevel {
@@ -632,6 +639,48 @@ static int prepare_sampler(Ctx *c, int level)
             sys.cfg.coarse_degree = sys.cfg.coarse_ratio <= 8.0 ? 3 : 4;
         } else
             sys.cfg.max_vlevels = 0;
+    }
+    {
+        // SPD form of the sampler system (the elimination /root/reference/src/PDESampler_Legacy.cpp:172-176,284-323 makes):
+        // s = (B u - f) / (alpha W) turns [M B^T; B -alpha W] [u; s] = [0; f] into
+        //   H u = alpha^-1 B^T W^-1 f,   H = M + alpha^-1 B^T W^-1 B   (symmetric positive definite).
+        // When alpha W dominates the Schur complement (short correlation length) H is well conditioned under Jacobi
+        // scaling and CG on its Nf rows moves ~40 % fewer bytes per iteration than MINRES on the N-row saddle system,
+        // at the same iteration count; otherwise (long correlation lengths: grad-div dominated) MINRES with the Schur
+        // V-cycle stays the method.
+        double lmin = 1.0;
+        for (int i = 0; i < Ne; ++i) {
+            double t = 0;
+            for (int p = S.rowptr[i]; p < S.rowptr[i + 1]; ++p) t += std::fabs(S.val[p]);
+            if (t > 0) lmin = std::min(lmin, L.alpha * L.Wdiag[i] / t);
+        }
+        sys.pcg = sys.cfg.method == 1 || (sys.cfg.method < 0 && lmin >= 1.0 / 20.0);
+        if (sys.pcg) {
+            std::vector<double> iaw(Ne);
+            for (int i = 0; i < Ne; ++i) iaw[i] = 1.0 / (L.alpha * L.Wdiag[i]);
+            HCsr Bsc = L.B;
+            for (int i = 0; i < Ne; ++i)
+                for (int p = Bsc.rowptr[i]; p < Bsc.rowptr[i + 1]; ++p) Bsc.val[p] *= iaw[i];
+            std::vector<Coo> e;
+            e.reserve(L.M.nnz() + L.B.nnz());
+            std::vector<double> hd(Nf, 0.0);
+            for (int i = 0; i < Nf; ++i) {
+                for (int p = L.M.rowptr[i]; p < L.M.rowptr[i + 1]; ++p) {
+                    e.push_back({i, L.M.col[p], L.M.val[p]});
+                    if (L.M.col[p] == i) hd[i] += L.M.val[p];
+                }
+                for (int p = Bt.rowptr[i]; p < Bt.rowptr[i + 1]; ++p) {
+                    e.push_back({i, Nf + Bt.col[p], Bt.val[p]});
+                    hd[i] += Bt.val[p] * Bt.val[p] * iaw[Bt.col[p]];
+                }
+            }
+            HCsr MBt = csr_from_coo(Nf, N, e);
+            for (int i = 0; i < Nf; ++i) hd[i] = hd[i] != 0.0 ? 1.0 / hd[i] : 1.0;
+            if ((rc = upload_csr(c, Bsc, sys.Bs))) return rc;
+            if ((rc = upload_csr(c, MBt, sys.MBt))) return rc;
+            if ((rc = to_device(c, hd, &sys.dinvH))) return rc;
+            if ((rc = to_device(c, iaw, &sys.inv_aw))) return rc;
+        }
     }
     if (sys.cfg.max_vlevels != 1 && (sys.cfg.amg == 1 || (sys.cfg.amg < 0 && couplings_anisotropic(S)))) {
         sys.own_P = aggregation_chain(S, 64, 16);
@@ -1242,9 +1291,59 @@ static void emit_minres(Program &pg, Solver &sv, bool x_nonzero, bool store_iter
 
 // Sampler solve: rhs_p = batched right-hand side at `level` (Ne rows); x0_p (nullable) initial guess of the Gaussian
 // field.  The field is left in rows [Nf, N) of ws.x.
+// Jacobi-preconditioned CG on the SPD form (see prepare_sampler).  Workspace: [p; t] = ws.u1 (N rows: the direction and
+// t = Bs p), q = H p in ws.q, the residual in ws.v0, the solution u in rows [0, Nf) of ws.x; the field
+// s = Bs u - f / (alpha W) is left in rows [Nf, N) of ws.x like the MINRES path leaves it.  Stopping rule: the
+// preconditioned residual norm sqrt(r . D^-1 r) <= max(rel * its initial value, abs), per realisation.
+static void emit_sampler_pcg(Program &pg, SaddleSys &sys, Off rhs_p, SolveWs &ws, bool store_iters)
+{
+    const int Nf = sys.Nf, Ne = sys.Ne, N = sys.N;
+    const VecRef P = vr(ws.u1, N), Pt = vr(ws.u1, N, Nf), Q = vr(ws.q, N), R = vr(ws.v0, N), X = vr(ws.x, N), Sx = vr(ws.x, N, Nf);
+    auto scale = [&](VecRef dst, double cb) {   // dst = cb * f / (alpha W)
+        Op &o = pg.add(OP_CHEB_FIRST, KC_MISC, Ne, 2.0 * Ne);
+        o.r = vr(rhs_p, Ne); o.d = dst; o.y = dst; o.fixed = sys.inv_aw; o.cb = cb;
+    };
+    emit_fill(pg, P, Nf, 0.0);
+    scale(Pt, 1.0);
+    scale(Sx, -1.0);
+    // r0 = alpha^-1 B^T W^-1 f = [M | B^T] [0; f / (alpha W)]
+    emit_spmm(pg, KC_SADDLE, EP_AX, sys.MBt, VNULL, P, R, VNULL, VNULL, nullptr, VNULL, 0, 0, -1, false, false, (double)Ne + Nf);
+    {   // p0 = z0 = D^-1 r0, dots[1] = r0 . z0
+        Op &o = pg.add(OP_CHEB_FIRST, KC_MASS, Nf, 2.0 * Nf);
+        o.flags = F_DOT;
+        o.r = R; o.d = P; o.y = P; o.fixed = sys.dinvH; o.cb = 1.0; o.slot = 1;
+    }
+    emit_fill(pg, X, Nf, 0.0);
+    { Op &o = pg.add(OP_CG_INIT, KC_SCALAR, 0, 0); o.slot = 1; }
+    const int loop_start = pg.pc();
+    const int check = pg.pc();
+    pg.add(OP_CHECK, KC_SCALAR, 0, 0);
+    emit_spmm(pg, KC_SADDLE, EP_AX, sys.Bs, VNULL, P, Pt, VNULL, VNULL, nullptr, VNULL, 0, 0, -1, false, false, (double)Nf + Ne);
+    emit_spmm(pg, KC_SADDLE, EP_AX, sys.MBt, VNULL, P, Q, VNULL, VNULL, nullptr, VNULL, 0, 0, 0, false, false, (double)N + Nf);
+    { Op &o = pg.add(OP_CG_ALPHA, KC_SCALAR, 0, 0); o.slot = 0; }
+    {
+        Op &o = pg.add(OP_CG_UPDATE, KC_SOLUPD, Nf, 6.0 * Nf);
+        o.x = P; o.r = Q; o.y = R; o.d = X; o.fixed = sys.dinvH; o.slot = 1;
+    }
+    { Op &o = pg.add(OP_CG_BETA, KC_SCALAR, 0, 0); o.slot = 1; }
+    {
+        Op &o = pg.add(OP_CG_DIR, KC_LANCZOS, Nf, 3.0 * Nf);
+        o.x = R; o.y = P; o.fixed = sys.dinvH;
+    }
+    { Op &o = pg.add(OP_JUMP, KC_SCALAR, 0, 0); o.a0 = loop_start; }
+    pg.ops[check].a0 = pg.pc();
+    // s = Bs u - f / (alpha W)
+    emit_spmm(pg, KC_SADDLE, EP_ADD, sys.Bs, VNULL, X, Sx, VNULL, VNULL, nullptr, VNULL, 1.0, 0, -1, false, false, (double)Nf + 2.0 * Ne);
+    { Op &o = pg.add(OP_STORE_ITERS, KC_SCALAR, 0, 0); o.y = store_iters ? vr(ws.iters) : VNULL; }
+}
+
 static void emit_sampler_solve(Program &pg, Ctx *c, int level, Off rhs_p, Off x0_p, SolveWs &ws, bool store_iters)
 {
     SaddleSys &sys = c->s[level].sys;
+    if (sys.pcg) {   // starts from u = 0: the prolongated coarse field (x0_p) is an initial guess for s only
+        emit_sampler_pcg(pg, sys, rhs_p, ws, store_iters);
+        return;
+    }
     Solver sv{&sys, &ws, VNULL};
     emit_fill(pg, vr(ws.b, sys.N), sys.Nf, 0.0);  // rhs_u = 0 (/root/reference/src/PDESampler.cpp:441-442)
     emit_copy(pg, vr(rhs_p, sys.Ne), vr(ws.b, sys.N, sys.Nf), sys.Ne);
@@ -1496,11 +1595,11 @@ static int run_program(Ctx *c, Program &pg, int nsamples, Off chunk, int max_row
         std::vector<Op> &ops = pg.ops;
         auto solo_kind = [](int k) {
             return k == OP_SPMM || k == OP_CHEB_FIRST || k == OP_LINCOMB3 || k == OP_SOL_UPDATE || k == OP_SETUP_SPMM || k == OP_FILL ||
-                   k == OP_COPY || k == OP_BROADCAST || k == OP_MAP_EXP;
+                   k == OP_COPY || k == OP_BROADCAST || k == OP_MAP_EXP || k == OP_CG_DIR;
         };
         auto scalar_kind = [](int k) {
             return k == OP_SC_INIT || k == OP_SC_ALPHA || k == OP_SC_BETA || k == OP_CHECK || k == OP_JUMP || k == OP_STORE_ITERS ||
-                   k == OP_LIKELIHOOD;
+                   k == OP_LIKELIHOOD || k == OP_CG_INIT || k == OP_CG_ALPHA || k == OP_CG_BETA;
         };
         for (Op &o : ops) {
             o.flags &= ~(F_SOLO | F_LOCAL_SYNC);
@@ -1741,6 +1840,7 @@ int pmc_set_option(pmc_handle c, const char *key, double value)
         else if (k == "coarse_ratio" && value > 1) g->coarse_ratio = value;
         else if (k == "omega" && value > 0) g->omega = value;
         else if (k == "max_vlevels") g->max_vlevels = (int)value;
+        else if (k == "method") g->method = (int)value;
         else if (k == "amg") g->amg = (int)value;
         else return fail(c, PMC_ERR_ARG, "pmc_set_option: bad key or value '%s' = %g", key, value);
         return PMC_OK;

@@ -42,7 +42,9 @@ enum { EP_AX = 0, EP_RESID = 1, EP_CHEB = 2, EP_ADD = 3 };
 
 enum {
     ST_BETA = 0, ST_IB, ST_IBPREV, ST_G0, ST_G1, ST_S0, ST_S1, ST_ETA, ST_GOAL, ST_ALPHA,
-    ST_CQ, ST_CV1, ST_CV0, ST_CW0, ST_CW1, ST_CU, ST_CX, ST_CXP, ST_COUNT
+    ST_CQ, ST_CV1, ST_CV0, ST_CW0, ST_CW1, ST_CU, ST_CX, ST_CXP,
+    ST_RZ, ST_CGA, ST_CGB,   // preconditioned CG: r.z, step length, direction coefficient
+    ST_COUNT
 };
 
 enum OpKind {
@@ -69,6 +71,12 @@ enum OpKind {
     OP_RNG,           // y[row][j] = (-g * N(mu,sigma)) * w_sqrt[row]  at stream position u0 + sample * a0 * n + row
     OP_CHEB_SMALL,    // whole Chebyshev iteration z = p(A) r on a level of at most SMALLN rows, iterates in shared memory
     OP_LIKELIHOOD,    // y[0][j] = exp(-sum_i (x[i][j] - fixed[i])^2 * ca) [* r[0][j]]   (n = number of observations)
+    // Jacobi-preconditioned CG on the SPD form of the sampler system (emit_sampler_pcg in pmc_b200.cu)
+    OP_CG_INIT,       // rz = dots[slot]; goal = max(rel sqrt(rz), abs); active = sqrt(rz) > goal
+    OP_CG_ALPHA,      // a = active ? rz / dots[slot] : 0          (dots[slot] = p . H p)
+    OP_CG_UPDATE,     // d += a x ; y -= a r ; dots[slot] = sum fixed[row] y[row]^2   (d = solution, x = p, y = residual, r = H p)
+    OP_CG_BETA,       // b = active ? dots[slot] / rz : 0; rz = dots[slot]; iterations, convergence
+    OP_CG_DIR,        // y = fixed[row] x + b y                     (y = p, x = residual)
     OP_KIND_COUNT
 };
 
@@ -824,6 +832,99 @@ __device__ __forceinline__ void sc_beta(const Op &o, Smem &sm, const ProgParams 
     if (o.a0) sm.st[ST_CXP][j] = cx;  // this iteration's solution update is deferred to the next one
 }
 
+// ---- Jacobi-preconditioned CG (sampler, SPD form): per-sample scalars; thread j < TW owns sample j of the tile ----------
+__device__ __forceinline__ void cg_init(const Op &o, int tile, Smem &sm, const ProgParams &P)
+{
+    const int j = threadIdx.x;
+    if (j >= TW) return;
+    const double rz = fmax(sm.dots[o.slot][j], 0.0);
+    const double eta = sqrt(rz);
+    const double goal = fmax(P.rel * eta, P.abs_);
+    sm.st[ST_RZ][j] = rz;
+    sm.st[ST_GOAL][j] = goal;
+    sm.st[ST_CGA][j] = 0.0;
+    sm.st[ST_CGB][j] = 0.0;
+    sm.active[j] = (tile * TW + j < P.nsamples) && (eta > goal);
+    sm.iters[j] = 0;
+}
+__device__ __forceinline__ void cg_alpha(const Op &o, Smem &sm)
+{
+    const int j = threadIdx.x;
+    if (j >= TW) return;
+    const double pq = sm.dots[o.slot][j];
+    double a = 0.0;
+    if (sm.active[j]) {
+        if (pq > 0.0) a = sm.st[ST_RZ][j] / pq;
+        else sm.active[j] = 0;   // breakdown (p = 0): nothing left to correct
+    }
+    sm.st[ST_CGA][j] = a;
+}
+__device__ __forceinline__ void cg_beta(const Op &o, Smem &sm, const ProgParams &P)
+{
+    const int j = threadIdx.x;
+    if (j >= TW) return;
+    double b = 0.0;
+    if (sm.active[j]) {
+        const double rzn = fmax(sm.dots[o.slot][j], 0.0), rz = sm.st[ST_RZ][j];
+        b = rz > 0.0 ? rzn / rz : 0.0;
+        sm.st[ST_RZ][j] = rzn;
+        const int it = sm.iters[j] + 1;
+        sm.iters[j] = it;
+        if (sqrt(rzn) <= sm.st[ST_GOAL][j] || it >= P.max_iter) sm.active[j] = 0;
+    }
+    sm.st[ST_CGB][j] = b;
+}
+
+// x += a p ; r -= a q ; rz' = sum dinv r^2   (a = 0 for converged samples: their vectors stay as they are)
+template <int NTt, int CS>
+__device__ __forceinline__ void op_cg_update(const Op &o, double *chunk, Smem &sm)
+{
+    const int sub = (threadIdx.x % LPR) * PW;
+    int r0, r1;
+    my_rows<CS>(o, sm, r0, r1);
+    const double *__restrict__ p = tp(o.x, chunk) + sub;
+    const double *__restrict__ q = tp(o.r, chunk) + sub;
+    double *__restrict__ res = tp(o.y, chunk) + sub;
+    double *__restrict__ xs = tp(o.d, chunk) + sub;
+    const D2 a = make_double2(sm.st[ST_CGA][sub], sm.st[ST_CGA][sub + 1]);
+    D2 acc = make_double2(0.0, 0.0);
+#pragma unroll 4
+    for (int row = r0 + threadIdx.x / LPR; row < r1; row += NTt / LPR) {
+        const size_t ro = (size_t)row * TW;
+        const D2 pv = ld2c(p + ro), qv = ld2c(q + ro);
+        D2 rv = ld2c(res + ro), xv = ld2c(xs + ro);
+        const double di = __ldg(o.fixed + row);
+        xv.x = fma(a.x, pv.x, xv.x);
+        xv.y = fma(a.y, pv.y, xv.y);
+        rv.x = fma(-a.x, qv.x, rv.x);
+        rv.y = fma(-a.y, qv.y, rv.y);
+        st2(xs + ro, xv);
+        st2(res + ro, rv);
+        acc.x = fma(di * rv.x, rv.x, acc.x);
+        acc.y = fma(di * rv.y, rv.y, acc.y);
+    }
+    block_dot<NTt, CS>(acc, sm, o.slot, false);
+}
+
+// p = dinv r + b p
+template <int NTt, int CS>
+__device__ __forceinline__ void op_cg_dir(const Op &o, double *chunk, const Smem &sm)
+{
+    const int sub = (threadIdx.x % LPR) * PW;
+    int r0, r1;
+    my_rows<CS>(o, sm, r0, r1);
+    const double *__restrict__ res = tp(o.x, chunk) + sub;
+    double *__restrict__ p = tp(o.y, chunk) + sub;
+    const D2 b = make_double2(sm.st[ST_CGB][sub], sm.st[ST_CGB][sub + 1]);
+#pragma unroll 4
+    for (int row = r0 + threadIdx.x / LPR; row < r1; row += NTt / LPR) {
+        const size_t ro = (size_t)row * TW;
+        const D2 rv = ld2c(res + ro), pv = ld2c(p + ro);
+        const double di = __ldg(o.fixed + row);
+        st2(p + ro, make_double2(fma(b.x, pv.x, di * rv.x), fma(b.y, pv.y, di * rv.y)));
+    }
+}
+
 // Noise generation fused with the SPDE right-hand-side scaling: thread (chunk c, sample j) jumps to stream position
 // u0 + sample * n + c * T and steps T times (PDESampler::Sample + :352-358 of src/PDESampler.cpp).
 template <int NTt, int CS>
@@ -990,6 +1091,11 @@ __global__ void __launch_bounds__(NTt, MINB) k_run_program(const ProgParams P)
             if (flags & F_WEIGHTED) op_cheb_small<NTt, CS, true>(o, chunk, sm, dyn_smem);
             else op_cheb_small<NTt, CS, false>(o, chunk, sm, dyn_smem);
             break;
+        case OP_CG_INIT: cg_init(o, tile, sm, P); break;
+        case OP_CG_ALPHA: cg_alpha(o, sm); break;
+        case OP_CG_BETA: cg_beta(o, sm, P); break;
+        case OP_CG_UPDATE: op_cg_update<NTt, CS>(o, chunk, sm); break;
+        case OP_CG_DIR: op_cg_dir<NTt, CS>(o, chunk, sm); break;
         case OP_LIKELIHOOD:
             // BayesianInverseProblem::ComputeLikelihood / ComputeR (/root/reference/src/BayesianInverseProblem.cpp:190-218)
             if (threadIdx.x < TW && crank == 0) {
