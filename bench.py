@@ -170,6 +170,64 @@ def workload_config(world):
 
 
 # ------------------------------------------------------------------------------------------------------------------
+SPE10_SAMPLES = [8, 32, 128, 512]      # realisations per GPU on levels 0 (fine) .. 3, one MLMC_Manager::InitRun
+
+
+def run_spe10(args, rank, world, local, dist, dev):
+    """BASELINE.json configs[4] as a bounded, driver-visible leg: the SPE10-size hierarchy (60 x 220 x 85 cells of
+    20 x 10 x 2 ft, 4 levels, N = 4.5 M / 577 k / 75 k / 10 k, correlation length 100, the SPE10 boundary attributes --
+    examples/SPE10/SPE10_MLMC.cpp with spe10_3D_parameters.xml) and one InitRun with SPE10_SAMPLES realisations per GPU
+    and level (weak scaling), level after level; per level the device time of its launch (max over ranks), the
+    algorithmic GB/s of the solver kernel, and the Darcy MINRES iterations per solve on 4 realisations."""
+    import torch
+    from common import spe10_problem, make_context
+    t0 = time.perf_counter()
+    p = spe10_problem(args.spe10_scale, 4)
+    ctx = make_context(p, True, REL, 1e-14, 3000, device=local)
+    setup_s = time.perf_counter() - t0
+    nl = p["nlevels"]
+    pos, base = {}, 0
+    for lev in range(nl - 1, -1, -1):
+        Ne = p["sampler"][lev].Ne
+        pos[lev] = base + rank * SPE10_SAMPLES[lev] * Ne
+        base += world * SPE10_SAMPLES[lev] * Ne
+    per_level, total_ms, sums = {}, 0.0, np.zeros((nl, 9))
+    for lev in range(nl - 1, -1, -1):
+        ns = SPE10_SAMPLES[lev]
+        ctx.mlmc_level_batch(lev, min(ns, 8), pos[lev])              # warm-up: workspace and program of the level
+        if dist is not None:
+            dist.barrier()
+        ctx.reset_stats()
+        _, _, its = ctx.mlmc_level_batch(lev, ns, pos[lev], sums=sums[lev])
+        k = ctx.kernel_stats()["kernel"]
+        ms = float(k["ms"])
+        if dist is not None:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        # Darcy iterations per solve on this level (4 realisations of the level's own field)
+        xi = ctx.sampler_sample_batch(lev, 4, pos[lev])
+        kf, _, _ = ctx.sampler_eval_batch(lev, xi, want_embed=False)
+        _, _, _, dits = ctx.darcy_solve_batch(lev, kf)
+        per_level[f"level{lev}"] = {"N": int(p["darcy"][lev].N), "samples": ns * world, "ms": ms,
+                                    "samples_per_s": ns * world / (ms * 1e-3),
+                                    "kernel_gbs_per_gpu": k["algo_bytes"] / max(k["ms"] * 1e-3, 1e-12) / 1e9,
+                                    "iterations_per_sample": its / ns, "darcy_its_per_solve": float(np.mean(dits))}
+        total_ms += ms
+    if dist is not None:
+        t = torch.from_numpy(sums).to(dev)
+        dist.all_reduce(t)
+        sums = t.cpu().numpy()
+    ctx.close()
+    est = float((sums[:, 1] / (np.array(SPE10_SAMPLES) * world)).sum())
+    return {"workload": "SPE10_MLMC.cpp geometry: %dx%dx%d hex cells (20x10x2 ft at scale 1), 4 levels, corlen 100, SPE10 BCs, "
+                        "unit mass coefficient" % tuple(p["grid"]),
+            "level_samples_per_gpu": SPE10_SAMPLES, "n_gpus": world, "rel_tol": REL, "value": sum(SPE10_SAMPLES) * world / (total_ms * 1e-3),
+            "unit": "samples/s", "ms_per_initrun": total_ms, "host_setup_s": setup_s, "mlmc_estimate": est,
+            "per_level": per_level, "timing": "CUDA events around each level's launch, max over ranks, levels run one after another"}
+
+
+# ------------------------------------------------------------------------------------------------------------------
 def run_product(args):
     import torch
     rank = int(os.environ.get("RANK", "0"))
@@ -278,24 +336,38 @@ def run_product(args):
     st = solo[dom]
     kst = st["kernel"]
     classes = [n for n in st if n != "kernel"]
-    traffic, traffic_note = None, None
-    try:   # DRAM bytes of the dominant launch from the committed ncu capture (per launch, like algo_bytes of the solo pass)
-        tj = json.load(open(os.path.join(ROOT, "profiles", "r1i_traffic.json")))
-        traffic = float(tj["dram_bytes_read"] + tj["dram_bytes_write"])
-        traffic_note = (f"dram__bytes_read.sum + dram__bytes_write.sum of one level-0 launch, {tj['source']}; algorithmic "
-                        f"bytes of that launch {tj['algo_bytes'] / 1e9:.2f} GB")
-    except Exception:
-        pass
+    # DRAM bytes of the dominant launch: counters need ncu, so they come from the committed capture of this very launch
+    # (profiles/r2_traffic.json, tools/profile_tools.py) -- but only while the capture was taken from the kernel sources
+    # this run is built from (hash of csrc/); a stale capture reports null instead of a number that no longer holds.
+    traffic, traffic_note, frac_dram = None, None, None
+    try:
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        from profile_tools import kernel_source_hash
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r2_traffic.json")))
+        if tj.get("kernel_source_hash") == kernel_source_hash():
+            traffic = float(tj["dram_bytes_read"] + tj["dram_bytes_write"])
+            frac_dram = traffic / max(kst["ms"] * 1e-3, 1e-12) / 1e9 / peak
+            traffic_note = (f"dram__bytes_read.sum + dram__bytes_write.sum of one level-{dom} launch, {tj['source']} (kernel source "
+                            f"hash {tj['kernel_source_hash']} = this build); frac_dram = those bytes / this run's solo launch time / peak")
+        else:
+            traffic_note = (f"profiles/r2_traffic.json was captured from kernel sources {tj.get('kernel_source_hash')}, this build is "
+                            f"{kernel_source_hash()}: stale, not reported")
+    except Exception as e:
+        traffic_note = f"no capture: {type(e).__name__}"
     roofline = {"bound": "hbm",
                 "kernel": "k_run_program (tile-persistent solver: a whole level batch per launch; the 3 level batches of a "
                           "step run as 3 concurrent launches)",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                "frac_dram": frac_dram,
                 "traffic_note": traffic_note,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
                 "launches": n_launch, "algo_bytes_per_launch": total_bytes / max(1, n_launch),
                 "avg_launch_us": 1e3 * sum(x["kernel"]["ms"] for x in stats) / max(1, n_launch),
                 "definition": "algorithmic bytes of all launches in the timed region / CUDA-event time of the timed region "
-                              "(launches overlap; lower bound)",
+                              "(launches overlap; lower bound).  Algorithmic bytes: 32-byte rows of the batched vectors an "
+                              "operation reads and writes (DESIGN.md section 5); inside the Krylov loops only the realisations "
+                              "of a tile that are still iterating are credited, and the coarsest-level Chebyshev iteration, "
+                              "whose iterates live in shared memory, is credited its inputs and result once",
                 "share_of_step": 1.0,
                 f"solo_level{dom}_launch": {"achieved": kst["algo_bytes"] / max(kst["ms"] * 1e-3, 1e-12) / 1e9,
                                             "frac": kst["algo_bytes"] / max(kst["ms"] * 1e-3, 1e-12) / 1e9 / peak,
@@ -401,6 +473,19 @@ def run_product(args):
         cpu = {"value": sum(smp) / tcpu, "unit": "samples/s", "cores": threads, "kind": "port",
                "sample": f"{smp[0]}/{smp[1]}/{smp[2]} samples on levels 0/1/2 (1:3:6 like the workload), "
                          f"{tcpu:.1f} s, {threads} OpenMP threads over samples, same tolerances"}
+    # ---- configs[4]: SPE10-scale leg (bounded; its own hierarchy and handle) ----
+    for j in jobs:
+        if j[3] not in ctxs:
+            j[3].close()
+    for c in ctxs:
+        c.close()
+    jobs, ctxs = [], []
+    spe10 = None
+    if not args.no_spe10:
+        try:
+            spe10 = run_spe10(args, rank, world, local, dist, dev)
+        except Exception as e:      # the headline line must not be lost to the secondary configuration
+            spe10 = {"error": f"{type(e).__name__}: {e}"}
     if rank == 0:
         mean_y = sums[:, 1] / (np.array(LEVEL_SAMPLES) * world)
         out = {"metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
@@ -413,7 +498,7 @@ def run_product(args):
                        "api": "sampler_sample_batch / sampler_eval_batch / darcy_solve_batch with page-locked host buffers; levels "
                               f"concurrent (sub-batches per level: {E2E_PARTS})",
                        "mlmc_estimate": float((sums_e2e[:, 1] / (np.array(LEVEL_SAMPLES) * world)).sum())},
-               "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "clocks": clk}
+               "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "clocks": clk, "config_spe10": spe10}
         print(json.dumps(out), flush=True)
     for j in jobs:
         if j[3] not in ctxs:
@@ -434,6 +519,8 @@ def main():
     ap.add_argument("--impl", default="product", choices=["product", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-clocks", action="store_true", help="do not poll nvidia-smi during the timed region")
+    ap.add_argument("--no-spe10", action="store_true", help="skip the SPE10-scale leg (BASELINE configs[4])")
+    ap.add_argument("--spe10-scale", type=float, default=1.0, help="shrink the SPE10 grid (1.0 = 60x220x85)")
     ap.add_argument("--clock-ms", type=int, default=100, help="nvidia-smi polling period")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -111,6 +111,7 @@ struct PrecCfg {
     int coarse_degree = 8;     // Chebyshev steps on the coarsest V-cycle level
     double coarse_ratio = 30.0;
     double omega = 1.0;        // over-correction factor of the piecewise-constant coarse-grid correction
+    bool omega_user = false;   // set through pmc_set_option: keep it whatever coarse spaces are chosen
     int max_vlevels = 0;       // 0: as deep as the hierarchy allows; -1 (sampler): decide from the mass term
     int method = -1;           // sampler only: 0 = MINRES on the saddle system, 1 = Jacobi-PCG on its SPD form (u eliminated
                                // system (M + alpha^-1 B^T W^-1 B) u = alpha^-1 B^T W^-1 f), -1 = PCG when alpha W dominates
@@ -834,6 +835,10 @@ static int prepare_darcy(Ctx *c, int level)
             sys.own_P = aggregation_chain(S1, 64, 16);
             Ps.clear();
             for (const HCsr &P : sys.own_P) Ps.push_back(&P);
+            // pairwise aggregates (4 rows per aggregate along the strong direction) need less over-correction than the
+            // hierarchy's 8-element agglomerates: measured on the SPE10 geometry at half scale, omega = 1.0 / 1.25 / 1.5 /
+            // 1.75 / 2.5 -> 143 / 104 / 94 / 99 / 152 Darcy iterations per solve (tools/spe10_prec_sweep.py)
+            if (!sys.cfg.omega_user) sys.cfg.omega = 1.5;
         }
     }
     if (sys.cfg.max_vlevels > 0 && (int)Ps.size() > sys.cfg.max_vlevels - 1) Ps.resize(sys.cfg.max_vlevels - 1);
@@ -1133,8 +1138,8 @@ static void emit_vcycle(Program &pg, Solver &sv, int m, VecRef r, VecRef zout, V
         op.lo = 1.0 / cfg.coarse_ratio;
         if (pg.fuse_coarse && sys.d_coarse_coef && L.n <= SMALLN && L.S.max_width > 0) {
             // one operation for the whole iteration; the result always lands in zout
-            Op &o = pg.add(OP_CHEB_SMALL, KC_SCHUR, L.n,
-                           cfg.coarse_degree * (L.n * (5.0 + (sys.weighted ? 1 : 0)) + op.vrows) - 2.0 * L.n - op.vrows);
+            // the iterates stay in shared memory: only r, 1/l1 and the weights are read and the result written, once
+            Op &o = pg.add(OP_CHEB_SMALL, KC_SCHUR, L.n, L.n * (2.0 + (sys.weighted ? 1 : 0)) + op.vrows);
             o.flags = (sys.weighted ? F_WEIGHTED : 0) | (dot_slot >= 0 ? (F_DOT | F_DOT_ACC) : 0);
             o.rowptr = L.S.soff; o.pk = L.S.spk; o.val = sys.d_coarse_coef; o.fixed = op.dinv_f;
             o.r = r; o.y = zout; o.v = op.V; o.w = op.dinv_b;
@@ -1280,6 +1285,7 @@ static void emit_minres(Program &pg, Solver &sv, bool x_nonzero, bool store_iter
         std::swap(w0, w1);
     }
     { Op &o = pg.add(OP_JUMP, KC_SCALAR, 0, 0); o.a0 = loop_start; }
+    for (int i = loop_start; i < pg.pc(); ++i) pg.ops[i].flags |= F_INLOOP;
     // leaving after the first iteration of a pair: apply its deferred update (w0 of that iteration = ws.w0)
     const int exit_a = pg.pc();
     if (defer_x) { Op &o = pg.add(OP_SOL_UPDATE, KC_SOLUPD, N, 3.0 * N); o.y = vr(ws.w0, N); o.d = vr(ws.x, N); o.a0 = 3; }
@@ -1331,6 +1337,7 @@ static void emit_sampler_pcg(Program &pg, SaddleSys &sys, Off rhs_p, SolveWs &ws
         o.x = R; o.y = P; o.fixed = sys.dinvH;
     }
     { Op &o = pg.add(OP_JUMP, KC_SCALAR, 0, 0); o.a0 = loop_start; }
+    for (int i = loop_start; i < pg.pc(); ++i) pg.ops[i].flags |= F_INLOOP;
     pg.ops[check].a0 = pg.pc();
     // s = Bs u - f / (alpha W)
     emit_spmm(pg, KC_SADDLE, EP_ADD, sys.Bs, VNULL, X, Sx, VNULL, VNULL, nullptr, VNULL, 1.0, 0, -1, false, false, (double)Nf + 2.0 * Ne);
@@ -1838,7 +1845,7 @@ int pmc_set_option(pmc_handle c, const char *key, double value)
         else if (k == "schur_ratio" && value > 1) g->schur_ratio = value;
         else if (k == "coarse_degree" && value >= 1) g->coarse_degree = (int)value;
         else if (k == "coarse_ratio" && value > 1) g->coarse_ratio = value;
-        else if (k == "omega" && value > 0) g->omega = value;
+        else if (k == "omega" && value > 0) { g->omega = value; g->omega_user = true; }
         else if (k == "max_vlevels") g->max_vlevels = (int)value;
         else if (k == "method") g->method = (int)value;
         else if (k == "amg") g->amg = (int)value;

@@ -86,7 +86,8 @@ enum {
     F_STAGED = 1024,  // no slice of the operator is wider than STW: its entries are staged through shared memory
     // grid-group mode only (a tile owned by G CTAs of a cooperative launch):
     F_SOLO = 2048,       // small operation: executed by the group's first CTA alone
-    F_LOCAL_SYNC = 4096  // nothing this operation writes is read by another CTA before the next group barrier
+    F_LOCAL_SYNC = 4096, // nothing this operation writes is read by another CTA before the next group barrier
+    F_INLOOP = 8192      // inside a Krylov loop: its bytes are credited for the realisations of the tile still iterating only
 };
 
 // kernel classes for the in-kernel time/byte accounting (same meaning as PMC_K_* in include/pmc_b200.h)
@@ -1120,7 +1121,14 @@ __global__ void __launch_bounds__(NTt, MINB) k_run_program(const ProgParams P)
             }
             sm.cyc[o.kclass] += (unsigned long long)(clock64() - t0);
             if (crank == 0) {  // bytes and operation counts once per tile
-                sm.cbytes[o.kclass] += o.bytes;
+                double b = o.bytes;
+                if (flags & F_INLOOP) {   // rows are 4 realisations wide: the lanes of converged ones move, but are not credited
+                    int na = 0;
+#pragma unroll
+                    for (int j = 0; j < TW; ++j) na += sm.active[j] ? 1 : 0;
+                    b *= 0.25 * (double)na;
+                }
+                sm.cbytes[o.kclass] += b;
                 sm.cops[o.kclass] += 1u;
             }
         }

@@ -206,3 +206,15 @@ def reference_enlarged_problem(with_transfer=True):
     return dict(levels=orig, embed_levels=emb, sampler=SL, darcy=DL if with_transfer else None,
                 alpha=H.spde_alpha(0.1), g=H.matern_scaling_coefficient(0.1, 3), nlevels=3, inside=inside, gobs=gobs,
                 noise=0.1)
+
+
+@functools.lru_cache(maxsize=None)
+def spe10_problem(scale=0.25, nlevels=4):
+    """BASELINE configs[4] at reduced size: `Create_SPE10_Mesh(3, {60,220,85}, {20,10,2})` cells
+    (`/root/reference/src/MeshUtilities.cpp:21-37`: 1200 x 2200 x 170 ft), correlation length 100
+    (`examples/SPE10/spe10_3D_parameters.xml:20`), the SPE10 boundary attributes (`:45-49`), unit mass coefficient
+    (`examples/SPE10/SPE10_MLMC.cpp:209`).  The cells keep their 10 : 5 : 1 aspect ratio whatever the scale."""
+    n = [max(8, int(round(x * scale))) for x in (60, 220, 85)]
+    L = H.build_box_hierarchy(n, [1200.0, 2200.0, 170.0], nlevels)
+    return dict(levels=L, sampler=H.build_sampler_levels(L), darcy=H.build_darcy_levels(L, **H.SPE10_BC),
+                alpha=H.spde_alpha(100.0), g=H.matern_scaling_coefficient(100.0, 3), nlevels=nlevels, grid=n)
