@@ -2,6 +2,7 @@
 // error convention of the host layer: C-ABI status codes become std::runtime_error, which the reference drivers
 // catch in main (/root/reference/examples/MLMC.cpp:277-282).
 #pragma once
+#include <cstdlib>
 #include <memory>
 #include <stdexcept>
 #include <string>
@@ -18,6 +19,18 @@ public:
     ~B200Device() { pmc_destroy(h_); }
     B200Device(const B200Device &) = delete;
     B200Device &operator=(const B200Device &) = delete;
+    /// The device context the reference-signature constructors (which have no device argument) share: created on first
+    /// use on GPU PMC_DEVICE / LOCAL_RANK (default 0) with room for `nlevels` levels.
+    static std::shared_ptr<B200Device> Default(int nlevels = 16)
+    {
+        static std::shared_ptr<B200Device> d;
+        if (!d) {
+            const char *e = std::getenv("PMC_DEVICE");
+            if (!e) e = std::getenv("LOCAL_RANK");
+            d = std::make_shared<B200Device>(e ? std::atoi(e) : 0, nlevels);
+        }
+        return d;
+    }
     pmc_handle handle() const { return h_; }
     int nlevels() const { return nlevels_; }
     void check(int rc, const char *what) const

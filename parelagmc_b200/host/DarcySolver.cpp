@@ -36,6 +36,7 @@ void DarcySolver::BuildHierachySpaces()
 void DarcySolver::SolveFwd(int ilevel, mfem::Vector &k_over_k_ref, double &Q, double &C)
 {
     // assemble -> solve -> Q = obs . sol, C = #dofs (src/DarcySolver.cpp:416-437)
+    if (!built_) BuildHierachySpaces();   // reference-signature set-up: upload after the last Build* / Set* call
     if (k_over_k_ref.Size() != hier_->darcy[ilevel].Ne)
         throw std::runtime_error("DarcySolver::SolveFwd: coefficient vector has the wrong size");
     dev_->check(pmc_darcy_solve_batch(dev_->handle(), ilevel, 1, k_over_k_ref.GetData(), &Q, &C, nullptr, nullptr),
@@ -46,6 +47,7 @@ void DarcySolver::SolveFwd_RtnPressure(int ilevel, mfem::Vector &k_over_k_ref, m
                                        bool compute_Q)
 {
     // src/DarcySolver.cpp:439-470: same solve, also returns the pressure block
+    if (!built_) BuildHierachySpaces();
     const DarcyLevelData &d = hier_->darcy[ilevel];
     if (k_over_k_ref.Size() != d.Ne) throw std::runtime_error("DarcySolver::SolveFwd_RtnPressure: wrong size");
     mfem::Vector sol(d.Nf + d.Ne);

@@ -12,6 +12,21 @@ class DarcySolver : public PhysicalMLSolver {
 public:
     DarcySolver(std::shared_ptr<const HierarchyData> hier, std::shared_ptr<B200Device> dev,
                 parelag::ParameterList &master_list);
+#ifdef PARELAGMC_B200_WITH_PARELAG
+    /// The reference's constructor and set-up calls, verbatim (/root/reference/src/DarcySolver.hpp:40-42, :55-95): the
+    /// hierarchy is built by ParELAG on the host, once; the last set-up call made before the first solve uploads it.
+    DarcySolver(const std::shared_ptr<mfem::ParMesh> &mesh, parelag::ParameterList &prec_params);
+    void BuildHierachySpaces(std::vector<std::shared_ptr<parelag::AgglomeratedTopology>> &topos,
+                             std::unique_ptr<mfem::BilinearFormIntegrator> massIntegrator);
+    void BuildVolumeObservationFunctional(mfem::LinearFormIntegrator *observationFunctional_u,
+                                          mfem::LinearFormIntegrator *observationFunctional_p);
+    void BuildBdrObservationFunctional(mfem::LinearFormIntegrator *observationFunctional);
+    void SetEssBdrConditions(mfem::Array<int> &ess_bc, mfem::VectorCoefficient &u_bdr);
+    void BuildForcingTerms(mfem::VectorCoefficient &f, mfem::Coefficient &p_bdr, mfem::Coefficient &q);
+    std::vector<std::shared_ptr<parelag::DeRhamSequence>> &GetSequence() override { return sequence_; }
+    mfem::FiniteElementSpace *GetPressureSpace() const override { return pspace_; }
+    mfem::FiniteElementSpace *GetVelocitySpace() const { return uspace_; }
+#endif
     virtual ~DarcySolver() = default;
     DarcySolver(DarcySolver const &) = delete;
     DarcySolver &operator=(DarcySolver const &) = delete;
@@ -34,5 +49,13 @@ private:
     std::shared_ptr<B200Device> dev_;
     std::vector<int> nnz_;
     bool built_ = false;
+#ifdef PARELAGMC_B200_WITH_PARELAG
+    void carry_down(std::vector<double> DarcyLevelData::*field, bool with_projector);
+    std::shared_ptr<mfem::ParMesh> mesh_;
+    std::vector<std::shared_ptr<parelag::DeRhamSequence>> sequence_;
+    std::shared_ptr<HierarchyData> own_hier_;
+    mfem::FiniteElementSpace *uspace_ = nullptr, *pspace_ = nullptr;
+    int uform_ = 0, pform_ = 0;
+#endif
 };
 }  // namespace parelagmc

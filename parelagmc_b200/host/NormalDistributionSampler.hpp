@@ -13,6 +13,9 @@ class NormalDistributionSampler {
 public:
     /// Constructor (mean mu, variance sigma2); `dev` is the device context shared with the sampler/solver.
     NormalDistributionSampler(double mu, double sigma2, std::shared_ptr<B200Device> dev);
+    /// The reference's constructor, verbatim (/root/reference/src/NormalDistributionSampler.hpp:31): the engine lives on
+    /// the process-wide default device (B200Device::Default).
+    NormalDistributionSampler(double mu, double sigma2) : NormalDistributionSampler(mu, sigma2, B200Device::Default()) {}
     ~NormalDistributionSampler() = default;
     NormalDistributionSampler(NormalDistributionSampler const &) = delete;
     NormalDistributionSampler(NormalDistributionSampler &&) = delete;

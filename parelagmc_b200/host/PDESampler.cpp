@@ -32,6 +32,9 @@ PDESampler::PDESampler(std::shared_ptr<const HierarchyData> hier, NormalDistribu
 void PDESampler::BuildHierarchy()
 {
     if (built_) return;
+#ifdef PARELAGMC_B200_WITH_PARELAG
+    if (!hier_ && mesh_) ExtractFromSequences();   // constructed from a mesh: ParELAG's hierarchy -> plain arrays
+#endif
     auto &dev = *Device();
     for (int l = 0; l < hier_->nlevels; ++l) {
         const SamplerLevelData &s = hier_->sampler[l];

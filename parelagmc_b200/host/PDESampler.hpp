@@ -14,6 +14,21 @@ public:
     /// already-built hierarchy data is handed over (see INTEGRATION.md for the ParELAG-side extraction).
     PDESampler(std::shared_ptr<const HierarchyData> hier, NormalDistributionSampler &dist_sampler,
                parelag::ParameterList &master_list);
+#ifdef PARELAGMC_B200_WITH_PARELAG
+    /// The reference's constructor, verbatim (/root/reference/src/PDESampler.hpp:52-55).  BuildDeRhamSequence /
+    /// SetDeRhamSequence then BuildHierarchy as in the reference's drivers; the hierarchy data is extracted from the
+    /// DeRham sequences (parelag/ParelagExtract.hpp) at BuildHierarchy.
+    PDESampler(const std::shared_ptr<mfem::ParMesh> &mesh_, NormalDistributionSampler &dist_sampler,
+               parelag::ParameterList &master_list);
+    void BuildDeRhamSequence(std::vector<std::shared_ptr<parelag::AgglomeratedTopology>> &topology) override;
+    void SetDeRhamSequence(std::vector<std::shared_ptr<parelag::DeRhamSequence>> &sequence) override;
+    mfem::HypreParMatrix *GetTrueP(int level) override { return Ps_[level].get(); }
+    void SaveMeshGLVis(const std::string prefix) const override;
+    void SaveFieldGLVis(int level, const mfem::Vector &coeff, const std::string prefix) const override;
+    double ComputeL2Error(int level, const mfem::Vector &coeff, double exact) const override;
+    double ComputeMaxError(int level, const mfem::Vector &coeff, double exact) const override;
+    int GetGlobalNumberOfDofs(int level) const { return GetNumberOfDofs(level); }
+#endif
     virtual ~PDESampler() = default;
     PDESampler(PDESampler const &) = delete;
     PDESampler &operator=(PDESampler const &) = delete;
@@ -46,6 +61,15 @@ private:
     std::vector<int> out_size_;     // size of the field handed to the forward solver
     std::vector<size_t> nnz_;
     bool built_ = false;
+#ifdef PARELAGMC_B200_WITH_PARELAG
+    void prolongate_to_fine_grid(int level, const mfem::Vector &coeff, mfem::Vector &fine) const;
+    void ExtractFromSequences();
+    std::shared_ptr<mfem::ParMesh> mesh_;
+    std::vector<std::shared_ptr<parelag::DeRhamSequence>> sequence_;
+    std::vector<std::unique_ptr<mfem::HypreParMatrix>> Ps_;
+    std::shared_ptr<HierarchyData> own_hier_;
+    int uform_ = 0, sform_ = 0;
+#endif
 };
 
 /// EmbeddedPDESampler (/root/reference/src/EmbeddedPDESampler.hpp:46): the SPDE is solved on an enlarged MATCHING mesh

@@ -97,7 +97,6 @@ void ExtractDarcyLevel(parelag::DeRhamSequence &seq, int uform, int pform, bool 
     out.elem_ptr.assign(1, 0);
     for (int e = 0; e < out.Ne; ++e) {
         const int r0 = eI[e], r1 = eI[e + 1], n = r1 - r0;
-        std::vector<int> pos(Mel.Height() ? 0 : 0);
         for (int a = r0; a < r1; ++a) out.elem_dofs.push_back(rJ[eJ[a]]);
         const size_t base = out.elem_mat.size();
         out.elem_mat.resize(base + (size_t)n * n, 0.0);

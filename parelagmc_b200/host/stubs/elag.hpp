@@ -52,7 +52,7 @@ public:
     const mfem::SparseMatrix &GetProjectorMatrix();
 };
 
-class MultiVector;
+class MultiVector { public: ~MultiVector(); };
 class DeRhamSequenceFE;
 
 class DeRhamSequence {

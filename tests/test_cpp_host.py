@@ -36,6 +36,18 @@ def test_host_layer_builds_and_roundtrips_dump(tmp_path):
         assert out.returncode == 0 and "no CPU fallback" in out.stdout
 
 
+def test_reference_signatures_compile_against_stub_headers():
+    """The -DPARELAGMC_B200_WITH_PARELAG branch of the host layer -- the reference's verbatim constructors
+    (`PDESampler(const std::shared_ptr<mfem::ParMesh>&, NormalDistributionSampler&, parelag::ParameterList&)`,
+    `DarcySolver(const std::shared_ptr<mfem::ParMesh>&, parelag::ParameterList&)`, `NormalDistributionSampler(double,
+    double)`), the set-up calls, all MLSampler / PhysicalMLSolver virtuals, the ParELAG -> plain-array extraction and a
+    driver with the call sequence of the reference's MLMC.cpp -- compiles (g++ -fsyntax-only) against declaration-only
+    MFEM / ParELAG / MPI headers (parelagmc_b200/host/stubs); the real libraries are not in this image."""
+    out = subprocess.run(["make", "-C", os.path.join(ROOT, "parelagmc_b200", "host"), "parelag-syntax"], capture_output=True,
+                         text=True)
+    assert out.returncode == 0 and "parelag-syntax: ok" in out.stdout, out.stdout + out.stderr
+
+
 @pytest.mark.gpu
 def test_darcy_deterministic_ctest_regex(tmp_path):
     """PASS_REGULAR_EXPRESSION of DarcyDeterministicTest (/root/reference/examples/CMakeLists.txt:62-66)."""
