@@ -32,6 +32,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 METRIC = "MLMC samples/sec per level (SPDE sample + Darcy solve)"
 LEVEL_SAMPLES = [1000, 3000, 6000]   # levels 0 (fine) .. 2 (coarse); "Array number of samples"
 REL, ABS, MAXIT = 1e-6, 1e-12, 300   # CreateMLMCParameterList.hpp:67-69
+E2E_REUSE = os.environ.get("PMC_E2E_REUSE", "1") != "0"   # chained calls read the library's own previous results from device memory
 E2E_PARTS = [int(x) for x in os.environ.get("PMC_E2E_PARTS", "1,1,1").split(",")]   # sub-batches per level on the host-buffer path
 
 
@@ -166,7 +167,34 @@ def workload_config(world):
             "level_samples_per_gpu": LEVEL_SAMPLES, "samples_per_step": sum(LEVEL_SAMPLES) * world,
             "rel_tol": REL, "abs_tol": ABS, "max_iter": MAXIT,
             "l2_policy": "batched working set per level >> 126 MB L2 (level 0: ~2 GB of vectors per batch); no flush",
-            "parallelism": f"samples sharded over {world} GPU(s), one allreduce of 3x9 sums per step"}
+            "parallelism": f"samples sharded over {world} GPU(s), one ncclAllReduce of 3x9 sums per step through the C ABI "
+                           "(pmc_allreduce_sums)"}
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def pin_to_gpu_numa(local):
+    """Bind this rank's host threads (and therefore its page-locked buffers, which are placed on first touch) to the CPU
+    cores of the NUMA node its GPU hangs off: 8 ranks x 3 level threads otherwise float over both sockets and half of
+    the host<->device copies cross the socket interconnect.  Returns a note for the JSON line."""
+    try:
+        bdf = subprocess.run(["nvidia-smi", "-i", str(local), "--query-gpu=pci.bus_id", "--format=csv,noheader"],
+                             capture_output=True, text=True, timeout=20).stdout.strip().lower()
+        if len(bdf.split(":")[0]) == 8:          # nvidia-smi prints an 8-digit PCI domain, sysfs uses 4
+            bdf = bdf[4:]
+        node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read().strip())
+        if node < 0:
+            return "no NUMA information for the GPU (single node host)"
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return f"NUMA node {node} has no allowed CPU"
+        os.sched_setaffinity(0, cpus)
+        return f"rank bound to the {len(cpus)} CPUs of NUMA node {node} (GPU {bdf})"
+    except Exception as e:
+        return f"not bound ({type(e).__name__})"
 
 
 # ------------------------------------------------------------------------------------------------------------------
@@ -236,6 +264,7 @@ def run_product(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
     torch.cuda.set_device(local)
+    affinity_note = pin_to_gpu_numa(local)
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -262,6 +291,14 @@ def run_product(args):
     ctxs += [ctxs[0].clone() for _ in range(nl - 1)]          # pmc_clone: same hierarchy, own stream and workspace
     pool = ThreadPoolExecutor(max_workers=nl)
     stream = torch.cuda.current_stream()
+    if dist is not None:
+        # the per-level sums are all-reduced by the library's own NCCL communicator, through the C ABI
+        # (pmc_comm_unique_id / pmc_comm_init / pmc_allreduce_sums); torch.distributed only ships the 128-byte id and
+        # provides the barrier and the max-over-ranks of the timings the bench contract asks for
+        from parelagmc_b200 import capi
+        box = [capi.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        ctxs[0].comm_init(world, rank, box[0])
     pos = stream_positions(p, LEVEL_SAMPLES, rank, world)
     dev = torch.device("cuda", local)
 
@@ -277,9 +314,7 @@ def run_product(args):
                 for lev in range(nl)]
         its = sum(f.result()[2] for f in futs)
         if dist is not None:
-            t = torch.from_numpy(sums).to(dev)
-            dist.all_reduce(t)
-            sums = t.cpu().numpy()
+            ctxs[0].allreduce_sums(sums)      # ncclAllReduce of 3 x 9 doubles on the handle's stream
         return sums, its
 
     # ---- warm-up ----
@@ -397,6 +432,9 @@ def run_product(args):
                 d["sc"] = pinned_empty((n, Ne_l[lev + 1]))
                 d["emb"] = pinned_empty((n, Ne_l[lev + 1]))
             jobs.append((lev, bounds[i], n, ctxs[lev] if i == 0 else ctxs[0].clone(), d))
+    if E2E_REUSE:
+        for j in jobs:
+            j[3].set_option("cache_results", 1)
     pool_e2e = ThreadPoolExecutor(max_workers=len(jobs))
 
     def part_e2e(job):
@@ -406,28 +444,34 @@ def run_product(args):
         hi = ho = 0
         xi = ctx.sampler_sample_batch(lev, n, p0, out=b["xi"])                # Sample(level, xi)
         ho += xi.nbytes
+        # Every call writes its result to the caller's (page-locked) host vectors, as the reference's managers hold them.
+        # With REUSE (default; PMC_E2E_REUSE=0 switches it off) a vector that the library itself produced in the
+        # preceding call is not sent back to the device: the handle keeps its device copy (option "cache_results").
+        reuse = E2E_REUSE
         if lev == nl - 1:
-            s, _, _ = ctx.sampler_eval_batch(lev, xi, xi_level=lev, want_embed=False, out_s=b["s"])   # Eval(level, xi, s)
-            hi += xi.nbytes
+            s, _, _ = ctx.sampler_eval_batch(lev, None if reuse else xi, xi_level=lev, want_embed=False, out_s=b["s"],
+                                             nsamples=n)                       # Eval(level, xi, s)
+            hi += 0 if reuse else xi.nbytes
             ho += s.nbytes
-            q, c, _, _ = ctx.darcy_solve_batch(lev, s)                        # SolveFwd(level, s, q, c)
-            hi += s.nbytes
+            q, c, _, _ = ctx.darcy_solve_batch(lev, None if reuse else s, nsamples=n)     # SolveFwd(level, s, q, c)
+            hi += 0 if reuse else s.nbytes
             ho += q.nbytes
             y = q
         else:
-            sc, emb, _ = ctx.sampler_eval_batch(lev + 1, xi, xi_level=lev, use_init=0, out_s=b["sc"],
-                                                out_embed=b["emb"])            # Eval(l+1, xi, s, init, false)
-            hi += xi.nbytes
+            sc, emb, _ = ctx.sampler_eval_batch(lev + 1, None if reuse else xi, xi_level=lev, use_init=0, out_s=b["sc"],
+                                                out_embed=b["emb"], nsamples=n)  # Eval(l+1, xi, s, init, false)
+            hi += 0 if reuse else xi.nbytes
             ho += sc.nbytes + emb.nbytes
-            qc, cc, _, _ = ctx.darcy_solve_batch(lev + 1, sc)
-            hi += sc.nbytes
+            qc, cc, _, _ = ctx.darcy_solve_batch(lev + 1, None if reuse else sc, nsamples=n)
+            hi += 0 if reuse else sc.nbytes
             ho += qc.nbytes
-            sf, _, _ = ctx.sampler_eval_batch(lev, xi, xi_level=lev, init_s=emb, init_level=lev + 1, use_init=1,
-                                              want_embed=False, out_s=b["s"])  # Eval(l, xi, s, init, true)
-            hi += xi.nbytes + emb.nbytes
+            sf, _, _ = ctx.sampler_eval_batch(lev, None if reuse else xi, xi_level=lev, init_s=None if reuse else emb,
+                                              init_level=lev + 1, use_init=1, want_embed=False, out_s=b["s"],
+                                              nsamples=n)                      # Eval(l, xi, s, init, true)
+            hi += 0 if reuse else xi.nbytes + emb.nbytes
             ho += sf.nbytes
-            q, c, _, _ = ctx.darcy_solve_batch(lev, sf)
-            hi += sf.nbytes
+            q, c, _, _ = ctx.darcy_solve_batch(lev, None if reuse else sf, nsamples=n)
+            hi += 0 if reuse else sf.nbytes
             ho += q.nbytes
             y = q - qc
             c = c + cc
@@ -444,9 +488,7 @@ def run_product(args):
         for lev, row, _, _ in res:
             sums[lev] += row
         if dist is not None:
-            t = torch.from_numpy(sums).to(dev)
-            dist.all_reduce(t)
-            sums = t.cpu().numpy()
+            ctxs[0].allreduce_sums(sums)
         return sums
 
     e2e_steps = max(1, min(args.steps, 3))
@@ -495,6 +537,9 @@ def run_product(args):
                "mlmc_estimate": float(mean_y.sum()),
                "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": int(h2d),
                        "d2h_bytes_per_step": int(d2h), "steps": e2e_steps,
+                       "h2d_gbs_per_gpu": h2d / max(ms_e * 1e-3 / e2e_steps, 1e-12) / 1e9,
+                       "d2h_gbs_per_gpu": d2h / max(ms_e * 1e-3 / e2e_steps, 1e-12) / 1e9,
+                       "reuse_device_results": E2E_REUSE, "cpu_affinity": affinity_note,
                        "api": "sampler_sample_batch / sampler_eval_batch / darcy_solve_batch with page-locked host buffers; levels "
                               f"concurrent (sub-batches per level: {E2E_PARTS})",
                        "mlmc_estimate": float((sums_e2e[:, 1] / (np.array(LEVEL_SAMPLES) * world)).sum())},

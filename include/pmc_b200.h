@@ -86,7 +86,8 @@ int pmc_set_preconditioner(pmc_handle h, int mass_degree, int schur_degree, doub
  * operations with at most this many rows run on its first CTA), "stage_operators" (0 = read operator entries from L2
  * instead of staging them through shared memory with TMA bulk copies), "defer_x" (0 = update the MINRES solution
  * every iteration instead of once per iteration pair), "single_wave" (1 = prefer one wave of smaller CTAs), and
- * "renumber" (0 = keep the caller's numbering of the RT dofs inside the library; to be set before the uploads). */
+ * "renumber" (0 = keep the caller's numbering of the RT dofs inside the library; to be set before the uploads), and
+ * "cache_results" (see pmc_sampler_eval_batch). */
 int pmc_set_option(pmc_handle h, const char *key, double value);
 /* Largest number of realisations processed per kernel launch (0 = choose from free device memory), and
  * how many MINRES iterations are queued between convergence checks. */
@@ -177,6 +178,11 @@ int pmc_sampler_sample_batch(pmc_handle h, int level, int nsamples, uint64_t pos
  * is the coarser Gaussian field, prolongated to `level` as the initial guess (:496-511).  s_out
  * [nsamples][Ne(level)] receives exp(field) if lognormal else the field (:529-533); embed_s_out (may be
  * NULL) receives the Gaussian field (:523-527); iters_out (may be NULL) the MINRES iterations per sample. */
+/* Chained calls (the managers' sequence Sample -> Eval -> SolveFwd on the same realisations): with the option
+ * "cache_results" = 1 the handle keeps the results of pmc_sampler_sample_batch (noise) and pmc_sampler_eval_batch (s_out,
+ * embed_s_out) in device memory as well, and a following call may pass NULL for xi, for init_s (with use_init > 0) and,
+ * in pmc_darcy_solve_batch, for k: the input is then taken from device memory instead of being copied from the host again
+ * (same level and nsamples as the call that produced it, else PMC_ERR_STATE).  Results are still written to the host. */
 int pmc_sampler_eval_batch(pmc_handle h, int level, int xi_level, int nsamples, const double *xi,
                            const double *init_s, int init_level, int use_init,
                            double *s_out, double *embed_s_out, int *iters_out);

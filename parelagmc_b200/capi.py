@@ -302,18 +302,24 @@ class Context:
         self._ck(self._L.pmc_sampler_sample_batch(self._h, level, nsamples, C.c_uint64(pos0), _d(out)))
         return out
 
-    def sampler_eval_batch(self, level: int, xi: np.ndarray, xi_level: Optional[int] = None,
+    def sampler_eval_batch(self, level: int, xi: Optional[np.ndarray], xi_level: Optional[int] = None,
                            init_s: Optional[np.ndarray] = None, init_level: int = 0, use_init: int = -1,
                            want_embed: bool = True, out_s: Optional[np.ndarray] = None,
-                           out_embed: Optional[np.ndarray] = None):
-        """Returns (s [n, Ne], embed_s [n, Ne] | None, iters [n])."""
-        xi = np.ascontiguousarray(xi, dtype=np.float64)
-        if xi.ndim == 1:
-            xi = xi[None, :]
-        n = xi.shape[0]
-        if xi_level is None:
-            xi_level = self.Ne.index(xi.shape[1])
-        assert xi.shape[1] == self.Ne[xi_level]
+                           out_embed: Optional[np.ndarray] = None, nsamples: Optional[int] = None):
+        """Returns (s [n, Ne], embed_s [n, Ne] | None, iters [n]).  With the option "cache_results" set, xi = None
+        (give xi_level and nsamples) takes the noise of the preceding `sampler_sample_batch` from device memory, and
+        use_init > 0 with init_s = None the Gaussian field of the preceding `sampler_eval_batch`."""
+        if xi is None:
+            assert xi_level is not None and nsamples is not None
+            n = int(nsamples)
+        else:
+            xi = np.ascontiguousarray(xi, dtype=np.float64)
+            if xi.ndim == 1:
+                xi = xi[None, :]
+            n = xi.shape[0]
+            if xi_level is None:
+                xi_level = self.Ne.index(xi.shape[1])
+            assert xi.shape[1] == self.Ne[xi_level]
         if init_s is not None:
             init_s = np.ascontiguousarray(init_s, dtype=np.float64).reshape(n, -1)
             assert init_s.shape[1] == self.Ne[init_level]
@@ -326,13 +332,18 @@ class Context:
         return s, emb, it
 
     # -- Darcy -------------------------------------------------------------------------------------
-    def darcy_solve_batch(self, level: int, k: np.ndarray, want_sol: bool = False):
-        """Returns (Q [n], C [n], sol [n, N] | None, iters [n])."""
-        k = np.ascontiguousarray(k, dtype=np.float64)
-        if k.ndim == 1:
-            k = k[None, :]
-        n = k.shape[0]
-        assert k.shape[1] == self.dNe[level]
+    def darcy_solve_batch(self, level: int, k: Optional[np.ndarray], want_sol: bool = False, nsamples: Optional[int] = None):
+        """Returns (Q [n], C [n], sol [n, N] | None, iters [n]).  With the option "cache_results" set, k = None (give
+        nsamples) takes the coefficient the preceding `sampler_eval_batch` on this level produced from device memory."""
+        if k is None:
+            assert nsamples is not None
+            n = int(nsamples)
+        else:
+            k = np.ascontiguousarray(k, dtype=np.float64)
+            if k.ndim == 1:
+                k = k[None, :]
+            n = k.shape[0]
+            assert k.shape[1] == self.dNe[level]
         Q = np.empty(n)
         Cc = np.empty(n)
         sol = np.empty((n, self.dNe[level] + self.dNf[level])) if want_sol else None

@@ -240,6 +240,12 @@ struct pmc_context_s {
     Arena arena;
     std::shared_ptr<DevStore> store;
     int num_sms = 148;   // multiProcessorCount of the handle's device
+    // device-resident copies of the most recent per-sample results (option "cache_results"): the noise of
+    // pmc_sampler_sample_batch, and s_out / embed_s_out of pmc_sampler_eval_batch, in the host layout [nsamples][n]; a
+    // following call that passes NULL for the corresponding input reads them instead of a host buffer
+    struct ResultCache { double *p = nullptr; size_t cap = 0; int level = -1, ns = 0, n = 0; bool valid = false; };
+    bool cache_results = false;
+    ResultCache cache[3];
     // NCCL communicator over the ranks that share the sample budget (pmc_comm_init); null for a single rank
     void *nccl_comm = nullptr;
     int comm_ranks = 1, comm_rank = 0;
@@ -1692,15 +1698,45 @@ static int rng_launch(Ctx *c, int mode, uint64_t pos0, uint64_t pstride, uint64_
     return PMC_OK;
 }
 
+enum { CACHE_XI = 0, CACHE_FIELD = 1, CACHE_EMB = 2 };
+
+// keep rows [s0, s0 + ns) of a result (n values per realisation, host layout, currently at `src` on the device)
+static int cache_store(Ctx *c, int slot, int level, int nsamples, int s0, int ns, int n, const double *src)
+{
+    if (!c->cache_results) return PMC_OK;
+    pmc_context_s::ResultCache &R = c->cache[slot];
+    const size_t need = (size_t)nsamples * n;
+    if (R.cap < need) {
+        if (R.p) { cudaStreamSynchronize(c->stream); cudaFree(R.p); }
+        R.p = nullptr; R.cap = 0; R.valid = false;
+        CK(cudaMalloc((void **)&R.p, need * sizeof(double)));
+        R.cap = need;
+    }
+    CK(cudaMemcpyAsync(R.p + (size_t)s0 * n, src, (size_t)ns * n * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+    R.level = level; R.ns = nsamples; R.n = n; R.valid = true;
+    return PMC_OK;
+}
+static const double *cache_lookup(Ctx *c, int slot, int level, int nsamples, int n, const char *what)
+{
+    const pmc_context_s::ResultCache &R = c->cache[slot];
+    if (!c->cache_results || !R.valid || R.level != level || R.ns != nsamples || R.n != n) {
+        fail(c, PMC_ERR_STATE, "%s is NULL but the handle holds no matching device-resident result (option cache_results, "
+                               "same level and number of realisations as the call that produced it)", what);
+        return nullptr;
+    }
+    return R.p;
+}
+
 static dim3 grid1d(size_t n) { return dim3((unsigned)std::min<size_t>((n + 255) / 256, 148 * 16)); }
 
 // host [ns][n] -> tile-major batched (via the staging buffer `stage`)
 static int upload_rows(Ctx *c, const double *host, int ns, int n, double *stage, Off dst, Off chunk, int mode, double neg_g,
-                       const double *w_sqrt, const int *rowmap = nullptr)
+                       const double *w_sqrt, const int *rowmap = nullptr, const double *dev_src = nullptr)
 {
     const int ntiles = (ns + TW - 1) / TW;
     double *d = (double *)c->arena.base + dst;
-    CK(cudaMemcpyAsync(stage, host, (size_t)ns * n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    if (dev_src) stage = const_cast<double *>(dev_src);   // already on the device in the host layout (result cache)
+    else CK(cudaMemcpyAsync(stage, host, (size_t)ns * n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
     const size_t total = (size_t)ntiles * n * TW;
     if (mode == 1) launch(c, PMC_K_MISC, (double)total * 16.0, k_to_tiles<1>, grid1d(total), dim3(256), n, chunk, ntiles, ns, (const double *)stage, d, neg_g, w_sqrt, rowmap);
     else launch(c, PMC_K_MISC, (double)total * 16.0, k_to_tiles<0>, grid1d(total), dim3(256), n, chunk, ntiles, ns, (const double *)stage, d, neg_g, w_sqrt, rowmap);
@@ -1771,6 +1807,7 @@ void pmc_destroy(pmc_handle c)
     cudaStreamSynchronize(c->stream);
     if (c->nccl_comm) pmc_comm_destroy(c);
     if (c->d_comm_buf) cudaFree(c->d_comm_buf);
+    for (auto &R : c->cache) if (R.p) cudaFree(R.p);
     c->store.reset();   // frees the operators with the last handle that shares them
     if (c->arena.base) cudaFree(c->arena.base);
     cudaFree(c->d_pstats);
@@ -1852,6 +1889,7 @@ int pmc_set_option(pmc_handle c, const char *key, double value)
         else return fail(c, PMC_ERR_ARG, "pmc_set_option: bad key or value '%s' = %g", key, value);
         return PMC_OK;
     }
+    if (k == "cache_results") { c->cache_results = value != 0; return PMC_OK; }
     if (k == "max_batch" && value >= 0) c->max_batch = (int)value;
     else if (k == "cta_threads") c->force_nt = (int)value;
     else if (k == "cluster_size") c->force_cs = (int)value;
@@ -2017,7 +2055,7 @@ int pmc_clone(pmc_handle src, pmc_handle *out)
     c->cfg_sampler = src->cfg_sampler; c->cfg_darcy = src->cfg_darcy;
     c->max_batch = src->max_batch; c->force_nt = src->force_nt; c->force_cs = src->force_cs; c->staging = src->staging;
     c->defer_x = src->defer_x; c->fuse_coarse = src->fuse_coarse; c->single_wave = src->single_wave; c->renumber = src->renumber;
-    c->force_group = src->force_group; c->solo_rows = src->solo_rows;
+    c->force_group = src->force_group; c->solo_rows = src->solo_rows; c->cache_results = src->cache_results;
     c->store = src->store;   // one copy of the operators per device, freed with the last handle that uses them
     c->s = src->s;           // level descriptors: host arrays by value, device pointers into the shared store
     c->d = src->d;
@@ -2187,7 +2225,7 @@ int pmc_rng_init(pmc_handle c, double mu, double sigma, int nparts, int mypart)
     return PMC_OK;
 }
 
-static int rng_fill_common(Ctx *c, int mode, uint64_t pos, int64_t n, void *out)
+static int rng_fill_common(Ctx *c, int mode, uint64_t pos, int64_t n, void *out, int cache_level = -1, int cache_ns = 0)
 {
     if (!c || n < 0 || (n > 0 && !out)) return PMC_ERR_ARG;
     if (n == 0) return PMC_OK;
@@ -2200,6 +2238,9 @@ static int rng_fill_common(Ctx *c, int mode, uint64_t pos, int64_t n, void *out)
     rc = rng_launch(c, mode, pos, T, (uint64_t)n, nj, T, 1, T, T, 0.0, nullptr, (double *)c->arena.base,
                     (int32_t *)c->arena.base);
     if (rc) return rc;
+    if (cache_level >= 0 && cache_ns > 0 &&
+        (rc = cache_store(c, CACHE_XI, cache_level, cache_ns, 0, cache_ns, (int)(n / cache_ns), (const double *)c->arena.base)))
+        return rc;
     CK(cudaMemcpyAsync(out, c->arena.base, (size_t)n * esz, cudaMemcpyDeviceToHost, c->stream));
     return finish(c);
 }
@@ -2229,7 +2270,7 @@ int pmc_sampler_sample_batch(pmc_handle c, int level, int nsamples, uint64_t pos
     if (!c) return PMC_ERR_ARG;
     if (level < 0 || level >= c->nlevels || !c->s[level].set) return fail(c, PMC_ERR_STATE, "sampler level %d not uploaded", level);
     // realisation j occupies positions pos0 + j*Ne ... : a flat fill of nsamples*Ne values
-    return rng_fill_common(c, 1, pos0, (int64_t)nsamples * c->s[level].Ne, xi_out);
+    return rng_fill_common(c, 1, pos0, (int64_t)nsamples * c->s[level].Ne, xi_out, level, nsamples);
 }
 
 // ---- sampler Eval ---------------------------------------------------------------------------------
@@ -2265,10 +2306,10 @@ int pmc_sampler_eval_batch(pmc_handle c, int level, int xi_level, int nsamples, 
 {
     int rc = check_level(c, level, true, false);
     if (rc) return rc;
-    if (nsamples < 0 || !xi || !s_out) return fail(c, PMC_ERR_ARG, "pmc_sampler_eval_batch: bad arguments");
+    if (nsamples < 0 || !s_out) return fail(c, PMC_ERR_ARG, "pmc_sampler_eval_batch: bad arguments");
     if (xi_level < 0 || xi_level > level || !c->s[xi_level].set)
         return fail(c, PMC_ERR_ARG, "xi_level %d must be an uploaded level <= level %d", xi_level, level);
-    const bool warm = use_init > 0 && init_s != nullptr;
+    const bool warm = use_init > 0 && (init_s != nullptr || (c->cache_results && c->cache[CACHE_EMB].valid));
     if (warm && (init_level < level || init_level >= c->nlevels || !c->s[init_level].set))
         return fail(c, PMC_ERR_ARG, "init_level %d must be an uploaded level >= level %d", init_level, level);
     for (int l = xi_level; l < level; ++l)
@@ -2282,6 +2323,9 @@ int pmc_sampler_eval_batch(pmc_handle c, int level, int xi_level, int nsamples, 
     SaddleSys &sys = L.sys;
     const int Ne = L.Ne, Nex = c->s[xi_level].Ne, Nei = warm ? c->s[init_level].Ne : 0;
     const int nmax = std::max(Nex, std::max(Ne, Nei));
+    const double *xi_dev = nullptr, *init_dev = nullptr;
+    if (!xi && !(xi_dev = cache_lookup(c, CACHE_XI, xi_level, nsamples, Nex, "xi"))) return PMC_ERR_STATE;
+    if (warm && !init_s && !(init_dev = cache_lookup(c, CACHE_EMB, init_level, nsamples, Nei, "init_s"))) return PMC_ERR_STATE;
     // the program (identical for every batch): restrict, optional prolongated initial guess, solve
     Rows ar;
     SolveWs ws;
@@ -2316,12 +2360,18 @@ int pmc_sampler_eval_batch(pmc_handle c, int level, int xi_level, int nsamples, 
         const int ld = pad_ld(ns);
         double *stage = (double *)c->arena.base + (size_t)(ld / TW) * (size_t)chunk;
         // rhs_s = -g * xi * w_sqrt at xi_level (:352-358 / :423-428)
-        if ((rc = upload_rows(c, xi + (size_t)s0 * Nex, ns, Nex, stage, bufA, chunk, 1, -c->s[xi_level].g, c->s[xi_level].w_sqrt))) return rc;
-        if (warm && (rc = upload_rows(c, init_s + (size_t)s0 * Nei, ns, Nei, stage, t1, chunk, 0, 0.0, nullptr))) return rc;
+        if ((rc = upload_rows(c, xi ? xi + (size_t)s0 * Nex : nullptr, ns, Nex, stage, bufA, chunk, 1, -c->s[xi_level].g,
+                              c->s[xi_level].w_sqrt, nullptr, xi_dev ? xi_dev + (size_t)s0 * Nex : nullptr))) return rc;
+        if (warm && (rc = upload_rows(c, init_s ? init_s + (size_t)s0 * Nei : nullptr, ns, Nei, stage, t1, chunk, 0, 0.0, nullptr,
+                                      nullptr, init_dev ? init_dev + (size_t)s0 * Nei : nullptr))) return rc;
         if ((rc = run_program(c, pg, ns, chunk, sys.N))) return rc;
         const Off field = ws.x + (Off)sys.Nf * TW;  // rows [Nf, N) of the solution
         if ((rc = download_rows(c, fout, chunk, ns, Nout, stage, s_out + (size_t)s0 * Nout, L.lognormal != 0))) return rc;
-        if (embed_s_out && (rc = download_rows(c, field, chunk, ns, Ne, stage, embed_s_out + (size_t)s0 * Ne, false))) return rc;
+        if ((rc = cache_store(c, CACHE_FIELD, level, nsamples, s0, ns, Nout, stage))) return rc;
+        if (embed_s_out) {
+            if ((rc = download_rows(c, field, chunk, ns, Ne, stage, embed_s_out + (size_t)s0 * Ne, false))) return rc;
+            if ((rc = cache_store(c, CACHE_EMB, level, nsamples, s0, ns, Ne, stage))) return rc;
+        }
         if (iters_out) {
             itbuf.resize(ns);
             if ((rc = download_rows(c, ws.iters, chunk, ns, 1, stage, itbuf.data(), false))) return rc;
@@ -2339,7 +2389,7 @@ static int darcy_host_batch(Ctx *c, int level, int nsamples, const double *k, co
 {
     int rc = check_level(c, level, false, true);
     if (rc) return rc;
-    if (nsamples < 0 || !k) return fail(c, PMC_ERR_ARG, "Darcy batch: bad arguments");
+    if (nsamples < 0) return fail(c, PMC_ERR_ARG, "Darcy batch: bad arguments");
     if (nsamples == 0) return PMC_OK;
     CK(cudaSetDevice(c->device));
     DarcyLevel &L = c->d[level];
@@ -2349,6 +2399,8 @@ static int darcy_host_batch(Ctx *c, int level, int nsamples, const double *k, co
     SolveWs ws;
     carve_solve(ar, sys, ws);
     const Off k_ext = ar.alloc(Ne + 1), Qrow = ar.alloc(1);
+    const double *k_dev = nullptr;
+    if (!k && !(k_dev = cache_lookup(c, CACHE_FIELD, level, nsamples, Ne, "k"))) return PMC_ERR_STATE;
     Program pg;
     pg.staging = c->staging;
     pg.defer_x = c->defer_x;
@@ -2370,7 +2422,8 @@ static int darcy_host_batch(Ctx *c, int level, int nsamples, const double *k, co
         const int ns = std::min(B, nsamples - s0);
         const int ld = pad_ld(ns);
         double *stage = (double *)c->arena.base + (size_t)(ld / TW) * (size_t)chunk;
-        if ((rc = upload_rows(c, k + (size_t)s0 * Ne, ns, Ne, stage, k_ext, chunk, 0, 0.0, nullptr))) return rc;
+        if ((rc = upload_rows(c, k ? k + (size_t)s0 * Ne : nullptr, ns, Ne, stage, k_ext, chunk, 0, 0.0, nullptr, nullptr,
+                              k_dev ? k_dev + (size_t)s0 * Ne : nullptr))) return rc;
         if (apply_only) {
             if ((rc = upload_rows(c, xin + (size_t)s0 * N, ns, N, stage, ws.x, chunk, 0, 0.0, nullptr, L.d_rowmap))) return rc;
             if ((rc = run_program(c, pg, ns, chunk, N))) return rc;

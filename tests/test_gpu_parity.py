@@ -174,6 +174,35 @@ def test_sampler_methods_agree(orc, prob):
             c.close()
 
 
+def test_chained_calls_reuse_device_results(prob):
+    """Option "cache_results": Sample -> Eval -> SolveFwd with NULL for the vectors the library itself just produced
+    gives bitwise the results of passing the host copies back; a mismatching request fails loudly."""
+    from common import make_context
+    from parelagmc_b200.capi import PmcError
+    c = make_context(prob, True, 1e-6, 1e-12, 300, options={"cache_results": 1})
+    try:
+        lev, n = 0, 9
+        xi = c.sampler_sample_batch(lev, n, 4242)
+        sc_h, emb_h, _ = c.sampler_eval_batch(lev + 1, xi, xi_level=lev, use_init=0)
+        qc_h = c.darcy_solve_batch(lev + 1, sc_h)[0]
+        sf_h, _, _ = c.sampler_eval_batch(lev, xi, xi_level=lev, init_s=emb_h, init_level=lev + 1, use_init=1, want_embed=False)
+        q_h = c.darcy_solve_batch(lev, sf_h)[0]
+        c.sampler_sample_batch(lev, n, 4242)                                     # same noise again, now chained
+        sc_d, emb_d, _ = c.sampler_eval_batch(lev + 1, None, xi_level=lev, use_init=0, nsamples=n)
+        qc_d = c.darcy_solve_batch(lev + 1, None, nsamples=n)[0]
+        sf_d, _, _ = c.sampler_eval_batch(lev, None, xi_level=lev, init_s=None, init_level=lev + 1, use_init=1, want_embed=False,
+                                          nsamples=n)
+        q_d = c.darcy_solve_batch(lev, None, nsamples=n)[0]
+        for a, b in ((sc_h, sc_d), (emb_h, emb_d), (qc_h, qc_d), (sf_h, sf_d), (q_h, q_d)):
+            assert np.array_equal(a, b)
+        with pytest.raises(PmcError):
+            c.darcy_solve_batch(lev, None, nsamples=n + 1)
+        with pytest.raises(PmcError):
+            c.sampler_eval_batch(lev + 1, None, xi_level=lev + 1, nsamples=n)
+    finally:
+        c.close()
+
+
 def test_sampler_eval_coarse_noise_and_warm_start(ctx, orc, prob):
     """Eval(l+1, xi_l, ., init, false) then Eval(l, xi_l, ., init, true) as in MLMC_Manager.cpp:150-155."""
     from oracle.binding import Yarn5
