@@ -133,6 +133,10 @@ struct SaddleSys {
     double *d_coarse_coef = nullptr;  // {ca_j, cb_j} of the coarsest level's Chebyshev iteration (OP_CHEB_SMALL)
     // sampler, SPD form (emit_sampler_pcg): Bs = diag(1/(alpha W)) B (Ne x Nf), MBt = [M | B^T] (Nf x N),
     // dinvH = 1/diag(M + alpha^-1 B^T W^-1 B), inv_aw = 1/(alpha W)
+    // Darcy: the block operator split by row block for the apply inside the Krylov loop: Au = [M(k) | B^T] (Nf x N,
+    // weighted) and Bp = B (Ne x Nf, plain: no weight gathers on the pressure rows)
+    bool split_apply = false;
+    DevCsr Au, Bp;
     bool pcg = false;
     DevCsr Bs, MBt;
     double *dinvH = nullptr, *inv_aw = nullptr;
@@ -227,6 +231,7 @@ struct pmc_context_s {
     bool staging = true;  // stage operator entries through shared memory (option "stage_operators")
     bool defer_x = true;  // option "defer_x"
     bool fuse_coarse = true;  // option "fuse_coarse"
+    bool split_apply = true;  // option "split_apply": Darcy operator applied per row block (RT rows weighted, pressure rows plain)
     bool renumber = true;  // option "renumber": first-touch renumbering of the RT dofs inside the library
     bool single_wave = false;  // option "single_wave": prefer one wave of smaller CTAs over a mostly empty second wave
     std::vector<SamplerLevel> s;
@@ -788,6 +793,15 @@ static int prepare_darcy(Ctx *c, int level)
         for (int p = Be.rowptr[i]; p < Be.rowptr[i + 1]; ++p) eA.push_back({Nf + i, Be.col[p], -1, Be.val[p]});
     int rc;
     {
+        {   // rows [0, Nf) of A as their own weighted operator, rows [Nf, N) = B as a plain one
+            std::vector<WEntry> eU;
+            for (const WEntry &t : eA)
+                if (t.r < Nf) eU.push_back(t);
+            HWCsr Au = wcsr_from_entries(Nf, N, eU);
+            if ((rc = upload_wcsr(c, Au, sys.Au, Ne))) return rc;
+            if ((rc = upload_csr(c, Be, sys.Bp))) return rc;
+            sys.split_apply = true;
+        }
         HWCsr A = wcsr_from_entries(N, N, eA);
         if ((rc = upload_wcsr(c, A, sys.A, Ne))) return rc;
         HWCsr M = wcsr_from_entries(Nf, Nf, eM);
@@ -953,6 +967,7 @@ struct Program {
     bool staging = true;  // stage operator entries through shared memory where the slices fit (F_STAGED)
     bool defer_x = true;  // MINRES: apply the solution updates of an iteration pair in one pass (option "defer_x")
     bool fuse_coarse = true;  // coarsest Chebyshev iteration as one shared-memory operation (option "fuse_coarse")
+    bool split_apply = true;  // Darcy block operator applied as two operations (option "split_apply")
     int pc() const { return (int)ops.size(); }
     Op &add(int kind, int kclass, int n, double rows_moved, double matrix_bytes = 0.0)
     {
@@ -1197,6 +1212,15 @@ static void emit_prec(Program &pg, Solver &sv, Off r, Off z, int dot_slot, bool 
 static void emit_saddle(Program &pg, Solver &sv, int ep, Off x, Off y, Off r, int dot_slot)
 {
     SaddleSys &sys = *sv.sys;
+    if (ep == EP_AX && sys.split_apply && pg.split_apply) {
+        // q_u = [M(k) | B^T] u over the RT rows (weighted), q_p = B u_u over the pressure rows (plain); the fused dot u . q
+        // accumulates over the two operations
+        emit_spmm(pg, KC_SADDLE, EP_AX, sys.Au, sv.k_ext, vr(x, sys.N), vr(y, sys.N), VNULL, VNULL, nullptr, VNULL, 0, 0, dot_slot,
+                  false, false, (double)sys.N + sys.Nf + sys.Ne);
+        emit_spmm(pg, KC_SADDLE, EP_AX, sys.Bp, VNULL, vr(x, sys.N), vr(y, sys.N, sys.Nf), dot_slot >= 0 ? vr(x, sys.N, sys.Nf) : VNULL,
+                  VNULL, nullptr, VNULL, 0, 0, dot_slot, dot_slot >= 0, false, (double)sys.Ne);   // u was credited above
+        return;
+    }
     emit_spmm(pg, KC_SADDLE, ep, sys.A, sv.k_ext, vr(x, sys.N), vr(y, sys.N), r >= 0 ? vr(r, sys.N) : VNULL, VNULL, nullptr, VNULL, 0,
               0, dot_slot, false, false, (ep == EP_RESID ? 3.0 : 2.0) * sys.N + (sys.weighted ? sys.Ne : 0));
 }
@@ -1890,6 +1914,7 @@ int pmc_set_option(pmc_handle c, const char *key, double value)
         return PMC_OK;
     }
     if (k == "cache_results") { c->cache_results = value != 0; return PMC_OK; }
+    if (k == "split_apply") { c->split_apply = value != 0; return PMC_OK; }
     if (k == "max_batch" && value >= 0) c->max_batch = (int)value;
     else if (k == "cta_threads") c->force_nt = (int)value;
     else if (k == "cluster_size") c->force_cs = (int)value;
@@ -2055,7 +2080,7 @@ int pmc_clone(pmc_handle src, pmc_handle *out)
     c->cfg_sampler = src->cfg_sampler; c->cfg_darcy = src->cfg_darcy;
     c->max_batch = src->max_batch; c->force_nt = src->force_nt; c->force_cs = src->force_cs; c->staging = src->staging;
     c->defer_x = src->defer_x; c->fuse_coarse = src->fuse_coarse; c->single_wave = src->single_wave; c->renumber = src->renumber;
-    c->force_group = src->force_group; c->solo_rows = src->solo_rows; c->cache_results = src->cache_results;
+    c->force_group = src->force_group; c->solo_rows = src->solo_rows; c->cache_results = src->cache_results; c->split_apply = src->split_apply;
     c->store = src->store;   // one copy of the operators per device, freed with the last handle that uses them
     c->s = src->s;           // level descriptors: host arrays by value, device pointers into the shared store
     c->d = src->d;
@@ -2335,6 +2360,7 @@ int pmc_sampler_eval_batch(pmc_handle c, int level, int xi_level, int nsamples, 
     pg.staging = c->staging;
     pg.defer_x = c->defer_x;
     pg.fuse_coarse = c->fuse_coarse;
+    pg.split_apply = c->split_apply;
     const Off rhs = emit_restrict(pg, c, xi_level, level, bufA, bufB);
     const Off t1 = (rhs == bufA) ? bufB : bufA;
     Off x0 = -1;
@@ -2405,6 +2431,7 @@ static int darcy_host_batch(Ctx *c, int level, int nsamples, const double *k, co
     pg.staging = c->staging;
     pg.defer_x = c->defer_x;
     pg.fuse_coarse = c->fuse_coarse;
+    pg.split_apply = c->split_apply;
     if (apply_only) {
         Solver sv{&sys, &ws, vr(k_ext, Ne + 1)};
         emit_fill(pg, vr(k_ext, Ne + 1, Ne), 1, 1.0);  // weight of the fixed entries
@@ -2498,6 +2525,7 @@ static int level_batch(Ctx *c, int level, int nlevels, int nsamples, uint64_t po
     pg.staging = c->staging;
     pg.defer_x = c->defer_x;
     pg.fuse_coarse = c->fuse_coarse;
+    pg.split_apply = c->split_apply;
     // Sample(level, xi) fused with rhs_s = -g W^{1/2} xi  (/root/reference/src/PDESampler.cpp:336-340, :352-358)
     {
         Op &o = pg.add(OP_RNG, KC_RNG, Ne, Ne);
@@ -2714,6 +2742,7 @@ int pmc_bayes_level_batch(pmc_handle c, int level, int nlevels, int nsamples, ui
     pg.staging = c->staging;
     pg.defer_x = c->defer_x;
     pg.fuse_coarse = c->fuse_coarse;
+    pg.split_apply = c->split_apply;
     std::vector<int> rng_ops;
     for (int draw = 0; draw < 2; ++draw) {  // draw 0: zxi -> Z (likelihood); draw 1: xi -> R = Q * likelihood
         rng_ops.push_back(pg.pc());

@@ -376,6 +376,9 @@ __device__ __forceinline__ void op_spmm(const Op &o, double *chunk, Smem &sm, St
     const double *__restrict__ x = tp(o.x, chunk) + sub;
     double *__restrict__ y = tp(o.y, chunk) + sub;
     const double *__restrict__ r = (EP == EP_RESID || EP == EP_CHEB) ? tp(o.r, chunk) + sub : nullptr;
+    // EP_AX with a fused dot: the partner of row i is x[i], or -- when the rows of this operation are a block of a larger
+    // operator whose columns start elsewhere -- the vector given in o.r
+    const double *__restrict__ xd = (EP == EP_AX && DOT && o.r.off >= 0) ? tp(o.r, chunk) + sub : x;
     double *__restrict__ d = (EP == EP_CHEB) ? tp(o.d, chunk) + sub : nullptr;
     const double *__restrict__ V = WEIGHTED ? tp(o.v, chunk) + sub : nullptr;
     const double *__restrict__ dinvb = (EP == EP_CHEB && BDINV) ? tp(o.w, chunk) + sub : nullptr;
@@ -430,7 +433,8 @@ __device__ __forceinline__ void op_spmm(const Op &o, double *chunk, Smem &sm, St
                 else { const double t = __ldg(o.fixed + row); di = make_double2(t, t); }
                 if (ca != 0.0) dv = ld2c(d + ro);
             }
-            if (EP == EP_CHEB || (DOT && !dot_r)) xr = ld2c(x + ro);
+            if (EP == EP_CHEB) xr = ld2c(x + ro);
+            else if (DOT && !dot_r) xr = ld2c(xd + ro);
         }
         const unsigned char *base;
         int w;
@@ -480,7 +484,8 @@ __device__ __forceinline__ void op_spmm(const Op &o, double *chunk, Smem &sm, St
                 else { const double t = __ldg(o.fixed + row); di = make_double2(t, t); }
                 if (ca != 0.0) dv = ld2c(d + ro);
             }
-            if (EP == EP_CHEB || (DOT && !dot_r)) xr = ld2c(x + ro);
+            if (EP == EP_CHEB) xr = ld2c(x + ro);
+            else if (DOT && !dot_r) xr = ld2c(xd + ro);
 #endif
             D2 out;
             if (EP == EP_AX) {

@@ -573,3 +573,107 @@ class ML_BayesRatio_Manager:
                         ("E[Y_Z] ", self.eYZ), ("Var[Y_Z] ", self.varYZ), ("C_l ", self.eC)):
             os.write(name.ljust(42) + "  ".join("%.8g" % x for x in v) + "\n")
         os.write("=" * 79 + "\n")
+
+
+# ratio columns of /root/reference/src/ML_BayesRatio_Splitting_Manager.hpp:67-70
+BR.update(YRatio2=12, YRatio=13, ABS_YRatio=14, Ratio2=15, Ratio=16, ABS_Ratio=17)
+
+
+class ML_BayesRatio_Splitting_Manager(ML_BayesRatio_Manager):
+    """`parelagmc::ML_BayesRatio_Splitting_Manager` (`/root/reference/src/ML_BayesRatio_Splitting_Manager.hpp:35-130`):
+    the multilevel estimator of E_post[Q] = E[R / Z] ("divide, then sum": the per-realisation ratio q = R / Z and its
+    level difference Y = q_l - q_{l+1}, hpp:381-394).  Same device call per level as `ML_BayesRatio_Manager`
+    (`pmc_bayes_level_batch`: the rows carry R, Y_R, Z, Y_Z of every realisation); the six ratio sums (hpp:342-347,
+    :417-422) are formed from the rows, and the sample allocation follows the ratio's variance (hpp:603-737)."""
+
+    def InitRun(self, level_nsamples_init: Sequence[int]):
+        local = np.zeros((self.nlevels, BR["NVAR"]))
+        round_time = np.zeros(self.nlevels)
+        for ilevel in range(self.nlevels - 1, -1, -1):
+            n = int(level_nsamples_init[ilevel])
+            Ne = self.backend.Ne[ilevel]
+            first, count = split_samples(n, self.comm.rank, self.comm.size)
+            t0 = time.perf_counter()
+            if count > 0:
+                _, rows, _ = self.backend.bayes_level_batch(ilevel, count, self.stream_pos + 2 * first * Ne,
+                                                            nlevels=self.nlevels, want_rows=True, sums=local[ilevel])
+                R, YR, Z, YZ = rows[:, 0], rows[:, 1], rows[:, 2], rows[:, 3]
+                q = R / Z
+                if ilevel == self.nlevels - 1:
+                    y = q                                             # hpp:342-347
+                else:
+                    y = q - (R - YR) / (Z - YZ)                       # q - r_c / z_c (hpp:390-394)
+                local[ilevel, BR["Ratio"]] += q.sum()
+                local[ilevel, BR["ABS_Ratio"]] += np.abs(q).sum()
+                local[ilevel, BR["Ratio2"]] += (q * q).sum()
+                local[ilevel, BR["YRatio"]] += y.sum()
+                local[ilevel, BR["ABS_YRatio"]] += np.abs(y).sum()
+                local[ilevel, BR["YRatio2"]] += (y * y).sum()
+            round_time[ilevel] += time.perf_counter() - t0
+            self.stream_pos += 2 * n * Ne
+            self.level_nsamples[ilevel] += n
+        gsums, gtime = self.comm.reduce_sums_and_times(local, round_time)
+        self.sums += gsums
+        self.level_time += gtime * self.comm.size
+        self.computeNSamplesMSE()
+
+    def computeNSamplesMSE(self):
+        """hpp:603-737: everything `ML_BayesRatio_Manager` reports, but bias, estimator variance and the sample allocation
+        from the ratio's level differences."""
+        super().computeNSamplesMSE()
+        L, n = self.nlevels, self.level_nsamples.astype(np.float64)
+        e = self.sums / n[:, None]
+        self.eRatio, self.eABS_Ratio = e[:, BR["Ratio"]].copy(), e[:, BR["ABS_Ratio"]].copy()
+        self.eYRatio, self.eABS_YRatio = e[:, BR["YRatio"]].copy(), e[:, BR["ABS_YRatio"]].copy()
+        unb = n / (n - 1.0)
+        self.varRatio = (e[:, BR["Ratio2"]] - self.eRatio ** 2) * unb
+        self.varYRatio = (e[:, BR["YRatio2"]] - self.eYRatio ** 2) * unb
+        M = self.M
+        self.alpha = expWRegression(self.eYRatio, M, 1)
+        self.alphaABS = expWRegression(self.eABS_YRatio, M, 1)
+        self.beta = expWRegression(self.varYRatio, M, 1)
+        self.gamma = expWRegression(self.cost, M, 0)
+        if L == 1:
+            bias2 = 0.0
+        else:
+            m = M[0] / M[1]
+            if L > 3:
+                bias2 = max(m ** (2.0 * self.alphaABS) * self.eABS_YRatio[1] ** 2, self.eABS_YRatio[0] ** 2) / (
+                    (m ** (-2.0 * self.alphaABS) - 1.0) ** 2)
+            elif L == 3:
+                bias2 = self.eABS_YRatio[0] ** 2 / ((m ** (-self.alphaABS) - 1.0) ** 2)
+            else:
+                bias2 = self.eABS_YRatio[0] ** 2
+        self.expected_discretization_error2 = bias2
+        if self.auto_eps2:
+            self.eps2 = bias2 / (1.0 - self.ratio)
+        self.ml_estimator_variance = float(np.sum(self.varYRatio / n))
+        self.actualMSE = bias2 + self.ml_estimator_variance
+        prop = float(np.sum(np.sqrt(np.maximum(self.varYRatio, 0) * self.cost))) / (self.ratio * self.eps2)
+        for i in range(L):
+            missings = prop * math.sqrt(max(self.varYRatio[i], 0) / self.cost[i]) - n[i]
+            self.level_nsamples_missing[i] = max(int(math.ceil(missings)), 0)
+
+    def estimate(self) -> float:
+        """Posterior expectation: sum_l E[Y_ratio,l]."""
+        return float(np.sum(self.eYRatio))
+
+
+class SL_BayesRatio_Manager(ML_BayesRatio_Manager):
+    """`parelagmc::SL_BayesRatio_Manager` (`/root/reference/src/SL_BayesRatio_Manager.hpp:32-150`): single level
+    (level 0), E_post[Q] = E[R] / E[Z]; its loop (hpp:240-255) is the coarsest-level loop of the multilevel manager."""
+
+    def __init__(self, comm, backend, params: Optional[dict] = None, out=sys.stdout, stream_pos: int = 0):
+        params = dict(params or {})
+        params.setdefault("Array number of samples", [int(params.get("Number of samples", 10))])
+        super().__init__(comm, 1, backend, params, out=out, stream_pos=stream_pos)
+
+
+class SL_BayesRatio_Splitting_Manager(ML_BayesRatio_Splitting_Manager):
+    """`parelagmc::SL_BayesRatio_Splitting_Manager` (`/root/reference/src/SL_BayesRatio_Splitting_Manager.hpp:32-152`):
+    single level, E_post[Q] = E[R / Z]."""
+
+    def __init__(self, comm, backend, params: Optional[dict] = None, out=sys.stdout, stream_pos: int = 0):
+        params = dict(params or {})
+        params.setdefault("Array number of samples", [int(params.get("Number of samples", 10))])
+        super().__init__(comm, 1, backend, params, out=out, stream_pos=stream_pos)

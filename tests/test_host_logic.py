@@ -277,3 +277,45 @@ def test_bayes_ratio_manager():
     assert 1.0 < est < 4.0            # a posterior mean of the effective permeability of the same order as the prior's
     # stream bookkeeping: level 1 first (12 samples x 2 draws), then level 0
     assert m.stream_pos == p["pos_after_setup"] + 2 * 12 * be.Ne[1] + 2 * 6 * be.Ne[0]
+
+
+def test_ratio_splitting_and_single_level_managers():
+    """The remaining ratio managers of the reference (SL_BayesRatio_Manager, SL_/ML_BayesRatio_Splitting_Manager): the
+    ratio sums formed from the device call's rows against a direct evaluation, single level = the multilevel manager with
+    one level, and the "divide, then sum" estimate."""
+    from common import bayes_problem
+    p = bayes_problem()
+    be = OracleBackend(p, threads=4)
+    for lev in range(p["nlevels"]):
+        be.o.set_observations(lev, p["gobs"][lev], p["G_obs"], p["noise"])
+    params = {"Array number of samples": [5, 9], "Mean square error": 1e6}
+    m = MG.ML_BayesRatio_Splitting_Manager(None, 2, be, params, out=None, stream_pos=p["pos_after_setup"])
+    m.wallTime = False
+    m.Run()
+    # direct evaluation of the rows the manager saw (same stream positions: level 1 first)
+    pos = p["pos_after_setup"]
+    _, r1 = be.o.bayes_level(1, 9, pos, nthreads=2, nlevels=2)
+    _, r0 = be.o.bayes_level(0, 5, pos + 2 * 9 * be.Ne[1], nthreads=2, nlevels=2)
+    q1 = r1[:, 0] / r1[:, 2]
+    q0 = r0[:, 0] / r0[:, 2]
+    y0 = q0 - (r0[:, 0] - r0[:, 1]) / (r0[:, 2] - r0[:, 3])
+    assert m.sums[1, MG.BR["Ratio"]] == pytest.approx(q1.sum()) and m.sums[1, MG.BR["YRatio2"]] == pytest.approx((q1 * q1).sum())
+    assert m.sums[0, MG.BR["YRatio"]] == pytest.approx(y0.sum()) and m.sums[0, MG.BR["ABS_Ratio"]] == pytest.approx(np.abs(q0).sum())
+    assert m.estimate() == pytest.approx(y0.mean() + q1.mean())
+    assert m.ml_estimator_variance == pytest.approx(np.var(y0, ddof=1) / 5 + np.var(q1, ddof=1) / 9)
+    # single-level managers on level 0
+    sl = MG.SL_BayesRatio_Manager(None, be, {"Number of samples": 6, "Mean square error": 1e6}, out=None,
+                                  stream_pos=p["pos_after_setup"])
+    sl.wallTime = False
+    sl.Run()
+    ml1 = MG.ML_BayesRatio_Manager(None, 1, be, {"Array number of samples": [6], "Mean square error": 1e6}, out=None,
+                                   stream_pos=p["pos_after_setup"])
+    ml1.wallTime = False
+    ml1.Run()
+    assert np.array_equal(sl.sums, ml1.sums) and sl.estimate() == ml1.estimate()
+    sls = MG.SL_BayesRatio_Splitting_Manager(None, be, {"Number of samples": 6, "Mean square error": 1e6}, out=None,
+                                             stream_pos=p["pos_after_setup"])
+    sls.wallTime = False
+    sls.Run()
+    _, r = be.o.bayes_level(0, 6, p["pos_after_setup"], nthreads=2, nlevels=1)
+    assert sls.estimate() == pytest.approx((r[:, 0] / r[:, 2]).mean())
