@@ -408,6 +408,10 @@ __device__ __forceinline__ void op_spmm(const Op &o, double *chunk, Smem &sm, St
             else wnext = k1 - k0;
         }
     }
+#ifdef PMC_SPMM_SYNC   // experiment: keep the warps of a CTA within a window of passes (L1 reuse between adjacent slices)
+    const int maxp = (sl_end - r0 / SLICE + NW - 1) / NW;   // passes of the busiest warp: the same for every thread
+    int pass = 0;
+#endif
     for (; sl < sl_end; sl += NW) {
         const int row = sl * SLICE + rs;
         const bool live = row < r1;
@@ -520,7 +524,14 @@ __device__ __forceinline__ void op_spmm(const Op &o, double *chunk, Smem &sm, St
             wnext = n1 - n0;
             st ^= 1;
         }
+#ifdef PMC_SPMM_SYNC
+        if ((++pass % PMC_SPMM_SYNC) == 0) __syncthreads();
+#endif
     }
+#ifdef PMC_SPMM_SYNC
+    while (pass < maxp)
+        if ((++pass % PMC_SPMM_SYNC) == 0) __syncthreads();
+#endif
     if (DOT) block_dot<NTt, CS>(acc, sm, o.slot, (o.flags & F_DOT_ACC) != 0);
 }
 
