@@ -174,8 +174,26 @@ def workload_config(world):
 # ------------------------------------------------------------------------------------------------------------------
 def pin_to_gpu_numa(local):
     """Bind this rank's host threads (and therefore its page-locked buffers, which are placed on first touch) to the CPU
-    cores of the NUMA node its GPU hangs off: 8 ranks x 3 level threads otherwise float over both sockets and half of
-    the host<->device copies cross the socket interconnect.  Returns a note for the JSON line."""
+    cores next to its GPU: 8 ranks x 3 level threads otherwise float over both sockets and half of the host<->device
+    copies cross the socket interconnect.  The core set comes from NVML (nvmlDeviceGetCpuAffinity, what `nvidia-smi topo -m`
+    prints), else from the GPU's sysfs numa_node.  Returns a note for the JSON line."""
+    allowed = os.sched_getaffinity(0)
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local)
+        words = (max(allowed) // 64) + 1
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = {64 * w + b for w, m in enumerate(mask) for b in range(64) if (int(m) >> b) & 1} & allowed
+        if cpus and cpus != allowed:
+            os.sched_setaffinity(0, cpus)
+            return f"rank bound to the {len(cpus)} CPUs NVML lists for GPU {local} (of {len(allowed)} allowed)"
+        if cpus == allowed:
+            return f"NVML lists all {len(allowed)} allowed CPUs for GPU {local}: nothing to bind"
+    except Exception as e:
+        nvml_err = type(e).__name__
+    else:
+        nvml_err = "empty mask"
     try:
         bdf = subprocess.run(["nvidia-smi", "-i", str(local), "--query-gpu=pci.bus_id", "--format=csv,noheader"],
                              capture_output=True, text=True, timeout=20).stdout.strip().lower()
@@ -183,18 +201,18 @@ def pin_to_gpu_numa(local):
             bdf = bdf[4:]
         node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read().strip())
         if node < 0:
-            return "no NUMA information for the GPU (single node host)"
+            return f"no CPU affinity information for the GPU (NVML: {nvml_err}; sysfs numa_node = -1)"
         cpus = set()
         for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
             a, _, b = part.partition("-")
             cpus.update(range(int(a), int(b or a) + 1))
-        cpus &= os.sched_getaffinity(0)
+        cpus &= allowed
         if not cpus:
             return f"NUMA node {node} has no allowed CPU"
         os.sched_setaffinity(0, cpus)
         return f"rank bound to the {len(cpus)} CPUs of NUMA node {node} (GPU {bdf})"
     except Exception as e:
-        return f"not bound ({type(e).__name__})"
+        return f"not bound (NVML: {nvml_err}; sysfs: {type(e).__name__})"
 
 
 # ------------------------------------------------------------------------------------------------------------------
