@@ -458,6 +458,167 @@ def build_tet_hierarchy(n_fine: int, length: float, nlevels: int) -> List[LevelD
 
 
 # --------------------------------------------------------------------------------------
+# unstructured agglomerates (what `BuildTopologyAlgebraic` + ParELAG's order-0 coarsening yield)
+# --------------------------------------------------------------------------------------
+def greedy_partition(level: LevelData, target: int, seed: int = 0) -> np.ndarray:
+    """Connected, irregular agglomerates of about `target` elements each, grown breadth-first from random seeds over the
+    element-face-element graph (a METIS stand-in: `/root/reference/src/Utilities.cpp:125-155` asks METIS for contiguous
+    k-way parts of about `coarsening_factor` elements)."""
+    inc = sp.csr_matrix((np.ones(level.B.nnz), level.B.indices, level.B.indptr), shape=level.B.shape)
+    adj = sp.csr_matrix(inc @ inc.T)
+    adj.setdiag(0)
+    adj.eliminate_zeros()
+    rng = np.random.default_rng(seed)
+    part = np.full(level.Ne, -1, dtype=np.int64)
+    npart = 0
+    for e0 in rng.permutation(level.Ne):
+        if part[e0] >= 0:
+            continue
+        size = int(rng.integers(max(2, target // 2), target + target // 2 + 1))
+        front, members = [int(e0)], [int(e0)]
+        part[e0] = npart
+        while front and len(members) < size:
+            e = front.pop(0)
+            nb = adj.indices[adj.indptr[e]:adj.indptr[e + 1]]
+            for j in rng.permutation(nb):
+                if part[j] < 0 and len(members) < size:
+                    part[j] = npart
+                    members.append(int(j))
+                    front.append(int(j))
+        npart += 1
+    # merge singletons into a neighbour so that every agglomerate has interior faces or at least two elements
+    sizes = np.bincount(part, minlength=npart)
+    for e in np.nonzero(sizes[part] == 1)[0]:
+        nb = adj.indices[adj.indptr[e]:adj.indptr[e + 1]]
+        if nb.size:
+            part[e] = part[nb[0]]
+    _, part = np.unique(part, return_inverse=True)
+    return part.astype(np.int64)
+
+
+def coarsen_by_agglomeration(fine: LevelData, part: np.ndarray) -> LevelData:
+    """The order-0 coarse spaces ParELAG builds on arbitrary agglomerates (`DeRhamSequence::Coarsen`, reached from
+    `/root/reference/src/PDESampler.cpp:166-171`, `src/DarcySolver.cpp:160-170`): one L2 dof per agglomerate (piecewise
+    constants), one RT dof per agglomerated face (the set of fine faces shared by the same two agglomerates, or lying on
+    the boundary with the same attribute), whose basis function has a flux trace proportional to the fine faces' share and
+    is extended into the two agglomerates by the minimum-energy flux with constant divergence (local mixed problems).
+    Fills `fine.P_u`, `fine.P_s` and returns the coarse `LevelData`: dof lists of the agglomerates, their dense local mass
+    blocks `P_A^T M_A P_A` (up to ~20 x 20: rows far wider than the 6-7 entries of the structured meshes), `D`, `W`,
+    boundary data.  `D_f P_u = P_s D_c` holds by construction."""
+    Ne, Nf = fine.Ne, fine.Nf
+    nA = int(part.max()) + 1
+    Binc = sp.csr_matrix(fine.B)                        # signed incidence (+1: the face's + direction leaves the element)
+    Bt = Binc.T.tocsr()
+    vol = fine.Wdiag
+    volA = np.bincount(part, weights=vol, minlength=nA)
+    battr = np.zeros(Nf, dtype=np.int64)
+    battr[fine.bdr_face] = fine.bdr_attr
+    # ---- coarse faces ----
+    key_of, faces_of, F_low, F_high, F_attr, interior_of = {}, [], [], [], [], [[] for _ in range(nA)]
+    face_sign = np.zeros(Nf)                             # +1 if the fine face's + direction agrees with its coarse face's
+    cface = np.full(Nf, -1, dtype=np.int64)
+    for f in range(Nf):
+        els = Bt.indices[Bt.indptr[f]:Bt.indptr[f + 1]]
+        sg = Bt.data[Bt.indptr[f]:Bt.indptr[f + 1]]
+        if els.size == 2 and part[els[0]] == part[els[1]]:
+            interior_of[part[els[0]]].append(f)
+            continue
+        if els.size == 2:
+            a, b = (0, 1) if part[els[0]] < part[els[1]] else (1, 0)
+            key = (int(part[els[a]]), int(part[els[b]]), 0)
+            sign = sg[a]                                 # + direction of the coarse face: out of the lower agglomerate
+        else:
+            key = (int(part[els[0]]), -1, int(battr[f]))
+            sign = sg[0]                                 # boundary: outward
+        if key not in key_of:
+            key_of[key] = len(faces_of)
+            faces_of.append([])
+            F_low.append(key[0]); F_high.append(key[1]); F_attr.append(key[2])
+        F = key_of[key]
+        faces_of[F].append(f)
+        cface[f] = F
+        face_sign[f] = sign
+    nF = len(faces_of)
+    # ---- agglomerate-local fine mass matrices (unit coefficient) ----
+    ne = np.diff(fine.elem_ptr)
+    el_of = [np.nonzero(part == A)[0] for A in range(nA)]
+    cfaces_of = [[] for _ in range(nA)]
+    for F in range(nF):
+        cfaces_of[F_low[F]].append(F)
+        if F_high[F] >= 0:
+            cfaces_of[F_high[F]].append(F)
+    rows_u, cols_u, vals_u = [], [], []
+    c_ptr, c_dofs, c_mats, c_mptr = [0], [], [], [0]
+    for A in range(nA):
+        els = el_of[A]
+        bnd = [f for F in cfaces_of[A] for f in faces_of[F]]
+        inte = interior_of[A]
+        loc = {f: i for i, f in enumerate(inte + bnd)}
+        nI, nL = len(inte), len(inte) + len(bnd)
+        MA = np.zeros((nL, nL))
+        BA = np.zeros((els.size, nL))
+        for r, e in enumerate(els):
+            d = fine.elem_dofs[fine.elem_ptr[e]:fine.elem_ptr[e + 1]]
+            Me = fine.elem_mat[fine.elem_mat_ptr[e]:fine.elem_mat_ptr[e + 1]].reshape(ne[e], ne[e])
+            idx = [loc[int(f)] for f in d]
+            MA[np.ix_(idx, idx)] += Me
+            for p_ in range(Binc.indptr[e], Binc.indptr[e + 1]):
+                BA[r, loc[int(Binc.indices[p_])]] = Binc.data[p_]
+        PA = np.zeros((nL, len(cfaces_of[A])))
+        for c, F in enumerate(cfaces_of[A]):
+            g = np.zeros(nL)
+            ff = faces_of[F]
+            for f in ff:
+                g[loc[f]] = face_sign[f] / len(ff)        # total flux 1 through F in its + direction
+            sigma = 1.0 if F_low[F] == A else -1.0       # ... which leaves A (lower agglomerate) or enters it
+            if nI > 0:
+                K = np.zeros((nI + els.size, nI + els.size))
+                K[:nI, :nI] = MA[:nI, :nI]
+                K[:nI, nI:] = BA[:, :nI].T
+                K[nI:, :nI] = BA[:, :nI]
+                rhs = np.concatenate([-MA[:nI, nI:] @ g[nI:], sigma * vol[els] / volA[A] - BA[:, nI:] @ g[nI:]])
+                g[:nI] = np.linalg.lstsq(K, rhs, rcond=None)[0][:nI]
+            PA[:, c] = g
+        for f, i in loc.items():
+            for c, F in enumerate(cfaces_of[A]):
+                if PA[i, c] != 0.0 and (i < nI or cface[f] == F):
+                    # a boundary fine face belongs to one coarse face only; its value is written by the lower agglomerate
+                    if i >= nI and F_low[F] != A:
+                        continue
+                    rows_u.append(f); cols_u.append(F); vals_u.append(PA[i, c])
+        Mc = PA.T @ MA @ PA
+        c_dofs.extend(cfaces_of[A])
+        c_ptr.append(len(c_dofs))
+        c_mats.append(0.5 * (Mc + Mc.T).ravel())
+        c_mptr.append(c_mptr[-1] + Mc.size)
+    fine.P_u = _csr(sp.coo_matrix((vals_u, (rows_u, cols_u)), shape=(Nf, nF)))
+    fine.P_s = _csr(sp.coo_matrix((np.ones(Ne), (np.arange(Ne), part)), shape=(Ne, nA)))
+    # ---- coarse D, B, boundary ----
+    r, c, v = [], [], []
+    for F in range(nF):
+        r.append(F_low[F]); c.append(F); v.append(1.0)
+        if F_high[F] >= 0:
+            r.append(F_high[F]); c.append(F); v.append(-1.0)
+    Binc_c = _csr(sp.coo_matrix((v, (r, c)), shape=(nA, nF)))
+    D_c = _csr(sp.diags(1.0 / volA) @ Binc_c)
+    bsel = [F for F in range(nF) if F_high[F] < 0]
+    return LevelData(dim=fine.dim, Ne=nA, Nf=nF, elem_ptr=np.array(c_ptr, dtype=np.int32),
+                     elem_dofs=np.array(c_dofs, dtype=np.int32), elem_mat_ptr=np.array(c_mptr, dtype=np.int64),
+                     elem_mat=np.concatenate(c_mats), Wdiag=volA.copy(), D=D_c, B=Binc_c,
+                     bdr_face=np.array(bsel, dtype=np.int32), bdr_attr=np.array([F_attr[F] for F in bsel], dtype=np.int32),
+                     bdr_sign=np.ones(len(bsel)))
+
+
+def build_agglomerated_hierarchy(fine: LevelData, nlevels: int, target: int = 8, seed: int = 0) -> List[LevelData]:
+    """`fine` plus nlevels - 1 levels of irregular agglomerates of about `target` elements (unstructured coarsening)."""
+    levels = [fine]
+    for l in range(nlevels - 1):
+        part = greedy_partition(levels[-1], target, seed + l)
+        levels.append(coarsen_by_agglomeration(levels[-1], part))
+    return levels
+
+
+# --------------------------------------------------------------------------------------
 # host-once setup that the reference performs in BuildHierarchy / Build*Functional
 # --------------------------------------------------------------------------------------
 @dataclass

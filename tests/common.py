@@ -218,3 +218,15 @@ def spe10_problem(scale=0.25, nlevels=4):
     L = H.build_box_hierarchy(n, [1200.0, 2200.0, 170.0], nlevels)
     return dict(levels=L, sampler=H.build_sampler_levels(L), darcy=H.build_darcy_levels(L, **H.SPE10_BC),
                 alpha=H.spde_alpha(100.0), g=H.matern_scaling_coefficient(100.0, 3), nlevels=nlevels, grid=n)
+
+
+@functools.lru_cache(maxsize=None)
+def agglomerated_problem(n=8, nlevels=3, corlen=0.3, target=8, seed=1, tets=False):
+    """Unstructured coarsening ("Unstructured coarsening" = true in the reference's drivers: METIS agglomerates +
+    ParELAG's order-0 coarse spaces, /root/reference/src/Utilities.cpp:125-155): hex n^3 (or Kuhn tetrahedra) on [0,2]^3
+    with irregular agglomerates of ~`target` elements per level; coarse agglomerates have 4-18 faces, so the operators
+    have rows of up to ~35 entries (the structured meshes stop at 7)."""
+    fine = (H.build_tet_hierarchy(n, 2.0, 1) if tets else H.build_box_hierarchy([n] * 3, [2.0] * 3, 1))[0]
+    L = H.build_agglomerated_hierarchy(fine, nlevels, target=target, seed=seed)
+    return dict(levels=L, sampler=H.build_sampler_levels(L), darcy=H.build_darcy_levels(L, **H.MLMC_DEFAULT_BC),
+                alpha=H.spde_alpha(corlen), g=H.matern_scaling_coefficient(corlen, 3), nlevels=nlevels)

@@ -695,3 +695,37 @@ def test_full_size_workload_properties():
     finally:
         c.close()
         c1.close()
+
+
+@pytest.mark.parametrize("tets", [False, True])
+def test_unstructured_agglomerates_match_oracle(tets):
+    """Irregular agglomerates with ParELAG-style order-0 coarse spaces (what "Unstructured coarsening" hands over): dense
+    agglomerate mass blocks of up to ~18 x 18, operator rows of up to ~35 entries (beyond the 8-entry staging buffers:
+    the entries of those slices are read from L2).  Darcy solutions, sampler fields and MLMC rows on every level against
+    the oracle."""
+    from common import agglomerated_problem, make_context, make_oracle
+    p = agglomerated_problem(n=4 if tets else 8, nlevels=3, tets=tets)
+    o = make_oracle(p)
+    c = make_context(p, True, 1e-12, 1e-30, 3000)
+    try:
+        rng = np.random.default_rng(8)
+        for lev in range(p["nlevels"]):
+            d, sl = p["darcy"][lev], p["sampler"][lev]
+            k = np.exp(rng.standard_normal((3, d.Ne)))
+            Q, C, sol, it = c.darcy_solve_batch(lev, k, want_sol=True)
+            xi = rng.standard_normal((3, sl.Ne))
+            s, emb, _ = c.sampler_eval_batch(lev, xi)
+            for j in range(3):
+                Qo, _, so, _ = o.darcy_solve(lev, k[j], want_sol=True)
+                assert rel_l2(sol[j], so) < FIELD_TOL and Q[j] == pytest.approx(Qo, rel=1e-8)
+                fo, eo, _ = o.sampler_eval(lev, xi[j])
+                assert rel_l2(emb[j], eo) < FIELD_TOL and rel_l2(s[j], fo) < FIELD_TOL
+        pos = 0
+        for lev, ns in [(2, 5), (1, 6), (0, 5)]:
+            sums, rows, _ = c.mlmc_level_batch(lev, ns, pos, want_rows=True)
+            osums, orows, _ = o.mlmc_level(lev, ns, pos, nthreads=2)
+            assert np.allclose(rows[:, :3], orows[:, :3], rtol=1e-7, atol=1e-9)
+            assert np.allclose(sums, osums, rtol=1e-6)
+            pos += ns * p["sampler"][lev].Ne
+    finally:
+        c.close()

@@ -316,3 +316,36 @@ def test_bayes_level_oracle():
         assert rows[j, 4] == 2 * p["darcy"][0].N + 2 * p["darcy"][1].N
     assert sums[10] == pytest.approx(rows[:, 0].sum()) and sums[4] == pytest.approx(rows[:, 2].sum())
     assert 0.0 < rows[:, 2].min() and rows[:, 2].max() <= 1.0
+
+
+def test_agglomerated_hierarchy_properties_and_oracle_solves():
+    """Unstructured agglomerates: the coarse spaces commute with the divergence and are Galerkin (exact sequence
+    D_f P_u = P_s D_c, P_u^T M_f P_u = M_c); the oracle's solves on every level agree with a sparse direct solve."""
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spla
+    from common import agglomerated_problem
+    p = agglomerated_problem()
+    L = p["levels"]
+    for l in range(p["nlevels"] - 1):
+        f, c = L[l], L[l + 1]
+        assert abs(f.D @ f.P_u - f.P_s @ c.D).max() < 1e-10
+        assert abs(f.P_u.T @ f.assemble_M() @ f.P_u - c.assemble_M()).max() < 1e-12
+    assert max(np.diff(L[1].elem_ptr)) > 8                      # wider than anything the structured meshes produce
+    o = make_oracle(p)
+    rng = np.random.default_rng(4)
+    for lev in range(p["nlevels"]):
+        d, lv = p["darcy"][lev], L[lev]
+        k = np.exp(rng.standard_normal(d.Ne))
+        Q, C, sol, _ = o.darcy_solve(lev, k, want_sol=True)
+        M = lv.assemble_M(k)
+        ess = d.ess_u != 0
+        A = sp.bmat([[M, d.B.T], [d.B, None]]).tolil()
+        rhs = d.rhs.copy()
+        for i in np.nonzero(ess)[0]:
+            A[i, :] = 0
+            A[:, i] = 0
+            A[i, i] = 1
+            rhs[i] = 0
+        ref = spla.spsolve(A.tocsc(), rhs)
+        assert rel_l2(sol, ref) < 1e-8
+        assert Q == pytest.approx(d.obs @ ref, rel=1e-8) and C == d.N
