@@ -928,8 +928,9 @@ SPE10_BC = dict(ess_attr=[1, 0, 1, 0, 1, 1], obs_attr=[0, 1, 0, 0, 0, 0], inflow
 # binary dump read by the C++ host layer (parelagmc_b200/host/HierarchyData.cpp)
 # --------------------------------------------------------------------------------------
 def dump_problem(path: str, sampler_levels: List[SamplerLevel], darcy_levels: List[DarcyLevel], dim: int,
-                 corlen: float) -> None:
-    """Write the host-once hierarchy data in the "PMCH2" layout of `HierarchyData::Load`."""
+                 corlen: float, gobs: Optional[Sequence[np.ndarray]] = None) -> None:
+    """Write the host-once hierarchy data in the "PMCH2" layout of `HierarchyData::Load` ("PMCH3" when the observation
+    functionals of a BayesianInverseProblem, `gobs[level]` = array [m, Ne], travel with it)."""
     import struct
 
     def ivec(f, a):
@@ -953,7 +954,7 @@ def dump_problem(path: str, sampler_levels: List[SamplerLevel], darcy_levels: Li
         dvec(f, m.data)
 
     with open(path, "wb") as f:
-        f.write(b"PMCH2\0\0\0")
+        f.write(b"PMCH3\0\0\0" if gobs is not None else b"PMCH2\0\0\0")
         f.write(struct.pack("<iid", len(sampler_levels), dim, corlen))
         for s, d in zip(sampler_levels, darcy_levels):
             f.write(struct.pack("<ii", s.Ne, s.Nf))
@@ -973,3 +974,7 @@ def dump_problem(path: str, sampler_levels: List[SamplerLevel], darcy_levels: Li
             dvec(f, d.ess_data)
             dvec(f, d.rhs)
             dvec(f, d.obs)
+        if gobs is not None:
+            f.write(struct.pack("<i", int(np.asarray(gobs[0]).shape[0])))
+            for g in gobs:
+                dvec(f, np.asarray(g).ravel())

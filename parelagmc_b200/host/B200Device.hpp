@@ -32,6 +32,9 @@ public:
         return d;
     }
     pmc_handle handle() const { return h_; }
+    /// The NormalDistributionSampler whose (mu, sigma, split) the handle's generator currently carries: several samplers
+    /// can share one device (the prior and the observation noise of BayesianInverseProblem), each re-binds when it is used.
+    const void *rng_owner = nullptr;
     int nlevels() const { return nlevels_; }
     void check(int rc, const char *what) const
     {

@@ -51,7 +51,8 @@ HierarchyData HierarchyData::Load(const std::string &path)
     Reader r(path);
     char magic[8];
     r.raw(magic, 8);
-    if (memcmp(magic, "PMCH2\0\0\0", 8) != 0) throw std::runtime_error("HierarchyData::Load: bad magic in " + path);
+    const bool v3 = memcmp(magic, "PMCH3\0\0\0", 8) == 0;
+    if (!v3 && memcmp(magic, "PMCH2\0\0\0", 8) != 0) throw std::runtime_error("HierarchyData::Load: bad magic in " + path);
     HierarchyData h;
     h.nlevels = r.i32();
     h.dim = r.i32();
@@ -71,6 +72,16 @@ HierarchyData HierarchyData::Load(const std::string &path)
         d.elem_ptr = r.ivec(); d.elem_dofs = r.ivec(); d.elem_mat = r.dvec();
         d.B = r.csr(); d.Pp = r.csr();
         d.ess_u = r.ivec(); d.ess_data = r.dvec(); d.rhs = r.dvec(); d.obs = r.dvec();
+    }
+    if (v3) {
+        h.n_obs = r.i32();
+        if (h.n_obs < 0 || h.n_obs > 4096) throw std::runtime_error("HierarchyData::Load: bad number of observations");
+        h.gobs.resize(h.nlevels);
+        for (int l = 0; l < h.nlevels; ++l) {
+            h.gobs[l] = r.dvec();
+            if (h.gobs[l].size() != (size_t)h.n_obs * (size_t)h.darcy[l].Ne)
+                throw std::runtime_error("HierarchyData::Load: observation functionals of the wrong size");
+        }
     }
     return h;
 }

@@ -38,7 +38,13 @@ struct HierarchyData {
     double corlen = 0.1;
     std::vector<SamplerLevelData> sampler;
     std::vector<DarcyLevelData> darcy;
-    // Reads the binary dump (magic "PMCH2"); throws std::runtime_error on malformed input.
+    // BayesianInverseProblem set-up data (src/BayesianInverseProblem.cpp:46-104), optional: n_obs pressure functionals
+    // g_obs_func[i][level], stored per level as [n_obs][Ne(level)] (un-normalised: element volumes of the marked elements
+    // on level 0, P^T of the finer one below)
+    int n_obs = 0;
+    std::vector<std::vector<double>> gobs;
+    // Reads the binary dump (magic "PMCH2", or "PMCH3" = PMCH2 + the observation functionals); throws
+    // std::runtime_error on malformed input.
     static HierarchyData Load(const std::string &path);
 };
 

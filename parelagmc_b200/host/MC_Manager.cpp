@@ -50,6 +50,7 @@ void MC_Manager::InitRun(int nsamples)
     if (batched && nsamples > 0) {
         // the ranks own disjoint slices of the realisations; one all-reduce of {sums, time} per InitRun (RankComm.hpp)
         pmc_handle h = bs->Device()->handle();
+        bs->Distribution().Bind();
         if (rank > 1 && !comm_ready) {
             InitDeviceComm(comm, h);
             comm_ready = true;

@@ -98,6 +98,7 @@ void MLMC_Manager::InitRun(std::vector<int> &level_nsamples_init)
         // stream positions are the ones the reference's sequential Sample() calls would have consumed: coarsest level
         // first, then nlevels-2 .. 0 (src/MLMC_Manager.cpp:110,140).
         pmc_handle main_h = bs->Device()->handle();
+        bs->Distribution().Bind();
         if (rank > 1 && !comm_ready) {   // the ranks own disjoint slices of every level's realisations (RankComm.hpp)
             InitDeviceComm(comm, main_h);
             comm_ready = true;

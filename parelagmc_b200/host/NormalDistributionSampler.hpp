@@ -30,6 +30,8 @@ public:
     void operator()(mfem::Vector &v);
 
     /// Stream position of the next draw / reserve `n` draws for a batched device-side generation.
+    /// Make the device generator carry this sampler's distribution (no-op while it already does).
+    void Bind();
     uint64_t Position() const { return pos_; }
     uint64_t Advance(uint64_t n) { uint64_t p = pos_; pos_ += n; return p; }
     const std::shared_ptr<B200Device> &Device() const { return dev_; }
@@ -37,6 +39,7 @@ public:
 private:
     std::shared_ptr<B200Device> dev_;
     double mu_, sigma_;
+    int nparts_ = 1, mypart_ = 0;
     uint64_t pos_ = 0;
 };
 }  // namespace parelagmc

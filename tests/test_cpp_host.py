@@ -25,7 +25,7 @@ def _dump(tmp_path, n, nl):
 def test_host_layer_builds_and_roundtrips_dump(tmp_path):
     from parelagmc_b200 import capi
     capi.build()
-    for f in ("libparelagmc_b200_host.so", "MLMC.exe", "SLMC.exe", "DarcyTest.exe"):
+    for f in ("libparelagmc_b200_host.so", "MLMC.exe", "SLMC.exe", "DarcyTest.exe", "PDESamplerTest.exe", "LikelihoodExample.exe"):
         assert os.path.exists(os.path.join(LIB, f))
     p, path = _dump(tmp_path, 4, 2)
     assert os.path.getsize(path) > 1000
@@ -88,3 +88,29 @@ def test_cpp_slmc_driver(tmp_path):
     out = subprocess.run([os.path.join(LIB, "SLMC.exe"), "--hierarchy", path, "--nsamples", "16", "--mse", "1e6",
                           "--log", str(tmp_path / "SLMC.dat")], capture_output=True, text=True, timeout=600).stdout
     assert "FINAL SLMC ERRORS" in out and "SLMC Manager Errors:" in out
+
+
+@pytest.mark.gpu
+def test_cpp_drivers_reproduce_reference_ctest_regexes(tmp_path):
+    """The reference's ctest PASS_REGULAR_EXPRESSIONs (/root/reference/examples/CMakeLists.txt:83-115) applied to the
+    output of the C++ drivers of the host layer (per-sample Sample / Eval / SolveFwd_RtnPressure through the reference's
+    class interfaces and BayesianInverseProblem), on the reference's default problems in MFEM's element numbering."""
+    from common import reference_enlarged_problem, reference_sampler_problem
+    p = reference_sampler_problem()
+    path = str(tmp_path / "sampler.pmch")
+    H.dump_problem(path, p["sampler"], p["darcy"], 3, 0.1)
+    out = subprocess.run([os.path.join(LIB, "PDESamplerTest.exe"), "--hierarchy", path], capture_output=True, text=True,
+                         timeout=600).stdout
+    for rx in (r"1.2593[0-9]*", r"9.3103[0-9]*", r"6.3853[0-9]*"):        # PDESamplerTest (:83-87)
+        assert re.search(rx, out), out
+    q = reference_enlarged_problem()
+    path = str(tmp_path / "bayes.pmch")
+    H.dump_problem(path, q["sampler"], q["darcy"], 3, 0.1, gobs=q["gobs"])
+    out = subprocess.run([os.path.join(LIB, "LikelihoodExample.exe"), "--hierarchy", path], capture_output=True, text=True,
+                         timeout=600).stdout
+    for rx in (r"L = 0 : 0.9279[0-9]*", r"L = 1 : 0.9578[0-9]*", r"L = 2 : 0.9269[0-9]*"):     # LikelihoodEvaluation (:97-102)
+        assert re.search(rx, out), out
+    out = subprocess.run([os.path.join(LIB, "LikelihoodExample.exe"), "--hierarchy", path, "--ratio-mc"], capture_output=True,
+                         text=True, timeout=600).stdout
+    # BayesianInverseProblem_MC_RatioEstimator (:110-115)
+    assert re.search(r"0 [ ]*  1.987[0-9 ]*  0.07749[0-9 ]* 0.8569[0-9 ]*  0.009691[0-9 ]* 2.319[0-9 ]*  2.332[0-9 ]*", out), out
