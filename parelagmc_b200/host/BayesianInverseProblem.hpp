@@ -34,6 +34,7 @@ public:
     PhysicalMLSolver &GetSolver() { return solver; }
     MLSampler &GetPrior() { return prior; }
     const mfem::Vector &ObservationalData() const { return G_obs; }
+    void SetObservationalData(const mfem::Vector &g) { G_obs = g; }
     double Noise() const { return noise; }
     /// Hand functionals, G_obs and the noise variance to the device (needed by the batched ratio-estimator loops).
     void UploadObservations(B200Device &dev);

@@ -25,7 +25,8 @@ def _dump(tmp_path, n, nl):
 def test_host_layer_builds_and_roundtrips_dump(tmp_path):
     from parelagmc_b200 import capi
     capi.build()
-    for f in ("libparelagmc_b200_host.so", "MLMC.exe", "SLMC.exe", "DarcyTest.exe", "PDESamplerTest.exe", "LikelihoodExample.exe"):
+    for f in ("libparelagmc_b200_host.so", "MLMC.exe", "SLMC.exe", "DarcyTest.exe", "PDESamplerTest.exe", "LikelihoodExample.exe",
+              "RatioEstimator_MLMC.exe"):
         assert os.path.exists(os.path.join(LIB, f))
     p, path = _dump(tmp_path, 4, 2)
     assert os.path.getsize(path) > 1000
@@ -114,3 +115,23 @@ def test_cpp_drivers_reproduce_reference_ctest_regexes(tmp_path):
                          text=True, timeout=600).stdout
     # BayesianInverseProblem_MC_RatioEstimator (:110-115)
     assert re.search(r"0 [ ]*  1.987[0-9 ]*  0.07749[0-9 ]* 0.8569[0-9 ]*  0.009691[0-9 ]* 2.319[0-9 ]*  2.332[0-9 ]*", out), out
+
+
+@pytest.mark.gpu
+def test_cpp_bayes_ratio_manager(tmp_path):
+    """C++ ML_BayesRatio_Manager: the batched level loops (pmc_bayes_level_batch) against the reference's per-sample loop
+    through BayesianInverseProblem (same stream positions), and against the Python twin."""
+    from common import bayes_problem
+    from parelagmc_b200 import managers as MG
+    p = bayes_problem()
+    path = str(tmp_path / "bayes8.pmch")
+    H.dump_problem(path, p["sampler"], p["darcy"], 3, 0.1, gobs=p["gobs"])
+    args = [os.path.join(LIB, "RatioEstimator_MLMC.exe"), "--hierarchy", path, "--samples", "5,9", "--mse", "1e6", "--rel-tol",
+            "1e-10", "--dof-cost"]
+    outs = [subprocess.run(args + extra, capture_output=True, text=True, timeout=600).stdout for extra in ([], ["--per-sample"])]
+    est = [float(re.findall(r"Ratio Estimate\s+([-0-9.e+]+)", o)[-1]) for o in outs]
+    assert "FINAL ML_BayesRatio_Manager ERRORS" in outs[0]
+    assert est[0] == pytest.approx(est[1], rel=1e-6)
+    ey = [[float(x) for x in re.findall(r"E\[Y_R\]\s+(.*)", o)[-1].split()] for o in outs]
+    assert np.allclose(ey[0], ey[1], rtol=1e-6)
+    assert 1.0 < est[0] < 4.0
