@@ -79,7 +79,10 @@ int pmc_set_preconditioner(pmc_handle h, int mass_degree, int schur_degree, doub
  * src/PDESampler_Legacy.cpp:172-176 -- , -1 = CG when alpha W dominates the Schur complement, i.e. for short correlation
  * lengths), max_vlevels (depth of the Schur V-cycle; 0 = full hierarchy, -1 = decide from the mass
  * term, sampler only), amg (coarse spaces of the Schur V-cycle: 0 = the hierarchy's L2 prolongators, 1 = strength-aware
- * pairwise aggregation built at set-up, -1 = aggregation only when the couplings are anisotropic)}; and the launch
+ * pairwise aggregation built at set-up, -1 = aggregation only when the couplings are anisotropic), amg_passes (pairwise
+ * matching passes per level of that aggregation: aggregates of up to 2^passes rows; default 3), amg_smooth (damping of the
+ * Jacobi step that smooths its tentative prolongators at set-up -- smoothed aggregation on the strength-filtered operator at
+ * k = 1; 0 = plain aggregation; default 0.9)}; and the launch
  * shape of the solver kernel (all optional, the library chooses): "max_batch", "cta_threads" (64/128/256/512),
  * "cluster_size" (1/2/4/8 CTAs of a thread-block cluster per tile of 4 realisations), "group_size" (G > 1: G co-resident
  * CTAs of a cooperative launch per tile, for one or two tiles of very large levels; -1 = never), "solo_rows" (in a group,

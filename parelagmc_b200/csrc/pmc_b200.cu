@@ -112,6 +112,11 @@ struct PrecCfg {
     double coarse_ratio = 30.0;
     double omega = 1.0;        // over-correction factor of the piecewise-constant coarse-grid correction
     bool omega_user = false;   // set through pmc_set_option: keep it whatever coarse spaces are chosen
+    int amg_passes = 0;        // aggregation coarse spaces only: pairwise matching passes per level (aggregates of up to
+                               // 2^passes rows); 0 = default (3)
+    double amg_smooth = -1.0;  // aggregation coarse spaces only: damping of one Jacobi smoothing step applied to the tentative
+                               // prolongators at set-up (smoothed aggregation on the strength-filtered operator at k = 1,
+                               // fixed across realisations); 0 = plain aggregation, < 0 = default (0.9)
     int max_vlevels = 0;       // 0: as deep as the hierarchy allows; -1 (sampler): decide from the mass term
     int method = -1;           // sampler only: 0 = MINRES on the saddle system, 1 = Jacobi-PCG on its SPD form (u eliminated
                                // system (M + alpha^-1 B^T W^-1 B) u = alpha^-1 B^T W^-1 f), -1 = PCG when alpha W dominates
@@ -231,6 +236,7 @@ struct pmc_context_s {
     bool staging = true;  // stage operator entries through shared memory (option "stage_operators")
     bool defer_x = true;  // option "defer_x"
     bool fuse_coarse = true;  // option "fuse_coarse"
+    bool stage_wide = true;   // option "stage_wide": slices wider than the staging buffers are staged chunk by chunk
     bool split_apply = true;  // option "split_apply": Darcy operator applied per row block (RT rows weighted, pressure rows plain)
     bool renumber = true;  // option "renumber": first-touch renumbering of the RT dofs inside the library
     bool single_wave = false;  // option "single_wave": prefer one wave of smaller CTAs over a mostly empty second wave
@@ -554,15 +560,53 @@ static HCsr pairwise_aggregate(const HCsr &S, double theta)
 
 // Aggregation chain: two pairwise passes per level (aggregates of up to four strongly coupled nodes: semi-coarsening
 // along the strong direction of anisotropic operators), Galerkin coarse operators, until the level is small.
-static std::vector<HCsr> aggregation_chain(HCsr S, int min_size, int max_levels)
+// P <- (I - omega D_f^-1 S_f) P with S_f the strength-filtered operator (couplings weaker than theta times the row's
+// strongest are lumped onto the diagonal, so the smoothing widens P along the strong direction only and the Galerkin
+// operators stay sparse) -- smoothed aggregation with a prolongator that is fixed across realisations.
+static HCsr smooth_prolongator(const HCsr &S, const HCsr &P, double omega, double theta)
+{
+    const int n = S.rows;
+    HCsr Sf;
+    Sf.rows = Sf.cols = n;
+    Sf.rowptr.assign(n + 1, 0);
+    std::vector<double> diag(n, 0.0);
+    for (int i = 0; i < n; ++i) {
+        double smax = 0.0, d = 0.0;
+        for (int p = S.rowptr[i]; p < S.rowptr[i + 1]; ++p)
+            if (S.col[p] != i) smax = std::max(smax, -S.val[p]);
+        for (int p = S.rowptr[i]; p < S.rowptr[i + 1]; ++p) {
+            const int j = S.col[p];
+            if (j == i) d += S.val[p];
+            else if (-S.val[p] >= theta * smax && smax > 0.0) { Sf.col.push_back(j); Sf.val.push_back(S.val[p]); }
+            else d += S.val[p];   // weak coupling: lumped
+        }
+        Sf.col.push_back(i);
+        Sf.val.push_back(d);
+        diag[i] = d;
+        Sf.rowptr[i + 1] = (int)Sf.col.size();
+    }
+    HCsr SP = csr_matmul(Sf, P);
+    std::vector<Coo> e;
+    e.reserve(SP.col.size() + P.col.size());
+    for (int i = 0; i < n; ++i) {
+        for (int p = P.rowptr[i]; p < P.rowptr[i + 1]; ++p) e.push_back({i, P.col[p], P.val[p]});
+        const double w = diag[i] > 0.0 ? omega / diag[i] : 0.0;
+        for (int p = SP.rowptr[i]; p < SP.rowptr[i + 1]; ++p) e.push_back({i, SP.col[p], -w * SP.val[p]});
+    }
+    return csr_from_coo(n, P.cols, e);
+}
+
+static std::vector<HCsr> aggregation_chain(HCsr S, int min_size, int max_levels, double smooth = 0.0, int passes = 2)
 {
     std::vector<HCsr> Ps;
     while (S.rows > min_size && (int)Ps.size() < max_levels) {
-        HCsr P1 = pairwise_aggregate(S, 0.25);
-        HCsr S1 = csr_matmul(csr_transpose(P1), csr_matmul(S, P1));
-        HCsr P2 = pairwise_aggregate(S1, 0.25);
-        HCsr P = csr_matmul(P1, P2);
+        HCsr P = pairwise_aggregate(S, 0.25);
+        for (int pass = 1; pass < passes; ++pass) {
+            HCsr Sp = csr_matmul(csr_transpose(P), csr_matmul(S, P));
+            P = csr_matmul(P, pairwise_aggregate(Sp, 0.25));
+        }
         if (P.cols > 0.8 * S.rows) break;
+        if (smooth > 0.0) P = smooth_prolongator(S, P, smooth, 0.25);
         S = csr_matmul(csr_transpose(P), csr_matmul(S, P));
         Ps.push_back(std::move(P));
     }
@@ -695,7 +739,9 @@ static int prepare_sampler(Ctx *c, int level)
         }
     }
     if (sys.cfg.max_vlevels != 1 && (sys.cfg.amg == 1 || (sys.cfg.amg < 0 && couplings_anisotropic(S)))) {
-        sys.own_P = aggregation_chain(S, 64, 16);
+        if (sys.cfg.amg_smooth < 0.0) sys.cfg.amg_smooth = 0.9;   // sampler at half-scale SPE10: 80 -> 67 its, 36.7 -> 29.7 ms
+        if (sys.cfg.amg_passes <= 0) sys.cfg.amg_passes = 3;
+        sys.own_P = aggregation_chain(S, 64, 16, sys.cfg.amg_smooth, sys.cfg.amg_passes);
         Ps.clear();
         for (const HCsr &P : sys.own_P) Ps.push_back(&P);
     }
@@ -852,13 +898,18 @@ static int prepare_darcy(Ctx *c, int level)
             for (int p = Bs.rowptr[i]; p < Bs.rowptr[i + 1]; ++p) Bs.val[p] /= (Md[Bs.col[p]] > 0 ? Md[Bs.col[p]] : 1.0);
         HCsr S1 = csr_matmul(Bs, Bet);
         if (sys.cfg.amg == 1 || couplings_anisotropic(S1)) {
-            sys.own_P = aggregation_chain(S1, 64, 16);
+            // Smoothed aggregation: aggregates of up to 8 rows along the strong couplings (three pairwise passes), tentative
+            // prolongators smoothed by one damped Jacobi step on the strength-filtered operator at k = 1 (fixed across
+            // realisations; the Galerkin values stay per sample).  Measured on the SPE10 geometry at half scale
+            // (tools/spe10_prec_sweep.py), Darcy iterations per solve / ms for 8 realisations: plain aggregates of 4 with
+            // omega 2.5 / 1.5: 152 / 94 its, 93 / 59 ms; smoothed (0.9) aggregates of 4, omega 1.25: 40 its, 59 ms (denser
+            // coarse operators eat the gain); smoothed aggregates of 8, omega 1.25: 59 its, 41.5 ms.
+            if (sys.cfg.amg_smooth < 0.0) sys.cfg.amg_smooth = 0.9;
+            if (sys.cfg.amg_passes <= 0) sys.cfg.amg_passes = 3;
+            sys.own_P = aggregation_chain(S1, 64, 16, sys.cfg.amg_smooth, sys.cfg.amg_passes);
             Ps.clear();
             for (const HCsr &P : sys.own_P) Ps.push_back(&P);
-            // pairwise aggregates (4 rows per aggregate along the strong direction) need less over-correction than the
-            // hierarchy's 8-element agglomerates: measured on the SPE10 geometry at half scale, omega = 1.0 / 1.25 / 1.5 /
-            // 1.75 / 2.5 -> 143 / 104 / 94 / 99 / 152 Darcy iterations per solve (tools/spe10_prec_sweep.py)
-            if (!sys.cfg.omega_user) sys.cfg.omega = 1.5;
+            if (!sys.cfg.omega_user) sys.cfg.omega = sys.cfg.amg_smooth > 0.0 ? 1.25 : 1.5;
         }
     }
     if (sys.cfg.max_vlevels > 0 && (int)Ps.size() > sys.cfg.max_vlevels - 1) Ps.resize(sys.cfg.max_vlevels - 1);
@@ -968,6 +1019,7 @@ struct Program {
     bool defer_x = true;  // MINRES: apply the solution updates of an iteration pair in one pass (option "defer_x")
     bool fuse_coarse = true;  // coarsest Chebyshev iteration as one shared-memory operation (option "fuse_coarse")
     bool split_apply = true;  // Darcy block operator applied as two operations (option "split_apply")
+    bool chunked = true;      // wide slices staged chunk by chunk instead of read from L2 (option "stage_wide")
     int pc() const { return (int)ops.size(); }
     Op &add(int kind, int kclass, int n, double rows_moved, double matrix_bytes = 0.0)
     {
@@ -991,7 +1043,8 @@ static void emit_spmm(Program &pg, int kclass, int ep, const DevCsr &A, VecRef V
     Op &o = pg.add(OP_SPMM, kclass, A.rows, rows_moved, A.matrix_bytes());
     o.flags = (ep << F_EP_SHIFT) | (A.weighted ? F_WEIGHTED : 0) | ((ep == EP_CHEB && A.weighted) ? F_BDINV : 0) |
               (dot_slot >= 0 ? F_DOT : 0) | (dot_acc ? F_DOT_ACC : 0) | (dot_with_r ? F_DOT_WITH_R : 0) |
-              ((pg.staging && A.max_width <= STW) ? F_STAGED : 0);
+              ((pg.staging && A.max_width <= STW) ? F_STAGED : 0) |
+              ((pg.staging && pg.chunked && A.max_width > STW) ? F_CHUNKED : 0);
     o.rowptr = A.soff; o.pk = A.spk;
     o.fixed = dinv_fixed;
     o.x = x; o.y = y; o.r = r; o.d = d; o.w = dinv_b; o.v = V;
@@ -1910,11 +1963,14 @@ int pmc_set_option(pmc_handle c, const char *key, double value)
         else if (k == "max_vlevels") g->max_vlevels = (int)value;
         else if (k == "method") g->method = (int)value;
         else if (k == "amg") g->amg = (int)value;
+        else if (k == "amg_smooth" && value >= 0) g->amg_smooth = value;
+        else if (k == "amg_passes" && value >= 1 && value <= 6) g->amg_passes = (int)value;
         else return fail(c, PMC_ERR_ARG, "pmc_set_option: bad key or value '%s' = %g", key, value);
         return PMC_OK;
     }
     if (k == "cache_results") { c->cache_results = value != 0; return PMC_OK; }
     if (k == "split_apply") { c->split_apply = value != 0; return PMC_OK; }
+    if (k == "stage_wide") { c->stage_wide = value != 0; return PMC_OK; }
     if (k == "max_batch" && value >= 0) c->max_batch = (int)value;
     else if (k == "cta_threads") c->force_nt = (int)value;
     else if (k == "cluster_size") c->force_cs = (int)value;
@@ -2080,7 +2136,7 @@ int pmc_clone(pmc_handle src, pmc_handle *out)
     c->cfg_sampler = src->cfg_sampler; c->cfg_darcy = src->cfg_darcy;
     c->max_batch = src->max_batch; c->force_nt = src->force_nt; c->force_cs = src->force_cs; c->staging = src->staging;
     c->defer_x = src->defer_x; c->fuse_coarse = src->fuse_coarse; c->single_wave = src->single_wave; c->renumber = src->renumber;
-    c->force_group = src->force_group; c->solo_rows = src->solo_rows; c->cache_results = src->cache_results; c->split_apply = src->split_apply;
+    c->force_group = src->force_group; c->solo_rows = src->solo_rows; c->cache_results = src->cache_results; c->split_apply = src->split_apply; c->stage_wide = src->stage_wide;
     c->store = src->store;   // one copy of the operators per device, freed with the last handle that uses them
     c->s = src->s;           // level descriptors: host arrays by value, device pointers into the shared store
     c->d = src->d;
@@ -2361,6 +2417,7 @@ int pmc_sampler_eval_batch(pmc_handle c, int level, int xi_level, int nsamples, 
     pg.defer_x = c->defer_x;
     pg.fuse_coarse = c->fuse_coarse;
     pg.split_apply = c->split_apply;
+    pg.chunked = c->stage_wide;
     const Off rhs = emit_restrict(pg, c, xi_level, level, bufA, bufB);
     const Off t1 = (rhs == bufA) ? bufB : bufA;
     Off x0 = -1;
@@ -2432,6 +2489,7 @@ static int darcy_host_batch(Ctx *c, int level, int nsamples, const double *k, co
     pg.defer_x = c->defer_x;
     pg.fuse_coarse = c->fuse_coarse;
     pg.split_apply = c->split_apply;
+    pg.chunked = c->stage_wide;
     if (apply_only) {
         Solver sv{&sys, &ws, vr(k_ext, Ne + 1)};
         emit_fill(pg, vr(k_ext, Ne + 1, Ne), 1, 1.0);  // weight of the fixed entries
@@ -2526,6 +2584,7 @@ static int level_batch(Ctx *c, int level, int nlevels, int nsamples, uint64_t po
     pg.defer_x = c->defer_x;
     pg.fuse_coarse = c->fuse_coarse;
     pg.split_apply = c->split_apply;
+    pg.chunked = c->stage_wide;
     // Sample(level, xi) fused with rhs_s = -g W^{1/2} xi  (/root/reference/src/PDESampler.cpp:336-340, :352-358)
     {
         Op &o = pg.add(OP_RNG, KC_RNG, Ne, Ne);
@@ -2743,6 +2802,7 @@ int pmc_bayes_level_batch(pmc_handle c, int level, int nlevels, int nsamples, ui
     pg.defer_x = c->defer_x;
     pg.fuse_coarse = c->fuse_coarse;
     pg.split_apply = c->split_apply;
+    pg.chunked = c->stage_wide;
     std::vector<int> rng_ops;
     for (int draw = 0; draw < 2; ++draw) {  // draw 0: zxi -> Z (likelihood); draw 1: xi -> R = Q * likelihood
         rng_ops.push_back(pg.pc());

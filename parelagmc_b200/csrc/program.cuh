@@ -87,6 +87,7 @@ enum {
     // grid-group mode only (a tile owned by G CTAs of a cooperative launch):
     F_SOLO = 2048,       // small operation: executed by the group's first CTA alone
     F_LOCAL_SYNC = 4096, // nothing this operation writes is read by another CTA before the next group barrier
+    F_CHUNKED = 16384,   // slices wider than STW: their entries are staged chunk by chunk (op_spmm_chunked)
     F_INLOOP = 8192      // inside a Krylov loop: its bytes are credited for the realisations of the tile still iterating only
 };
 
@@ -532,6 +533,137 @@ __device__ __forceinline__ void op_spmm(const Op &o, double *chunk, Smem &sm, St
     while (pass < maxp)
         if ((++pass % PMC_SPMM_SYNC) == 0) __syncthreads();
 #endif
+    if (DOT) block_dot<NTt, CS>(acc, sm, o.slot, (o.flags & F_DOT_ACC) != 0);
+}
+
+// ---- sparse apply for operators with slices wider than the staging buffers (unstructured agglomerates, smoothed
+// aggregation: rows of 10-40 entries) -------------------------------------------------------------------------------
+// Same arithmetic as op_spmm in the same order (bitwise the same results as reading the entries from L2), but a wide
+// slice is staged CHUNK by chunk of STW entries: the pipeline unit is (slice, chunk) instead of slice, each unit is three
+// TMA bulk copies (values, columns, weight indices of the chunk are not adjacent in the packed slice), the row sum is
+// carried across the chunks of a slice and the epilogue runs after the last one.
+template <int NTt, int CS, int EP, bool WEIGHTED, bool BDINV, bool DOT>
+__device__ __forceinline__ void op_spmm_chunked(const Op &o, double *chunk, Smem &sm, StageCtx &sc)
+{
+    constexpr int ES = WEIGHTED ? 16 : 12;
+    constexpr int NW = NTt / 32;
+    const int sub = (threadIdx.x % LPR) * PW;
+    const double *__restrict__ x = tp(o.x, chunk) + sub;
+    double *__restrict__ y = tp(o.y, chunk) + sub;
+    const double *__restrict__ r = (EP == EP_RESID || EP == EP_CHEB) ? tp(o.r, chunk) + sub : nullptr;
+    const double *__restrict__ xd = (EP == EP_AX && DOT && o.r.off >= 0) ? tp(o.r, chunk) + sub : x;
+    double *__restrict__ d = (EP == EP_CHEB) ? tp(o.d, chunk) + sub : nullptr;
+    const double *__restrict__ V = WEIGHTED ? tp(o.v, chunk) + sub : nullptr;
+    const double *__restrict__ dinvb = (EP == EP_CHEB && BDINV) ? tp(o.w, chunk) + sub : nullptr;
+    const int *__restrict__ off = o.rowptr;
+    const unsigned char *__restrict__ pk = o.pk;
+    const double ca = o.ca, cb = o.cb;
+    const bool dot_r = (o.flags & F_DOT_WITH_R) != 0;
+    D2 acc = make_double2(0.0, 0.0);
+    int r0, r1;
+    my_rows<CS>(o, sm, r0, r1);
+    const int sl_end = r1 > r0 ? (r1 + SLICE - 1) / SLICE : 0;
+    const int rs = (threadIdx.x & 31) / LPR;
+    const bool lane0 = (threadIdx.x & 31) == 0;
+    // a unit: chunk c of slice sl (w entries from packed entry k0); sl >= sl_end: none
+    int u_sl[3], u_c[3], u_w[3], u_k0[3];
+    auto first_unit = [&](int j, int sl) {
+        u_sl[j] = sl; u_c[j] = 0; u_w[j] = 0; u_k0[j] = 0;
+        if (sl < sl_end) {
+            u_k0[j] = __ldg(off + sl);
+            u_w[j] = __ldg(off + sl + 1) - u_k0[j];
+        }
+    };
+    auto next_unit = [&](int j, int i) {   // unit j := the one after unit i
+        if ((u_c[i] + 1) * STW < u_w[i]) { u_sl[j] = u_sl[i]; u_c[j] = u_c[i] + 1; u_w[j] = u_w[i]; u_k0[j] = u_k0[i]; }
+        else first_unit(j, u_sl[i] + NW);
+    };
+    auto issue = [&](int j, int buf) {
+        if (!lane0 || u_sl[j] >= sl_end) return;
+        const int kk = min(STW, u_w[j] - u_c[j] * STW);
+        const uint32_t bar = sc.bar + 8 * buf;
+        const uint32_t dst = smem_u32(sc.buf + buf);
+        mbar_arrive_tx(bar, (uint32_t)max(kk, 0) * (SLICE * ES));
+        if (kk <= 0) return;
+        const unsigned char *base = pk + (size_t)u_k0[j] * (SLICE * ES);
+        const size_t w = (size_t)u_w[j], c0 = (size_t)u_c[j] * STW;
+        bulk_g2s(dst, base + c0 * (SLICE * 8), (uint32_t)kk * (SLICE * 8), bar);
+        bulk_g2s(dst + kk * (SLICE * 8), base + w * (SLICE * 8) + c0 * (SLICE * 4), (uint32_t)kk * (SLICE * 4), bar);
+        if (WEIGHTED)
+            bulk_g2s(dst + kk * (SLICE * 12), base + w * (SLICE * 12) + c0 * (SLICE * 4), (uint32_t)kk * (SLICE * 4), bar);
+    };
+    first_unit(0, r0 / SLICE + (threadIdx.x >> 5));
+    next_unit(1, 0);
+    issue(0, 0);
+    issue(1, 1);
+    int st = 0;
+    D2 s = make_double2(0.0, 0.0);
+    while (u_sl[0] < sl_end) {
+        next_unit(2, 1);
+        mbar_wait(sc.bar + 8 * st, (sc.phase >> st) & 1u);
+        sc.phase ^= 1u << st;
+        const int kk = max(0, min(STW, u_w[0] - u_c[0] * STW));
+        const unsigned char *base = sc.buf[st].bytes;
+        const double *__restrict__ eval = reinterpret_cast<const double *>(base) + rs;
+        const int *__restrict__ ecol = reinterpret_cast<const int *>(base + (size_t)kk * (SLICE * 8)) + rs;
+        const int *__restrict__ ewid = ecol + kk * SLICE;
+#pragma unroll 4
+        for (int k = 0; k < kk; ++k) {
+            const double c = eval[k * SLICE];
+            const D2 xv = ld2c(x + (size_t)ecol[k * SLICE] * TW);
+            if (WEIGHTED) {
+                const D2 wv = ld2c(V + (size_t)ewid[k * SLICE] * TW);
+                s.x = fma(c * wv.x, xv.x, s.x);
+                s.y = fma(c * wv.y, xv.y, s.y);
+            } else {
+                s.x = fma(c, xv.x, s.x);
+                s.y = fma(c, xv.y, s.y);
+            }
+        }
+        __syncwarp();   // every lane is done with buffer st before it is refilled
+        issue(2, st);
+        if ((u_c[0] + 1) * STW >= u_w[0]) {   // last chunk of the slice: epilogue
+            const int row = u_sl[0] * SLICE + rs;
+            if (row < r1) {
+                const size_t ro = (size_t)row * TW;
+                D2 rv = make_double2(0.0, 0.0), di = rv, dv = rv, xr = rv, yv = rv;
+                if (EP == EP_RESID || EP == EP_CHEB) rv = ld2c(r + ro);
+                if (EP == EP_ADD) yv = ld2c(y + ro);
+                if (EP == EP_CHEB) {
+                    if (BDINV) di = ld2c(dinvb + ro);
+                    else { const double t = __ldg(o.fixed + row); di = make_double2(t, t); }
+                    if (ca != 0.0) dv = ld2c(d + ro);
+                    xr = ld2c(x + ro);
+                } else if (DOT && !dot_r) xr = ld2c(xd + ro);
+                D2 out;
+                if (EP == EP_AX) out = s;
+                else if (EP == EP_RESID) out = make_double2(rv.x - s.x, rv.y - s.y);
+                else if (EP == EP_ADD) out = make_double2(fma(ca, s.x, yv.x), fma(ca, s.y, yv.y));
+                else {
+                    D2 dn = make_double2(cb * di.x * (rv.x - s.x), cb * di.y * (rv.y - s.y));
+                    if (ca != 0.0) {
+                        dn.x = fma(ca, dv.x, dn.x);
+                        dn.y = fma(ca, dv.y, dn.y);
+                    }
+                    st2(d + ro, dn);
+                    out = make_double2(xr.x + dn.x, xr.y + dn.y);
+                    if (DOT && dot_r) {
+                        acc.x = fma(out.x, rv.x, acc.x);
+                        acc.y = fma(out.y, rv.y, acc.y);
+                    }
+                }
+                st2(y + ro, out);
+                if (DOT && !dot_r) {
+                    acc.x = fma(out.x, xr.x, acc.x);
+                    acc.y = fma(out.y, xr.y, acc.y);
+                }
+            }
+            s = make_double2(0.0, 0.0);
+        }
+        u_sl[0] = u_sl[1]; u_c[0] = u_c[1]; u_w[0] = u_w[1]; u_k0[0] = u_k0[1];
+        u_sl[1] = u_sl[2]; u_c[1] = u_c[2]; u_w[1] = u_w[2]; u_k0[1] = u_k0[2];
+        st ^= 1;
+    }
     if (DOT) block_dot<NTt, CS>(acc, sm, o.slot, (o.flags & F_DOT_ACC) != 0);
 }
 
@@ -1011,6 +1143,7 @@ __global__ void __launch_bounds__(NTt, MINB) k_run_program(const ProgParams P)
 #define PMC_SPMM(EP_, W_, BD_, DOT_)                                                          \
     do {                                                                                      \
         if (flags & F_STAGED) op_spmm<NTt, CS, EP_, W_, BD_, DOT_, true>(o, chunk, sm, sc);   \
+        else if (flags & F_CHUNKED) op_spmm_chunked<NTt, CS, EP_, W_, BD_, DOT_>(o, chunk, sm, sc); \
         else op_spmm<NTt, CS, EP_, W_, BD_, DOT_, false>(o, chunk, sm, sc);                   \
     } while (0)
             if (ep == EP_AX) {

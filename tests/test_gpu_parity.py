@@ -720,12 +720,16 @@ def test_unstructured_agglomerates_match_oracle(tets):
                 assert rel_l2(sol[j], so) < FIELD_TOL and Q[j] == pytest.approx(Qo, rel=1e-8)
                 fo, eo, _ = o.sampler_eval(lev, xi[j])
                 assert rel_l2(emb[j], eo) < FIELD_TOL and rel_l2(s[j], fo) < FIELD_TOL
+        c_l2 = make_context(p, True, 1e-12, 1e-30, 3000, options={"stage_wide": 0})   # wide slices read from L2 instead
         pos = 0
         for lev, ns in [(2, 5), (1, 6), (0, 5)]:
             sums, rows, _ = c.mlmc_level_batch(lev, ns, pos, want_rows=True)
             osums, orows, _ = o.mlmc_level(lev, ns, pos, nthreads=2)
             assert np.allclose(rows[:, :3], orows[:, :3], rtol=1e-7, atol=1e-9)
             assert np.allclose(sums, osums, rtol=1e-6)
+            _, rows2, _ = c_l2.mlmc_level_batch(lev, ns, pos, want_rows=True)
+            assert np.array_equal(rows, rows2)       # chunk-staged and L2-read entries: the same arithmetic in the same order
             pos += ns * p["sampler"][lev].Ne
+        c_l2.close()
     finally:
         c.close()
