@@ -112,6 +112,8 @@ struct PrecCfg {
     double coarse_ratio = 30.0;
     double omega = 1.0;        // over-correction factor of the piecewise-constant coarse-grid correction
     bool omega_user = false;   // set through pmc_set_option: keep it whatever coarse spaces are chosen
+    double p_smooth = 0.0;     // hierarchy coarse spaces: damping of one Jacobi step (on the operator at k = 1) applied to the
+                               // hierarchy's piecewise-constant L2 prolongators at set-up; 0 = use them as uploaded
     int amg_passes = 0;        // aggregation coarse spaces only: pairwise matching passes per level (aggregates of up to
                                // 2^passes rows); 0 = default (3)
     double amg_smooth = -1.0;  // aggregation coarse spaces only: damping of one Jacobi smoothing step applied to the tentative
@@ -910,6 +912,19 @@ static int prepare_darcy(Ctx *c, int level)
             Ps.clear();
             for (const HCsr &P : sys.own_P) Ps.push_back(&P);
             if (!sys.cfg.omega_user) sys.cfg.omega = sys.cfg.amg_smooth > 0.0 ? 1.25 : 1.5;
+        } else if (sys.cfg.p_smooth > 0.0 && !Ps.empty()) {
+            // the hierarchy's own agglomerates, prolongators smoothed like the aggregation path's (fixed across realisations)
+            HCsr Sl = S1;
+            for (const HCsr *P0 : std::vector<const HCsr *>(Ps)) {
+                if (P0->rows != Sl.rows) break;
+                HCsr P = smooth_prolongator(Sl, *P0, sys.cfg.p_smooth, 0.25);
+                Sl = csr_matmul(csr_transpose(P), csr_matmul(Sl, P));
+                sys.own_P.push_back(std::move(P));
+            }
+            if (sys.own_P.size() == Ps.size()) {
+                Ps.clear();
+                for (const HCsr &P : sys.own_P) Ps.push_back(&P);
+            } else sys.own_P.clear();
         }
     }
     if (sys.cfg.max_vlevels > 0 && (int)Ps.size() > sys.cfg.max_vlevels - 1) Ps.resize(sys.cfg.max_vlevels - 1);
@@ -1964,6 +1979,7 @@ int pmc_set_option(pmc_handle c, const char *key, double value)
         else if (k == "method") g->method = (int)value;
         else if (k == "amg") g->amg = (int)value;
         else if (k == "amg_smooth" && value >= 0) g->amg_smooth = value;
+        else if (k == "p_smooth" && value >= 0) g->p_smooth = value;
         else if (k == "amg_passes" && value >= 1 && value <= 6) g->amg_passes = (int)value;
         else return fail(c, PMC_ERR_ARG, "pmc_set_option: bad key or value '%s' = %g", key, value);
         return PMC_OK;
