@@ -76,8 +76,12 @@ int pmc_set_preconditioner(pmc_handle h, int mass_degree, int schur_degree, doub
  * <k> in {mass_degree, schur_degree, schur_ratio, coarse_degree, coarse_ratio, omega (over-correction factor of the
  * coarse-grid correction), method (sampler only: 0 = MINRES on the saddle system [M B^T; B -alpha W], 1 = Jacobi-preconditioned CG
  * on its SPD form (M + alpha^-1 B^T W^-1 B) u = alpha^-1 B^T W^-1 f, s = (B u - f) / (alpha W) -- the elimination of
- * src/PDESampler_Legacy.cpp:172-176 -- , -1 = CG when alpha W dominates the Schur complement, i.e. for short correlation
- * lengths), max_vlevels (depth of the Schur V-cycle; 0 = full hierarchy, -1 = decide from the mass
+ * src/PDESampler_Legacy.cpp:172-176 -- , 2 = Chebyshev semi-iteration on the same SPD form: the operator does not depend
+ * on the realisation, so its spectrum is computed once at set-up and the number of steps for the requested residual
+ * reduction is known a priori (no dot products; the true residual norm is still checked per realisation after the steps),
+ * -1 = the SPD form (Chebyshev) when alpha W dominates the Schur complement, i.e. for short correlation lengths,
+ * MINRES otherwise), mass_scale (relative scaling of the Jacobi mass block against the Schur block of the MINRES
+ * preconditioner; default 1), max_vlevels (depth of the Schur V-cycle; 0 = full hierarchy, -1 = decide from the mass
  * term, sampler only), amg (coarse spaces of the Schur V-cycle: 0 = the hierarchy's L2 prolongators, 1 = strength-aware
  * pairwise aggregation built at set-up, -1 = aggregation only when the couplings are anisotropic), amg_passes (pairwise
  * matching passes per level of that aggregation: aggregates of up to 2^passes rows; default 3), amg_smooth (damping of the
@@ -88,7 +92,8 @@ int pmc_set_preconditioner(pmc_handle h, int mass_degree, int schur_degree, doub
  * CTAs of a cooperative launch per tile, for one or two tiles of very large levels; -1 = never), "solo_rows" (in a group,
  * operations with at most this many rows run on its first CTA), "stage_operators" (0 = read operator entries from L2
  * instead of staging them through shared memory with TMA bulk copies), "defer_x" (0 = update the MINRES solution
- * every iteration instead of once per iteration pair), "single_wave" (1 = prefer one wave of smaller CTAs), and
+ * every iteration instead of once per iteration pair), "cheb_three_term" (0 = keep a separate update vector in the sampler's
+ * Chebyshev steps instead of reading the previous iterate from the buffer a step overwrites), "single_wave" (1 = prefer one wave of smaller CTAs), and
  * "renumber" (0 = keep the caller's numbering of the RT dofs inside the library; to be set before the uploads), and
  * "cache_results" (see pmc_sampler_eval_batch). */
 int pmc_set_option(pmc_handle h, const char *key, double value);

@@ -194,4 +194,73 @@ inline double dense_lambda_max_scaled(const double *A, int n, int iters = 200)
     return std::max(1.0, std::min(1.05 * lam, cap));
 }
 
+// Extreme eigenvalues of a symmetric positive definite operator given by its action (Lanczos without
+// reorthogonalisation: the extreme Ritz values converge first and ghost copies do not move them; the extreme
+// eigenvalues of the Lanczos tridiagonal matrix by Sturm-sequence bisection).  lo_out >= lambda_min and hi_out <=
+// lambda_max (Ritz values lie inside the spectrum): callers widen the interval by a safety margin.
+template <typename Apply>
+inline void lanczos_extremes(int n, int steps, Apply &&apply, double *lo_out, double *hi_out)
+{
+    *lo_out = *hi_out = 1.0;
+    if (n <= 0) return;
+    steps = std::max(1, std::min(steps, n));
+    std::vector<double> v(n), vp(n, 0.0), w(n), al, be;
+    uint64_t s = 0x9E3779B97F4A7C15ULL;
+    double nrm = 0;
+    for (int i = 0; i < n; ++i) {
+        s = s * 6364136223846793005ULL + 1442695040888963407ULL;
+        v[i] = (double)(s >> 40) / (double)(1 << 24) - 0.5;
+        nrm += v[i] * v[i];
+    }
+    nrm = std::sqrt(nrm);
+    for (int i = 0; i < n; ++i) v[i] /= nrm;
+    double beta = 0;
+    for (int k = 0; k < steps; ++k) {
+        apply(v.data(), w.data());
+        double a = 0;
+        for (int i = 0; i < n; ++i) a += w[i] * v[i];
+        double b2 = 0;
+        for (int i = 0; i < n; ++i) {
+            w[i] -= a * v[i] + beta * vp[i];
+            b2 += w[i] * w[i];
+        }
+        al.push_back(a);
+        beta = std::sqrt(b2);
+        if (beta <= 1e-14 * std::fabs(a) || k + 1 == steps) break;
+        be.push_back(beta);
+        for (int i = 0; i < n; ++i) {
+            vp[i] = v[i];
+            v[i] = w[i] / beta;
+        }
+    }
+    const int m = (int)al.size();
+    double glo = al[0], ghi = al[0];   // Gershgorin interval of the tridiagonal matrix
+    for (int i = 0; i < m; ++i) {
+        const double r = (i > 0 ? std::fabs(be[i - 1]) : 0.0) + (i + 1 < m ? std::fabs(be[i]) : 0.0);
+        glo = std::min(glo, al[i] - r);
+        ghi = std::max(ghi, al[i] + r);
+    }
+    auto count_below = [&](double x) {   // number of eigenvalues of T below x
+        int c = 0;
+        double q = al[0] - x;
+        if (q < 0) ++c;
+        for (int i = 1; i < m; ++i) {
+            if (q == 0.0) q = 1e-300;
+            q = al[i] - x - be[i - 1] * be[i - 1] / q;
+            if (q < 0) ++c;
+        }
+        return c;
+    };
+    auto kth = [&](int k) {   // k-th smallest eigenvalue of T (0-based)
+        double a = glo, b = ghi;
+        for (int it = 0; it < 200 && b - a > 1e-14 * std::max(std::fabs(a), std::fabs(b)); ++it) {
+            const double mid = 0.5 * (a + b);
+            if (count_below(mid) > k) b = mid; else a = mid;
+        }
+        return 0.5 * (a + b);
+    };
+    *lo_out = kth(0);
+    *hi_out = kth(m - 1);
+}
+
 }  // namespace pmc

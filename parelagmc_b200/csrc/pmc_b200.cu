@@ -111,6 +111,8 @@ struct PrecCfg {
     int coarse_degree = 8;     // Chebyshev steps on the coarsest V-cycle level
     double coarse_ratio = 30.0;
     double omega = 1.0;        // over-correction factor of the piecewise-constant coarse-grid correction
+    double mass_scale = 1.0;   // relative scaling of the two preconditioner blocks: the Jacobi mass block is (mass_scale * theta * D)^-1
+                               // (MINRES is invariant under a common factor, so one parameter covers both blocks; degree 1 only)
     bool omega_user = false;   // set through pmc_set_option: keep it whatever coarse spaces are chosen
     double p_smooth = 0.0;     // hierarchy coarse spaces: damping of one Jacobi step (on the operator at k = 1) applied to the
                                // hierarchy's piecewise-constant L2 prolongators at set-up; 0 = use them as uploaded
@@ -121,7 +123,8 @@ struct PrecCfg {
                                // fixed across realisations); 0 = plain aggregation, < 0 = default (0.9)
     int max_vlevels = 0;       // 0: as deep as the hierarchy allows; -1 (sampler): decide from the mass term
     int method = -1;           // sampler only: 0 = MINRES on the saddle system, 1 = Jacobi-PCG on its SPD form (u eliminated
-                               // system (M + alpha^-1 B^T W^-1 B) u = alpha^-1 B^T W^-1 f), -1 = PCG when alpha W dominates
+                               // system (M + alpha^-1 B^T W^-1 B) u = alpha^-1 B^T W^-1 f), 2 = Chebyshev semi-iteration on
+                               // the same SPD form, -1 = the SPD form when alpha W dominates (PMC_SAMPLER_AUTO picks 1 or 2)
     int amg = -1;              // Schur V-cycle coarse spaces: 0 the hierarchy's own L2 prolongators, 1 strength-aware
                                // pairwise aggregation built here, -1 choose (aggregation when the couplings are anisotropic)
 };
@@ -147,6 +150,10 @@ struct SaddleSys {
     bool pcg = false;
     DevCsr Bs, MBt;
     double *dinvH = nullptr, *inv_aw = nullptr;
+    // spectrum of diag(H)^-1 H (Lanczos at set-up, widened by a safety margin): the Chebyshev semi-iteration of
+    // emit_sampler_cheb runs on [h_lo, h_hi]
+    bool cheb = false;
+    double h_lo = 0.0, h_hi = 0.0;
 };
 
 struct SamplerLevel {
@@ -237,6 +244,7 @@ struct pmc_context_s {
     size_t grp_cap = 0;
     bool staging = true;  // stage operator entries through shared memory (option "stage_operators")
     bool defer_x = true;  // option "defer_x"
+    bool cheb3 = true;    // option "cheb_three_term": sampler Chebyshev steps without a separate update vector
     bool fuse_coarse = true;  // option "fuse_coarse"
     bool stage_wide = true;   // option "stage_wide": slices wider than the staging buffers are staged chunk by chunk
     bool split_apply = true;  // option "split_apply": Darcy operator applied per row block (RT rows weighted, pressure rows plain)
@@ -632,6 +640,13 @@ static bool couplings_anisotropic(const HCsr &S)
 }
 
 // ---- sampler system (everything fixed across samples) ---------------------------------------------------
+// sampler.method = -1 and the SPD form applies: Chebyshev semi-iteration (default) or PCG (PMC_SAMPLER_AUTO=pcg)
+static bool sampler_auto_cheb()
+{
+    const char *e = getenv("PMC_SAMPLER_AUTO");
+    return !(e && std::string(e) == "pcg");
+}
+
 static int prepare_sampler(Ctx *c, int level)
 {
     SamplerLevel &L = c->s[level];
@@ -712,7 +727,8 @@ static int prepare_sampler(Ctx *c, int level)
             for (int p = S.rowptr[i]; p < S.rowptr[i + 1]; ++p) t += std::fabs(S.val[p]);
             if (t > 0) lmin = std::min(lmin, L.alpha * L.Wdiag[i] / t);
         }
-        sys.pcg = sys.cfg.method == 1 || (sys.cfg.method < 0 && lmin >= 1.0 / 20.0);
+        sys.pcg = sys.cfg.method == 1 || sys.cfg.method == 2 || (sys.cfg.method < 0 && lmin >= 1.0 / 20.0);
+        sys.cheb = sys.pcg && (sys.cfg.method == 2 || (sys.cfg.method < 0 && sampler_auto_cheb()));
         if (sys.pcg) {
             std::vector<double> iaw(Ne);
             for (int i = 0; i < Ne; ++i) iaw[i] = 1.0 / (L.alpha * L.Wdiag[i]);
@@ -738,6 +754,29 @@ static int prepare_sampler(Ctx *c, int level)
             if ((rc = upload_csr(c, MBt, sys.MBt))) return rc;
             if ((rc = to_device(c, hd, &sys.dinvH))) return rc;
             if ((rc = to_device(c, iaw, &sys.inv_aw))) return rc;
+            if (sys.cheb) {
+                // extreme eigenvalues of D^-1/2 H D^-1/2, D = diag(H) (hd holds 1/diag): H is the same for every realisation,
+                // so the number of Chebyshev steps for a given residual reduction is known before the first solve
+                std::vector<double> ds(Nf), t1(Nf), t2(Ne);
+                for (int i = 0; i < Nf; ++i) ds[i] = std::sqrt(hd[i]);
+                auto applyH = [&](const double *x, double *y) {
+                    for (int i = 0; i < Nf; ++i) t1[i] = ds[i] * x[i];
+                    csr_mult(L.M, t1.data(), y);
+                    csr_mult(L.B, t1.data(), t2.data());
+                    for (int i = 0; i < Ne; ++i) t2[i] *= iaw[i];
+                    for (int i = 0; i < Nf; ++i) {
+                        double a = 0;
+                        for (int p = Bt.rowptr[i]; p < Bt.rowptr[i + 1]; ++p) a += Bt.val[p] * t2[Bt.col[p]];
+                        y[i] = ds[i] * (y[i] + a);
+                    }
+                };
+                double lo = 1.0, hi = 1.0;
+                lanczos_extremes(Nf, 80, applyH, &lo, &hi);
+                sys.h_hi = 1.01 * hi;
+                sys.h_lo = 0.96 * lo;
+                if (getenv("PMC_DEBUG_CHEB")) fprintf(stderr, "[pmc] sampler level %d: spectrum of D^-1 H in [%.5f, %.5f] (Ritz), using [%.5f, %.5f]\n", level, lo, hi, sys.h_lo, sys.h_hi);
+                if (!(sys.h_lo > 0.0) || !(sys.h_hi > sys.h_lo)) sys.cheb = false;
+            }
         }
     }
     if (sys.cfg.max_vlevels != 1 && (sys.cfg.amg == 1 || (sys.cfg.amg < 0 && couplings_anisotropic(S)))) {
@@ -1032,6 +1071,7 @@ struct Program {
     std::vector<Op> ops;
     bool staging = true;  // stage operator entries through shared memory where the slices fit (F_STAGED)
     bool defer_x = true;  // MINRES: apply the solution updates of an iteration pair in one pass (option "defer_x")
+    bool cheb3 = true;    // sampler Chebyshev semi-iteration in three-term form (option "cheb_three_term")
     bool fuse_coarse = true;  // coarsest Chebyshev iteration as one shared-memory operation (option "fuse_coarse")
     bool split_apply = true;  // Darcy block operator applied as two operations (option "split_apply")
     bool chunked = true;      // wide slices staged chunk by chunk instead of read from L2 (option "stage_wide")
@@ -1268,8 +1308,9 @@ static void emit_prec(Program &pg, Solver &sv, Off r, Off z, int dot_slot, bool 
     op.V = sv.k_ext;
     op.dinv_f = sys.weighted ? nullptr : sys.dinvM_fixed;
     op.dinv_b = sys.weighted ? vr(ws.dinvM, sys.Nf) : VNULL;
-    op.lo = sys.m_lo;
-    op.hi = sys.m_hi;
+    const double ms = sys.cfg.mass_degree == 1 ? sys.cfg.mass_scale : 1.0;
+    op.lo = sys.m_lo * ms;
+    op.hi = sys.m_hi * ms;
     op.vrows = sys.weighted ? sys.Ne : 0;
     op.kclass = KC_MASS;
     emit_cheb(pg, op, vr(r, sys.N), vr(ws.mu_d, sys.Nf), sys.cfg.mass_degree, true, vr(z, sys.N), vr(ws.mu_z, sys.Nf), dot_slot,
@@ -1355,7 +1396,7 @@ static void emit_minres(Program &pg, Solver &sv, bool x_nonzero, bool store_iter
             o.x = vr(q, N); o.r = vr(v1, N); o.y = vr(v0, N);
             if (fuse_jacobi) {
                 // z_u = dinvM v0_u / theta written straight into the u block of q (q's own rows are read first)
-                const double theta = 0.5 * (sys.m_hi + sys.m_lo);
+                const double theta = 0.5 * (sys.m_hi + sys.m_lo) * sys.cfg.mass_scale;
                 o.flags = F_DOT | (sys.weighted ? F_BDINV : 0);
                 o.d = vr(q, N);
                 o.w = sys.weighted ? vr(ws.dinvM, sys.Nf) : VNULL;
@@ -1442,9 +1483,94 @@ static void emit_sampler_pcg(Program &pg, SaddleSys &sys, Off rhs_p, SolveWs &ws
     { Op &o = pg.add(OP_STORE_ITERS, KC_SCALAR, 0, 0); o.y = store_iters ? vr(ws.iters) : VNULL; }
 }
 
+// Chebyshev semi-iteration on the SPD form H u = b0 (same system and same stopping rule as emit_sampler_pcg).  H does not
+// depend on the realisation, so the spectrum [lo, hi] of diag(H)^-1 H is computed once at set-up and m Chebyshev steps
+// reduce the D^-1-norm of every residual by at least 1 / T_m((hi + lo) / (hi - lo)) <= rel: the step count is known
+// before the solve, no step needs a dot product, and a step is two sparse applies with the whole update in the second
+// one's epilogue (t = Bs z; d = ca d + cb D^-1 (b0 - [M | B^T][z; t]); z' = z + d): N + 4 Nf + (Nf + Ne) rows per step
+// against 12 Nf + 2 Ne for a PCG iteration.  After the m steps the true residual norm is evaluated and checked per
+// realisation; tiles that still hold an unconverged realisation run further (restarted) blocks of steps.
+// Workspace: the iterates ping-pong between [z; t] = ws.u1 and ws.q (N rows each), d = ws.w0, b0 = ws.v0, the residual
+// of the check = ws.w1; the field s = Bs u - f / (alpha W) is left in rows [Nf, N) of ws.x like the other paths leave it.
+static void emit_sampler_cheb(Program &pg, SaddleSys &sys, Off rhs_p, SolveWs &ws, bool store_iters, double rel, int maxit)
+{
+    const int Nf = sys.Nf, Ne = sys.Ne, N = sys.N;
+    VecRef Z[2] = {vr(ws.u1, N), vr(ws.q, N)}, Zt[2] = {vr(ws.u1, N, Nf), vr(ws.q, N, Nf)};
+    const VecRef R = vr(ws.v0, N), D = vr(ws.w0, N), RES = vr(ws.w1, N), Sx = vr(ws.x, N, Nf);
+    const double lo = sys.h_lo, hi = sys.h_hi;
+    const double theta = 0.5 * (hi + lo), sigma = (hi + lo) / (hi - lo);
+    const double want = rel > 0.0 && rel < 1.0 ? rel : 1e-16;
+    int m = (int)std::ceil(std::acosh(1.0 / want) / std::acosh(sigma));
+    m = std::max(2, std::min(m, std::max(2, maxit)));
+    auto scale = [&](VecRef dst, double cb) {   // dst = cb * f / (alpha W)
+        Op &o = pg.add(OP_CHEB_FIRST, KC_MISC, Ne, 2.0 * Ne);
+        o.r = vr(rhs_p, Ne); o.d = dst; o.y = dst; o.fixed = sys.inv_aw; o.cb = cb;
+    };
+    // Three-term form (default): the update d = z - z_prev is not stored; the step reads the previous iterate from the
+    // buffer it overwrites: z' = z + ca (z - z_prev) + cb D^-1 (b0 - H z), one row pass less per step.
+    const bool three = pg.cheb3;
+    auto step = [&](int cur, double ca, double cb) {   // Z[1 - cur] = Z[cur] + d,  d = ca d + cb D^-1 (b0 - H Z[cur])
+        emit_spmm(pg, KC_SADDLE, EP_AX, sys.Bs, VNULL, Z[cur], Zt[cur], VNULL, VNULL, nullptr, VNULL, 0, 0, -1, false, false, (double)Nf + Ne);
+        emit_spmm(pg, KC_SADDLE, EP_CHEB, sys.MBt, VNULL, Z[cur], Z[1 - cur], R, three ? VNULL : D, sys.dinvH, VNULL, ca, cb, -1, false,
+                  false, (double)N + (three ? 3.0 : 4.0) * Nf - (ca == 0.0 ? Nf : 0));
+        if (three) pg.ops.back().flags |= F_THREE;
+    };
+    auto check = [&](int cur, int steps_done) {   // dots[1] = r . D^-1 r with r = b0 - H Z[cur]; convergence per realisation
+        emit_spmm(pg, KC_SADDLE, EP_AX, sys.Bs, VNULL, Z[cur], Zt[cur], VNULL, VNULL, nullptr, VNULL, 0, 0, -1, false, false, (double)Nf + Ne);
+        emit_spmm(pg, KC_SADDLE, EP_RESID, sys.MBt, VNULL, Z[cur], RES, R, VNULL, nullptr, VNULL, 0, 0, -1, false, false, (double)N + 2.0 * Nf);
+        {
+            Op &o = pg.add(OP_CHEB_FIRST, KC_MASS, Nf, 2.0 * Nf);   // the scaled residual lands in the idle iterate buffer
+            o.flags = F_DOT;
+            o.r = RES; o.d = Z[1 - cur]; o.y = Z[1 - cur]; o.fixed = sys.dinvH; o.cb = 1.0; o.slot = 1;
+        }
+        { Op &o = pg.add(OP_CHB_CHECK, KC_SCALAR, 0, 0); o.slot = 1; o.a0 = steps_done; }
+    };
+    emit_fill(pg, Z[0], Nf, 0.0);
+    if (three) emit_fill(pg, Z[1], Nf, 0.0);   // z_0 = 0 is the "previous iterate" of the second step
+    scale(Zt[0], 1.0);
+    scale(Sx, -1.0);
+    // b0 = alpha^-1 B^T W^-1 f = [M | B^T] [0; f / (alpha W)]
+    emit_spmm(pg, KC_SADDLE, EP_AX, sys.MBt, VNULL, Z[0], R, VNULL, VNULL, nullptr, VNULL, 0, 0, -1, false, false, (double)Ne + Nf);
+    {   // first step from u = 0: z1 = d = D^-1 b0 / theta;  dots[1] = b0 . D^-1 b0 / theta
+        Op &o = pg.add(OP_CHEB_FIRST, KC_MASS, Nf, (three ? 2.0 : 3.0) * Nf);
+        o.flags = F_DOT;
+        o.r = R; o.d = three ? Z[0] : D; o.y = Z[0]; o.fixed = sys.dinvH; o.cb = 1.0 / theta; o.slot = 1;
+    }
+    { Op &o = pg.add(OP_CHB_INIT, KC_SCALAR, 0, 0); o.slot = 1; o.ca = theta; }
+    const int loop_start = pg.pc();
+    std::vector<int> exits;
+    exits.push_back(pg.pc());
+    pg.add(OP_CHECK, KC_SCALAR, 0, 0);
+    std::vector<double> cf = cheb_coefficients(lo, hi, m);
+    int cur = 0;
+    for (int j = 1; j < m; ++j) { step(cur, cf[2 * j], cf[2 * j + 1]); cur ^= 1; }
+    check(cur, m);
+    exits.push_back(pg.pc());
+    pg.add(OP_CHECK, KC_SCALAR, 0, 0);
+    // restarted blocks (an even number of steps, so that the iterate returns to the same buffer) until every realisation of
+    // the tile meets the stopping rule; only reached if the spectrum estimate was too narrow
+    const int m2 = std::max(2, 2 * ((m + 3) / 4));
+    std::vector<double> cf2 = cheb_coefficients(lo, hi, m2);
+    const int restart = pg.pc();
+    for (int j = 0; j < m2; ++j) { step(cur, cf2[2 * j], cf2[2 * j + 1]); cur ^= 1; }
+    check(cur, m2);
+    exits.push_back(pg.pc());
+    pg.add(OP_CHECK, KC_SCALAR, 0, 0);
+    { Op &o = pg.add(OP_JUMP, KC_SCALAR, 0, 0); o.a0 = restart; }
+    for (int i = loop_start; i < pg.pc(); ++i) pg.ops[i].flags |= F_INLOOP;
+    for (int e : exits) pg.ops[e].a0 = pg.pc();
+    // s = Bs u - f / (alpha W)
+    emit_spmm(pg, KC_SADDLE, EP_ADD, sys.Bs, VNULL, Z[cur], Sx, VNULL, VNULL, nullptr, VNULL, 1.0, 0, -1, false, false, (double)Nf + 2.0 * Ne);
+    { Op &o = pg.add(OP_STORE_ITERS, KC_SCALAR, 0, 0); o.y = store_iters ? vr(ws.iters) : VNULL; }
+}
+
 static void emit_sampler_solve(Program &pg, Ctx *c, int level, Off rhs_p, Off x0_p, SolveWs &ws, bool store_iters)
 {
     SaddleSys &sys = c->s[level].sys;
+    if (sys.pcg && sys.cheb) {
+        emit_sampler_cheb(pg, sys, rhs_p, ws, store_iters, c->rel, c->maxit);
+        return;
+    }
     if (sys.pcg) {   // starts from u = 0: the prolongated coarse field (x0_p) is an initial guess for s only
         emit_sampler_pcg(pg, sys, rhs_p, ws, store_iters);
         return;
@@ -1704,7 +1830,7 @@ static int run_program(Ctx *c, Program &pg, int nsamples, Off chunk, int max_row
         };
         auto scalar_kind = [](int k) {
             return k == OP_SC_INIT || k == OP_SC_ALPHA || k == OP_SC_BETA || k == OP_CHECK || k == OP_JUMP || k == OP_STORE_ITERS ||
-                   k == OP_LIKELIHOOD || k == OP_CG_INIT || k == OP_CG_ALPHA || k == OP_CG_BETA;
+                   k == OP_LIKELIHOOD || k == OP_CG_INIT || k == OP_CG_ALPHA || k == OP_CG_BETA || k == OP_CHB_INIT || k == OP_CHB_CHECK;
         };
         for (Op &o : ops) {
             o.flags &= ~(F_SOLO | F_LOCAL_SYNC);
@@ -1975,6 +2101,7 @@ int pmc_set_option(pmc_handle c, const char *key, double value)
         else if (k == "coarse_degree" && value >= 1) g->coarse_degree = (int)value;
         else if (k == "coarse_ratio" && value > 1) g->coarse_ratio = value;
         else if (k == "omega" && value > 0) { g->omega = value; g->omega_user = true; }
+        else if (k == "mass_scale" && value > 0) g->mass_scale = value;
         else if (k == "max_vlevels") g->max_vlevels = (int)value;
         else if (k == "method") g->method = (int)value;
         else if (k == "amg") g->amg = (int)value;
@@ -1992,6 +2119,7 @@ int pmc_set_option(pmc_handle c, const char *key, double value)
     else if (k == "cluster_size") c->force_cs = (int)value;
     else if (k == "stage_operators") c->staging = value != 0;
     else if (k == "defer_x") c->defer_x = value != 0;
+    else if (k == "cheb_three_term") c->cheb3 = value != 0;
     else if (k == "fuse_coarse") c->fuse_coarse = value != 0;
     else if (k == "single_wave") c->single_wave = value != 0;
     else if (k == "renumber") {
@@ -2151,7 +2279,7 @@ int pmc_clone(pmc_handle src, pmc_handle *out)
     c->rel = src->rel; c->abs_ = src->abs_; c->maxit = src->maxit;
     c->cfg_sampler = src->cfg_sampler; c->cfg_darcy = src->cfg_darcy;
     c->max_batch = src->max_batch; c->force_nt = src->force_nt; c->force_cs = src->force_cs; c->staging = src->staging;
-    c->defer_x = src->defer_x; c->fuse_coarse = src->fuse_coarse; c->single_wave = src->single_wave; c->renumber = src->renumber;
+    c->defer_x = src->defer_x; c->cheb3 = src->cheb3; c->fuse_coarse = src->fuse_coarse; c->single_wave = src->single_wave; c->renumber = src->renumber;
     c->force_group = src->force_group; c->solo_rows = src->solo_rows; c->cache_results = src->cache_results; c->split_apply = src->split_apply; c->stage_wide = src->stage_wide;
     c->store = src->store;   // one copy of the operators per device, freed with the last handle that uses them
     c->s = src->s;           // level descriptors: host arrays by value, device pointers into the shared store
@@ -2431,6 +2559,7 @@ int pmc_sampler_eval_batch(pmc_handle c, int level, int xi_level, int nsamples, 
     Program pg;
     pg.staging = c->staging;
     pg.defer_x = c->defer_x;
+    pg.cheb3 = c->cheb3;
     pg.fuse_coarse = c->fuse_coarse;
     pg.split_apply = c->split_apply;
     pg.chunked = c->stage_wide;
@@ -2503,6 +2632,7 @@ static int darcy_host_batch(Ctx *c, int level, int nsamples, const double *k, co
     Program pg;
     pg.staging = c->staging;
     pg.defer_x = c->defer_x;
+    pg.cheb3 = c->cheb3;
     pg.fuse_coarse = c->fuse_coarse;
     pg.split_apply = c->split_apply;
     pg.chunked = c->stage_wide;
@@ -2598,6 +2728,7 @@ static int level_batch(Ctx *c, int level, int nlevels, int nsamples, uint64_t po
     Program pg;
     pg.staging = c->staging;
     pg.defer_x = c->defer_x;
+    pg.cheb3 = c->cheb3;
     pg.fuse_coarse = c->fuse_coarse;
     pg.split_apply = c->split_apply;
     pg.chunked = c->stage_wide;
@@ -2816,6 +2947,7 @@ int pmc_bayes_level_batch(pmc_handle c, int level, int nlevels, int nsamples, ui
     Program pg;
     pg.staging = c->staging;
     pg.defer_x = c->defer_x;
+    pg.cheb3 = c->cheb3;
     pg.fuse_coarse = c->fuse_coarse;
     pg.split_apply = c->split_apply;
     pg.chunked = c->stage_wide;

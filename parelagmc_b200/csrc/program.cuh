@@ -77,6 +77,9 @@ enum OpKind {
     OP_CG_UPDATE,     // d += a x ; y -= a r ; dots[slot] = sum fixed[row] y[row]^2   (d = solution, x = p, y = residual, r = H p)
     OP_CG_BETA,       // b = active ? dots[slot] / rz : 0; rz = dots[slot]; iterations, convergence
     OP_CG_DIR,        // y = fixed[row] x + b y                     (y = p, x = residual)
+    // Chebyshev semi-iteration on the SPD form of the sampler system (emit_sampler_cheb in pmc_b200.cu)
+    OP_CHB_INIT,      // eta0 = sqrt(ca dots[slot]); goal = max(rel eta0, abs); active = valid && eta0 > goal; iterations = 0
+    OP_CHB_CHECK,     // iterations += a0; active &= sqrt(dots[slot]) > goal && iterations < max_iter   (dots[slot] = r . D^-1 r)
     OP_KIND_COUNT
 };
 
@@ -88,7 +91,9 @@ enum {
     F_SOLO = 2048,       // small operation: executed by the group's first CTA alone
     F_LOCAL_SYNC = 4096, // nothing this operation writes is read by another CTA before the next group barrier
     F_CHUNKED = 16384,   // slices wider than STW: their entries are staged chunk by chunk (op_spmm_chunked)
-    F_INLOOP = 8192      // inside a Krylov loop: its bytes are credited for the realisations of the tile still iterating only
+    F_INLOOP = 8192,     // inside a Krylov loop: its bytes are credited for the realisations of the tile still iterating only
+    F_THREE = 32768      // EP_CHEB in three-term form: the update d = z - z_prev is taken from the output buffer (which holds the
+                         // previous iterate) instead of a separate vector: y = x + ca (x - y) + cb dinv (r - A x)
 };
 
 // kernel classes for the in-kernel time/byte accounting (same meaning as PMC_K_* in include/pmc_b200.h)
@@ -368,7 +373,7 @@ __device__ __forceinline__ D2 gather_fixed(const double *__restrict__ eval, cons
 //   that do not depend on the sample (B, B^T, identity rows) point at a weight row holding the constant 1.
 //   Packed sliced ELL: slice s occupies bytes [off[s], off[s+1]) * 16 * ES of `pk` (ES = 16 weighted, 12 plain) as
 //   [val: w*16 doubles][col: w*16 ints][widx: w*16 ints], entry k of row r at index k * 16 + r.
-template <int NTt, int CS, int EP, bool WEIGHTED, bool BDINV, bool DOT, bool STAGED>
+template <int NTt, int CS, int EP, bool WEIGHTED, bool BDINV, bool DOT, bool STAGED, bool THREE = false>
 __device__ __forceinline__ void op_spmm(const Op &o, double *chunk, Smem &sm, StageCtx &sc)
 {
     constexpr int ES = WEIGHTED ? 16 : 12;
@@ -380,7 +385,7 @@ __device__ __forceinline__ void op_spmm(const Op &o, double *chunk, Smem &sm, St
     // EP_AX with a fused dot: the partner of row i is x[i], or -- when the rows of this operation are a block of a larger
     // operator whose columns start elsewhere -- the vector given in o.r
     const double *__restrict__ xd = (EP == EP_AX && DOT && o.r.off >= 0) ? tp(o.r, chunk) + sub : x;
-    double *__restrict__ d = (EP == EP_CHEB) ? tp(o.d, chunk) + sub : nullptr;
+    double *__restrict__ d = (EP == EP_CHEB && !THREE) ? tp(o.d, chunk) + sub : nullptr;
     const double *__restrict__ V = WEIGHTED ? tp(o.v, chunk) + sub : nullptr;
     const double *__restrict__ dinvb = (EP == EP_CHEB && BDINV) ? tp(o.w, chunk) + sub : nullptr;
     const int *__restrict__ off = o.rowptr;
@@ -436,7 +441,7 @@ __device__ __forceinline__ void op_spmm(const Op &o, double *chunk, Smem &sm, St
             if (EP == EP_CHEB) {
                 if (BDINV) di = ld2c(dinvb + ro);
                 else { const double t = __ldg(o.fixed + row); di = make_double2(t, t); }
-                if (ca != 0.0) dv = ld2c(d + ro);
+                if (ca != 0.0) dv = THREE ? ld2c(y + ro) : ld2c(d + ro);
             }
             if (EP == EP_CHEB) xr = ld2c(x + ro);
             else if (DOT && !dot_r) xr = ld2c(xd + ro);
@@ -487,7 +492,7 @@ __device__ __forceinline__ void op_spmm(const Op &o, double *chunk, Smem &sm, St
             if (EP == EP_CHEB) {
                 if (BDINV) di = ld2c(dinvb + ro);
                 else { const double t = __ldg(o.fixed + row); di = make_double2(t, t); }
-                if (ca != 0.0) dv = ld2c(d + ro);
+                if (ca != 0.0) dv = THREE ? ld2c(y + ro) : ld2c(d + ro);
             }
             if (EP == EP_CHEB) xr = ld2c(x + ro);
             else if (DOT && !dot_r) xr = ld2c(xd + ro);
@@ -502,10 +507,11 @@ __device__ __forceinline__ void op_spmm(const Op &o, double *chunk, Smem &sm, St
             } else {  // EP_CHEB: d = ca d + cb dinv (r - A z);  z_out = z + d
                 D2 dn = make_double2(cb * di.x * (rv.x - s.x), cb * di.y * (rv.y - s.y));
                 if (ca != 0.0) {
+                    if (THREE) dv = make_double2(xr.x - dv.x, xr.y - dv.y);
                     dn.x = fma(ca, dv.x, dn.x);
                     dn.y = fma(ca, dv.y, dn.y);
                 }
-                st2(d + ro, dn);
+                if (!THREE) st2(d + ro, dn);
                 out = make_double2(xr.x + dn.x, xr.y + dn.y);
                 if (DOT && dot_r) {
                     acc.x = fma(out.x, rv.x, acc.x);
@@ -542,7 +548,7 @@ __device__ __forceinline__ void op_spmm(const Op &o, double *chunk, Smem &sm, St
 // slice is staged CHUNK by chunk of STW entries: the pipeline unit is (slice, chunk) instead of slice, each unit is three
 // TMA bulk copies (values, columns, weight indices of the chunk are not adjacent in the packed slice), the row sum is
 // carried across the chunks of a slice and the epilogue runs after the last one.
-template <int NTt, int CS, int EP, bool WEIGHTED, bool BDINV, bool DOT>
+template <int NTt, int CS, int EP, bool WEIGHTED, bool BDINV, bool DOT, bool THREE = false>
 __device__ __forceinline__ void op_spmm_chunked(const Op &o, double *chunk, Smem &sm, StageCtx &sc)
 {
     constexpr int ES = WEIGHTED ? 16 : 12;
@@ -552,7 +558,7 @@ __device__ __forceinline__ void op_spmm_chunked(const Op &o, double *chunk, Smem
     double *__restrict__ y = tp(o.y, chunk) + sub;
     const double *__restrict__ r = (EP == EP_RESID || EP == EP_CHEB) ? tp(o.r, chunk) + sub : nullptr;
     const double *__restrict__ xd = (EP == EP_AX && DOT && o.r.off >= 0) ? tp(o.r, chunk) + sub : x;
-    double *__restrict__ d = (EP == EP_CHEB) ? tp(o.d, chunk) + sub : nullptr;
+    double *__restrict__ d = (EP == EP_CHEB && !THREE) ? tp(o.d, chunk) + sub : nullptr;
     const double *__restrict__ V = WEIGHTED ? tp(o.v, chunk) + sub : nullptr;
     const double *__restrict__ dinvb = (EP == EP_CHEB && BDINV) ? tp(o.w, chunk) + sub : nullptr;
     const int *__restrict__ off = o.rowptr;
@@ -632,7 +638,7 @@ __device__ __forceinline__ void op_spmm_chunked(const Op &o, double *chunk, Smem
                 if (EP == EP_CHEB) {
                     if (BDINV) di = ld2c(dinvb + ro);
                     else { const double t = __ldg(o.fixed + row); di = make_double2(t, t); }
-                    if (ca != 0.0) dv = ld2c(d + ro);
+                    if (ca != 0.0) dv = THREE ? ld2c(y + ro) : ld2c(d + ro);
                     xr = ld2c(x + ro);
                 } else if (DOT && !dot_r) xr = ld2c(xd + ro);
                 D2 out;
@@ -642,10 +648,11 @@ __device__ __forceinline__ void op_spmm_chunked(const Op &o, double *chunk, Smem
                 else {
                     D2 dn = make_double2(cb * di.x * (rv.x - s.x), cb * di.y * (rv.y - s.y));
                     if (ca != 0.0) {
+                        if (THREE) dv = make_double2(xr.x - dv.x, xr.y - dv.y);
                         dn.x = fma(ca, dv.x, dn.x);
                         dn.y = fma(ca, dv.y, dn.y);
                     }
-                    st2(d + ro, dn);
+                    if (!THREE) st2(d + ro, dn);
                     out = make_double2(xr.x + dn.x, xr.y + dn.y);
                     if (DOT && dot_r) {
                         acc.x = fma(out.x, rv.x, acc.x);
@@ -1024,6 +1031,29 @@ __device__ __forceinline__ void cg_beta(const Op &o, Smem &sm, const ProgParams 
     sm.st[ST_CGB][j] = b;
 }
 
+// ---- Chebyshev semi-iteration (sampler, SPD form): the step count for the requested reduction is known a priori from the
+// spectrum of the (sample-independent) operator; the true residual norm is checked after every block of steps ----------
+__device__ __forceinline__ void chb_init(const Op &o, int tile, Smem &sm, const ProgParams &P)
+{
+    const int j = threadIdx.x;
+    if (j >= TW) return;
+    const double eta = sqrt(fmax(o.ca * sm.dots[o.slot][j], 0.0));
+    const double goal = fmax(P.rel * eta, P.abs_);
+    sm.st[ST_GOAL][j] = goal;
+    sm.active[j] = (tile * TW + j < P.nsamples) && (eta > goal);
+    sm.iters[j] = 0;
+}
+__device__ __forceinline__ void chb_check(const Op &o, Smem &sm, const ProgParams &P)
+{
+    const int j = threadIdx.x;
+    if (j >= TW) return;
+    if (sm.active[j]) {
+        const int it = sm.iters[j] + o.a0;
+        sm.iters[j] = it;
+        if (sqrt(fmax(sm.dots[o.slot][j], 0.0)) <= sm.st[ST_GOAL][j] || it >= P.max_iter) sm.active[j] = 0;
+    }
+}
+
 // x += a p ; r -= a q ; rz' = sum dinv r^2   (a = 0 for converged samples: their vectors stay as they are)
 template <int NTt, int CS>
 __device__ __forceinline__ void op_cg_update(const Op &o, double *chunk, Smem &sm)
@@ -1155,6 +1185,11 @@ __global__ void __launch_bounds__(NTt, MINB) k_run_program(const ProgParams P)
                 PMC_SPMM(EP_ADD, false, false, false);
             } else {
                 if (w) { if (dot) PMC_SPMM(EP_CHEB, true, true, true); else PMC_SPMM(EP_CHEB, true, true, false); }
+                else if (flags & F_THREE) {
+                    if (flags & F_STAGED) op_spmm<NTt, CS, EP_CHEB, false, false, false, true, true>(o, chunk, sm, sc);
+                    else if (flags & F_CHUNKED) op_spmm_chunked<NTt, CS, EP_CHEB, false, false, false, true>(o, chunk, sm, sc);
+                    else op_spmm<NTt, CS, EP_CHEB, false, false, false, false, true>(o, chunk, sm, sc);
+                }
                 else   { if (dot) PMC_SPMM(EP_CHEB, false, false, true); else PMC_SPMM(EP_CHEB, false, false, false); }
             }
 #undef PMC_SPMM
@@ -1244,6 +1279,8 @@ __global__ void __launch_bounds__(NTt, MINB) k_run_program(const ProgParams P)
         case OP_CG_INIT: cg_init(o, tile, sm, P); break;
         case OP_CG_ALPHA: cg_alpha(o, sm); break;
         case OP_CG_BETA: cg_beta(o, sm, P); break;
+        case OP_CHB_INIT: chb_init(o, tile, sm, P); break;
+        case OP_CHB_CHECK: chb_check(o, sm, P); break;
         case OP_CG_UPDATE: op_cg_update<NTt, CS>(o, chunk, sm); break;
         case OP_CG_DIR: op_cg_dir<NTt, CS>(o, chunk, sm); break;
         case OP_LIKELIHOOD:

@@ -149,26 +149,31 @@ def test_sampler_eval_matches_oracle(ctx, orc, prob):
 
 
 def test_sampler_methods_agree(orc, prob):
-    """The sampler system solved as MINRES on the saddle form ("sampler.method" = 0) and as Jacobi-PCG on its SPD form
-    (= 1; the default picks it for short correlation lengths): same fields, equal to the oracle's (which runs MINRES on the
-    saddle form with its own preconditioner) to the field tolerance; also through a cluster split."""
+    """The sampler system solved as MINRES on the saddle form ("sampler.method" = 0), as Jacobi-PCG on its SPD form (= 1)
+    and by the Chebyshev semi-iteration on the SPD form (= 2; the default for short correlation lengths): same fields,
+    equal to the oracle's (which runs MINRES on the saddle form with its own preconditioner) to the field tolerance; also
+    through a cluster split."""
     from oracle.binding import Yarn5
     from common import make_context
-    ctxs = {m: make_context(prob, True, 1e-12, 1e-30, 2000, options={"sampler.method": m}) for m in (0, 1)}
+    ctxs = {m: make_context(prob, True, 1e-12, 1e-30, 2000, options={"sampler.method": m}) for m in (0, 1, 2)}
     ctxs["1c"] = make_context(prob, True, 1e-12, 1e-30, 2000, options={"sampler.method": 1, "cluster_size": 2, "cta_threads": 256})
+    ctxs["2c"] = make_context(prob, True, 1e-12, 1e-30, 2000, options={"sampler.method": 2, "cluster_size": 2, "cta_threads": 256})
     try:
         for lev in range(prob["nlevels"]):
             Ne = prob["sampler"][lev].Ne
             n = 5
             xi = Yarn5().jump(977 * lev + 3).normals(n * Ne).reshape(n, Ne)
             res = {m: c.sampler_eval_batch(lev, xi) for m, c in ctxs.items()}
-            print(f"sampler level {lev}: MINRES its {res[0][2].max()}, PCG its {res[1][2].max()}")
+            print(f"sampler level {lev}: MINRES its {res[0][2].max()}, PCG its {res[1][2].max()}, Chebyshev steps {res[2][2].max()}")
             for j in range(n):
                 so, eo, _ = orc.sampler_eval(lev, xi[j])
                 for m in ctxs:
                     assert rel_l2(res[m][1][j], eo) < FIELD_TOL, (lev, m)
                     assert rel_l2(res[m][0][j], so) < FIELD_TOL, (lev, m)
             assert res[1][2].max() < 2000 and res[0][2].max() < 2000
+            # the a-priori step count suffices: no restarted block (every realisation reports the same count, and it is
+            # within a few steps of what PCG needs times the Chebyshev / CG ratio)
+            assert res[2][2].min() == res[2][2].max() and res[2][2].max() <= 3 * res[1][2].max() + 4
     finally:
         for c in ctxs.values():
             c.close()
