@@ -180,6 +180,7 @@ struct DarcyLevel {
     std::vector<double> elem_mat, ess_data, rhs, obs;
     HCsr B, Pp;
     double *d_rhs_bc = nullptr, *d_obs = nullptr, *d_ess_u_data = nullptr;
+    int obs_nnz = 0;          // non-zero entries of obs
     int *d_rowmap = nullptr;  // caller's numbering of the N unknowns -> the library's (RT dofs renumbered for locality)
     std::vector<int> h_rowmap;
     // Bayesian inverse problem: m normalised pressure functionals [m][Ne], observed data and noise variance
@@ -245,6 +246,7 @@ struct pmc_context_s {
     bool staging = true;  // stage operator entries through shared memory (option "stage_operators")
     bool defer_x = true;  // option "defer_x"
     bool cheb3 = true;    // option "cheb_three_term": sampler Chebyshev steps without a separate update vector
+    bool qoi_only = true; // option "qoi_only": Darcy solves that return Q only never form the solution vector
     bool fuse_coarse = true;  // option "fuse_coarse"
     bool stage_wide = true;   // option "stage_wide": slices wider than the staging buffers are staged chunk by chunk
     bool split_apply = true;  // option "split_apply": Darcy operator applied per row block (RT rows weighted, pressure rows plain)
@@ -918,6 +920,8 @@ static int prepare_darcy(Ctx *c, int level)
         if ((rc = to_device(c, b, &L.d_rhs_bc))) return rc;
         if ((rc = to_device(c, eu, &L.d_ess_u_data))) return rc;
         if ((rc = to_device(c, L.obs, &L.d_obs))) return rc;
+        L.obs_nnz = 0;
+        for (double v : L.obs) L.obs_nnz += v != 0.0 ? 1 : 0;
     }
     // Schur complement S(k) = Be diag(M(k))^-1 Be^T: pattern, unique-value map T_0 and the Galerkin chain
     std::vector<const HCsr *> Ps;
@@ -1072,6 +1076,7 @@ struct Program {
     bool staging = true;  // stage operator entries through shared memory where the slices fit (F_STAGED)
     bool defer_x = true;  // MINRES: apply the solution updates of an iteration pair in one pass (option "defer_x")
     bool cheb3 = true;    // sampler Chebyshev semi-iteration in three-term form (option "cheb_three_term")
+    bool qoi_only = true; // Darcy MINRES carries obs . x by scalar recurrences when only Q is returned (option "qoi_only")
     bool fuse_coarse = true;  // coarsest Chebyshev iteration as one shared-memory operation (option "fuse_coarse")
     bool split_apply = true;  // Darcy block operator applied as two operations (option "split_apply")
     bool chunked = true;      // wide slices staged chunk by chunk instead of read from L2 (option "stage_wide")
@@ -1369,26 +1374,38 @@ static void emit_darcy_setup(Program &pg, Solver &sv)
 }
 
 // Preconditioned MINRES; ws.b and ws.x are set by earlier operations (x_nonzero: x holds an initial guess).
-static void emit_minres(Program &pg, Solver &sv, bool x_nonzero, bool store_iters)
+// qoi (with qoi_row): only Q = qoi . x is wanted and x starts from 0: the functional is carried by scalar recurrences (see
+// sc_beta) driven by qoi . z_k, one sparse dot per iteration; the direction vectors w and the solution x are never formed
+// (no OP_SOL_UPDATE: 5 N of the ~21 N rows an iteration moves).  qoi_rows = number of non-zero entries of qoi.
+static void emit_minres(Program &pg, Solver &sv, bool x_nonzero, bool store_iters, const double *qoi = nullptr, Off qoi_row = -1,
+                        int qoi_rows = 0)
 {
     SaddleSys &sys = *sv.sys;
     SolveWs &ws = *sv.ws;
     const int N = sys.N;
+    const bool functional = qoi != nullptr && !x_nonzero;
     if (x_nonzero) emit_saddle(pg, sv, EP_RESID, ws.x, ws.v1, ws.b, -1);
     else emit_copy(pg, vr(ws.b, N), vr(ws.v1, N), N);
     emit_fill(pg, vr(ws.v0, N), N, 0.0);
-    emit_fill(pg, vr(ws.w0, N), N, 0.0);
-    emit_fill(pg, vr(ws.w1, N), N, 0.0);
+    if (!functional) {
+        emit_fill(pg, vr(ws.w0, N), N, 0.0);
+        emit_fill(pg, vr(ws.w1, N), N, 0.0);
+    }
     emit_prec(pg, sv, ws.v1, ws.u1, 1);
     { Op &o = pg.add(OP_SC_INIT, KC_SCALAR, 0, 0); o.slot = 1; }
     std::vector<int> exits_a, exits_b;
-    const bool defer_x = pg.defer_x;
+    const bool defer_x = pg.defer_x && !functional;
     exits_b.push_back(pg.pc());
     pg.add(OP_CHECK, KC_SCALAR, 0, 0);
     const int loop_start = pg.pc();
     Off v0 = ws.v0, v1 = ws.v1, w0 = ws.w0, w1 = ws.w1, u1 = ws.u1, q = ws.q;
     for (int parity = 0; parity < 2; ++parity) {
         emit_saddle(pg, sv, EP_AX, u1, q, -1, 0);
+        if (functional) {   // dots[3] = qoi . z_k (rows with a zero weight are not read)
+            Op &o = pg.add(OP_DOT_FIXED, KC_SOLUPD, N, (double)qoi_rows);
+            o.fixed = qoi;
+            o.x = vr(u1, N);
+        }
         { Op &o = pg.add(OP_SC_ALPHA, KC_SCALAR, 0, 0); o.slot = 0; }
         const bool fuse_jacobi = sys.cfg.mass_degree == 1;
         {
@@ -1410,8 +1427,8 @@ static void emit_minres(Program &pg, Solver &sv, bool x_nonzero, bool store_iter
         // The solution update x += cx w of the first iteration of a pair is deferred and applied together with the
         // second one's (which reads that direction vector anyway): one read and one write of x less per pair, the same
         // floating-point operations in the same order.
-        { Op &o = pg.add(OP_SC_BETA, KC_SCALAR, 0, 0); o.slot = 1; o.a0 = defer_x && parity == 0 ? 1 : 0; }
-        {
+        { Op &o = pg.add(OP_SC_BETA, KC_SCALAR, 0, 0); o.slot = 1; o.a0 = defer_x && parity == 0 ? 1 : 0; o.a1 = functional ? 1 : 0; }
+        if (!functional) {
             const int mode = !defer_x ? 0 : (parity == 0 ? 1 : 2);
             Op &o = pg.add(OP_SOL_UPDATE, KC_SOLUPD, N, mode == 1 ? 4.0 * N : 6.0 * N);
             o.y = vr(w0, N); o.r = vr(w1, N); o.x = vr(u1, N); o.d = vr(ws.x, N);
@@ -1431,6 +1448,7 @@ static void emit_minres(Program &pg, Solver &sv, bool x_nonzero, bool store_iter
     const int exit_b = pg.pc();
     for (int e : exits_a) pg.ops[e].a0 = exit_a;
     for (int e : exits_b) pg.ops[e].a0 = exit_b;
+    if (functional) { Op &o = pg.add(OP_STORE_Q, KC_SCALAR, 0, 0); o.y = vr(qoi_row); }
     { Op &o = pg.add(OP_STORE_ITERS, KC_SCALAR, 0, 0); o.y = store_iters ? vr(ws.iters) : VNULL; }
 }
 
@@ -1585,7 +1603,8 @@ static void emit_sampler_solve(Program &pg, Ctx *c, int level, Off rhs_p, Off x0
 }
 
 // Darcy solve: k_ext = batched [Ne+1 rows] (row Ne = 1).  Q_dev[sample] receives obs . sol.
-static void emit_darcy_solve(Program &pg, Ctx *c, int level, Off k_ext, SolveWs &ws, Off Q_row, bool store_iters)
+// need_sol = false: the caller reads Q only (SolveFwd), so the solve may skip forming the solution (option "qoi_only").
+static void emit_darcy_solve(Program &pg, Ctx *c, int level, Off k_ext, SolveWs &ws, Off Q_row, bool store_iters, bool need_sol = true)
 {
     DarcyLevel &L = c->d[level];
     SaddleSys &sys = L.sys;
@@ -1598,6 +1617,10 @@ static void emit_darcy_solve(Program &pg, Ctx *c, int level, Off k_ext, SolveWs 
         { Op &o = pg.add(OP_BROADCAST, KC_MISC, sys.Nf, sys.Nf); o.fixed = L.d_ess_u_data; o.y = vr(ws.mu_z, sys.Nf); }
         emit_spmm(pg, KC_SADDLE, EP_RESID, L.Mbc, sv.k_ext, vr(ws.mu_z, sys.Nf), vr(ws.b, N), vr(ws.b, N), VNULL, nullptr, VNULL, 0,
                   0, -1, false, false, 3.0 * sys.Nf + sys.Ne);
+    }
+    if (!need_sol && Q_row >= 0 && pg.qoi_only) {
+        emit_minres(pg, sv, false, store_iters, L.d_obs, Q_row, L.obs_nnz);   // p_sol = 0 (:629), Q = obs . sol (:427)
+        return;
     }
     emit_fill(pg, vr(ws.x, N), N, 0.0);  // p_sol = 0 (:629)
     emit_minres(pg, sv, false, store_iters);
@@ -1830,7 +1853,7 @@ static int run_program(Ctx *c, Program &pg, int nsamples, Off chunk, int max_row
         };
         auto scalar_kind = [](int k) {
             return k == OP_SC_INIT || k == OP_SC_ALPHA || k == OP_SC_BETA || k == OP_CHECK || k == OP_JUMP || k == OP_STORE_ITERS ||
-                   k == OP_LIKELIHOOD || k == OP_CG_INIT || k == OP_CG_ALPHA || k == OP_CG_BETA || k == OP_CHB_INIT || k == OP_CHB_CHECK;
+                   k == OP_LIKELIHOOD || k == OP_CG_INIT || k == OP_CG_ALPHA || k == OP_CG_BETA || k == OP_CHB_INIT || k == OP_CHB_CHECK || k == OP_STORE_Q;
         };
         for (Op &o : ops) {
             o.flags &= ~(F_SOLO | F_LOCAL_SYNC);
@@ -2120,6 +2143,7 @@ int pmc_set_option(pmc_handle c, const char *key, double value)
     else if (k == "stage_operators") c->staging = value != 0;
     else if (k == "defer_x") c->defer_x = value != 0;
     else if (k == "cheb_three_term") c->cheb3 = value != 0;
+    else if (k == "qoi_only") c->qoi_only = value != 0;
     else if (k == "fuse_coarse") c->fuse_coarse = value != 0;
     else if (k == "single_wave") c->single_wave = value != 0;
     else if (k == "renumber") {
@@ -2279,7 +2303,7 @@ int pmc_clone(pmc_handle src, pmc_handle *out)
     c->rel = src->rel; c->abs_ = src->abs_; c->maxit = src->maxit;
     c->cfg_sampler = src->cfg_sampler; c->cfg_darcy = src->cfg_darcy;
     c->max_batch = src->max_batch; c->force_nt = src->force_nt; c->force_cs = src->force_cs; c->staging = src->staging;
-    c->defer_x = src->defer_x; c->cheb3 = src->cheb3; c->fuse_coarse = src->fuse_coarse; c->single_wave = src->single_wave; c->renumber = src->renumber;
+    c->defer_x = src->defer_x; c->cheb3 = src->cheb3; c->qoi_only = src->qoi_only; c->fuse_coarse = src->fuse_coarse; c->single_wave = src->single_wave; c->renumber = src->renumber;
     c->force_group = src->force_group; c->solo_rows = src->solo_rows; c->cache_results = src->cache_results; c->split_apply = src->split_apply; c->stage_wide = src->stage_wide;
     c->store = src->store;   // one copy of the operators per device, freed with the last handle that uses them
     c->s = src->s;           // level descriptors: host arrays by value, device pointers into the shared store
@@ -2560,6 +2584,7 @@ int pmc_sampler_eval_batch(pmc_handle c, int level, int xi_level, int nsamples, 
     pg.staging = c->staging;
     pg.defer_x = c->defer_x;
     pg.cheb3 = c->cheb3;
+    pg.qoi_only = c->qoi_only;
     pg.fuse_coarse = c->fuse_coarse;
     pg.split_apply = c->split_apply;
     pg.chunked = c->stage_wide;
@@ -2633,6 +2658,7 @@ static int darcy_host_batch(Ctx *c, int level, int nsamples, const double *k, co
     pg.staging = c->staging;
     pg.defer_x = c->defer_x;
     pg.cheb3 = c->cheb3;
+    pg.qoi_only = c->qoi_only;
     pg.fuse_coarse = c->fuse_coarse;
     pg.split_apply = c->split_apply;
     pg.chunked = c->stage_wide;
@@ -2642,7 +2668,7 @@ static int darcy_host_batch(Ctx *c, int level, int nsamples, const double *k, co
         emit_saddle(pg, sv, EP_AX, ws.x, ws.q, -1, -1);
     } else {
         emit_fill(pg, vr(k_ext, Ne + 1, Ne), 1, 1.0);
-        emit_darcy_solve(pg, c, level, k_ext, ws, Qrow, true);
+        emit_darcy_solve(pg, c, level, k_ext, ws, Qrow, true, sol_out != nullptr);
     }
     const Off chunk = ar.peak;
     const size_t per_sample = (size_t)chunk * 8 / TW + (size_t)N * 8 + 64;
@@ -2729,6 +2755,7 @@ static int level_batch(Ctx *c, int level, int nlevels, int nsamples, uint64_t po
     pg.staging = c->staging;
     pg.defer_x = c->defer_x;
     pg.cheb3 = c->cheb3;
+    pg.qoi_only = c->qoi_only;
     pg.fuse_coarse = c->fuse_coarse;
     pg.split_apply = c->split_apply;
     pg.chunked = c->stage_wide;
@@ -2767,7 +2794,7 @@ static int level_batch(Ctx *c, int level, int nlevels, int nsamples, uint64_t po
             ar.top = mark;
             SolveWs ws;
             carve_solve(ar, DC.sys, ws);
-            emit_darcy_solve(pg, c, level + 1, k_ext, ws, Qc, false);
+            emit_darcy_solve(pg, c, level + 1, k_ext, ws, Qc, false, false);
         }
         // initial guess for the fine solve: prolongated coarse Gaussian field (:496-511)
         emit_spmm(pg, KC_TRANSFER, EP_AX, SF.dP, VNULL, vr(s_c, Nec), vr(x0_f, Ne), VNULL, VNULL, nullptr, VNULL, 0, 0, -1, false,
@@ -2792,7 +2819,7 @@ static int level_batch(Ctx *c, int level, int nlevels, int nsamples, uint64_t po
         ar.top = mark;
         SolveWs ws;
         carve_solve(ar, DF.sys, ws);
-        emit_darcy_solve(pg, c, level, k_ext, ws, Qf, false);
+        emit_darcy_solve(pg, c, level, k_ext, ws, Qf, false, false);
     }
     const Off chunk = ar.peak;
     const size_t per_sample = (size_t)chunk * 8 / TW + 64 + 40;
@@ -2948,6 +2975,7 @@ int pmc_bayes_level_batch(pmc_handle c, int level, int nlevels, int nsamples, ui
     pg.staging = c->staging;
     pg.defer_x = c->defer_x;
     pg.cheb3 = c->cheb3;
+    pg.qoi_only = c->qoi_only;
     pg.fuse_coarse = c->fuse_coarse;
     pg.split_apply = c->split_apply;
     pg.chunked = c->stage_wide;

@@ -44,6 +44,7 @@ enum {
     ST_BETA = 0, ST_IB, ST_IBPREV, ST_G0, ST_G1, ST_S0, ST_S1, ST_ETA, ST_GOAL, ST_ALPHA,
     ST_CQ, ST_CV1, ST_CV0, ST_CW0, ST_CW1, ST_CU, ST_CX, ST_CXP,
     ST_RZ, ST_CGA, ST_CGB,   // preconditioned CG: r.z, step length, direction coefficient
+    ST_OM0, ST_OM1, ST_QACC, // MINRES for a linear functional of the solution only: obs . w (two generations) and obs . x
     ST_COUNT
 };
 
@@ -80,6 +81,7 @@ enum OpKind {
     // Chebyshev semi-iteration on the SPD form of the sampler system (emit_sampler_cheb in pmc_b200.cu)
     OP_CHB_INIT,      // eta0 = sqrt(ca dots[slot]); goal = max(rel eta0, abs); active = valid && eta0 > goal; iterations = 0
     OP_CHB_CHECK,     // iterations += a0; active &= sqrt(dots[slot]) > goal && iterations < max_iter   (dots[slot] = r . D^-1 r)
+    OP_STORE_Q,       // y[0][j] = obs . x accumulated by the functional-only MINRES (OP_SC_BETA with a1 = 1)
     OP_KIND_COUNT
 };
 
@@ -923,6 +925,9 @@ __device__ __forceinline__ void sc_init(const Op &o, int tile, Smem &sm, const P
     sm.st[ST_ETA][j] = eta;
     sm.st[ST_GOAL][j] = goal;
     sm.st[ST_CXP][j] = 0.0;
+    sm.st[ST_OM0][j] = 0.0;
+    sm.st[ST_OM1][j] = 0.0;
+    sm.st[ST_QACC][j] = 0.0;
     sm.active[j] = (sample < P.nsamples) && (eta > goal);
     sm.iters[j] = 0;
 }
@@ -979,6 +984,16 @@ __device__ __forceinline__ void sc_beta(const Op &o, Smem &sm, const ProgParams 
         sm.st[ST_IBPREV][j] = ib;
         sm.st[ST_BETA][j] = beta_new;
         sm.st[ST_IB][j] = safe_inv(beta_new);
+        if (o.a1) {
+            // Only a linear functional Q = obs . x of the solution is wanted (DarcySolver::SolveFwd returns Q and C, not the
+            // solution): x = sum_k cx_k w_k with w_k = cw0 w_{k-2} + cw1 w_{k-1} + cu z_k, so obs . w_k obeys the same recurrence
+            // driven by the scalars obs . z_k (dots[3], an OP_DOT_FIXED earlier in this iteration) and the direction vectors
+            // and the solution vector are never formed.
+            const double om = fma(cw0, sm.st[ST_OM0][j], fma(cw1, sm.st[ST_OM1][j], cu * sm.dots[3][j]));
+            sm.st[ST_OM0][j] = sm.st[ST_OM1][j];
+            sm.st[ST_OM1][j] = om;
+            sm.st[ST_QACC][j] = fma(cx, om, sm.st[ST_QACC][j]);
+        }
         if (fabs(eta) <= sm.st[ST_GOAL][j] || it >= P.max_iter || beta_new == 0.0) sm.active[j] = 0;
     }
     sm.st[ST_CW0][j] = cw0;
@@ -1252,7 +1267,7 @@ __global__ void __launch_bounds__(NTt, MINB) k_run_program(const ProgParams P)
             }
             block_dot<NTt, CS>(acc, sm, 3, false);
             __syncthreads();
-            if (threadIdx.x < TW && crank == 0) tp(o.y, chunk)[threadIdx.x] = sm.dots[3][threadIdx.x];
+            if (threadIdx.x < TW && crank == 0 && o.y.off >= 0) tp(o.y, chunk)[threadIdx.x] = sm.dots[3][threadIdx.x];
         } break;
         case OP_SC_INIT: sc_init(o, tile, sm, P); break;
         case OP_SC_ALPHA: sc_alpha(o, sm); break;
@@ -1281,6 +1296,9 @@ __global__ void __launch_bounds__(NTt, MINB) k_run_program(const ProgParams P)
         case OP_CG_BETA: cg_beta(o, sm, P); break;
         case OP_CHB_INIT: chb_init(o, tile, sm, P); break;
         case OP_CHB_CHECK: chb_check(o, sm, P); break;
+        case OP_STORE_Q:
+            if (threadIdx.x < TW && crank == 0) tp(o.y, chunk)[threadIdx.x] = sm.st[ST_QACC][threadIdx.x];
+            break;
         case OP_CG_UPDATE: op_cg_update<NTt, CS>(o, chunk, sm); break;
         case OP_CG_DIR: op_cg_dir<NTt, CS>(o, chunk, sm); break;
         case OP_LIKELIHOOD:
