@@ -180,7 +180,9 @@ struct DarcyLevel {
     std::vector<double> elem_mat, ess_data, rhs, obs;
     HCsr B, Pp;
     double *d_rhs_bc = nullptr, *d_obs = nullptr, *d_ess_u_data = nullptr;
-    int obs_nnz = 0;          // non-zero entries of obs
+    int obs_nnz = 0;          // non-zero entries of obs, and their (row, value) list for the functional-only solves
+    int *d_obs_idx = nullptr;
+    double *d_obs_val = nullptr;
     int *d_rowmap = nullptr;  // caller's numbering of the N unknowns -> the library's (RT dofs renumbered for locality)
     std::vector<int> h_rowmap;
     // Bayesian inverse problem: m normalised pressure functionals [m][Ne], observed data and noise variance
@@ -920,8 +922,13 @@ static int prepare_darcy(Ctx *c, int level)
         if ((rc = to_device(c, b, &L.d_rhs_bc))) return rc;
         if ((rc = to_device(c, eu, &L.d_ess_u_data))) return rc;
         if ((rc = to_device(c, L.obs, &L.d_obs))) return rc;
-        L.obs_nnz = 0;
-        for (double v : L.obs) L.obs_nnz += v != 0.0 ? 1 : 0;
+        std::vector<int> oi;
+        std::vector<double> ov;
+        for (size_t i = 0; i < L.obs.size(); ++i)
+            if (L.obs[i] != 0.0) { oi.push_back((int)i); ov.push_back(L.obs[i]); }
+        L.obs_nnz = (int)oi.size();
+        if ((rc = to_device(c, oi, &L.d_obs_idx))) return rc;
+        if ((rc = to_device(c, ov, &L.d_obs_val))) return rc;
     }
     // Schur complement S(k) = Be diag(M(k))^-1 Be^T: pattern, unique-value map T_0 and the Galerkin chain
     std::vector<const HCsr *> Ps;
@@ -1378,12 +1385,12 @@ static void emit_darcy_setup(Program &pg, Solver &sv)
 // sc_beta) driven by qoi . z_k, one sparse dot per iteration; the direction vectors w and the solution x are never formed
 // (no OP_SOL_UPDATE: 5 N of the ~21 N rows an iteration moves).  qoi_rows = number of non-zero entries of qoi.
 static void emit_minres(Program &pg, Solver &sv, bool x_nonzero, bool store_iters, const double *qoi = nullptr, Off qoi_row = -1,
-                        int qoi_rows = 0)
+                        int qoi_rows = 0, const int *qoi_idx = nullptr)
 {
     SaddleSys &sys = *sv.sys;
     SolveWs &ws = *sv.ws;
     const int N = sys.N;
-    const bool functional = qoi != nullptr && !x_nonzero;
+    const bool functional = qoi != nullptr && qoi_idx != nullptr && !x_nonzero;
     if (x_nonzero) emit_saddle(pg, sv, EP_RESID, ws.x, ws.v1, ws.b, -1);
     else emit_copy(pg, vr(ws.b, N), vr(ws.v1, N), N);
     emit_fill(pg, vr(ws.v0, N), N, 0.0);
@@ -1401,9 +1408,10 @@ static void emit_minres(Program &pg, Solver &sv, bool x_nonzero, bool store_iter
     Off v0 = ws.v0, v1 = ws.v1, w0 = ws.w0, w1 = ws.w1, u1 = ws.u1, q = ws.q;
     for (int parity = 0; parity < 2; ++parity) {
         emit_saddle(pg, sv, EP_AX, u1, q, -1, 0);
-        if (functional) {   // dots[3] = qoi . z_k (rows with a zero weight are not read)
-            Op &o = pg.add(OP_DOT_FIXED, KC_SOLUPD, N, (double)qoi_rows);
-            o.fixed = qoi;
+        if (functional) {   // dots[3] = qoi . z_k over the non-zero entries of the functional (qoi = their values, qoi_idx their rows)
+            Op &o = pg.add(OP_DOT_SPARSE, KC_SOLUPD, qoi_rows, (double)qoi_rows);
+            o.val = qoi;
+            o.col = qoi_idx;
             o.x = vr(u1, N);
         }
         { Op &o = pg.add(OP_SC_ALPHA, KC_SCALAR, 0, 0); o.slot = 0; }
@@ -1619,7 +1627,7 @@ static void emit_darcy_solve(Program &pg, Ctx *c, int level, Off k_ext, SolveWs 
                   0, -1, false, false, 3.0 * sys.Nf + sys.Ne);
     }
     if (!need_sol && Q_row >= 0 && pg.qoi_only) {
-        emit_minres(pg, sv, false, store_iters, L.d_obs, Q_row, L.obs_nnz);   // p_sol = 0 (:629), Q = obs . sol (:427)
+        emit_minres(pg, sv, false, store_iters, L.d_obs_val, Q_row, L.obs_nnz, L.d_obs_idx);   // p_sol = 0 (:629), Q = obs . sol (:427)
         return;
     }
     emit_fill(pg, vr(ws.x, N), N, 0.0);  // p_sol = 0 (:629)

@@ -82,6 +82,7 @@ enum OpKind {
     OP_CHB_INIT,      // eta0 = sqrt(ca dots[slot]); goal = max(rel eta0, abs); active = valid && eta0 > goal; iterations = 0
     OP_CHB_CHECK,     // iterations += a0; active &= sqrt(dots[slot]) > goal && iterations < max_iter   (dots[slot] = r . D^-1 r)
     OP_STORE_Q,       // y[0][j] = obs . x accumulated by the functional-only MINRES (OP_SC_BETA with a1 = 1)
+    OP_DOT_SPARSE,    // dots[3][j] = sum_i val[i] * x[col[i]][j]   (n = non-zero entries of a sparse fixed functional)
     OP_KIND_COUNT
 };
 
@@ -1268,6 +1269,20 @@ __global__ void __launch_bounds__(NTt, MINB) k_run_program(const ProgParams P)
             block_dot<NTt, CS>(acc, sm, 3, false);
             __syncthreads();
             if (threadIdx.x < TW && crank == 0 && o.y.off >= 0) tp(o.y, chunk)[threadIdx.x] = sm.dots[3][threadIdx.x];
+        } break;
+        case OP_DOT_SPARSE: {
+            const int sub = (threadIdx.x % LPR) * PW;
+            const double *x = tp(o.x, chunk) + sub;
+            D2 acc = make_double2(0.0, 0.0);
+            int r0, r1;
+            my_rows<CS>(o, sm, r0, r1);
+            for (int i = r0 + threadIdx.x / LPR; i < r1; i += NTt / LPR) {
+                const double w = __ldg(o.val + i);
+                const D2 xv = ld2c(x + (size_t)__ldg(o.col + i) * TW);
+                acc.x = fma(w, xv.x, acc.x);
+                acc.y = fma(w, xv.y, acc.y);
+            }
+            block_dot<NTt, CS>(acc, sm, 3, false);
         } break;
         case OP_SC_INIT: sc_init(o, tile, sm, P); break;
         case OP_SC_ALPHA: sc_alpha(o, sm); break;
