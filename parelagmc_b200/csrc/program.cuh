@@ -725,23 +725,37 @@ __device__ __forceinline__ void op_lincomb3(const Op &o, double *chunk, Smem &sm
     const int nj = o.a0;
     const double cb = o.cb;
     D2 acc = make_double2(0.0, 0.0);
+    // rows [r0, rj): with the fused Jacobi block; rows [rj, r1): the plain update.  Two branch-free loops (the loads of a
+    // conditional body cannot be hoisted over the stores of the previous row); a thread keeps the rows it had in the
+    // single loop, so the partial sums of the dot are added in the same order.
+    const int rj = JACOBI ? min(r1, max(r0, nj)) : r0;
+    int row = r0 + threadIdx.x / LPR;
+    if (JACOBI) {
 #pragma unroll 4
-    for (int row = r0 + threadIdx.x / LPR; row < r1; row += NTt / LPR) {
+        for (; row < rj; row += NTt / LPR) {
+            const size_t ro = (size_t)row * TW;
+            const D2 qv = ld2c(q + ro), vv = ld2c(v1 + ro);
+            D2 cv = make_double2(0.0, 0.0);
+            if (anyc) cv = ld2c(v0 + ro);
+            D2 di;
+            if (BDINV) di = ld2c(dinvb + ro);
+            else { const double t = __ldg(o.fixed + row); di = make_double2(t, t); }
+            const D2 vn = make_double2(fma(a.x, qv.x, fma(b.x, vv.x, c.x * cv.x)), fma(a.y, qv.y, fma(b.y, vv.y, c.y * cv.y)));
+            st2(v0 + ro, vn);
+            const D2 zn = make_double2(cb * di.x * vn.x, cb * di.y * vn.y);
+            st2(z + ro, zn);
+            acc.x = fma(zn.x, vn.x, acc.x);
+            acc.y = fma(zn.y, vn.y, acc.y);
+        }
+    }
+#pragma unroll 4
+    for (; row < r1; row += NTt / LPR) {
         const size_t ro = (size_t)row * TW;
         const D2 qv = ld2c(q + ro), vv = ld2c(v1 + ro);
         D2 cv = make_double2(0.0, 0.0);
         if (anyc) cv = ld2c(v0 + ro);
         const D2 vn = make_double2(fma(a.x, qv.x, fma(b.x, vv.x, c.x * cv.x)), fma(a.y, qv.y, fma(b.y, vv.y, c.y * cv.y)));
         st2(v0 + ro, vn);
-        if (JACOBI && row < nj) {
-            D2 di;
-            if (BDINV) di = ld2c(dinvb + ro);
-            else { const double t = __ldg(o.fixed + row); di = make_double2(t, t); }
-            const D2 zn = make_double2(cb * di.x * vn.x, cb * di.y * vn.y);
-            st2(z + ro, zn);
-            acc.x = fma(zn.x, vn.x, acc.x);
-            acc.y = fma(zn.y, vn.y, acc.y);
-        }
     }
     if (JACOBI) block_dot<NTt, CS>(acc, sm, o.slot, false);
 }
@@ -802,6 +816,35 @@ __device__ __forceinline__ void op_sol_update(const Op &o, double *chunk, Smem &
     }
 }
 
+// one Chebyshev step of op_cheb_small for row `row`: the operator entries (and, weighted, the weight rows) are read from
+// shared memory (SH: staged once per operation) or through the read-only path from L2
+template <bool WEIGHTED, bool SH>
+__device__ __forceinline__ D2 cheb_small_row_sum(const int *__restrict__ off, const unsigned char *__restrict__ pk, const double *__restrict__ V,
+                                                 const double *zin, int row)
+{
+    constexpr int ES = WEIGHTED ? 16 : 12;
+    const int sl = row / SLICE, rs = row % SLICE;
+    const int k0 = __ldg(off + sl), w = __ldg(off + sl + 1) - k0;
+    const unsigned char *base = pk + (size_t)k0 * (SLICE * ES);
+    const double *eval = reinterpret_cast<const double *>(base) + rs;
+    const int *ecol = reinterpret_cast<const int *>(base + (size_t)w * (SLICE * 8)) + rs;
+    const int *ewid = ecol + w * SLICE;
+    D2 s = make_double2(0.0, 0.0);
+    for (int k = 0; k < w; ++k) {
+        const double c = SH ? eval[k * SLICE] : __ldg(eval + k * SLICE);
+        const D2 xv = ld2c(zin + (size_t)(SH ? ecol[k * SLICE] : __ldg(ecol + k * SLICE)) * TW);
+        if (WEIGHTED) {
+            const D2 wv = ld2c(V + (size_t)(SH ? ewid[k * SLICE] : __ldg(ewid + k * SLICE)) * TW);
+            s.x = fma(c * wv.x, xv.x, s.x);
+            s.y = fma(c * wv.y, xv.y, s.y);
+        } else {
+            s.x = fma(c, xv.x, s.x);
+            s.y = fma(c, xv.y, s.y);
+        }
+    }
+    return s;
+}
+
 // The coarsest level of the Schur V-cycle (and the whole Schur preconditioner of the coarsest mesh level) is a
 // Chebyshev iteration of degree a0 on a few dozen rows.  As separate operations every step costs the fixed latency of
 // an operation (operation fetch, first memory round trip, barrier: 4-14 k cycles for 2 KB of data).  Here the whole
@@ -817,11 +860,38 @@ __device__ __forceinline__ void op_cheb_small(const Op &o, double *chunk, Smem &
     const bool mine = cluster_rank<CS>(sm) == 0;
     const double *__restrict__ r = tp(o.r, chunk) + sub;
     double *__restrict__ zg = tp(o.y, chunk) + sub;
-    const double *__restrict__ V = WEIGHTED ? tp(o.v, chunk) + sub : nullptr;
+    const double *V = WEIGHTED ? tp(o.v, chunk) + sub : nullptr;
     const double *__restrict__ dinvb = WEIGHTED ? tp(o.w, chunk) + sub : nullptr;
     const double *__restrict__ coef = o.val;
     double *zs0 = reinterpret_cast<double *>(scratch) + sub, *zs1 = zs0 + SMALLN * TW, *ds = zs1 + SMALLN * TW;
     constexpr int ES = WEIGHTED ? 16 : 12;
+    // The operator's entries and the tile's weight rows are copied into shared memory once (when the CTA's staging area has
+    // room behind the iterates): every step then reads them at shared-memory latency instead of paying two dependent L2
+    // round trips (entries -> weights).  o.a1 = number of weight rows (weighted operators).
+    constexpr size_t AVAIL = (size_t)(NTt / 32) * NSTAGE * sizeof(WarpStage);
+    constexpr size_t ITER_BYTES = 3 * (size_t)SMALLN * TW * sizeof(double);
+    const int nsl = (n + SLICE - 1) / SLICE;
+    const size_t ebytes = (size_t)__ldg(o.rowptr + nsl) * (SLICE * ES);
+    const size_t vbytes = WEIGHTED ? (size_t)o.a1 * TW * sizeof(double) : 0;
+    const bool staged = deg > 1 && AVAIL > ITER_BYTES && ebytes + vbytes <= AVAIL - ITER_BYTES && (!WEIGHTED || o.a1 > 0);
+    const unsigned char *pk = o.pk;
+    if (mine && staged) {
+        unsigned char *se = scratch + ITER_BYTES;
+        const uint4 *src = reinterpret_cast<const uint4 *>(o.pk);
+        uint4 *dst = reinterpret_cast<uint4 *>(se);
+        const int ne16 = (int)(ebytes / 16);
+        for (int i = threadIdx.x; i < ne16; i += NTt) dst[i] = __ldg(src + i);
+        pk = se;
+        if (WEIGHTED) {
+            double *sv = reinterpret_cast<double *>(se + ebytes);
+            const double2 *vsrc = reinterpret_cast<const double2 *>(tp(o.v, chunk));
+            double2 *vdst = reinterpret_cast<double2 *>(sv);
+            const int nv16 = (int)(vbytes / 16);
+            for (int i = threadIdx.x; i < nv16; i += NTt) vdst[i] = vsrc[i];
+            V = sv + sub;
+        }
+        // the first step (j = 0) reads neither; the barrier that ends it publishes the copies
+    }
     D2 acc = make_double2(0.0, 0.0);
     if (mine) {
         double *zin = zs0, *zout = zs1;
@@ -838,25 +908,8 @@ __device__ __forceinline__ void op_cheb_small(const Op &o, double *chunk, Smem &
                     dn = make_double2(cb * di.x * rv.x, cb * di.y * rv.y);
                     zn = dn;
                 } else {       // EP_CHEB: d = ca d + cb dinv (r - A z);  z' = z + d
-                    const int sl = row / SLICE, rs = row % SLICE;
-                    const int k0 = __ldg(o.rowptr + sl), w = __ldg(o.rowptr + sl + 1) - k0;
-                    const unsigned char *base = o.pk + (size_t)k0 * (SLICE * ES);
-                    const double *__restrict__ eval = reinterpret_cast<const double *>(base) + rs;
-                    const int *__restrict__ ecol = reinterpret_cast<const int *>(base + (size_t)w * (SLICE * 8)) + rs;
-                    const int *__restrict__ ewid = ecol + w * SLICE;
-                    D2 s = make_double2(0.0, 0.0);
-                    for (int k = 0; k < w; ++k) {
-                        const double c = __ldg(eval + k * SLICE);
-                        const D2 xv = ld2c(zin + (size_t)__ldg(ecol + k * SLICE) * TW);
-                        if (WEIGHTED) {
-                            const D2 wv = ld2c(V + (size_t)__ldg(ewid + k * SLICE) * TW);
-                            s.x = fma(c * wv.x, xv.x, s.x);
-                            s.y = fma(c * wv.y, xv.y, s.y);
-                        } else {
-                            s.x = fma(c, xv.x, s.x);
-                            s.y = fma(c, xv.y, s.y);
-                        }
-                    }
+                    const D2 s = staged ? cheb_small_row_sum<WEIGHTED, true>(o.rowptr, pk, V, zin, row)
+                                        : cheb_small_row_sum<WEIGHTED, false>(o.rowptr, pk, V, zin, row);
                     dn = make_double2(cb * di.x * (rv.x - s.x), cb * di.y * (rv.y - s.y));
                     if (ca != 0.0) {
                         const D2 dv = ld2c(ds + ro);
