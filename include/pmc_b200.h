@@ -80,7 +80,9 @@ int pmc_set_preconditioner(pmc_handle h, int mass_degree, int schur_degree, doub
  * on the realisation, so its spectrum is computed once at set-up and the number of steps for the requested residual
  * reduction is known a priori (no dot products; the true residual norm is still checked per realisation after the steps),
  * -1 = the SPD form (Chebyshev) when alpha W dominates the Schur complement, i.e. for short correlation lengths,
- * MINRES otherwise), mass_scale (relative scaling of the Jacobi mass block against the Schur block of the MINRES
+ * MINRES otherwise), cheb_lo_scale / cheb_hi_scale (sampler: safety margins on the Ritz estimates of the extreme
+ * eigenvalues the Chebyshev interval is built from; defaults 0.96 / 1.01), schur_degree_coarse (smoother degree on the
+ * V-levels between the finest and the coarsest; 0 = as schur_degree, -1 = choose), mass_scale (relative scaling of the Jacobi mass block against the Schur block of the MINRES
  * preconditioner; default 1), max_vlevels (depth of the Schur V-cycle; 0 = full hierarchy, -1 = decide from the mass
  * term, sampler only), amg (coarse spaces of the Schur V-cycle: 0 = the hierarchy's L2 prolongators, 1 = strength-aware
  * pairwise aggregation built at set-up, -1 = aggregation only when the couplings are anisotropic), amg_passes (pairwise
@@ -92,7 +94,9 @@ int pmc_set_preconditioner(pmc_handle h, int mass_degree, int schur_degree, doub
  * CTAs of a cooperative launch per tile, for one or two tiles of very large levels; -1 = never), "solo_rows" (in a group,
  * operations with at most this many rows run on its first CTA), "stage_operators" (0 = read operator entries from L2
  * instead of staging them through shared memory with TMA bulk copies), "defer_x" (0 = update the MINRES solution
- * every iteration instead of once per iteration pair), "cheb_three_term" (0 = keep a separate update vector in the sampler's
+ * every iteration instead of once per iteration pair), "qoi_only" (0 = Darcy solves form the solution vector even when the
+ * caller reads Q only; by default such solves carry Q = obs . x by scalar recurrences of the MINRES coefficients),
+ * "cheb_three_term" (0 = keep a separate update vector in the sampler's
  * Chebyshev steps instead of reading the previous iterate from the buffer a step overwrites), "single_wave" (1 = prefer one wave of smaller CTAs), and
  * "renumber" (0 = keep the caller's numbering of the RT dofs inside the library; to be set before the uploads), and
  * "cache_results" (see pmc_sampler_eval_batch). */

@@ -115,6 +115,9 @@ struct PrecCfg {
     int coarse_degree = 8;     // Chebyshev steps on the coarsest V-cycle level
     double coarse_ratio = 30.0;
     double omega = 1.0;        // over-correction factor of the piecewise-constant coarse-grid correction
+    double cheb_lo_scale = 0.96, cheb_hi_scale = 1.01;  // sampler, Chebyshev semi-iteration: safety margins applied to the Ritz
+                               // estimates of the extreme eigenvalues of diag(H)^-1 H (a too narrow interval is caught by the
+                               // residual check after the a-priori steps and costs restarted blocks; tests use that)
     double mass_scale = 1.0;   // relative scaling of the two preconditioner blocks: the Jacobi mass block is (mass_scale * theta * D)^-1
                                // (MINRES is invariant under a common factor, so one parameter covers both blocks; degree 1 only)
     bool omega_user = false;   // set through pmc_set_option: keep it whatever coarse spaces are chosen
@@ -780,8 +783,8 @@ static int prepare_sampler(Ctx *c, int level)
                 };
                 double lo = 1.0, hi = 1.0;
                 lanczos_extremes(Nf, 80, applyH, &lo, &hi);
-                sys.h_hi = 1.01 * hi;
-                sys.h_lo = 0.96 * lo;
+                sys.h_hi = sys.cfg.cheb_hi_scale * hi;
+                sys.h_lo = sys.cfg.cheb_lo_scale * lo;
                 if (getenv("PMC_DEBUG_CHEB")) fprintf(stderr, "[pmc] sampler level %d: spectrum of D^-1 H in [%.5f, %.5f] (Ritz), using [%.5f, %.5f]\n", level, lo, hi, sys.h_lo, sys.h_hi);
                 if (!(sys.h_lo > 0.0) || !(sys.h_hi > sys.h_lo)) sys.cheb = false;
             }
@@ -1982,7 +1985,7 @@ static const double *cache_lookup(Ctx *c, int slot, int level, int nsamples, int
     return R.p;
 }
 
-static dim3 grid1d(size_t n) { return dim3((unsigned)std::min<size_t>((n + 255) / 256, 148 * 16)); }
+static dim3 grid1d(const Ctx *c, size_t n) { return dim3((unsigned)std::min<size_t>((n + 255) / 256, (size_t)c->num_sms * 16)); }
 
 // host [ns][n] -> tile-major batched (via the staging buffer `stage`)
 static int upload_rows(Ctx *c, const double *host, int ns, int n, double *stage, Off dst, Off chunk, int mode, double neg_g,
@@ -1993,8 +1996,8 @@ static int upload_rows(Ctx *c, const double *host, int ns, int n, double *stage,
     if (dev_src) stage = const_cast<double *>(dev_src);   // already on the device in the host layout (result cache)
     else CK(cudaMemcpyAsync(stage, host, (size_t)ns * n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
     const size_t total = (size_t)ntiles * n * TW;
-    if (mode == 1) launch(c, PMC_K_MISC, (double)total * 16.0, k_to_tiles<1>, grid1d(total), dim3(256), n, chunk, ntiles, ns, (const double *)stage, d, neg_g, w_sqrt, rowmap);
-    else launch(c, PMC_K_MISC, (double)total * 16.0, k_to_tiles<0>, grid1d(total), dim3(256), n, chunk, ntiles, ns, (const double *)stage, d, neg_g, w_sqrt, rowmap);
+    if (mode == 1) launch(c, PMC_K_MISC, (double)total * 16.0, k_to_tiles<1>, grid1d(c, total), dim3(256), n, chunk, ntiles, ns, (const double *)stage, d, neg_g, w_sqrt, rowmap);
+    else launch(c, PMC_K_MISC, (double)total * 16.0, k_to_tiles<0>, grid1d(c, total), dim3(256), n, chunk, ntiles, ns, (const double *)stage, d, neg_g, w_sqrt, rowmap);
     return PMC_OK;
 }
 
@@ -2004,8 +2007,8 @@ static int download_rows(Ctx *c, Off src_off, Off chunk, int ns, int n, double *
 {
     const size_t total = (size_t)ns * n;
     const double *src = (const double *)c->arena.base + src_off;
-    if (do_exp) launch(c, PMC_K_MISC, (double)total * 16.0, k_from_tiles<1>, grid1d(total), dim3(256), n, chunk, ns, src, stage, rowmap);
-    else launch(c, PMC_K_MISC, (double)total * 16.0, k_from_tiles<0>, grid1d(total), dim3(256), n, chunk, ns, src, stage, rowmap);
+    if (do_exp) launch(c, PMC_K_MISC, (double)total * 16.0, k_from_tiles<1>, grid1d(c, total), dim3(256), n, chunk, ns, src, stage, rowmap);
+    else launch(c, PMC_K_MISC, (double)total * 16.0, k_from_tiles<0>, grid1d(c, total), dim3(256), n, chunk, ns, src, stage, rowmap);
     CK(cudaMemcpyAsync(host, stage, total * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     return PMC_OK;
 }
@@ -2140,6 +2143,8 @@ int pmc_set_option(pmc_handle c, const char *key, double value)
         else if (k == "coarse_ratio" && value > 1) g->coarse_ratio = value;
         else if (k == "omega" && value > 0) { g->omega = value; g->omega_user = true; }
         else if (k == "mass_scale" && value > 0) g->mass_scale = value;
+        else if (k == "cheb_lo_scale" && value > 0) g->cheb_lo_scale = value;
+        else if (k == "cheb_hi_scale" && value > 0) g->cheb_hi_scale = value;
         else if (k == "max_vlevels") g->max_vlevels = (int)value;
         else if (k == "method") g->method = (int)value;
         else if (k == "amg") g->amg = (int)value;
@@ -2524,7 +2529,7 @@ int pmc_rng_map(pmc_handle c, int64_t n, const int32_t *engine, double *out)
     double *d_out = (double *)c->arena.base;
     int32_t *d_in = (int32_t *)((char *)c->arena.base + off);
     CK(cudaMemcpyAsync(d_in, engine, (size_t)n * 4, cudaMemcpyHostToDevice, c->stream));
-    launch(c, PMC_K_RNG, (double)n * 12.0, k_rng_map, grid1d((size_t)n), dim3(256), n, (const int32_t *)d_in, d_out, c->mu, c->sigma);
+    launch(c, PMC_K_RNG, (double)n * 12.0, k_rng_map, grid1d(c, (size_t)n), dim3(256), n, (const int32_t *)d_in, d_out, c->mu, c->sigma);
     CK(cudaMemcpyAsync(out, d_out, (size_t)n * 8, cudaMemcpyDeviceToHost, c->stream));
     return finish(c);
 }
@@ -2841,13 +2846,17 @@ static int level_batch(Ctx *c, int level, int nlevels, int nsamples, uint64_t po
     int B = 0;
     if ((rc = size_batch(c, per_sample, 32, nsamples, &B))) return rc;
     if ((rc = ensure_pinned(c, 16 + (rows ? (size_t)B * 4 : 0)))) return rc;
-    const unsigned long long it0 = c->iters_seen;
+    // iterations of THIS call: the device counter is read (stream-ordered) before the first launch, because host-buffer
+    // calls made on the handle in between advance it without updating iters_seen
+    unsigned long long it0 = c->iters_seen;
     for (int s0 = 0; s0 < nsamples; s0 += B) {
         const int ns = std::min(B, nsamples - s0);
         const int ld = pad_ld(ns);
         double *out9 = (double *)c->arena.base + (size_t)(ld / TW) * (size_t)chunk;
         double *rows_d = rows ? out9 + 16 : nullptr;
         pg.ops[rng_op].u0 = pos0 + (uint64_t)s0 * (uint64_t)Ne;
+        if (s0 == 0)
+            CK(cudaMemcpyAsync(c->h_pinned + 11, &c->d_pstats->iters_total, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
         if ((rc = run_program(c, pg, ns, chunk, DF.sys.N))) return rc;
         launch(c, PMC_K_MISC, (double)ns * 16.0, k_mlmc_accumulate, dim3(1), dim3(256), ns, (const double *)c->arena.base, chunk,
                Qf, coarsest ? (Off)-1 : Qc, cost, out9, rows_d);
@@ -2856,6 +2865,7 @@ static int level_batch(Ctx *c, int level, int nlevels, int nsamples, uint64_t po
         if (rows) CK(cudaMemcpyAsync(c->h_pinned + 16, rows_d, (size_t)ns * 4 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
         if ((rc = finish(c))) return rc;
         const double *o = c->h_pinned;
+        if (s0 == 0) memcpy(&it0, c->h_pinned + 11, sizeof(unsigned long long));
         memcpy(&c->iters_seen, c->h_pinned + 10, sizeof(unsigned long long));
         if (mc) {
             // MC_Manager enum {Q2, Q, ABSQ, C} (/root/reference/src/MC_Manager.hpp:61)
@@ -3017,13 +3027,15 @@ int pmc_bayes_level_batch(pmc_handle c, int level, int nlevels, int nsamples, ui
     int B = 0;
     if ((rc = size_batch(c, per_sample, 40, nsamples, &B))) return rc;
     if ((rc = ensure_pinned(c, 32 + (rows ? (size_t)B * 5 : 0)))) return rc;
-    const unsigned long long it0 = c->iters_seen;
+    unsigned long long it0 = c->iters_seen;   // replaced by the device counter read before the first launch (see level_batch)
     for (int s0 = 0; s0 < nsamples; s0 += B) {
         const int ns = std::min(B, nsamples - s0);
         const int ld = pad_ld(ns);
         double *out20 = (double *)c->arena.base + (size_t)(ld / TW) * (size_t)chunk;
         double *rows_d = rows ? out20 + 32 : nullptr;
         for (int draw = 0; draw < 2; ++draw) pg.ops[rng_ops[draw]].u0 = pos0 + (uint64_t)(2 * (uint64_t)s0 + draw) * (uint64_t)Ne;
+        if (s0 == 0)
+            CK(cudaMemcpyAsync(c->h_pinned + 21, &c->d_pstats->iters_total, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
         if ((rc = run_program(c, pg, ns, chunk, DF.sys.N))) return rc;
         CK(cudaMemsetAsync(out20, 0, 20 * sizeof(double), c->stream));
         launch(c, PMC_K_MISC, (double)ns * 32.0, k_bayes_accumulate, dim3(1), dim3(256), ns, (const double *)c->arena.base, chunk,
@@ -3032,6 +3044,7 @@ int pmc_bayes_level_batch(pmc_handle c, int level, int nlevels, int nsamples, ui
         CK(cudaMemcpyAsync(c->h_pinned + 20, &c->d_pstats->iters_total, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
         if (rows) CK(cudaMemcpyAsync(c->h_pinned + 32, rows_d, (size_t)ns * 5 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
         if ((rc = finish(c))) return rc;
+        if (s0 == 0) memcpy(&it0, c->h_pinned + 21, sizeof(unsigned long long));
         memcpy(&c->iters_seen, c->h_pinned + 20, sizeof(unsigned long long));
         for (int k = 0; k < 20; ++k) sums[k] += c->h_pinned[k];
         if (rows) memcpy(rows + 5 * (size_t)s0, c->h_pinned + 32, (size_t)ns * 5 * sizeof(double));

@@ -179,6 +179,61 @@ def test_sampler_methods_agree(orc, prob):
             c.close()
 
 
+def test_chebyshev_sampler_restarts_when_the_spectrum_estimate_is_too_narrow(orc, prob):
+    """The Chebyshev semi-iteration runs an a-priori number of steps and then CHECKS the true residual norm per realisation.
+    With a deliberately wrong spectrum estimate ("sampler.cheb_lo_scale" = 2.5: the interval misses the lower part of the
+    spectrum, so the a-priori count is far too small) the check fails, the tiles run restarted blocks until the stopping
+    rule holds, and the fields still equal the oracle's to the field tolerance."""
+    from oracle.binding import Yarn5
+    from common import make_context
+    good = make_context(prob, True, 1e-12, 1e-30, 2000, options={"sampler.method": 2})
+    bad = make_context(prob, True, 1e-12, 1e-30, 2000, options={"sampler.method": 2, "sampler.cheb_lo_scale": 2.5})
+    try:
+        lev, n = 0, 6
+        Ne = prob["sampler"][lev].Ne
+        xi = Yarn5().jump(31).normals(n * Ne).reshape(n, Ne)
+        sg, eg, itg = good.sampler_eval_batch(lev, xi)
+        sb, eb, itb = bad.sampler_eval_batch(lev, xi)
+        print(f"a-priori steps {itg.max()}, with the narrow interval {itb.min()}..{itb.max()}")
+        assert itg.min() == itg.max()                 # no restart with the real estimate
+        assert itb.max() < 2000 and itb.max() != itg.max()          # restarted blocks were needed, and they ended
+        for j in range(n):
+            so, eo, _ = orc.sampler_eval(lev, xi[j])
+            assert rel_l2(eb[j], eo) < FIELD_TOL and rel_l2(sb[j], so) < FIELD_TOL
+            assert rel_l2(eg[j], eo) < FIELD_TOL
+    finally:
+        good.close()
+        bad.close()
+
+
+@pytest.mark.parametrize("shape", [{}, {"cluster_size": 2, "cta_threads": 256}, {"group_size": 5}])
+def test_functional_only_darcy_solve(prob, shape):
+    """DarcySolver::SolveFwd returns Q and C only.  The MINRES that carries Q = obs . x by scalar recurrences and never forms
+    the solution ("qoi_only", default) returns the Q of the solve that does form it, to round-off, after the same number of
+    iterations -- one CTA per tile, cluster-split and as a grid group; the fused level loop likewise."""
+    from common import make_context
+    c1 = make_context(prob, True, 1e-12, 1e-30, 2000, options=dict(shape))
+    c0 = make_context(prob, True, 1e-12, 1e-30, 2000, options=dict(shape, qoi_only=0))
+    try:
+        for lev in range(prob["nlevels"]):
+            d = prob["darcy"][lev]
+            k = np.exp(np.random.default_rng(5 + lev).standard_normal((7, d.Ne)))
+            Q1, C1, _, it1 = c1.darcy_solve_batch(lev, k)                   # functional only
+            Q0, C0, sol, it0 = c0.darcy_solve_batch(lev, k, want_sol=True)  # forms the solution
+            Qs, _, sol1, its = c1.darcy_solve_batch(lev, k, want_sol=True)  # the default handle forms it when it is asked for
+            assert np.array_equal(it1, it0) and np.array_equal(C1, C0)
+            assert np.allclose(Q1, Q0, rtol=1e-11, atol=1e-13)
+            assert np.allclose(Q0, sol @ np.asarray(d.obs), rtol=1e-12, atol=1e-14)
+            assert np.array_equal(sol1, sol) and np.array_equal(Qs, Q0)
+        for lev in (1, 0):
+            _, r1, i1 = c1.mlmc_level_batch(lev, 9, 77, want_rows=True)
+            _, r0, i0 = c0.mlmc_level_batch(lev, 9, 77, want_rows=True)
+            assert i1 == i0 and np.allclose(r1[:, :3], r0[:, :3], rtol=1e-10, atol=1e-12)
+    finally:
+        c1.close()
+        c0.close()
+
+
 def test_chained_calls_reuse_device_results(prob):
     """Option "cache_results": Sample -> Eval -> SolveFwd with NULL for the vectors the library itself just produced
     gives bitwise the results of passing the host copies back; a mismatching request fails loudly."""

@@ -319,3 +319,69 @@ def test_ratio_splitting_and_single_level_managers():
     sls.Run()
     _, r = be.o.bayes_level(0, 6, p["pos_after_setup"], nthreads=2, nlevels=1)
     assert sls.estimate() == pytest.approx((r[:, 0] / r[:, 2]).mean())
+
+
+def test_lanczos_extremes_of_the_set_up_toolkit(tmp_path):
+    """csrc/host_sparse.hpp: lanczos_extremes (the spectrum estimate behind the sampler's a-priori Chebyshev step count):
+    the extreme Ritz values of a Jacobi-scaled SPD operator after 80 steps against numpy's eigenvalues."""
+    import os, subprocess, textwrap
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    n = 20
+    src = tmp_path / "lz.cpp"
+    src.write_text(textwrap.dedent(f"""
+        #include "host_sparse.hpp"
+        #include <cstdio>
+        using namespace pmc;
+        int main() {{
+            const int n = {n}, N = n * n * n;   // 3D 7-point operator + mass term, Jacobi scaled
+            std::vector<double> d(N);
+            auto coef = [&](int i, int j, int k) {{ return 1.0 + 0.9 * std::sin(0.7 * i + 1.3 * j + 2.1 * k); }};
+            auto id = [&](int i, int j, int k) {{ return (k * n + j) * n + i; }};
+            auto raw = [&](const double *x, double *y) {{
+                for (int k = 0; k < n; ++k) for (int j = 0; j < n; ++j) for (int i = 0; i < n; ++i) {{
+                    const double c = coef(i, j, k);
+                    double s = (0.8 + 6.0 * c) * x[id(i, j, k)];
+                    if (i > 0) s -= 0.5 * (c + coef(i - 1, j, k)) * x[id(i - 1, j, k)];
+                    if (i + 1 < n) s -= 0.5 * (c + coef(i + 1, j, k)) * x[id(i + 1, j, k)];
+                    if (j > 0) s -= 0.5 * (c + coef(i, j - 1, k)) * x[id(i, j - 1, k)];
+                    if (j + 1 < n) s -= 0.5 * (c + coef(i, j + 1, k)) * x[id(i, j + 1, k)];
+                    if (k > 0) s -= 0.5 * (c + coef(i, j, k - 1)) * x[id(i, j, k - 1)];
+                    if (k + 1 < n) s -= 0.5 * (c + coef(i, j, k + 1)) * x[id(i, j, k + 1)];
+                    y[id(i, j, k)] = s;
+                }}
+            }};
+            for (int k = 0; k < n; ++k) for (int j = 0; j < n; ++j) for (int i = 0; i < n; ++i) d[id(i, j, k)] = 1.0 / std::sqrt(0.8 + 6.0 * coef(i, j, k));
+            std::vector<double> t(N);
+            auto op = [&](const double *x, double *y) {{
+                for (int i = 0; i < N; ++i) t[i] = d[i] * x[i];
+                raw(t.data(), y);
+                for (int i = 0; i < N; ++i) y[i] *= d[i];
+            }};
+            double lo, hi;
+            lanczos_extremes(N, 80, op, &lo, &hi);
+            std::printf("%.12f %.12f ", lo, hi);
+        }}
+        """))
+    exe = tmp_path / "lz"
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-I", os.path.join(root, "parelagmc_b200", "csrc"), "-o", str(exe), str(src)])
+    lo, hi = (float(v) for v in subprocess.check_output([str(exe)], text=True).split())
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spl
+    idx = np.arange(n ** 3).reshape(n, n, n)          # [k][j][i]
+    kk, jj, ii = np.meshgrid(np.arange(n), np.arange(n), np.arange(n), indexing="ij")
+    c = 1.0 + 0.9 * np.sin(0.7 * ii + 1.3 * jj + 2.1 * kk)
+    rows, cols, vals = [idx.ravel()], [idx.ravel()], [(0.8 + 6.0 * c).ravel()]
+    for ax in range(3):
+        a = [slice(None)] * 3; b = [slice(None)] * 3
+        a[ax] = slice(0, n - 1); b[ax] = slice(1, n)
+        w = -0.5 * (c[tuple(a)] + c[tuple(b)]).ravel()
+        rows += [idx[tuple(a)].ravel(), idx[tuple(b)].ravel()]
+        cols += [idx[tuple(b)].ravel(), idx[tuple(a)].ravel()]
+        vals += [w, w]
+    A = sp.csr_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))))
+    D = sp.diags(1.0 / np.sqrt(A.diagonal()))
+    As = D @ A @ D
+    e_hi = spl.eigsh(As, k=1, which="LA", return_eigenvectors=False)[0]
+    e_lo = spl.eigsh(As, k=1, sigma=0, which="LM", return_eigenvectors=False)[0]
+    # Ritz values lie inside the spectrum and have converged to the margins the library widens them by (4 % / 1 %)
+    assert e_lo - 1e-10 <= lo <= e_lo * 1.03 and e_hi * 0.995 <= hi <= e_hi + 1e-10, (lo, e_lo, hi, e_hi)
