@@ -787,6 +787,37 @@ static int prepare_sampler(Ctx *c, int level)
                 sys.h_lo = sys.cfg.cheb_lo_scale * lo;
                 if (getenv("PMC_DEBUG_CHEB")) fprintf(stderr, "[pmc] sampler level %d: spectrum of D^-1 H in [%.5f, %.5f] (Ritz), using [%.5f, %.5f]\n", level, lo, hi, sys.h_lo, sys.h_hi);
                 if (!(sys.h_lo > 0.0) || !(sys.h_hi > sys.h_lo)) sys.cheb = false;
+                // Self-test of the interval, once, on the host: the Chebyshev iteration the device will run, applied to a
+                // pseudo-random right-hand side, must deliver the reduction its step count promises.  An upper end below
+                // the true lambda_max (unconverged Lanczos) would make the iteration diverge on the device; in that case the
+                // level falls back to PCG, which needs no spectrum.  Skipped when the margins were set by hand.
+                if (sys.cheb && sys.cfg.cheb_lo_scale == 0.96 && sys.cfg.cheb_hi_scale == 1.01) {
+                    const double target = 1e-6;
+                    const double th = 0.5 * (sys.h_hi + sys.h_lo), de = 0.5 * (sys.h_hi - sys.h_lo), sg = th / de;
+                    const int m = std::max(2, (int)std::ceil(std::acosh(1.0 / target) / std::acosh(sg)));
+                    std::vector<double> cf = cheb_coefficients(sys.h_lo, sys.h_hi, m);
+                    std::vector<double> b(Nf), z(Nf, 0.0), d(Nf, 0.0), r(Nf);
+                    uint64_t sd = 0x2545F4914F6CDD1DULL;
+                    for (int i = 0; i < Nf; ++i) {
+                        sd = sd * 6364136223846793005ULL + 1442695040888963407ULL;
+                        b[i] = (double)(sd >> 40) / (double)(1 << 24) - 0.5;
+                    }
+                    // scaled system: A = D^-1/2 H D^-1/2 (applyH), plain Chebyshev (the device's D^-1 form is similar to it)
+                    double n0 = 0, n1 = 0;
+                    for (int i = 0; i < Nf; ++i) n0 += b[i] * b[i];
+                    for (int j = 0; j < m; ++j) {
+                        applyH(z.data(), r.data());
+                        for (int i = 0; i < Nf; ++i) {
+                            d[i] = cf[2 * j] * d[i] + cf[2 * j + 1] * (b[i] - r[i]);
+                            z[i] += d[i];
+                        }
+                    }
+                    applyH(z.data(), r.data());
+                    for (int i = 0; i < Nf; ++i) n1 += (b[i] - r[i]) * (b[i] - r[i]);
+                    const double red = std::sqrt(n1 / std::max(n0, 1e-300));
+                    if (getenv("PMC_DEBUG_CHEB")) fprintf(stderr, "[pmc] sampler level %d: Chebyshev self-test, %d steps: reduction %.3e (target %.0e)\n", level, m, red, target);
+                    if (!(red <= 1.5 * target)) sys.cheb = false;
+                }
             }
         }
     }
