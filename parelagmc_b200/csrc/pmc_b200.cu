@@ -114,6 +114,9 @@ struct PrecCfg {
     double schur_ratio = 4.0;  // smoother targets the eigenvalues in [1/ratio, 1] of the l1-scaled operator
     int coarse_degree = 8;     // Chebyshev steps on the coarsest V-cycle level
     double coarse_ratio = 30.0;
+    bool coarse_user = false;  // set through the API: keep them.  Otherwise Darcy with the hierarchy's own coarse spaces runs
+                               // degree 6 over [1/20, 1]: the coarsest level was over-solved (bench level batches 31.75 / 12.07 /
+                               // 1.75 -> 31.60 / 11.76 / 1.56 ms at 0.5 % more iterations)
     double omega = 1.0;        // over-correction factor of the piecewise-constant coarse-grid correction
     double cheb_lo_scale = 0.96, cheb_hi_scale = 1.01;  // sampler, Chebyshev semi-iteration: safety margins applied to the Ritz
                                // estimates of the extreme eigenvalues of diag(H)^-1 H (a too narrow interval is caught by the
@@ -1084,6 +1087,7 @@ static int prepare_darcy(Ctx *c, int level)
             sp = std::move(spc);
         }
     }
+    if (!sys.cfg.coarse_user && sys.own_P.empty()) { sys.cfg.coarse_degree = 6; sys.cfg.coarse_ratio = 20.0; }
     {
         std::vector<double> cc = cheb_coefficients(1.0 / sys.cfg.coarse_ratio, 1.0, sys.cfg.coarse_degree);
         if ((rc = to_device(c, cc, &sys.d_coarse_coef))) return rc;
@@ -2149,8 +2153,8 @@ int pmc_set_preconditioner(pmc_handle c, int mass_degree, int schur_degree, doub
         if (mass_degree > 0) g->mass_degree = mass_degree;
         if (schur_degree > 0) g->schur_degree = schur_degree;
         if (schur_ratio > 1.0) g->schur_ratio = schur_ratio;
-        if (coarse_degree > 0) g->coarse_degree = coarse_degree;
-        if (coarse_ratio > 1.0) g->coarse_ratio = coarse_ratio;
+        if (coarse_degree > 0) { g->coarse_degree = coarse_degree; g->coarse_user = true; }
+        if (coarse_ratio > 1.0) { g->coarse_ratio = coarse_ratio; g->coarse_user = true; }
     }
     return PMC_OK;
 }
@@ -2170,8 +2174,8 @@ int pmc_set_option(pmc_handle c, const char *key, double value)
         else if (k == "schur_degree" && value >= 1) g->schur_degree = (int)value;
         else if (k == "schur_degree_coarse" && value >= -1) g->schur_degree_coarse = (int)value;
         else if (k == "schur_ratio" && value > 1) g->schur_ratio = value;
-        else if (k == "coarse_degree" && value >= 1) g->coarse_degree = (int)value;
-        else if (k == "coarse_ratio" && value > 1) g->coarse_ratio = value;
+        else if (k == "coarse_degree" && value >= 1) { g->coarse_degree = (int)value; g->coarse_user = true; }
+        else if (k == "coarse_ratio" && value > 1) { g->coarse_ratio = value; g->coarse_user = true; }
         else if (k == "omega" && value > 0) { g->omega = value; g->omega_user = true; }
         else if (k == "mass_scale" && value > 0) g->mass_scale = value;
         else if (k == "cheb_lo_scale" && value > 0) g->cheb_lo_scale = value;
