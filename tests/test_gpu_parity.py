@@ -644,13 +644,14 @@ def test_grid_group_matches_single_cta(prob, group, solo):
         cg.close()
 
 
-@pytest.mark.parametrize("opt", ["stage_operators", "defer_x", "fuse_coarse", "renumber", "single_wave"])
+@pytest.mark.parametrize("opt", ["stage_operators", "defer_x", "fuse_coarse", "renumber", "single_wave", "cheb_three_term"])
 def test_kernel_variants_agree(prob, opt):
     """The performance switches do not change what is computed: operator entries staged by TMA or read from L2, the
     MINRES solution update deferred within an iteration pair or not, the coarsest Chebyshev iteration as one
     shared-memory operation or step by step (all bitwise), the library's internal renumbering
     of the RT dofs on or off (round-off: rows are summed in a different order; solutions cross the ABI in the caller's
-    numbering either way), one wave of smaller CTAs."""
+    numbering either way), one wave of smaller CTAs, the sampler's Chebyshev steps with or without a separate update
+    vector (round-off)."""
     from parelagmc_b200.capi import Context
     def run(value):
         c = Context(prob["nlevels"], 0)
