@@ -385,3 +385,58 @@ def test_lanczos_extremes_of_the_set_up_toolkit(tmp_path):
     e_lo = spl.eigsh(As, k=1, sigma=0, which="LM", return_eigenvectors=False)[0]
     # Ritz values lie inside the spectrum and have converged to the margins the library widens them by (4 % / 1 %)
     assert e_lo - 1e-10 <= lo <= e_lo * 1.03 and e_hi * 0.995 <= hi <= e_hi + 1e-10, (lo, e_lo, hi, e_hi)
+
+
+def test_functional_only_minres_recurrence():
+    """The algebra behind the functional-only Darcy solve (csrc/program.cuh: sc_beta with a1 = 1): in preconditioned MINRES
+    x = sum_k cx_k w_k with w_k = cw0 w_{k-2} + cw1 w_{k-1} + cu z_k, so omega_k = obs . w_k follows the same recurrence
+    driven by obs . z_k and Q = obs . x needs neither the direction vectors nor the solution.  numpy restatement of the
+    device's scalar recurrences (lazily normalised Lanczos vectors) on a random saddle-point system."""
+    import scipy.sparse as sp
+    rng = np.random.default_rng(3)
+    nu, npr = 60, 25
+    M = sp.diags(1.0 + rng.random(nu)) + 0.1 * sp.random(nu, nu, 0.05, random_state=1)
+    M = (M + M.T) * 0.5 + sp.identity(nu) * 0.5
+    B = sp.random(npr, nu, 0.2, random_state=2) + sp.eye(npr, nu)
+    A = sp.bmat([[M, B.T], [B, None]]).tocsr()
+    N = nu + npr
+    b = rng.standard_normal(N)
+    obs = np.where(rng.random(N) < 0.2, rng.standard_normal(N), 0.0)
+    dM = M.diagonal()
+    S = (B @ sp.diags(1 / dM) @ B.T).toarray()
+    Sinv = np.linalg.inv(S)
+    P = lambda r: np.concatenate([r[:nu] / dM, Sinv @ r[nu:]])
+    # state of the device program: unnormalised Lanczos vectors v0, v1, preconditioned u1 = P v1, scalars as in sc_init / sc_alpha / sc_beta
+    v0 = np.zeros(N); v1 = b.copy(); u1 = P(v1)
+    beta = np.sqrt(v1 @ u1); ib = 1 / beta; ibprev = 0.0
+    g0 = g1 = 1.0; s0 = s1 = 0.0; eta = beta
+    w0 = np.zeros(N); w1 = np.zeros(N); x = np.zeros(N)
+    om0 = om1 = 0.0; Q = 0.0
+    for it in range(200):
+        q = A @ u1
+        alpha = (u1 @ q) * ib * ib
+        zeta = obs @ u1                                    # OP_DOT_SPARSE
+        v0 = ib * q - alpha * ib * v1 - beta * ibprev * v0  # OP_LINCOMB3 (cq, cv1, cv0)
+        z = P(v0)
+        beta_new = np.sqrt(max(v0 @ z, 0.0))
+        delta = g1 * alpha - g0 * s1 * beta; rho3 = s0 * beta; rho2 = s1 * alpha + g0 * g1 * beta
+        rho1 = np.hypot(delta, beta_new); ir = 1 / rho1
+        cw0, cw1, cu = -rho3 * ir, -rho2 * ir, ib * ir
+        g0, g1 = g1, delta * ir
+        cx = g1 * eta
+        s0, s1 = s1, beta_new * ir
+        eta = -s1 * eta
+        wn = cw0 * w0 + cw1 * w1 + cu * u1                 # OP_SOL_UPDATE (the vectors the functional-only solve never forms)
+        x = x + cx * wn
+        w0, w1 = w1, wn
+        om = cw0 * om0 + cw1 * om1 + cu * zeta             # sc_beta, a1 = 1
+        om0, om1 = om1, om
+        Q += cx * om
+        ibprev, ib, beta = ib, 1 / beta_new, beta_new
+        v0, v1 = v1, v0
+        u1 = z
+        if abs(eta) < 1e-13 * abs(np.sqrt(b @ P(b))):
+            break
+    xs = np.linalg.solve(A.toarray(), b)
+    assert np.linalg.norm(x - xs) / np.linalg.norm(xs) < 1e-9           # the restated MINRES solves the system
+    assert abs(Q - obs @ x) <= 1e-12 * max(1.0, abs(obs @ x))           # and the scalar recurrence carries obs . x
