@@ -78,9 +78,12 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.perf_counter(), line.strip()))
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
+        """Summary of the samples that arrived in [t0, t1] (host clock: the timed region); nvidia-smi needs ~0.1 s before its
+        first sample, so the sampler is started before the warm-up steps and the window is cut out afterwards.  If no sample
+        falls into the window (a very short run) the nearest ones are used and the summary says so."""
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -90,7 +93,15 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for l in self.lines:
+        lines, window = self.lines, "timed region"
+        if t0 is not None and t1 is not None:
+            inside = [l for l in self.lines if t0 <= l[0] <= t1]
+            if inside:
+                lines = inside
+            elif self.lines:      # nearest samples (warm-up steps of the same workload run right before the region)
+                lines = sorted(self.lines, key=lambda l: min(abs(l[0] - t0), abs(l[0] - t1)))[:3]
+                window = "nearest samples (none fell into the timed region)"
+        for _, l in lines:
             f = [x.strip() for x in l.split(",")]
             if len(f) < 7:
                 continue
@@ -103,7 +114,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(n)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "window": window}
 
 
 # ------------------------------------------------------------------------------------------------------------------
@@ -338,18 +349,19 @@ def run_product(args):
             ctxs[0].allreduce_sums(sums)      # ncclAllReduce of 3 x 9 doubles on the handle's stream
         return sums, its
 
-    # ---- warm-up ----
+    # ---- warm-up (the clock sampler starts here: nvidia-smi takes ~0.1 s to deliver its first sample) ----
+    clocks = ClockSampler(local, args.clock_ms)
+    if rank == 0 and not args.no_clocks:
+        clocks.start()
     for _ in range(args.warmup):
         step()
     # ---- timed region: CUDA events on the launching stream; the library also brackets every launch of its
     #      persistent solver kernel (one per level batch, 3 per step) with events on the same stream ----
-    clocks = ClockSampler(local, args.clock_ms)
-    if rank == 0 and not args.no_clocks:
-        clocks.start()
     for c in ctxs:
         c.reset_stats()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_host0 = time.perf_counter()
     e0.record(stream)
     its_total = 0
     for _ in range(args.steps):
@@ -357,9 +369,10 @@ def run_product(args):
         its_total += its
     e1.record(stream)
     barrier()
+    t_host1 = time.perf_counter()
     ms = e0.elapsed_time(e1)
     stats = [c.kernel_stats() for c in ctxs]
-    clk = clocks.stop() if rank == 0 else None
+    clk = clocks.stop(t_host0, t_host1) if rank == 0 else None
     if dist is not None:
         t = torch.tensor([ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -601,7 +614,7 @@ def main():
     ap.add_argument("--no-clocks", action="store_true", help="do not poll nvidia-smi during the timed region")
     ap.add_argument("--no-spe10", action="store_true", help="skip the SPE10-scale leg (BASELINE configs[4])")
     ap.add_argument("--spe10-scale", type=float, default=1.0, help="shrink the SPE10 grid (1.0 = 60x220x85)")
-    ap.add_argument("--clock-ms", type=int, default=100, help="nvidia-smi polling period")
+    ap.add_argument("--clock-ms", type=int, default=20, help="nvidia-smi polling period (the default run times ~120 ms)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
