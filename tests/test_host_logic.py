@@ -440,3 +440,29 @@ def test_functional_only_minres_recurrence():
     xs = np.linalg.solve(A.toarray(), b)
     assert np.linalg.norm(x - xs) / np.linalg.norm(xs) < 1e-9           # the restated MINRES solves the system
     assert abs(Q - obs @ x) <= 1e-12 * max(1.0, abs(obs @ x))           # and the scalar recurrence carries obs . x
+
+
+def test_bench_clock_sampler_windows_the_timed_region():
+    """bench.py's ClockSampler: nvidia-smi lines are time-stamped on arrival and only those inside the timed region count;
+    throttle reasons are collected from them; with no sample inside the window the nearest ones are reported as such."""
+    import importlib.util, os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(root, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+
+    class _P:
+        def terminate(self): pass
+        def wait(self, timeout=None): return 0
+    cs = bench.ClockSampler(0, 20)
+    cs.proc = _P()
+    mk = lambda sm, pc="Not Active": f"{sm}, 1965, 700.0, Not Active, Not Active, Not Active, {pc}"
+    cs.lines = [(0.5, mk(900)), (1.01, mk(1950, "Active")), (1.05, mk(1965)), (1.09, mk(1960)), (2.0, mk(300))]
+    r = cs.stop(1.0, 1.1)
+    assert r["samples"] == 3 and r["sm_mhz"] == 1960.0 and r["sm_max_mhz"] == 1965.0
+    assert r["reasons"] == ["sw_power_cap"] and r["window"] == "timed region"
+    cs.proc = _P()
+    r = cs.stop(5.0, 5.1)
+    assert r["samples"] >= 1 and r["window"].startswith("nearest")
+    cs.proc = None
+    assert bench.ClockSampler(0).stop()["sm_mhz"] is None
