@@ -13,6 +13,10 @@ Findings recorded in DESIGN.md section 5 (iterations at rel 1e-6 on the 16^3 lev
   * mass block: Chebyshev degree 2 / 3 / exact M^-1 (Schur part unchanged)    29-30 / 28-29 / 25
   * fine solve started from the prolongated coarse solution of the same realisation: initial preconditioned residual
     0.11-0.21 of the zero start's, 24-27 instead of 27-29 iterations (exact Schur block)
+  * python tools/prec_prototype.py --consistent : the two blocks must approximate the SAME inverse of M.  With the Jacobi
+    mass block even the exact Schur complement B M^-1 B^T gives 27 iterations (lumped: 28); with a degree-2 Chebyshev mass
+    block the lumped Schur complement gives 26-27, but the consistent one, B p2(D^-1 M) D^-1 B^T (first-order Neumann
+    correction, a 13-point pattern), gives 16-17 (exact Schur complement: 16) -- each with an exact solve of the Schur block.
 """
 import os, sys
 import numpy as np, scipy.sparse as sp, scipy.sparse.linalg as spl
@@ -129,7 +133,32 @@ def make_prec(Mf, Bf, schur="cheb", mass="jacobi", omega=2.5, deg_mid=3):
     return apply
 
 
+def consistent_blocks():
+    for j in range(2):
+        xi = Yarn5().jump(4096 * j).normals(4096)
+        kf = orc.sampler_eval(0, xi)[0]
+        A0, M0, B0, b0 = darcy_mats(d0, kf)
+        dM = M0.diagonal(); Nf = M0.shape[0]
+        Dinv = sp.diags(1 / dM)
+        S1 = (B0 @ Dinv @ B0.T).tocsc()
+        S2 = (B0 @ (Dinv - Dinv @ (M0 - sp.diags(dM)) @ Dinv) @ B0.T).tocsc()
+        Sx = sp.csc_matrix(B0 @ spl.splu(M0.tocsc()).solve(B0.T.toarray()))
+        out = {}
+        for name, S in (("lumped", S1), ("Neumann-1", S2), ("exact", Sx)):
+            lu = spl.splu(S)
+            for mass in ("jacobi", "cheb2"):
+                def P(r, lu=lu, mass=mass):
+                    ru = r[:Nf]
+                    zu = ru / dM if mass == "jacobi" else cheb(M0, 1 / dM, ru, np.zeros(Nf), 2, 0.5, 1.5)
+                    return np.concatenate([zu, lu.solve(r[Nf:])])
+                out[f"S {name} / M {mass}"] = minres(A0, b0, P, np.zeros_like(b0), 1e-6 * np.sqrt(b0 @ P(b0)))[1]
+        print(f"realisation {j}: {out}; entries per row: lumped {S1.nnz / S1.shape[0]:.1f}, Neumann-1 {S2.nnz / S2.shape[0]:.1f}", flush=True)
+
+
 if __name__ == "__main__":
+    if "--consistent" in sys.argv:
+        consistent_blocks()
+        sys.exit(0)
     for j in range(3):
         xi = Yarn5().jump(4096 * j).normals(4096)
         kf = orc.sampler_eval(0, xi)[0]
