@@ -17,6 +17,7 @@ Findings recorded in DESIGN.md section 5 (iterations at rel 1e-6 on the 16^3 lev
     mass block even the exact Schur complement B M^-1 B^T gives 27 iterations (lumped: 28); with a degree-2 Chebyshev mass
     block the lumped Schur complement gives 26-27, but the consistent one, B p2(D^-1 M) D^-1 B^T (first-order Neumann
     correction, a 13-point pattern), gives 16-17 (exact Schur complement: 16) -- each with an exact solve of the Schur block.
+    With the device's V-cycle on the consistent Schur complement instead of the exact solve: 27-29 (over-correction 2.5-3).
 """
 import os, sys
 import numpy as np, scipy.sparse as sp, scipy.sparse.linalg as spl
